@@ -1,0 +1,180 @@
+/*
+ * vfk.h -- C ABI of the batched vfclik control cycle for NVIDIA B200 (sm_100a).
+ *
+ * The reference (arcoslab/vfclik) has no FFI/plugin interface: its boundary is
+ * process + YARP port + Python class.  This header is the boundary a maintainer
+ * binds with ctypes; each entry point names the reference
+ * code it replaces.  Plain C types only; no exceptions cross the ABI; every call
+ * returns VFK_OK (0) or a negative vfk_status and records a message retrievable
+ * with vfk_last_error().
+ *
+ * One "control cycle" of one instance =
+ *   FK + tool compose            scripts/vf:316-332         (Lafik/KDL FK)
+ *   field evaluation + saturation scripts/vf:276-293,344-347 (vfl attractor / decay repellers)
+ *   tool twist shift             scripts/vf:456-459         (PyKDL Twist.RefPoint)
+ *   velocity IK                  scripts/vf:461             (Lafik.getIKV, weighted DLS)
+ *   nullspace motion             scripts/nullspace:75-131,159-184
+ *   joint P controller           scripts/joint_p_controller:79-89,126-146
+ *   command mixer                src/command_mixer.py:71-82
+ *   velocity clamp + command     scripts/bridge:188-203
+ *   plant integration            (external joint_sim; explicit Euler)
+ *
+ * Data layout: every per-instance array is SoA, component-major: element
+ * (component c, instance i) lives at base[c * ld + i], with ld >= n_instances the
+ * leading dimension (in elements).  ld must be a multiple of 32 and every base
+ * pointer 128-byte aligned so that warp loads are full 128-byte lines and the
+ * obstacle tiles can be moved with cp.async.bulk (TMA).  Element type is float
+ * (precision 32) or double (precision 64) as chosen at vfk_create().
+ */
+#ifndef VFK_H_
+#define VFK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFK_VERSION 100          /* 0.1.0 */
+#define VFK_MAX_JOINTS 17
+#define VFK_N_PORTS 6            /* mixer inputs, order of scripts/bridge:593-596 */
+#define VFK_GOAL_COMPS 13        /* R_goal row-major (9), p_goal (3), slowdown distance (1) */
+#define VFK_POSE_COMPS 12        /* R row-major (9), p (3) */
+
+typedef enum vfk_status {
+    VFK_OK = 0,
+    VFK_ERR_INVALID = -1,        /* bad argument (message says which) */
+    VFK_ERR_UNSUPPORTED = -2,    /* e.g. n_joints without a compiled kernel, control mode with N != 7 */
+    VFK_ERR_CUDA = -3,           /* a CUDA runtime call failed */
+    VFK_ERR_NO_DEVICE = -4       /* no sm_100 device: there is no CPU fallback */
+} vfk_status;
+
+/* KDL joint types (PyKDL Joint.*); fixed segments are folded on the host. */
+enum { VFK_JOINT_NONE = 0, VFK_JOINT_ROTX, VFK_JOINT_ROTY, VFK_JOINT_ROTZ,
+       VFK_JOINT_TRANSX, VFK_JOINT_TRANSY, VFK_JOINT_TRANSZ };
+
+/* per-instance flag bits written to vfk_buffers.flags */
+enum { VFK_FLAG_AT_GOAL = 1,     /* scripts/joint_p_controller:135-146 (signed compare, no abs) */
+       VFK_FLAG_NS_LIMIT = 2,    /* scripts/nullspace:120-131 zeroed the nullspace command */
+       VFK_FLAG_NAN = 4,         /* src/command_mixer.py:71-75 */
+       VFK_FLAG_CLAMPED = 8 };   /* scripts/bridge:190-196 ratio < 1 */
+
+enum { VFK_NS_OFF = 0,           /* --no_nullspace (scripts/vfclik:73-79) */
+       VFK_NS_PROJECTOR = 1,     /* qdot_ns = gain * check((I - J^+ J) qdot0) */
+       VFK_NS_CONTROL = 2 };     /* reference 4-float control interface, 1-D nullspace (N = 7) */
+
+/* Serial chain: flange = base * prod_i ( Joint_i(q_i) * tip_i ).  Frames are 12
+ * doubles: R row-major (9) then p (3).  Replaces the PyKDL chain Lafik builds from
+ * config.segments (scripts/vf:153). */
+typedef struct vfk_chain_desc {
+    int32_t n_joints;
+    int32_t joint_type[VFK_MAX_JOINTS];
+    double base[12];
+    double tip[VFK_MAX_JOINTS][12];
+    double q_lo[VFK_MAX_JOINTS];
+    double q_hi[VFK_MAX_JOINTS];
+} vfk_chain_desc;
+
+/* Per-robot constants (uniform over the batch; kept in constant memory). */
+typedef struct vfk_params {
+    double ik_lambda;            /* damping of J^T (J J^T + lambda^2 I)^-1           (getIKV, scripts/vf:461) */
+    double ns_lambda;            /* damping of the projector's pseudo-inverse; 0 = pinv (scripts/nullspace:78) */
+    double dt;                   /* config.rate (scripts/bridge:91) */
+    double speed_scale;          /* speedScale (scripts/vf:137,197-207) */
+    double max_vel;              /* scripts/bridge:69,613-623 */
+    double jp_kp;                /* config.jpctrl_kp (scripts/joint_p_controller:56) */
+    double jp_delta;             /* 0.087 (scripts/joint_p_controller:57) */
+    double ns_gain;              /* 0.5 (scripts/nullspace:62,183) */
+    double ns_lookahead;         /* 0.3 (scripts/nullspace:121) */
+    double ns_limit_gain;        /* k of qdot0_i = -k (q_i - mid_i)/(hi_i - lo_i)^2 */
+    double rot_slowdown;         /* angle below which the rotational speed ramps down */
+    double goal_force;           /* +1  (scripts/object_feeder:236) */
+    double obst_force;           /* -10 (scripts/object_feeder:322) */
+    double obst_safe;            /* 0.001 (scripts/object_feeder:331), used when obst_comps == 4 */
+    double obst_order;           /* decay order, used when obst_comps == 4 */
+    double mixer_w[VFK_N_PORTS]; /* [vectorfield, nullspace, joint, mechanism, xtra1, xtra2] */
+    double w_task[6];            /* diag of set_tweights (scripts/vf:296-305) */
+    double w_joint[VFK_MAX_JOINTS]; /* diag of set_jweights (scripts/vf:306-309) */
+    double tool[12];             /* tool frame in the flange frame (scripts/vf:321-330) */
+    double jp_ref[VFK_MAX_JOINTS];  /* used when vfk_buffers.jp_ref == NULL (config.initial_joint_pos) */
+    double ns_control[4];        /* used in VFK_NS_CONTROL when vfk_buffers.ns_in == NULL */
+    int32_t ns_mode;             /* VFK_NS_* */
+    int32_t direct_control;      /* -1: auto = all mixer weights zero (scripts/bridge:604); 0 / 1 force */
+    int32_t integrate;           /* 1: q += dt * qdot_lim after every cycle (simulation plant) */
+    int32_t reserved;
+} vfk_params;
+
+/* Device buffers of one vfk_step() call.  NULL = not supplied / not wanted. */
+typedef struct vfk_buffers {
+    void*       q;               /* [N][ld]  in; out when params.integrate                    */
+    const void* goal;            /* [13][ld] attractor (vfl type 1) per instance                */
+    const void* obst;            /* [M][obst_comps][ld] decay repellers (vfl type 2): x,y,z,radius[,safe,order]; radius 0 = none */
+    const void* jp_ref;          /* [N][ld]  joint reference (/jpctrl/ref) or NULL -> params.jp_ref */
+    const void* ns_in;           /* PROJECTOR: qdot0 [N][ld] or NULL -> limit-avoidance gradient;
+                                    CONTROL:   control [4][ld] or NULL -> params.ns_control      */
+    void*       ns_lastvec;      /* CONTROL: [N][ld] in/out sign-continuity state (scripts/nullspace:91-107) */
+    const void* q_cmded;         /* [N][ld]  last commanded q (scripts/bridge:169-172) or NULL -> q */
+    const void* ext_cmd[3];      /* mixer ports 3..5 [N][ld] each, or NULL -> 0 */
+    void*       qdot_vf;         /* out [N][ld]  /vectorField/qdotOut   */
+    void*       qdot_ns;         /* out [N][ld]  /nullspace/qdotout     */
+    void*       qdot_jp;         /* out [N][ld]  /jpctrl/out            */
+    void*       qdot;            /* out [N][ld]  clamped mixer output qdot_lim (scripts/bridge:196) */
+    void*       cmd;             /* out [N][ld]  command sent to the plant (scripts/bridge:198-203) */
+    void*       pose;            /* out [12][ld] tool frame (/vectorField/pose) */
+    int32_t*    flags;           /* out [ld]     VFK_FLAG_* */
+} vfk_buffers;
+
+typedef struct vfk_ctx* vfk_handle;
+typedef struct vfk_session_s* vfk_session;
+
+int  vfk_version(void);
+void vfk_default_params(vfk_params* out, int n_joints);
+
+/* precision: 32 or 64.  device: CUDA ordinal.  Fails with VFK_ERR_NO_DEVICE when
+ * the device is not compute capability 10.x (no fallback path exists). */
+int  vfk_create(vfk_handle* out, const vfk_chain_desc* chain, int precision, int device);
+int  vfk_set_params(vfk_handle h, const vfk_params* p);
+int  vfk_get_params(vfk_handle h, vfk_params* out);
+void vfk_destroy(vfk_handle h);
+const char* vfk_last_error(vfk_handle h);   /* h may be NULL: last error of vfk_create */
+
+/* K fused control cycles over n_instances instances, stream-ordered on `stream`
+ * (a cudaStream_t, may be NULL).  No allocation, no synchronisation.
+ * Outputs hold the last cycle's values.  Returns the number of kernels launched
+ * (>= 1) or a negative vfk_status. */
+int  vfk_step(vfk_handle h, const vfk_buffers* bufs, int64_t n_instances, int64_t ld,
+              int n_obstacles, int obst_comps, int k_cycles, void* stream);
+
+/* Field visualisation query (scripts/vf:469-503): twist the composed field commands at
+ * arbitrary tool poses pose_in[12][ld]; twist_out[6][ld].  Same goal/obst layout. */
+int  vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst,
+                    void* twist_out, int64_t n_instances, int64_t ld, int n_obstacles,
+                    int obst_comps, void* stream);
+
+/* Weighted sum of command ports (src/command_mixer.py:78-82) on device buffers:
+ * out[c][i] = sum_p w[p] * cmds[p][c][i]; cmds[p] may be NULL (skipped). */
+int  vfk_mix(vfk_handle h, const void* const* cmds, const double* w, int n_ports, int n_channels,
+             void* out, int32_t* nan_flags, int64_t n_instances, int64_t ld, void* stream);
+
+/* ---- host-buffer sessions: the call a host-language plugin makes --------------
+ * A session owns resident device copies of the scene (goal, obstacles) and state,
+ * pinned staging buffers and a stream.  Host arrays are dense SoA [comps][n_instances]
+ * (leading dimension n_instances) of the handle's precision.  vfk_session_cycle()
+ * copies q host->device (if q_in != NULL), runs k_cycles fused cycles, copies the
+ * requested outputs device->host and synchronises. */
+int  vfk_session_create(vfk_handle h, int64_t n_instances, int n_obstacles, int obst_comps, vfk_session* out);
+int  vfk_session_set_goal(vfk_session s, const void* goal_host);            /* [13][n] */
+int  vfk_session_set_obstacles(vfk_session s, const void* obst_host);       /* [M][comps][n] */
+int  vfk_session_set_q(vfk_session s, const void* q_host);                  /* [N][n] */
+int  vfk_session_set_jp_ref(vfk_session s, const void* ref_host);           /* [N][n] or NULL -> params.jp_ref */
+int  vfk_session_set_ns_input(vfk_session s, const void* ns_host);          /* [N|4][n] or NULL */
+int  vfk_session_cycle(vfk_session s, const void* q_in_host, int k_cycles,
+                       void* qdot_out_host, void* q_out_host, int32_t* flags_out_host);
+int  vfk_session_read(vfk_session s, const char* what, void* out_host);     /* "qdot_vf","qdot_ns","qdot_jp","cmd","pose","q" */
+int  vfk_session_buffers(vfk_session s, vfk_buffers* out, int64_t* ld);     /* device view (for stream-ordered use) */
+void vfk_session_destroy(vfk_session s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFK_H_ */

@@ -1,0 +1,212 @@
+"""Generate ``tests/golden/*.npz`` by running the REAL reference code (test infrastructure).
+
+Run in the build container, where ``/root/reference`` exists:
+
+    python -m oracle.gen_golden
+
+Two pieces of the reference's hot path run under python 3:
+
+* ``src/command_mixer.py::CommandMixer`` -- imported with ``yarp`` and
+  ``arcospyu.config_parser`` stubbed (they are only used for ports / CLI parsing);
+* ``scripts/nullspace`` functions ``matrixrank, restrict, sign, nullspace,
+  move_in_nullspace, check_limits`` (``:67-131``) -- the module cannot be imported
+  (it opens YARP ports at import time and numpy 2 removed ``numpy.mat``), so the
+  ``FunctionDef`` nodes are extracted with ``ast`` and executed with
+  ``mat = numpy.asmatrix`` and the module globals ``nJoints, sig, lastvec``.
+
+Nothing is copied from the reference: its code is executed where it lies and only the
+inputs and outputs are stored.  The vectors pin ``oracle/refshape.py``'s restatements
+(``CommandMixer``, ``Nullspace``) and, through them, ``oracle/batch.py`` and the GPU.
+"""
+from __future__ import annotations
+
+import ast
+import io
+import os
+import sys
+import types
+from contextlib import redirect_stdout
+
+import numpy as np
+
+REF = os.environ.get("VFCLIK_REFERENCE", "/root/reference")
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+# ------------------------------------------------------------------------- loading the real code
+
+def load_real_command_mixer():
+    yarp = types.ModuleType("yarp")
+    arcospyu = types.ModuleType("arcospyu")
+    cp = types.ModuleType("arcospyu.config_parser")
+    cp.ConfigFileParser = object
+    arcospyu.config_parser = cp
+    saved = {k: sys.modules.get(k) for k in ("yarp", "arcospyu", "arcospyu.config_parser")}
+    sys.modules.update({"yarp": yarp, "arcospyu": arcospyu, "arcospyu.config_parser": cp})
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_command_mixer", os.path.join(REF, "src", "command_mixer.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod.CommandMixer
+
+
+def load_real_nullspace(n_joints: int) -> dict:
+    src = open(os.path.join(REF, "scripts", "nullspace")).read()
+    tree = ast.parse(src)
+    wanted = {"matrixrank", "restrict", "sign", "nullspace", "move_in_nullspace", "check_limits"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    mod = ast.Module(body=body, type_ignores=[])
+    from numpy import eye, matrix, zeros, sum, where
+    from numpy.linalg import norm, pinv, svd
+    glb = dict(svd=svd, norm=norm, pinv=pinv, sum=sum, where=where, mat=np.asmatrix, eye=eye, zeros=zeros,
+               matrix=matrix, nJoints=n_joints, sig=[1] * n_joints, lastvec=np.asmatrix(zeros((n_joints, n_joints))))
+    exec(compile(mod, "<reference scripts/nullspace>", "exec"), glb)
+    return glb
+
+
+class FakeValue:
+    def __init__(self, v):
+        self.v = v
+
+    def asDouble(self):
+        return float(self.v)
+
+
+class FakeBottle:
+    def __init__(self, vals):
+        self.vals = list(vals)
+
+    def size(self):
+        return len(self.vals)
+
+    def get(self, i):
+        return FakeValue(self.vals[i])
+
+
+class FakePort:
+    def __init__(self):
+        self.q = []
+
+    def push(self, vals):
+        self.q.append(FakeBottle(vals))
+
+    def read(self, wait=False):
+        return self.q.pop(0) if self.q else None
+
+
+# ------------------------------------------------------------------------- generators
+
+def gen_mixer(rng):
+    """A scripted sequence of port events through the real CommandMixer.read()."""
+    CommandMixer = load_real_command_mixer()
+    import time as _time
+    n, n_ports, steps = 7, 6, 12
+    now = [1000.0]
+    real_time = _time.time
+    _time.time = lambda: now[0]
+    try:
+        ports = [FakePort() for _ in range(n_ports)]
+        wport = FakePort()
+        mixer = CommandMixer(ports, wport, n, 2.0, [1.0, 1.0, 0.0, 0.0, 0.0, 0.0])
+        events = np.full((steps, n_ports, n), np.nan)      # NaN row = no bottle on that port in that step
+        wevents = np.full((steps, n_ports), np.nan)
+        short = np.zeros((steps, n_ports), dtype=bool)      # a wrong-length bottle arrived
+        dts = np.zeros(steps)
+        outs = np.zeros((steps, n))
+        weights_after = np.zeros((steps, n_ports))
+        for s in range(steps):
+            dts[s] = [0.01, 0.5, 0.01, 1.0, 0.8, 0.01, 0.3, 2.5, 0.01, 0.01, 0.7, 0.01][s]
+            now[0] += dts[s]
+            for p in range(n_ports):
+                r = rng.random()
+                if s == 0 or r < 0.45:
+                    v = rng.normal(size=n)
+                    events[s, p] = v
+                    ports[p].push(v)
+                elif r < 0.55:
+                    short[s, p] = True
+                    ports[p].push(rng.normal(size=n - 2))
+            if s in (3, 8):
+                w = rng.uniform(0, 1, size=(4 if s == 3 else 6))
+                wevents[s, :w.size] = w
+                wport.push(w)
+            with redirect_stdout(io.StringIO()):
+                outs[s] = mixer.read()
+            weights_after[s] = mixer.weights
+        # constructor contract: wrong number of initial weights -> zeros
+        with redirect_stdout(io.StringIO()):
+            m2 = CommandMixer([FakePort(), FakePort()], None, 3, 1.0, [1.0])
+        bad_init = np.asarray(m2.weights)
+    finally:
+        _time.time = real_time
+    return dict(mixer_events=events, mixer_wevents=wevents, mixer_short=short, mixer_dts=dts, mixer_out=outs,
+                mixer_weights_after=weights_after, mixer_bad_init_weights=bad_init)
+
+
+def lwr_chain():
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT_DIR)))
+    from vfclik_b200.config import PACKAGE_CONFIG_DIR, chain_from_config, config_filename, load_config
+    cfg = load_config(config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right"))
+    return chain_from_config(cfg), cfg
+
+
+def gen_nullspace(rng):
+    """Real restrict / nullspace / move_in_nullspace / check_limits on LWR Jacobians along a short
+    joint trajectory (sign continuity is stateful, so the call order is part of the fixture)."""
+    from oracle import batch
+    chain, cfg = lwr_chain()
+    steps = 10
+    q = np.zeros((steps, 7))
+    q[0] = cfg.initial_joint_pos
+    for s in range(1, steps):
+        q[s] = q[s - 1] + rng.normal(scale=0.05, size=7)
+    _, _, J = batch.fk_jac(chain, q)
+    glb = load_real_nullspace(7)
+    P = np.asmatrix(np.eye(6))
+    control = [0.7, -0.2, 0.1, 0.0]
+    B = np.zeros((steps, 7, 7))
+    qd = np.zeros((steps, 7))
+    basis = np.zeros((steps, 7))
+    limited = np.zeros((steps, 7))
+    hit = np.zeros(steps, dtype=bool)
+    limits = [[float(a), float(b)] for a, b in zip(chain.q_lo, chain.q_hi)]
+    for s in range(steps):
+        Jm = np.asmatrix(J[s])
+        B[s] = np.asarray(glb["restrict"](P, Jm))
+        qd[s] = glb["move_in_nullspace"](P, Jm, control)
+        basis[s] = np.asarray(glb["lastvec"])[:, 0]
+        with redirect_stdout(io.StringIO()):
+            out = glb["check_limits"](list(q[s]), list(qd[s] * (25.0 if s % 3 == 2 else 1.0)), limits)
+        limited[s] = out
+        hit[s] = all(v == 0 for v in out)
+    rank = int(glb["matrixrank"](np.asmatrix(J[0])))
+    # random (non-LWR) full-rank 6x7 Jacobians, fresh state per sample: projector only
+    Jr = rng.normal(size=(16, 6, 7))
+    Br = np.stack([np.asarray(load_real_nullspace(7)["restrict"](P, np.asmatrix(Jr[k]))) for k in range(16)])
+    return dict(ns_q=q, ns_J=J, ns_B=B, ns_control=np.asarray(control), ns_qdot=qd, ns_basis=basis,
+                ns_limited=limited, ns_hit=hit, ns_rank=np.asarray(rank), ns_Jrand=Jr, ns_Brand=Br)
+
+
+def main():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
+    os.makedirs(OUT_DIR, exist_ok=True)
+    rng = np.random.default_rng(20261018)
+    data = {}
+    data.update(gen_mixer(rng))
+    data.update(gen_nullspace(rng))
+    path = os.path.join(OUT_DIR, "reference_vectors.npz")
+    np.savez_compressed(path, **data)
+    print("wrote", path, {k: v.shape for k, v in data.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,219 @@
+"""CPU tests of the oracle itself: self-consistency and the reference golden vectors."""
+import io
+import os
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from oracle import batch, refshape
+from vfclik_b200 import workloads
+
+
+def test_fk_jacobian_finite_differences(lwr):
+    chain, _ = lwr
+    rng = np.random.default_rng(0)
+    q = rng.uniform(chain.q_lo, chain.q_hi, size=(64, 7))
+    R, p, J = batch.fk_jac(chain, q)
+    eps = 1e-6
+    for j in range(7):
+        qp, qm = q.copy(), q.copy()
+        qp[:, j] += eps
+        qm[:, j] -= eps
+        Rp, pp, _ = batch.fk_jac(chain, qp)
+        Rm, pm, _ = batch.fk_jac(chain, qm)
+        assert np.allclose((pp - pm) / (2 * eps), J[:, 0:3, j], atol=1e-8)
+        dR = ((Rp - Rm) / (2 * eps)) @ np.transpose(R, (0, 2, 1))
+        w = np.stack([dR[:, 2, 1], dR[:, 0, 2], dR[:, 1, 0]], axis=1)
+        assert np.allclose(w, J[:, 3:6, j], atol=1e-8)
+    # rotations stay orthonormal, home pose is the stretched arm: 0.31+0.40+0.39+0.078
+    assert np.allclose(R @ np.transpose(R, (0, 2, 1)), np.eye(3), atol=1e-12)
+    assert np.allclose(batch.fk_jac(chain, np.zeros((1, 7)))[1] - chain.base[9:12] + [0, 0, 0.31], [[0, 0, 1.178]])
+
+
+def test_fk_all_joint_types_finite_differences():
+    """RotX/RotY/Trans* joints (the kernel canonicalises them to Z joints on the host)."""
+    from vfclik_b200 import kdl
+    from vfclik_b200.config import chain_from_segments
+    segs = [kdl.Segment(kdl.Joint(t), kdl.Frame(kdl.Rotation.RotX(0.3 * (i + 1)) * kdl.Rotation.RotZ(0.2 * i),
+                                                 kdl.Vector(0.1 * i, 0.05, 0.2)))
+            for i, t in enumerate([kdl.Joint.RotX, kdl.Joint.TransY, kdl.Joint.RotY, kdl.Joint.RotZ,
+                                   kdl.Joint.TransX, kdl.Joint.TransZ])]
+    chain = chain_from_segments(segs, [[-1, 1]] * 6)
+    rng = np.random.default_rng(1)
+    q = rng.uniform(-1, 1, size=(16, 6))
+    R, p, J = batch.fk_jac(chain, q)
+    eps = 1e-6
+    for j in range(6):
+        qp, qm = q.copy(), q.copy()
+        qp[:, j] += eps
+        qm[:, j] -= eps
+        assert np.allclose((batch.fk_jac(chain, qp)[1] - batch.fk_jac(chain, qm)[1]) / (2 * eps), J[:, 0:3, j], atol=1e-8)
+
+
+def test_dls_closed_form_equals_svd_form(lwr):
+    chain, _ = lwr
+    rng = np.random.default_rng(2)
+    q = rng.uniform(chain.q_lo, chain.q_hi, size=(256, 7))
+    _, _, J = batch.fk_jac(chain, q)
+    tw = rng.normal(size=(256, 6))
+    prm = batch.Params(ik_lambda=0.05, w_task=(1, 2, 1, 0.5, 1, 1), w_joint=(1, 1, 0.5, 1, 2, 1, 1))
+    qd = batch.ikv_dls(prm, J, tw, 7)
+    wt, wj = np.asarray(prm.w_task), np.asarray(prm.w_joint)
+    for i in range(256):
+        Jw = np.diag(wt) @ J[i] @ np.diag(wj)
+        U, s, Vt = np.linalg.svd(Jw, full_matrices=False)
+        ref = wj * (Vt.T @ np.diag(s / (s * s + prm.ik_lambda ** 2)) @ U.T @ (wt * tw[i]))
+        assert np.allclose(qd[i], ref, rtol=1e-9, atol=1e-12)
+
+
+def test_projector_identities(lwr):
+    chain, _ = lwr
+    rng = np.random.default_rng(3)
+    q = rng.uniform(0.5 * chain.q_lo, 0.5 * chain.q_hi, size=(64, 7))
+    _, _, J = batch.fk_jac(chain, q)
+    x = rng.normal(size=(64, 7))
+    prm = batch.Params(ns_lambda=0.0)
+    Bx = batch.ns_project(prm, J, x)
+    assert np.allclose(np.einsum("ikn,in->ik", J, Bx), 0, atol=1e-9)          # J B x = 0
+    assert np.allclose(batch.ns_project(prm, J, Bx), Bx, atol=1e-9)           # idempotent
+    u = batch.ns_basis_1d(prm, J, np.zeros((64, 7)))
+    assert np.allclose(np.einsum("in,in->i", u, x)[:, None] * u, Bx, atol=1e-9)   # B = u u^T (1-D nullspace)
+
+
+def test_rot_axis_angle_round_trip():
+    rng = np.random.default_rng(4)
+    axis = rng.normal(size=(500, 3))
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    ang = np.concatenate([rng.uniform(0, np.pi, 480), np.pi - rng.uniform(0, 1e-6, 10), rng.uniform(0, 1e-7, 10)])
+    K = np.zeros((500, 3, 3))
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -axis[:, 2], axis[:, 1], axis[:, 2]
+    K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -axis[:, 0], -axis[:, 1], axis[:, 0]
+    R = np.eye(3) + np.sin(ang)[:, None, None] * K + (1 - np.cos(ang))[:, None, None] * (K @ K)
+    a2, g2 = batch.rot_axis_angle(R)
+    assert np.allclose(g2, ang, atol=1e-7)
+    big = ang > 1e-3
+    assert np.allclose((a2 * g2[:, None])[big], (axis * ang[:, None])[big], atol=1e-6) or \
+        np.allclose(np.abs(np.einsum("in,in->i", a2[big], axis[big])), 1, atol=1e-9)
+
+
+@pytest.mark.parametrize("ns_mode", [0, 1, 2])
+def test_batch_equals_reference_shaped_loop(lwr, ns_mode):
+    """oracle.batch (vectorised) and oracle.refshape (reference-shaped scalar loop) agree."""
+    chain, cfg = lwr
+    I, M = 24, 5
+    K = 4 if ns_mode != 2 else 1     # mode 2: LAPACK's first-cycle sign is arbitrary, so trajectories may mirror
+    w = workloads.random_batch(chain, I, M, seed=10 + ns_mode)
+    q = w["q"].T
+    goal = w["goal"].T
+    obst = w["obst"].reshape(M, 4, I).transpose(2, 0, 1)
+    # mode 2 (reference control interface) is the reference's algorithm only with the undamped pinv
+    prm = batch.Params(ns_mode=ns_mode, ns_lambda=0.0 if ns_mode == 2 else 0.1,
+                       jp_ref=tuple(cfg.initial_joint_pos), ns_control=(0.4, 0, 0, 0),
+                       mixer_w=(1.0, 1.0, 0.25, 0, 0, 0), tool=(0, -1, 0, 1, 0, 0, 0, 0, 1, 0.02, -0.01, 0.12))
+    out = batch.step(chain, prm, q, goal, obst, k_cycles=K)
+    for i in range(I):
+        g = goal[i]
+        g17 = [g[0], g[1], g[2], g[9], g[3], g[4], g[5], g[10], g[6], g[7], g[8], g[11], 0, 0, 0, 1, g[12]]
+        loop = refshape.ControlLoop(chain, prm, q[i], g17, obstacles=obst[i])
+        loop.run(K)
+        keys = ["qdot_vf", "qdot_jp", "qdot"] if ns_mode != 2 else ["qdot_vf", "qdot_jp"]
+        for k in keys + (["qdot_ns"] if ns_mode == 1 else []):
+            assert np.allclose(loop.last[k], out[k][i], rtol=1e-9, atol=1e-12), (i, k)
+        if ns_mode == 2:
+            # LAPACK's first-cycle sign is arbitrary: compare up to one global sign per instance
+            a, b = np.asarray(loop.last["qdot_ns"]), out["qdot_ns"][i]
+            assert np.allclose(a, b, rtol=1e-8, atol=1e-11) or np.allclose(a, -b, rtol=1e-8, atol=1e-11)
+        else:
+            assert np.allclose(loop.q, out["q"][i], rtol=1e-10, atol=1e-12)
+            assert loop.last["flags"] == out["flags"][i]
+        T = np.asarray(loop.last["pose"]).reshape(4, 4)
+        assert np.allclose(np.concatenate([T[:3, :3].reshape(9), T[:3, 3]]), out["pose"][i], atol=1e-12)
+
+
+def test_config1_runs_and_converges(lwr):
+    """BASELINE config 1: single LWR, goal of old/system_start.sh.old:346, 3 obstacles, 1000 cycles."""
+    chain, cfg = lwr
+    w = workloads.config1(chain, cfg)
+    prm = batch.Params(jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate)
+    out = batch.step(chain, prm, w["q"].T, w["goal"].T, w["obst"].reshape(3, 4, 1).transpose(2, 0, 1), k_cycles=1000)
+    assert np.all(np.isfinite(out["q"]))
+    d0 = np.linalg.norm(batch.fk_jac(chain, w["q"].T)[1][0] - w["goal"][9:12, 0])
+    d1 = np.linalg.norm(out["pose"][0, 9:12] - w["goal"][9:12, 0])
+    assert d1 < 0.02 < d0            # reached the goal's slow-down ball
+    assert np.all(out["q"] >= chain.q_lo - 1e-9) and np.all(out["q"] <= chain.q_hi + 1e-9)
+
+
+# ------------------------------------------------------------------ golden vectors (real reference code)
+
+def test_golden_command_mixer(golden):
+    """refshape.CommandMixer reproduces the real src/command_mixer.py on a scripted port sequence."""
+    ev, wev, short = golden["mixer_events"], golden["mixer_wevents"], golden["mixer_short"]
+    steps, n_ports, n = ev.shape
+    now = [1000.0]
+    ports = [refshape.Port() for _ in range(n_ports)]
+    wport = refshape.Port()
+    mixer = refshape.CommandMixer(ports, wport, n, 2.0, [1.0, 1.0, 0.0, 0.0, 0.0, 0.0], clock=lambda: now[0])
+    for s in range(steps):
+        now[0] += float(golden["mixer_dts"][s])
+        for p in range(n_ports):
+            if not np.isnan(ev[s, p, 0]):
+                ports[p].write_list(ev[s, p])
+            elif short[s, p]:
+                ports[p].write_list([0.0] * (n - 2))
+        wv = wev[s][~np.isnan(wev[s])]
+        if wv.size:
+            wport.write_list(wv)
+        with redirect_stdout(io.StringIO()):
+            out = mixer.read()
+        assert np.array_equal(np.asarray(out), golden["mixer_out"][s]), s       # bit-exact: same op order
+        assert np.array_equal(np.asarray(mixer.weights), golden["mixer_weights_after"][s])
+    with redirect_stdout(io.StringIO()):
+        m2 = refshape.CommandMixer([refshape.Port(), refshape.Port()], None, 3, 1.0, [1.0])
+    assert np.array_equal(np.asarray(m2.weights), golden["mixer_bad_init_weights"])
+
+
+def test_golden_nullspace(golden, lwr):
+    """refshape.Nullspace and oracle.batch reproduce the real scripts/nullspace functions."""
+    chain, _ = lwr
+    q, J = golden["ns_q"], golden["ns_J"]
+    assert np.allclose(batch.fk_jac(chain, q)[2], J, atol=1e-14)       # fixture J is this oracle's J
+    ns = refshape.Nullspace(7, ns_lambda=0.0)
+    control = list(golden["ns_control"])
+    limits = [[float(a), float(b)] for a, b in zip(chain.q_lo, chain.q_hi)]
+    prm0 = batch.Params(ns_lambda=0.0)
+    lastvec = np.zeros((1, 7))
+    for s in range(q.shape[0]):
+        B = ns.restrict(np.eye(6), J[s])
+        assert np.allclose(B, golden["ns_B"][s], atol=1e-10)
+        qd = ns.move_in_nullspace(np.eye(6), J[s], control)
+        assert np.allclose(qd, golden["ns_qdot"][s], atol=1e-10)
+        scaled = [v * (25.0 if s % 3 == 2 else 1.0) for v in golden["ns_qdot"][s]]
+        out, hit = refshape.Nullspace.check_limits(list(q[s]), scaled, limits)
+        assert np.allclose(out, golden["ns_limited"][s], atol=1e-12) and hit == bool(golden["ns_hit"][s])
+        # batch oracle: projector columns and the 1-D basis (up to the LAPACK first-cycle sign)
+        Bb = np.stack([batch.ns_project(prm0, J[s:s + 1], np.eye(7)[j:j + 1])[0] for j in range(7)], axis=1)
+        assert np.allclose(Bb, golden["ns_B"][s], atol=1e-9)
+        u = batch.ns_basis_1d(prm0, J[s:s + 1], lastvec)
+        lastvec = u
+        g = golden["ns_basis"][s]
+        assert np.allclose(u[0], g, atol=1e-8) or np.allclose(u[0], -g, atol=1e-8)
+    assert np.any(golden["ns_hit"]) and not np.all(golden["ns_hit"])
+    assert int(golden["ns_rank"]) == 6
+    # sign continuity: the batch basis never flips between consecutive cycles, like the reference's
+    Jr = golden["ns_Jrand"]
+    for k in range(Jr.shape[0]):
+        Bb = np.stack([batch.ns_project(prm0, Jr[k:k + 1], np.eye(7)[j:j + 1])[0] for j in range(7)], axis=1)
+        assert np.allclose(Bb, golden["ns_Brand"][k], atol=1e-9)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference only exists in the build container")
+def test_golden_is_reproducible_from_reference(golden):
+    """Regenerating from the real reference gives the committed vectors (guards a stale fixture)."""
+    from oracle import gen_golden
+    rng = np.random.default_rng(20261018)
+    data = gen_golden.gen_mixer(rng)
+    data.update(gen_golden.gen_nullspace(rng))
+    for k, v in data.items():
+        assert np.allclose(np.asarray(v, dtype=np.float64), np.asarray(golden[k], dtype=np.float64), equal_nan=True,
+                           atol=1e-12), k

@@ -1,0 +1,547 @@
+// vfk_api.cu -- C ABI (include/vfk.h) over the fused control-cycle kernel.
+//
+// Host side only prepares constants and launches; there is no CPU compute path:
+// vfk_create() fails with VFK_ERR_NO_DEVICE when no sm_100 GPU is present.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/vfk.h"
+#include "vfk_kernels.cuh"
+
+using namespace vfk;
+
+// -------------------------------------------------------------------------------- context
+struct vfk_ctx {
+    vfk_chain_desc chain;       // as given
+    vfk_chain_desc canon;       // every joint about / along Z
+    vfk_params params;
+    int precision;
+    int device;
+    int sm_count;
+    KConst<float> cf;
+    KConst<double> cd;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(vfk_ctx* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define VFK_CUDA(h, call)                                                                   \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail((h), VFK_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// -------------------------------------------------------------------------------- frames (host, double)
+static void frame_mul(const double* a, const double* b, double* o) {
+    double r[12];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+        r[9 + i] = a[3 * i] * b[9] + a[3 * i + 1] * b[10] + a[3 * i + 2] * b[11] + a[9 + i];
+    }
+    memcpy(o, r, sizeof r);
+}
+
+// RotX/RotY/TransX/TransY joints are conjugated into Z joints:  Joint_axis(q) = C JointZ(q) C^T
+// with C e_z = e_axis.  C is appended to the frame before the joint and C^T prepended to its tip,
+// so the kernel only ever rotates about / translates along the local Z axis.
+static void canonicalise_chain(const vfk_chain_desc& in, vfk_chain_desc& out) {
+    out = in;
+    static const double CX[12] = {0, 0, 1, 0, 1, 0, -1, 0, 0, 0, 0, 0};    // RotY(+pi/2): z -> x
+    static const double CXt[12] = {0, 0, -1, 0, 1, 0, 1, 0, 0, 0, 0, 0};
+    static const double CY[12] = {1, 0, 0, 0, 0, 1, 0, -1, 0, 0, 0, 0};    // RotX(-pi/2): z -> y
+    static const double CYt[12] = {1, 0, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0};
+    for (int j = 0; j < in.n_joints; ++j) {
+        const int t = in.joint_type[j];
+        const double *C = nullptr, *Ct = nullptr;
+        if (t == VFK_JOINT_ROTX || t == VFK_JOINT_TRANSX) { C = CX; Ct = CXt; }
+        if (t == VFK_JOINT_ROTY || t == VFK_JOINT_TRANSY) { C = CY; Ct = CYt; }
+        if (C) {
+            double* prev = (j == 0) ? out.base : out.tip[j - 1];
+            frame_mul(prev, C, prev);
+            frame_mul(Ct, out.tip[j], out.tip[j]);
+        }
+        out.joint_type[j] = (t >= VFK_JOINT_TRANSX) ? VFK_JOINT_TRANSZ : VFK_JOINT_ROTZ;
+    }
+}
+
+template <typename T>
+static void build_const(const vfk_ctx& h, KConst<T>& c) {
+    memset(&c, 0, sizeof c);
+    const vfk_chain_desc& ch = h.canon;
+    const vfk_params& p = h.params;
+    const int n = ch.n_joints;
+    for (int k = 0; k < 12; ++k) c.base[k] = (T)ch.base[k];
+    bool unit = true;
+    for (int j = 0; j < n; ++j) {
+        for (int k = 0; k < 12; ++k) c.tip[j][k] = (T)ch.tip[j][k];
+        c.q_lo[j] = (T)ch.q_lo[j];
+        c.q_hi[j] = (T)ch.q_hi[j];
+        const double rng = ch.q_hi[j] - ch.q_lo[j];
+        c.ns_q0_scale[j] = (T)(-p.ns_limit_gain / (rng * rng));
+        c.ns_mid[j] = (T)(0.5 * (ch.q_lo[j] + ch.q_hi[j]));
+        c.w_joint[j] = (T)p.w_joint[j];
+        c.jp_ref[j] = (T)p.jp_ref[j];
+        if (p.w_joint[j] != 1.0) unit = false;
+        if (ch.joint_type[j] == VFK_JOINT_TRANSZ) c.prismatic_mask |= (1 << j);
+    }
+    bool all_zero = true;
+    for (int k = 0; k < 6; ++k) {
+        c.w_task[k] = (T)p.w_task[k];
+        c.mixer_w[k] = (T)p.mixer_w[k];
+        if (p.w_task[k] != 1.0) unit = false;
+        if (p.mixer_w[k] != 0.0) all_zero = false;
+    }
+    static const double ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    c.tool_identity = memcmp(p.tool, ident, sizeof ident) == 0;
+    for (int k = 0; k < 12; ++k) c.tool[k] = (T)p.tool[k];
+    for (int k = 0; k < 4; ++k) c.ns_control[k] = (T)p.ns_control[k];
+    c.ik_lambda2 = (T)(p.ik_lambda * p.ik_lambda);
+    c.ns_lambda2 = (T)(p.ns_lambda * p.ns_lambda);
+    c.dt = (T)p.dt;
+    c.speed_scale = (T)p.speed_scale;
+    c.max_vel = (T)p.max_vel;
+    c.jp_kp = (T)p.jp_kp;
+    c.jp_delta = (T)p.jp_delta;
+    c.ns_gain = (T)p.ns_gain;
+    c.ns_lookahead = (T)p.ns_lookahead;
+    c.rot_slowdown = (T)p.rot_slowdown;
+    c.goal_force = (T)p.goal_force;
+    c.obst_force = (T)p.obst_force;
+    c.obst_safe_inv = (T)(p.obst_safe > 0 ? 1.0 / p.obst_safe : INFINITY);
+    c.obst_order = (T)p.obst_order;
+    c.ns_mode = p.ns_mode;
+    c.direct_control = p.direct_control < 0 ? (all_zero ? 1 : 0) : (p.direct_control ? 1 : 0);
+    c.integrate = p.integrate ? 1 : 0;
+    c.unit_weights = unit ? 1 : 0;
+    c.share_factor = (unit && p.ns_lambda == p.ik_lambda) ? 1 : 0;
+}
+
+// -------------------------------------------------------------------------------- public: lifecycle
+extern "C" int vfk_version(void) { return VFK_VERSION; }
+
+extern "C" void vfk_default_params(vfk_params* p, int n_joints) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->ik_lambda = 0.1;
+    p->ns_lambda = 0.1;
+    p->dt = 0.01;
+    p->speed_scale = 0.2;
+    p->max_vel = 1.0;
+    p->jp_kp = 1.5;
+    p->jp_delta = 0.087;
+    p->ns_gain = 0.5;
+    p->ns_lookahead = 0.3;
+    p->ns_limit_gain = 1.0;
+    p->rot_slowdown = 0.09;
+    p->goal_force = 1.0;
+    p->obst_force = -10.0;
+    p->obst_safe = 0.001;
+    p->obst_order = 20.0;
+    p->mixer_w[0] = p->mixer_w[1] = 1.0;
+    for (int k = 0; k < 6; ++k) p->w_task[k] = 1.0;
+    for (int j = 0; j < VFK_MAX_JOINTS; ++j) p->w_joint[j] = 1.0;
+    p->tool[0] = p->tool[4] = p->tool[8] = 1.0;
+    p->ns_mode = VFK_NS_PROJECTOR;
+    p->direct_control = -1;
+    p->integrate = 1;
+    (void)n_joints;
+}
+
+static bool n_supported(int n) { return n == 6 || n == 7 || n == 10 || n == 17; }
+
+static int check_params(vfk_ctx* h, const vfk_params* p) {
+    if (!(p->ik_lambda >= 0) || !(p->ns_lambda >= 0)) return fail(h, VFK_ERR_INVALID, "lambda must be >= 0");
+    if (p->ik_lambda == 0 && h->precision == 32)
+        return fail(h, VFK_ERR_INVALID, "ik_lambda = 0 is outside the FP32 mode's domain (use precision 64)");
+    if (p->ns_mode < 0 || p->ns_mode > 2) return fail(h, VFK_ERR_INVALID, "ns_mode must be 0, 1 or 2");
+    if (p->ns_mode == VFK_NS_CONTROL && h->chain.n_joints != 7)
+        return fail(h, VFK_ERR_UNSUPPORTED, "VFK_NS_CONTROL needs a 1-D nullspace (n_joints = 7), got %d joints",
+                    h->chain.n_joints);
+    if (!(p->max_vel >= 0)) return fail(h, VFK_ERR_INVALID, "max_vel must be >= 0");
+    return VFK_OK;
+}
+
+extern "C" int vfk_create(vfk_handle* out, const vfk_chain_desc* chain, int precision, int device) {
+    if (!out || !chain) return fail(nullptr, VFK_ERR_INVALID, "vfk_create: null argument");
+    *out = nullptr;
+    if (precision != 32 && precision != 64) return fail(nullptr, VFK_ERR_INVALID, "precision must be 32 or 64");
+    const int n = chain->n_joints;
+    if (n < 1 || n > VFK_MAX_JOINTS) return fail(nullptr, VFK_ERR_INVALID, "n_joints %d out of range", n);
+    if (!n_supported(n))
+        return fail(nullptr, VFK_ERR_UNSUPPORTED, "no kernel compiled for n_joints = %d (have 6, 7, 10, 17)", n);
+    for (int j = 0; j < n; ++j) {
+        if (chain->joint_type[j] < VFK_JOINT_ROTX || chain->joint_type[j] > VFK_JOINT_TRANSZ)
+            return fail(nullptr, VFK_ERR_INVALID, "joint %d: type %d (fold fixed segments on the host)", j, chain->joint_type[j]);
+        if (!(chain->q_lo[j] < chain->q_hi[j])) return fail(nullptr, VFK_ERR_INVALID, "joint %d: limits must satisfy lo < hi", j);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, VFK_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, VFK_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, VFK_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, VFK_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+    vfk_ctx* h = new (std::nothrow) vfk_ctx();
+    if (!h) return fail(nullptr, VFK_ERR_INVALID, "out of host memory");
+    h->chain = *chain;
+    canonicalise_chain(h->chain, h->canon);
+    h->precision = precision;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    vfk_default_params(&h->params, n);
+    build_const(*h, h->cf);
+    build_const(*h, h->cd);
+    *out = h;
+    return VFK_OK;
+}
+
+extern "C" int vfk_set_params(vfk_handle h, const vfk_params* p) {
+    if (!h || !p) return fail(h, VFK_ERR_INVALID, "vfk_set_params: null argument");
+    int rc = check_params(h, p);
+    if (rc != VFK_OK) return rc;
+    h->params = *p;
+    build_const(*h, h->cf);
+    build_const(*h, h->cd);
+    return VFK_OK;
+}
+
+extern "C" int vfk_get_params(vfk_handle h, vfk_params* out) {
+    if (!h || !out) return fail(h, VFK_ERR_INVALID, "vfk_get_params: null argument");
+    *out = h->params;
+    return VFK_OK;
+}
+
+extern "C" void vfk_destroy(vfk_handle h) { delete h; }
+
+extern "C" const char* vfk_last_error(vfk_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+// -------------------------------------------------------------------------------- public: step
+static int check_layout(vfk_ctx* h, const void* ptr, const char* name, bool required) {
+    if (!ptr) return required ? fail(h, VFK_ERR_INVALID, "buffer %s is required", name) : VFK_OK;
+    if (reinterpret_cast<uintptr_t>(ptr) & 127) return fail(h, VFK_ERR_INVALID, "buffer %s must be 128-byte aligned", name);
+    return VFK_OK;
+}
+
+template <typename T, int N>
+static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
+                        int obst_comps, int k_cycles, cudaStream_t st) {
+    KArgs<T> a;
+    memset(&a, 0, sizeof a);
+    a.q = static_cast<T*>(b->q);
+    a.goal = static_cast<const T*>(b->goal);
+    a.obst = static_cast<const T*>(b->obst);
+    a.jp_ref = static_cast<const T*>(b->jp_ref);
+    a.ns_in = static_cast<const T*>(b->ns_in);
+    a.ns_lastvec = static_cast<T*>(b->ns_lastvec);
+    a.q_cmded = static_cast<const T*>(b->q_cmded);
+    for (int e = 0; e < 3; ++e) a.ext_cmd[e] = static_cast<const T*>(b->ext_cmd[e]);
+    a.qdot_vf = static_cast<T*>(b->qdot_vf);
+    a.qdot_ns = static_cast<T*>(b->qdot_ns);
+    a.qdot_jp = static_cast<T*>(b->qdot_jp);
+    a.qdot = static_cast<T*>(b->qdot);
+    a.cmd = static_cast<T*>(b->cmd);
+    a.pose = static_cast<T*>(b->pose);
+    a.flags = b->flags;
+    a.n = n;
+    a.ld = ld;
+    a.n_obst = n_obst;
+    a.obst_comps = obst_comps;
+    a.k_cycles = k_cycles;
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    vfk_cycle_kernel<T, N><<<grid, kBlock, 0, st>>>(c, a);
+    VFK_CUDA(h, cudaGetLastError());
+    return 1;
+}
+
+template <typename T>
+static int dispatch_n(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
+                      int obst_comps, int k_cycles, cudaStream_t st) {
+    switch (h->chain.n_joints) {
+        case 6: return launch_cycle<T, 6>(h, c, b, n, ld, n_obst, obst_comps, k_cycles, st);
+        case 7: return launch_cycle<T, 7>(h, c, b, n, ld, n_obst, obst_comps, k_cycles, st);
+        case 10: return launch_cycle<T, 10>(h, c, b, n, ld, n_obst, obst_comps, k_cycles, st);
+        case 17: return launch_cycle<T, 17>(h, c, b, n, ld, n_obst, obst_comps, k_cycles, st);
+    }
+    return fail(h, VFK_ERR_UNSUPPORTED, "no kernel for n_joints = %d", h->chain.n_joints);
+}
+
+extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst, int obst_comps,
+                        int k_cycles, void* stream) {
+    if (!h || !b) return fail(h, VFK_ERR_INVALID, "vfk_step: null argument");
+    if (n < 0 || ld < n) return fail(h, VFK_ERR_INVALID, "need 0 <= n_instances <= ld (got n=%lld ld=%lld)", (long long)n, (long long)ld);
+    if (ld % 32) return fail(h, VFK_ERR_INVALID, "ld must be a multiple of 32 (got %lld)", (long long)ld);
+    if (n_obst < 0) return fail(h, VFK_ERR_INVALID, "n_obstacles must be >= 0");
+    if (obst_comps != 4 && obst_comps != 6) return fail(h, VFK_ERR_INVALID, "obst_comps must be 4 or 6");
+    if (k_cycles < 1) return fail(h, VFK_ERR_INVALID, "k_cycles must be >= 1");
+    int rc;
+    if ((rc = check_layout(h, b->q, "q", true)) || (rc = check_layout(h, b->goal, "goal", true)) ||
+        (rc = check_layout(h, b->obst, "obst", n_obst > 0)) || (rc = check_layout(h, b->jp_ref, "jp_ref", false)) ||
+        (rc = check_layout(h, b->ns_in, "ns_in", false)) ||
+        (rc = check_layout(h, b->ns_lastvec, "ns_lastvec", h->params.ns_mode == VFK_NS_CONTROL)) ||
+        (rc = check_layout(h, b->q_cmded, "q_cmded", false)) || (rc = check_layout(h, b->qdot_vf, "qdot_vf", false)) ||
+        (rc = check_layout(h, b->qdot_ns, "qdot_ns", false)) || (rc = check_layout(h, b->qdot_jp, "qdot_jp", false)) ||
+        (rc = check_layout(h, b->qdot, "qdot", false)) || (rc = check_layout(h, b->cmd, "cmd", false)) ||
+        (rc = check_layout(h, b->pose, "pose", false)) || (rc = check_layout(h, b->flags, "flags", false)))
+        return rc;
+    for (int e = 0; e < 3; ++e)
+        if ((rc = check_layout(h, b->ext_cmd[e], "ext_cmd", false))) return rc;
+    if (n == 0) return 0;
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->precision == 32) return dispatch_n<float>(h, h->cf, b, n, ld, n_obst, obst_comps, k_cycles, st);
+    return dispatch_n<double>(h, h->cd, b, n, ld, n_obst, obst_comps, k_cycles, st);
+}
+
+extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst, void* twist_out,
+                              int64_t n, int64_t ld, int n_obst, int obst_comps, void* stream) {
+    if (!h || !pose_in || !goal || !twist_out) return fail(h, VFK_ERR_INVALID, "vfk_field_eval: null argument");
+    if (n < 0 || ld < n || ld % 32) return fail(h, VFK_ERR_INVALID, "need 0 <= n <= ld, ld %% 32 == 0");
+    if (n_obst > 0 && !obst) return fail(h, VFK_ERR_INVALID, "obst is required when n_obstacles > 0");
+    if (obst_comps != 4 && obst_comps != 6) return fail(h, VFK_ERR_INVALID, "obst_comps must be 4 or 6");
+    if (n == 0) return 0;
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    if (h->precision == 32)
+        vfk_field_kernel<float><<<grid, kBlock, 0, st>>>(h->cf, (const float*)pose_in, (const float*)goal, (const float*)obst,
+                                                         (float*)twist_out, n, ld, n_obst, obst_comps);
+    else
+        vfk_field_kernel<double><<<grid, kBlock, 0, st>>>(h->cd, (const double*)pose_in, (const double*)goal,
+                                                          (const double*)obst, (double*)twist_out, n, ld, n_obst, obst_comps);
+    VFK_CUDA(h, cudaGetLastError());
+    return 1;
+}
+
+extern "C" int vfk_mix(vfk_handle h, const void* const* cmds, const double* w, int n_ports, int n_channels, void* out,
+                       int32_t* nan_flags, int64_t n, int64_t ld, void* stream) {
+    if (!h || !cmds || !w || !out) return fail(h, VFK_ERR_INVALID, "vfk_mix: null argument");
+    if (n_ports < 0 || n_ports > 8) return fail(h, VFK_ERR_INVALID, "n_ports must be in 0..8");
+    if (n_channels < 1) return fail(h, VFK_ERR_INVALID, "n_channels must be >= 1");
+    if (n < 0 || ld < n) return fail(h, VFK_ERR_INVALID, "need 0 <= n <= ld");
+    if (n == 0) return 0;
+    MixArgs m;
+    memset(&m, 0, sizeof m);
+    m.n_ports = n_ports;
+    for (int p = 0; p < n_ports; ++p) { m.cmds[p] = cmds[p]; m.w[p] = w[p]; }
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (h->precision == 32)
+        vfk_mix_kernel<float><<<grid, 256, 0, st>>>(m, (float*)out, nan_flags, n_channels, n, ld);
+    else
+        vfk_mix_kernel<double><<<grid, 256, 0, st>>>(m, (double*)out, nan_flags, n_channels, n, ld);
+    VFK_CUDA(h, cudaGetLastError());
+    return 1;
+}
+
+// -------------------------------------------------------------------------------- public: host-buffer sessions
+struct vfk_session_s {
+    vfk_ctx* h;
+    int64_t n, ld;
+    int n_obst, obst_comps, N;
+    size_t es;                       // element size
+    cudaStream_t stream;
+    char* dev;                       // one device slab
+    size_t dev_bytes;
+    vfk_buffers b;                   // device views into the slab
+    bool have_jp_ref, have_ns_in;
+    void *d_jp_ref, *d_ns_in;
+    char* pin;                       // pinned staging: q in (N), qdot/q out (2N) + flags
+    size_t pin_bytes;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int obst_comps, vfk_session* out) {
+    if (!h || !out) return fail(h, VFK_ERR_INVALID, "vfk_session_create: null argument");
+    *out = nullptr;
+    if (n < 1) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 1");
+    if (n_obst < 0 || (obst_comps != 4 && obst_comps != 6)) return fail(h, VFK_ERR_INVALID, "bad obstacle shape");
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    vfk_session_s* s = new (std::nothrow) vfk_session_s();
+    if (!s) return fail(h, VFK_ERR_INVALID, "out of host memory");
+    memset(&s->b, 0, sizeof s->b);
+    s->h = h;
+    s->n = n;
+    s->ld = (int64_t)align_up((size_t)n, 128);
+    s->n_obst = n_obst;
+    s->obst_comps = obst_comps;
+    s->N = h->chain.n_joints;
+    s->es = h->precision == 32 ? 4 : 8;
+    const size_t row = (size_t)s->ld * s->es;       // multiple of 512 bytes
+    const int N = s->N;
+    // rows: q N, goal 13, obst M*comps, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, flags (int32: <= 1 row)
+    const size_t rows = (size_t)N * 9 + 13 + (size_t)n_obst * obst_comps + 12 + 1;
+    s->dev_bytes = rows * row;
+    cudaError_t e = cudaMalloc((void**)&s->dev, s->dev_bytes);
+    if (e != cudaSuccess) { delete s; return fail(h, VFK_ERR_CUDA, "cudaMalloc(%zu): %s", rows * row, cudaGetErrorString(e)); }
+    e = cudaMemset(s->dev, 0, s->dev_bytes);
+    char* p = s->dev;
+    auto take = [&](size_t nrows) { char* r = p; p += nrows * row; return (void*)r; };
+    s->b.q = take(N);
+    s->b.goal = take(13);
+    s->b.obst = n_obst ? take((size_t)n_obst * obst_comps) : nullptr;
+    s->d_jp_ref = take(N);
+    s->d_ns_in = take(N);
+    s->b.ns_lastvec = take(N);
+    s->b.qdot_vf = take(N);
+    s->b.qdot_ns = take(N);
+    s->b.qdot_jp = take(N);
+    s->b.qdot = take(N);
+    s->b.cmd = take(N);
+    s->b.pose = take(12);
+    s->b.flags = (int32_t*)take(1);
+    s->have_jp_ref = s->have_ns_in = false;
+    s->pin_bytes = (size_t)N * 3 * (size_t)n * s->es + (size_t)n * 4;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&s->pin, s->pin_bytes);
+    if (e != cudaSuccess) {
+        cudaFree(s->dev);
+        delete s;
+        return fail(h, VFK_ERR_CUDA, "session allocation: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return VFK_OK;
+}
+
+// dense host [rows][n] -> device [rows][ld]
+static cudaError_t upload_rows(vfk_session_s* s, void* dst, const void* src, size_t rows) {
+    return cudaMemcpy2DAsync(dst, (size_t)s->ld * s->es, src, (size_t)s->n * s->es, (size_t)s->n * s->es, rows,
+                             cudaMemcpyHostToDevice, s->stream);
+}
+static cudaError_t download_rows(vfk_session_s* s, void* dst, const void* src, size_t rows, size_t es) {
+    return cudaMemcpy2DAsync(dst, (size_t)s->n * es, src, (size_t)s->ld * es, (size_t)s->n * es, rows,
+                             cudaMemcpyDeviceToHost, s->stream);
+}
+
+extern "C" int vfk_session_set_goal(vfk_session s, const void* g) {
+    if (!s || !g) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_set_goal: null argument");
+    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
+    VFK_CUDA(s->h, upload_rows(s, const_cast<void*>(s->b.goal), g, 13));
+    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
+    return VFK_OK;
+}
+extern "C" int vfk_session_set_obstacles(vfk_session s, const void* o) {
+    if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_obstacles: null session");
+    if (s->n_obst == 0) return VFK_OK;
+    if (!o) return fail(s->h, VFK_ERR_INVALID, "vfk_session_set_obstacles: null argument");
+    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
+    VFK_CUDA(s->h, upload_rows(s, const_cast<void*>(s->b.obst), o, (size_t)s->n_obst * s->obst_comps));
+    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
+    return VFK_OK;
+}
+extern "C" int vfk_session_set_q(vfk_session s, const void* q) {
+    if (!s || !q) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_set_q: null argument");
+    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
+    VFK_CUDA(s->h, upload_rows(s, s->b.q, q, s->N));
+    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
+    return VFK_OK;
+}
+extern "C" int vfk_session_set_jp_ref(vfk_session s, const void* r) {
+    if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_jp_ref: null session");
+    s->have_jp_ref = r != nullptr;
+    if (!r) return VFK_OK;
+    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
+    VFK_CUDA(s->h, upload_rows(s, s->d_jp_ref, r, s->N));
+    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
+    return VFK_OK;
+}
+extern "C" int vfk_session_set_ns_input(vfk_session s, const void* x) {
+    if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_ns_input: null session");
+    s->have_ns_in = x != nullptr;
+    if (!x) return VFK_OK;
+    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
+    const size_t rows = s->h->params.ns_mode == VFK_NS_CONTROL ? 4 : (size_t)s->N;
+    VFK_CUDA(s->h, upload_rows(s, s->d_ns_in, x, rows));
+    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
+    return VFK_OK;
+}
+
+extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, void* qdot_out, void* q_out,
+                                 int32_t* flags_out) {
+    if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_cycle: null session");
+    vfk_ctx* h = s->h;
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    const size_t blk = (size_t)s->N * (size_t)s->n * s->es;
+    char* pin_q = s->pin;
+    char* pin_qd = s->pin + blk;
+    char* pin_qo = s->pin + 2 * blk;
+    char* pin_fl = s->pin + 3 * blk;
+    if (q_in) {
+        memcpy(pin_q, q_in, blk);                                   // pageable -> pinned staging
+        VFK_CUDA(h, upload_rows(s, s->b.q, pin_q, s->N));
+    }
+    vfk_buffers b = s->b;
+    b.jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
+    b.ns_in = s->have_ns_in ? s->d_ns_in : nullptr;
+    if (!flags_out) b.flags = nullptr;
+    int rc = vfk_step(h, &b, s->n, s->ld, s->n_obst, s->obst_comps, k_cycles, s->stream);
+    if (rc < 0) return rc;
+    if (qdot_out) VFK_CUDA(h, download_rows(s, pin_qd, s->b.qdot, s->N, s->es));
+    if (q_out) VFK_CUDA(h, download_rows(s, pin_qo, s->b.q, s->N, s->es));
+    if (flags_out) VFK_CUDA(h, download_rows(s, pin_fl, s->b.flags, 1, 4));
+    VFK_CUDA(h, cudaStreamSynchronize(s->stream));
+    if (qdot_out) memcpy(qdot_out, pin_qd, blk);
+    if (q_out) memcpy(q_out, pin_qo, blk);
+    if (flags_out) memcpy(flags_out, pin_fl, (size_t)s->n * 4);
+    return rc;
+}
+
+extern "C" int vfk_session_read(vfk_session s, const char* what, void* out) {
+    if (!s || !what || !out) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_read: null argument");
+    const void* src = nullptr;
+    size_t rows = s->N;
+    if (!strcmp(what, "qdot_vf")) src = s->b.qdot_vf;
+    else if (!strcmp(what, "qdot_ns")) src = s->b.qdot_ns;
+    else if (!strcmp(what, "qdot_jp")) src = s->b.qdot_jp;
+    else if (!strcmp(what, "qdot")) src = s->b.qdot;
+    else if (!strcmp(what, "cmd")) src = s->b.cmd;
+    else if (!strcmp(what, "q")) src = s->b.q;
+    else if (!strcmp(what, "lastvec")) src = s->b.ns_lastvec;
+    else if (!strcmp(what, "pose")) { src = s->b.pose; rows = 12; }
+    else return fail(s->h, VFK_ERR_INVALID, "vfk_session_read: unknown field '%s'", what);
+    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
+    VFK_CUDA(s->h, download_rows(s, out, src, rows, s->es));
+    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
+    return VFK_OK;
+}
+
+extern "C" int vfk_session_buffers(vfk_session s, vfk_buffers* out, int64_t* ld) {
+    if (!s || !out) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_buffers: null argument");
+    *out = s->b;
+    out->jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
+    out->ns_in = s->have_ns_in ? s->d_ns_in : nullptr;
+    if (ld) *ld = s->ld;
+    return VFK_OK;
+}
+
+extern "C" void vfk_session_destroy(vfk_session s) {
+    if (!s) return;
+    cudaSetDevice(s->h->device);
+    cudaStreamSynchronize(s->stream);
+    cudaFreeHost(s->pin);
+    cudaFree(s->dev);
+    cudaStreamDestroy(s->stream);
+    delete s;
+}

@@ -1,0 +1,512 @@
+// vfk_kernels.cuh -- the fused vfclik control-cycle kernel for sm_100a.
+//
+// One thread = one manipulator instance; all per-instance state (q, frame, the 6xN
+// Jacobian, the 6x6 normal matrix) lives in registers across the K fused cycles.
+// Global arrays are SoA [component][ld]: a warp's access to one component is one
+// 128-byte (FP32) or 256-byte (FP64) contiguous line.  Robot constants (chain,
+// limits, gains) arrive as a __grid_constant__ kernel parameter, i.e. in the
+// constant bank, and are indexed at compile time only.
+//
+// Reference mapping (see include/vfk.h and SURVEY.md App. C.2):
+//   fk_jacobian()   scripts/vf:316-318, scripts/nullspace:175  (Lafik / KDL FK + Jacobian)
+//   field()         scripts/vf:276-293,344-347                 (vfl attractor + decay repellers)
+//   dls             scripts/vf:461                              (Lafik.getIKV)
+//   nullspace       scripts/nullspace:75-131,159-184
+//   jp controller   scripts/joint_p_controller:79-89,126-146
+//   mixer / clamp   src/command_mixer.py:71-82, scripts/bridge:188-203
+#pragma once
+#include <stdint.h>
+#include "vfk_math.cuh"
+
+namespace vfk {
+
+constexpr int kMaxJ = 17;
+constexpr int kBlock = 128;          // threads (= instances) per CTA
+
+// Kernel-side constants in the kernel's arithmetic type.  Joints are canonicalised on
+// the host (vfk_api.cu: canonicalise_chain) so that every joint acts about / along its
+// local Z axis: RotX/RotY/TransX/TransY are conjugated into the neighbouring tips.
+template <typename T>
+struct KConst {
+    T base[12];
+    T tip[kMaxJ][12];
+    T q_lo[kMaxJ], q_hi[kMaxJ];
+    T ns_q0_scale[kMaxJ];      // -k / (hi - lo)^2
+    T ns_mid[kMaxJ];
+    T w_joint[kMaxJ];
+    T jp_ref[kMaxJ];
+    T w_task[6];
+    T mixer_w[6];
+    T tool[12];
+    T ns_control[4];
+    T ik_lambda2, ns_lambda2, dt, speed_scale, max_vel, jp_kp, jp_delta;
+    T ns_gain, ns_lookahead, rot_slowdown, goal_force, obst_force, obst_safe_inv, obst_order;
+    int32_t prismatic_mask;    // bit j set: joint j is TransZ, else RotZ
+    int32_t ns_mode;
+    int32_t direct_control;    // resolved 0/1
+    int32_t integrate;
+    int32_t unit_weights;      // w_task and w_joint are all ones
+    int32_t share_factor;      // nullspace can reuse the IK Cholesky factor
+    int32_t tool_identity;
+};
+
+template <typename T>
+struct KArgs {
+    T* q;
+    const T* goal;
+    const T* obst;
+    const T* jp_ref;
+    const T* ns_in;
+    T* ns_lastvec;
+    const T* q_cmded;
+    const T* ext_cmd[3];
+    T* qdot_vf;
+    T* qdot_ns;
+    T* qdot_jp;
+    T* qdot;
+    T* cmd;
+    T* pose;
+    int32_t* flags;
+    int64_t n;
+    int64_t ld;
+    int32_t n_obst;
+    int32_t obst_comps;
+    int32_t k_cycles;
+};
+
+// ------------------------------------------------------------------------------ FK + J
+// T_{j+1} = T_j * RotZ(q_j) * tip_j.  Records the joint axis z_j = R_j[:,2] and origin
+// p_j before each joint, then forms J = [z x (p_e - p_j); z] (revolute) or [z; 0].
+template <typename T, int N>
+__device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
+                                            T (&R)[9], T (&p)[3], T (&Jl)[N][3], T (&Ja)[N][3]) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = c.base[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = c.base[9 + k];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        Ja[j][0] = R[2]; Ja[j][1] = R[5]; Ja[j][2] = R[8];
+        Jl[j][0] = p[0]; Jl[j][1] = p[1]; Jl[j][2] = p[2];      // holds p_j until p_e is known
+        if (c.prismatic_mask & (1 << j)) {
+            p[0] = fma(R[2], q[j], p[0]); p[1] = fma(R[5], q[j], p[1]); p[2] = fma(R[8], q[j], p[2]);
+        } else {
+            T s, co;
+            Prec<T>::sincos_(q[j], &s, &co);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const T a = R[3 * r + 0], b = R[3 * r + 1];
+                R[3 * r + 0] = fma(co, a, s * b);
+                R[3 * r + 1] = fma(co, b, -s * a);
+            }
+        }
+        const T* tp = c.tip[j];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            p[r] = fma(R[3 * r + 0], tp[9], fma(R[3 * r + 1], tp[10], fma(R[3 * r + 2], tp[11], p[r])));
+        T Rn[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+                Rn[3 * r + cc] = fma(R[3 * r + 0], tp[cc], fma(R[3 * r + 1], tp[3 + cc], R[3 * r + 2] * tp[6 + cc]));
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (c.prismatic_mask & (1 << j)) {
+            Jl[j][0] = Ja[j][0]; Jl[j][1] = Ja[j][1]; Jl[j][2] = Ja[j][2];
+            Ja[j][0] = Ja[j][1] = Ja[j][2] = T(0);
+        } else {
+            const T dx = p[0] - Jl[j][0], dy = p[1] - Jl[j][1], dz = p[2] - Jl[j][2];
+            Jl[j][0] = Ja[j][1] * dz - Ja[j][2] * dy;
+            Jl[j][1] = Ja[j][2] * dx - Ja[j][0] * dz;
+            Jl[j][2] = Ja[j][0] * dy - Ja[j][1] * dx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ field
+// Twist commanded by the composed field at tool frame (Rt, pt):
+//   V = normCart( goal_force * [unit(p_g - p); axis(R_g Rt^T)] + sum_k obst_force * decay_k ),
+//   v = speed * S0 * V_lin,  w = speed * S1 * V_rot.
+// goal_ptr / obst_ptr already point at this thread's instance column.
+template <typename T>
+__device__ __forceinline__ void field(const KConst<T>& c, const T (&Rt)[9], const T (&pt)[3],
+                                      const T* __restrict__ goal_ptr, const T* __restrict__ obst_ptr,
+                                      int64_t ld, int n_obst, int obst_comps, T (&v)[3], T (&w)[3]) {
+    T g[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) g[k] = __ldg(goal_ptr + k * ld);
+    // attractor, linear part
+    const T ex = g[9] - pt[0], ey = g[10] - pt[1], ez = g[11] - pt[2];
+    const T d2 = fma(ex, ex, fma(ey, ey, ez * ez));
+    const T invd = d2 > T(0) ? Prec<T>::rsqrt_pos(d2) : T(0);
+    const T dist = d2 * invd;
+    T V[3] = {c.goal_force * ex * invd, c.goal_force * ey * invd, c.goal_force * ez * invd};
+    // attractor, rotational part: R_err = R_g * Rt^T
+    T E[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+            E[3 * r + cc] = fma(g[3 * r + 0], Rt[3 * cc + 0], fma(g[3 * r + 1], Rt[3 * cc + 1], g[3 * r + 2] * Rt[3 * cc + 2]));
+    T qw, qx, qy, qz;
+    rot_to_quat<T>(E, qw, qx, qy, qz);
+    const T n2 = fma(qx, qx, fma(qy, qy, qz * qz));
+    const T invn = n2 > T(0) ? Prec<T>::rsqrt_pos(n2) : T(0);
+    const T angle = T(2) * Prec<T>::atan2_(n2 * invn, qw);
+    const T S1 = c.rot_slowdown > T(0) ? Prec<T>::fmin_(T(1), angle / c.rot_slowdown) : T(1);
+    const T S0 = g[12] > T(0) ? Prec<T>::fmin_(T(1), dist / g[12]) : T(1);
+    // decay repellers
+    T ax = T(0), ay = T(0), az = T(0);
+    for (int m = 0; m < n_obst; ++m) {
+        const T* o = obst_ptr + (int64_t)m * obst_comps * ld;
+        const T ox = __ldg(o), oy = __ldg(o + ld), oz = __ldg(o + 2 * ld), rad = __ldg(o + 3 * ld);
+        T safe_inv = c.obst_safe_inv, order = c.obst_order;
+        if (obst_comps >= 6) {
+            safe_inv = Prec<T>::rcp(__ldg(o + 4 * ld));
+            order = __ldg(o + 5 * ld);
+        }
+        const T dx = ox - pt[0], dy = oy - pt[1], dz = oz - pt[2];
+        const T dd = fma(dx, dx, fma(dy, dy, dz * dz));
+        const T inv = dd > T(0) ? Prec<T>::rsqrt_pos(dd) : T(0);
+        const T ratio = rad * Prec<T>::fmin_(inv, safe_inv);          // radius / max(d, safe)
+        const T decay = rad > T(0) ? Prec<T>::pow_pos(ratio, order) : T(0);
+        const T wgt = decay * inv;
+        ax = fma(wgt, dx, ax); ay = fma(wgt, dy, ay); az = fma(wgt, dz, az);
+    }
+    V[0] = fma(c.obst_force, ax, V[0]); V[1] = fma(c.obst_force, ay, V[1]); V[2] = fma(c.obst_force, az, V[2]);
+    // normCart: unit translational part (zero stays zero); pre-scale by the largest
+    // component so the squared norm cannot overflow in FP32.
+    const T big = Prec<T>::fmax_(Prec<T>::fabs_(V[0]), Prec<T>::fmax_(Prec<T>::fabs_(V[1]), Prec<T>::fabs_(V[2])));
+    if (big > T(0)) {
+        const T ib = Prec<T>::rcp(big);
+        V[0] *= ib; V[1] *= ib; V[2] *= ib;
+        const T nn = fma(V[0], V[0], fma(V[1], V[1], V[2] * V[2]));
+        const T inn = Prec<T>::rsqrt_pos(nn);
+        V[0] *= inn; V[1] *= inn; V[2] *= inn;
+    }
+    const T sl = c.speed_scale * S0;
+    v[0] = sl * V[0]; v[1] = sl * V[1]; v[2] = sl * V[2];
+    const T sr = c.speed_scale * S1 * c.goal_force * invn;
+    w[0] = sr * qx; w[1] = sr * qy; w[2] = sr * qz;
+}
+
+// ------------------------------------------------------------------------------ the fused kernel
+template <typename T, int N>
+__global__ void __launch_bounds__(kBlock)
+vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KArgs<T> a) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= a.n) return;
+    const int64_t ld = a.ld;
+
+    T q[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) q[j] = a.q[j * ld + i];
+
+    T lastv[N];
+    if (c.ns_mode == 2) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) lastv[j] = a.ns_lastvec[j * ld + i];
+    }
+
+    for (int cyc = 0; cyc < a.k_cycles; ++cyc) {
+        const bool last = (cyc == a.k_cycles - 1);
+        int flags = 0;
+
+        // 1. FK, Jacobian, tool frame
+        T R[9], p[3], Jl[N][3], Ja[N][3];
+        fk_jacobian<T, N>(c, q, R, p, Jl, Ja);
+        T Rt[9], pt[3], dp[3];
+        if (c.tool_identity) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Rt[k] = R[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { pt[k] = p[k]; dp[k] = T(0); }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const T off = fma(R[3 * r + 0], c.tool[9], fma(R[3 * r + 1], c.tool[10], R[3 * r + 2] * c.tool[11]));
+                pt[r] = p[r] + off;
+                dp[r] = p[r] - pt[r];
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc)
+                    Rt[3 * r + cc] = fma(R[3 * r + 0], c.tool[cc], fma(R[3 * r + 1], c.tool[3 + cc], R[3 * r + 2] * c.tool[6 + cc]));
+            }
+        }
+
+        // 2-4. field, saturation, reference-point shift to the flange
+        T tw[6];
+        {
+            T v[3], w[3];
+            field<T>(c, Rt, pt, a.goal + i, a.obst + i, ld, a.n_obst, a.obst_comps, v, w);
+            tw[0] = v[0] + (w[1] * dp[2] - w[2] * dp[1]);
+            tw[1] = v[1] + (w[2] * dp[0] - w[0] * dp[2]);
+            tw[2] = v[2] + (w[0] * dp[1] - w[1] * dp[0]);
+            tw[3] = w[0]; tw[4] = w[1]; tw[5] = w[2];
+        }
+
+        // 5. weighted damped least squares: qdot = Wj Jw^T (Jw Jw^T + l^2 I)^-1 Wt t
+        T A[21], invd[6];
+        T qd_vf[N];
+        {
+            if (!c.unit_weights) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) tw[k] *= c.w_task[k];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int s = 0; s <= r; ++s) {
+                    T acc = (r == s) ? c.ik_lambda2 : T(0);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        T jr = r < 3 ? Jl[j][r] : Ja[j][r - 3];
+                        T js = s < 3 ? Jl[j][s] : Ja[j][s - 3];
+                        if (!c.unit_weights) {
+                            const T wj2 = c.w_joint[j] * c.w_joint[j];
+                            jr *= c.w_task[r] * wj2;
+                            js *= c.w_task[s];
+                        }
+                        acc = fma(jr, js, acc);
+                    }
+                    A[tri(r, s)] = acc;
+                }
+            chol6<T>(A, invd);
+            chol6_fwd<T>(A, invd, tw);
+            chol6_bwd<T>(A, invd, tw);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                T acc = T(0);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    T jr = r < 3 ? Jl[j][r] : Ja[j][r - 3];
+                    if (!c.unit_weights) jr *= c.w_task[r];
+                    acc = fma(jr, tw[r], acc);
+                }
+                qd_vf[j] = c.unit_weights ? acc : acc * c.w_joint[j] * c.w_joint[j];
+            }
+        }
+
+        // 6. nullspace
+        T qd_ns[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) qd_ns[j] = T(0);
+        if (c.ns_mode != 0) {
+            if (!c.share_factor) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int s = 0; s <= r; ++s) {
+                        T acc = (r == s) ? c.ns_lambda2 : T(0);
+#pragma unroll
+                        for (int j = 0; j < N; ++j)
+                            acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], s < 3 ? Jl[j][s] : Ja[j][s - 3], acc);
+                        A[tri(r, s)] = acc;
+                    }
+                chol6<T>(A, invd);
+            }
+            T x[N];
+            if (c.ns_mode == 1) {
+                if (a.ns_in) {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) x[j] = __ldg(a.ns_in + j * ld + i);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) x[j] = c.ns_q0_scale[j] * (q[j] - c.ns_mid[j]);
+                }
+            } else {
+                // 1-D nullspace: pick the column of B = I - J^T A^-1 J with the largest
+                // diagonal entry B_jj = 1 - |L^-1 J[:,j]|^2 (first maximum wins).
+                int jstar = 0;
+                T best = T(-1);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    T col[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
+                    chol6_fwd<T>(A, invd, col);
+                    T s2 = T(0);
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) s2 = fma(col[r], col[r], s2);
+                    const T bjj = T(1) - s2;
+                    if (bjj > best) { best = bjj; jstar = j; }
+                }
+#pragma unroll
+                for (int j = 0; j < N; ++j) x[j] = (j == jstar) ? T(1) : T(0);
+            }
+            // raw = x - J^T A^-1 (J x)
+            T y[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                T acc = T(0);
+#pragma unroll
+                for (int j = 0; j < N; ++j) acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], x[j], acc);
+                y[r] = acc;
+            }
+            chol6_fwd<T>(A, invd, y);
+            chol6_bwd<T>(A, invd, y);
+            T raw[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                T acc = x[j];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc = fma(-(r < 3 ? Jl[j][r] : Ja[j][r - 3]), y[r], acc);
+                raw[j] = acc;
+            }
+            if (c.ns_mode == 2) {
+                T nn = T(0), dotl = T(0), l2 = T(0), amax = T(-1), vmax = T(0);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    nn = fma(raw[j], raw[j], nn);
+                    dotl = fma(raw[j], lastv[j], dotl);
+                    l2 = fma(lastv[j], lastv[j], l2);
+                    if (Prec<T>::fabs_(raw[j]) > amax) { amax = Prec<T>::fabs_(raw[j]); vmax = raw[j]; }
+                }
+                T sc = Prec<T>::rsqrt_pos(nn);
+                const bool neg = (l2 > T(0)) ? (dotl < T(0)) : (vmax < T(0));
+                if (neg) sc = -sc;
+                T c0 = a.ns_in ? __ldg(a.ns_in + i) : c.ns_control[0];
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    lastv[j] = raw[j] * sc;
+                    raw[j] = lastv[j] * c0;
+                }
+            }
+            // all-or-nothing lookahead limit check, then gain
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const T d = fma(c.ns_lookahead, raw[j], q[j]);
+                bad = bad || (d < c.q_lo[j]) || (d > c.q_hi[j]);
+            }
+            if (bad) flags |= 2;
+#pragma unroll
+            for (int j = 0; j < N; ++j) qd_ns[j] = bad ? T(0) : raw[j] * c.ns_gain;
+        }
+
+        // 7. joint P controller
+        T qd_jp[N];
+        {
+            bool all_reached = true;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                T ref = a.jp_ref ? __ldg(a.jp_ref + j * ld + i) : c.jp_ref[j];
+                ref = ref < c.q_lo[j] ? c.q_lo[j] : (ref > c.q_hi[j] ? c.q_hi[j] : ref);
+                const T err = ref - q[j];
+                qd_jp[j] = err * c.jp_kp;
+                all_reached = all_reached && (err < c.jp_delta);
+            }
+            if (all_reached) flags |= 1;
+        }
+
+        // 8-9. mixer, clamp
+        T mix[N];
+        T lead = T(0);
+        bool nan = false;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            T m = T(0);
+            m = fma(qd_vf[j], c.mixer_w[0], m);
+            m = fma(qd_ns[j], c.mixer_w[1], m);
+            m = fma(qd_jp[j], c.mixer_w[2], m);
+            nan = nan || (qd_vf[j] != qd_vf[j]) || (qd_ns[j] != qd_ns[j]) || (qd_jp[j] != qd_jp[j]);
+#pragma unroll
+            for (int e = 0; e < 3; ++e)
+                if (a.ext_cmd[e]) {
+                    const T x = __ldg(a.ext_cmd[e] + j * ld + i);
+                    nan = nan || (x != x);
+                    m = fma(x, c.mixer_w[3 + e], m);
+                }
+            mix[j] = m;
+            lead = Prec<T>::fmax_(lead, Prec<T>::fabs_(m));
+        }
+        if (nan) flags |= 4;
+        T ratio = T(1);
+        if (lead > c.max_vel) { ratio = c.max_vel / lead; flags |= 8; }
+
+        if (last) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const T qd = mix[j] * ratio;
+                if (a.qdot_vf) a.qdot_vf[j * ld + i] = qd_vf[j];
+                if (a.qdot_ns) a.qdot_ns[j * ld + i] = qd_ns[j];
+                if (a.qdot_jp) a.qdot_jp[j * ld + i] = qd_jp[j];
+                if (a.qdot) a.qdot[j * ld + i] = qd;
+                if (a.cmd) {
+                    const T qc = a.q_cmded ? __ldg(a.q_cmded + j * ld + i) : q[j];
+                    a.cmd[j * ld + i] = c.direct_control ? qd : (-qc + q[j] + qd);
+                }
+            }
+            if (a.pose) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a.pose[k * ld + i] = Rt[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) a.pose[(9 + k) * ld + i] = pt[k];
+            }
+            if (a.flags) a.flags[i] = flags;
+        }
+        // 10. plant
+        if (c.integrate) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) q[j] = fma(c.dt, mix[j] * ratio, q[j]);
+        }
+    }
+    if (c.integrate) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) a.q[j * ld + i] = q[j];
+    }
+    if (c.ns_mode == 2) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) a.ns_lastvec[j * ld + i] = lastv[j];
+    }
+}
+
+// ------------------------------------------------------------------------------ small kernels
+// Field query at given poses (scripts/vf:469-503).
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+vfk_field_kernel(const __grid_constant__ KConst<T> c, const T* __restrict__ pose, const T* __restrict__ goal,
+                 const T* __restrict__ obst, T* __restrict__ twist, int64_t n, int64_t ld, int n_obst, int obst_comps) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    T Rt[9], pt[3], v[3], w[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rt[k] = pose[k * ld + i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pt[k] = pose[(9 + k) * ld + i];
+    field<T>(c, Rt, pt, goal + i, obst + i, ld, n_obst, obst_comps, v, w);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { twist[k * ld + i] = v[k]; twist[(3 + k) * ld + i] = w[k]; }
+}
+
+struct MixArgs {
+    const void* cmds[8];
+    double w[8];
+    int n_ports;
+};
+
+// out[c][i] = sum_p w_p * cmds[p][c][i]  (src/command_mixer.py:78-82), NaN report (:71-75).
+template <typename T>
+__global__ void __launch_bounds__(256)
+vfk_mix_kernel(const __grid_constant__ MixArgs m, T* __restrict__ out, int32_t* __restrict__ nan_flags,
+               int n_channels, int64_t n, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    bool nan = false;
+    for (int ch = 0; ch < n_channels; ++ch) {
+        T acc = T(0);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            if (p < m.n_ports && m.cmds[p]) {
+                const T x = static_cast<const T*>(m.cmds[p])[(int64_t)ch * ld + i];
+                nan = nan || (x != x);
+                acc = fma(x, (T)m.w[p], acc);
+            }
+        }
+        out[(int64_t)ch * ld + i] = acc;
+    }
+    if (nan_flags) nan_flags[i] = nan ? 4 : 0;
+}
+
+}  // namespace vfk

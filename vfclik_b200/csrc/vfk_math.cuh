@@ -1,0 +1,128 @@
+// vfk_math.cuh -- per-thread math building blocks of the fused control-cycle kernel.
+//
+// Everything here works on values held in registers by ONE thread for ONE instance
+// (fully unrolled, compile-time indexed).  Precision-specific primitives live in
+// Prec<float> / Prec<double>: the FP32 path uses the MUFU approximations
+// (rsqrt / lg2 / ex2) whose error budget is stated in DESIGN.md (1e-4 relative on
+// qdot); the FP64 path uses correctly rounded sqrt / div and libdevice pow / atan2 /
+// sincos (1e-9 relative on qdot).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace vfk {
+
+template <typename T> struct Prec;
+
+template <> struct Prec<float> {
+    static __device__ __forceinline__ float rsqrt_pos(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    // x^y for x >= 0 through ex2(y * lg2(x)); x = 0 -> 0 for y > 0.
+    static __device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * __log2f(x)); }
+    static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float fabs_(float a) { return fabsf(a); }
+};
+
+template <> struct Prec<double> {
+    static __device__ __forceinline__ double rsqrt_pos(double x) { return 1.0 / sqrt(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double pow_pos(double x, double y) { return pow(x, y); }
+    static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+    static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+    static __device__ __forceinline__ double fmin_(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double fmax_(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double fabs_(double a) { return fabs(a); }
+};
+
+// ---- symmetric 6x6: packed lower triangle, index (i,j), i >= j -> i*(i+1)/2 + j
+__host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// In-place Cholesky A = L L^T of a packed SPD 6x6.  On return a[] holds L's strict
+// lower part and inv_d[j] = 1 / L[j][j] (the diagonal is only ever needed inverted).
+template <typename T>
+__device__ __forceinline__ void chol6(T (&a)[21], T (&inv_d)[6]) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        T s = a[tri(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-a[tri(j, k)], a[tri(j, k)], s);
+        const T id = Prec<T>::rsqrt_pos(s);
+        inv_d[j] = id;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            T t = a[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-a[tri(i, k)], a[tri(j, k)], t);
+            a[tri(i, j)] = t * id;
+        }
+    }
+}
+
+// Solve L z = b (forward) in place.
+template <typename T>
+__device__ __forceinline__ void chol6_fwd(const T (&l)[21], const T (&inv_d)[6], T (&b)[6]) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        T t = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) t = fma(-l[tri(i, k)], b[k], t);
+        b[i] = t * inv_d[i];
+    }
+}
+
+// Solve L^T y = z (backward) in place.
+template <typename T>
+__device__ __forceinline__ void chol6_bwd(const T (&l)[21], const T (&inv_d)[6], T (&b)[6]) {
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        T t = b[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) t = fma(-l[tri(k, i)], b[k], t);
+        b[i] = t * inv_d[i];
+    }
+}
+
+// Unit quaternion (w >= 0) of a rotation matrix given row-major m[9]; Shepperd's
+// branch selection keeps it well conditioned near angle = pi.  Matches
+// oracle/batch.py:rot_axis_angle.
+template <typename T>
+__device__ __forceinline__ void rot_to_quat(const T (&m)[9], T& w, T& x, T& y, T& z) {
+    const T t = m[0] + m[4] + m[8];
+    if (t > T(0)) {
+        const T s = Prec<T>::sqrt_(T(1) + t) * T(2);
+        const T is = Prec<T>::rcp(s);
+        w = T(0.25) * s;
+        x = (m[7] - m[5]) * is;
+        y = (m[2] - m[6]) * is;
+        z = (m[3] - m[1]) * is;
+    } else if (m[0] >= m[4] && m[0] >= m[8]) {          // argmax picks the first maximum
+        const T s = Prec<T>::sqrt_(Prec<T>::fmax_(T(1) + T(2) * m[0] - t, T(0))) * T(2);
+        const T is = Prec<T>::rcp(s);
+        x = T(0.25) * s;
+        y = (m[3] + m[1]) * is;
+        z = (m[6] + m[2]) * is;
+        w = (m[7] - m[5]) * is;
+    } else if (m[4] >= m[8]) {
+        const T s = Prec<T>::sqrt_(Prec<T>::fmax_(T(1) + T(2) * m[4] - t, T(0))) * T(2);
+        const T is = Prec<T>::rcp(s);
+        y = T(0.25) * s;
+        z = (m[7] + m[5]) * is;
+        x = (m[1] + m[3]) * is;
+        w = (m[2] - m[6]) * is;
+    } else {
+        const T s = Prec<T>::sqrt_(Prec<T>::fmax_(T(1) + T(2) * m[8] - t, T(0))) * T(2);
+        const T is = Prec<T>::rcp(s);
+        z = T(0.25) * s;
+        x = (m[2] + m[6]) * is;
+        y = (m[5] + m[7]) * is;
+        w = (m[3] - m[1]) * is;
+    }
+    if (w < T(0)) { w = -w; x = -x; y = -y; z = -z; }
+}
+
+}  // namespace vfk

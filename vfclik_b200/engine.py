@@ -1,0 +1,299 @@
+"""Batch engine: Python face of the fused control-cycle kernel (``libvfk.so``).
+
+``Engine`` wraps a ``vfk_handle`` (chain + per-robot constants); ``Engine.step`` runs K
+fused cycles on device buffers (torch CUDA tensors, SoA ``[comps, ld]``);
+``Engine.session`` opens a host-buffer session (numpy in / numpy out) whose scene
+(goal, obstacles) stays resident on the GPU between cycles -- the call the
+reference-facing host modules (``vf``, ``nullspace``, ``joint_p_controller``, ``bridge``)
+make.  There is no CPU path: constructing an ``Engine`` without ``libvfk.so`` or
+without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BuffersC, ParamsC, VfkError, NS_CONTROL, NS_OFF, NS_PROJECTOR)  # noqa: F401
+
+
+@dataclasses.dataclass
+class Params:
+    """Per-robot constants, mirror of ``vfk_params`` (include/vfk.h)."""
+    ik_lambda: float = 0.1
+    ns_lambda: float = 0.1
+    dt: float = 0.01
+    speed_scale: float = 0.2
+    max_vel: float = 1.0
+    jp_kp: float = 1.5
+    jp_delta: float = 0.087
+    ns_gain: float = 0.5
+    ns_lookahead: float = 0.3
+    ns_limit_gain: float = 1.0
+    rot_slowdown: float = 0.09
+    goal_force: float = 1.0
+    obst_force: float = -10.0
+    obst_safe: float = 0.001
+    obst_order: float = 20.0
+    mixer_w: Sequence[float] = (1.0, 1.0, 0.0, 0.0, 0.0, 0.0)
+    w_task: Sequence[float] = (1.0,) * 6
+    w_joint: Optional[Sequence[float]] = None
+    tool: Sequence[float] = (1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0)
+    jp_ref: Optional[Sequence[float]] = None
+    ns_control: Sequence[float] = (0.0, 0.0, 0.0, 0.0)
+    ns_mode: int = NS_PROJECTOR
+    direct_control: int = -1
+    integrate: int = 1
+
+    @staticmethod
+    def from_config(config, **over) -> "Params":
+        """Pick the attributes the reference reads from ``config``."""
+        kw = {}
+        for attr, key in (("speedScale", "speed_scale"), ("jpctrl_kp", "jp_kp"), ("max_vel", "max_vel"),
+                          ("rate", "dt"), ("ik_lambda", "ik_lambda"), ("ns_lambda", "ns_lambda"),
+                          ("ns_limit_gain", "ns_limit_gain")):
+            if hasattr(config, attr):
+                kw[key] = float(getattr(config, attr))
+        if hasattr(config, "initial_joint_pos"):
+            kw["jp_ref"] = tuple(float(v) for v in config.initial_joint_pos)
+        kw.update(over)
+        return Params(**kw)
+
+    def to_c(self, n_joints: int) -> ParamsC:
+        p = ParamsC()
+        for f in ("ik_lambda", "ns_lambda", "dt", "speed_scale", "max_vel", "jp_kp", "jp_delta", "ns_gain",
+                  "ns_lookahead", "ns_limit_gain", "rot_slowdown", "goal_force", "obst_force", "obst_safe",
+                  "obst_order"):
+            setattr(p, f, float(getattr(self, f)))
+        if len(self.mixer_w) != 6 or len(self.w_task) != 6 or len(self.tool) != 12 or len(self.ns_control) != 4:
+            raise ValueError("mixer_w/w_task need 6 values, tool 12, ns_control 4")
+        for k in range(6):
+            p.mixer_w[k] = float(self.mixer_w[k])
+            p.w_task[k] = float(self.w_task[k])
+        wj = [1.0] * n_joints if self.w_joint is None else list(self.w_joint)
+        ref = [0.0] * n_joints if self.jp_ref is None else list(self.jp_ref)
+        if len(wj) != n_joints or len(ref) != n_joints:
+            raise ValueError("w_joint / jp_ref need n_joints values")
+        for j in range(_lib.VFK_MAX_JOINTS):
+            p.w_joint[j] = float(wj[j]) if j < n_joints else 1.0
+            p.jp_ref[j] = float(ref[j]) if j < n_joints else 0.0
+        for k in range(12):
+            p.tool[k] = float(self.tool[k])
+        for k in range(4):
+            p.ns_control[k] = float(self.ns_control[k])
+        p.ns_mode, p.direct_control, p.integrate = int(self.ns_mode), int(self.direct_control), int(self.integrate)
+        return p
+
+
+def round_up(n: int, m: int = 128) -> int:
+    return (int(n) + m - 1) // m * m
+
+
+_BUF_FIELDS = ("q", "goal", "obst", "jp_ref", "ns_in", "ns_lastvec", "q_cmded", "qdot_vf", "qdot_ns", "qdot_jp",
+               "qdot", "cmd", "pose", "flags")
+
+
+def _dev_ptr(x) -> Optional[int]:
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        if not x.is_cuda:
+            raise TypeError("device buffers must be CUDA tensors")
+        if not x.is_contiguous():
+            raise ValueError("device buffers must be contiguous [comps, ld] tensors")
+        return x.data_ptr()
+    raise TypeError("expected a CUDA tensor or an integer device pointer, got %r" % type(x))
+
+
+class Engine:
+    def __init__(self, chain, precision: int = 32, device: int = 0, params: Optional[Params] = None):
+        self._lib = _lib.load()
+        self.chain = chain
+        self.n_joints = int(chain.n_joints)
+        self.precision = int(precision)
+        self.device = int(device)
+        self.np_dtype = np.float32 if precision == 32 else np.float64
+        self._h = C.c_void_p()
+        cdesc = _lib.chain_to_c(chain)
+        rc = self._lib.vfk_create(C.byref(self._h), C.byref(cdesc), self.precision, self.device)
+        if rc != 0:
+            raise VfkError(rc, self._lib.vfk_last_error(None).decode())
+        self.launches = 0                       # kernels launched through this engine
+        self.params = params if params is not None else Params()
+        self.set_params(self.params)
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.vfk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise VfkError(rc, self._lib.vfk_last_error(self._h).decode())
+        return rc
+
+    def set_params(self, params: Optional[Params] = None, **over):
+        if params is None:
+            params = self.params
+        if over:
+            params = dataclasses.replace(params, **over)
+        pc = params.to_c(self.n_joints)
+        self._check(self._lib.vfk_set_params(self._h, C.byref(pc)))
+        self.params = params
+        return params
+
+    @property
+    def torch_dtype(self):
+        import torch
+        return torch.float32 if self.precision == 32 else torch.float64
+
+    # -- device-buffer path
+    def step(self, bufs: Dict[str, object], n_instances: int, ld: int, n_obstacles: int, obst_comps: int = 4,
+             k_cycles: int = 1, stream: Optional[int] = None, ext_cmd=(None, None, None)) -> int:
+        """K fused cycles on device buffers; returns the number of kernels launched."""
+        b = BuffersC()
+        for f in _BUF_FIELDS:
+            setattr(b, f, _dev_ptr(bufs.get(f)))
+        for e in range(3):
+            b.ext_cmd[e] = _dev_ptr(ext_cmd[e])
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._check(self._lib.vfk_step(self._h, C.byref(b), int(n_instances), int(ld), int(n_obstacles),
+                                            int(obst_comps), int(k_cycles), C.c_void_p(stream)))
+        self.launches += rc
+        return rc
+
+    def field_eval(self, pose, goal, obst, twist_out, n_instances, ld, n_obstacles, obst_comps=4, stream=None) -> int:
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._check(self._lib.vfk_field_eval(self._h, _dev_ptr(pose), _dev_ptr(goal), _dev_ptr(obst),
+                                                  _dev_ptr(twist_out), int(n_instances), int(ld), int(n_obstacles),
+                                                  int(obst_comps), C.c_void_p(stream)))
+        self.launches += rc
+        return rc
+
+    def mix(self, cmds, weights, out, n_channels, n_instances, ld, nan_flags=None, stream=None) -> int:
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        n_ports = len(cmds)
+        arr = (C.c_void_p * n_ports)(*[_dev_ptr(c) for c in cmds])
+        w = (C.c_double * n_ports)(*[float(x) for x in weights])
+        rc = self._check(self._lib.vfk_mix(self._h, arr, w, n_ports, int(n_channels), _dev_ptr(out),
+                                           _dev_ptr(nan_flags), int(n_instances), int(ld), C.c_void_p(stream)))
+        self.launches += rc
+        return rc
+
+    def alloc(self, comps: int, ld: int, dtype=None):
+        """Zeroed device tensor ``[comps, ld]`` (torch's allocator returns >= 256-byte aligned blocks;
+        with ld a multiple of 128 every row is 128-byte aligned)."""
+        import torch
+        t = torch.zeros((comps, ld), dtype=dtype or self.torch_dtype, device="cuda:%d" % self.device)
+        assert t.data_ptr() % 128 == 0
+        return t
+
+    # -- host-buffer path
+    def session(self, n_instances: int, n_obstacles: int, obst_comps: int = 4) -> "Session":
+        return Session(self, n_instances, n_obstacles, obst_comps)
+
+
+class Session:
+    """Resident scene + state on the GPU; numpy arrays in and out (dense SoA ``[comps, n]``)."""
+
+    def __init__(self, engine: Engine, n_instances: int, n_obstacles: int, obst_comps: int = 4):
+        self.e = engine
+        self.n, self.m, self.comps = int(n_instances), int(n_obstacles), int(obst_comps)
+        self._s = C.c_void_p()
+        engine._check(engine._lib.vfk_session_create(engine._h, self.n, self.m, self.comps, C.byref(self._s)))
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s:
+            self.e._lib.vfk_session_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _arr(self, a, rows):
+        a = np.ascontiguousarray(a, dtype=self.e.np_dtype)
+        if a.shape != (rows, self.n):
+            raise ValueError("expected shape (%d, %d), got %r" % (rows, self.n, a.shape))
+        return a
+
+    def set_goal(self, goal):
+        a = self._arr(goal, 13)
+        self.e._check(self.e._lib.vfk_session_set_goal(self._s, _lib.np_ptr(a)))
+
+    def set_obstacles(self, obst):
+        if self.m == 0:
+            return
+        a = np.ascontiguousarray(obst, dtype=self.e.np_dtype).reshape(self.m * self.comps, -1)
+        a = self._arr(a, self.m * self.comps)
+        self.e._check(self.e._lib.vfk_session_set_obstacles(self._s, _lib.np_ptr(a)))
+
+    def set_q(self, q):
+        a = self._arr(q, self.e.n_joints)
+        self.e._check(self.e._lib.vfk_session_set_q(self._s, _lib.np_ptr(a)))
+
+    def set_jp_ref(self, ref):
+        if ref is None:
+            self.e._check(self.e._lib.vfk_session_set_jp_ref(self._s, None))
+        else:
+            a = self._arr(ref, self.e.n_joints)
+            self.e._check(self.e._lib.vfk_session_set_jp_ref(self._s, _lib.np_ptr(a)))
+
+    def set_ns_input(self, x):
+        if x is None:
+            self.e._check(self.e._lib.vfk_session_set_ns_input(self._s, None))
+        else:
+            rows = 4 if self.e.params.ns_mode == NS_CONTROL else self.e.n_joints
+            a = self._arr(x, rows)
+            self.e._check(self.e._lib.vfk_session_set_ns_input(self._s, _lib.np_ptr(a)))
+
+    def cycle(self, q_in=None, k_cycles: int = 1, qdot_out=None, q_out=None, flags_out=None) -> int:
+        """One host-facing call: H2D of q (if given), K fused cycles, D2H of the requested outputs.
+
+        Output arrays must be C-contiguous numpy arrays of the engine dtype, shape ``[N, n]``
+        (flags: int32 ``[n]``); they are filled in place.
+        """
+        N = self.e.n_joints
+
+        def out_ptr(a, shape, dt):
+            if a is None:
+                return None
+            if a.dtype != dt or a.shape != shape or not a.flags.c_contiguous:
+                raise ValueError("output array must be contiguous %s %r" % (dt, shape))
+            return _lib.np_ptr(a)
+
+        qp = None
+        if q_in is not None:
+            q_in = self._arr(q_in, N)
+            qp = _lib.np_ptr(q_in)
+        rc = self.e._check(self.e._lib.vfk_session_cycle(
+            self._s, qp, int(k_cycles), out_ptr(qdot_out, (N, self.n), self.e.np_dtype),
+            out_ptr(q_out, (N, self.n), self.e.np_dtype), out_ptr(flags_out, (self.n,), np.int32)))
+        self.e.launches += rc
+        return rc
+
+    def read(self, what: str) -> np.ndarray:
+        rows = 12 if what == "pose" else self.e.n_joints
+        out = np.empty((rows, self.n), dtype=self.e.np_dtype)
+        self.e._check(self.e._lib.vfk_session_read(self._s, what.encode(), _lib.np_ptr(out)))
+        return out

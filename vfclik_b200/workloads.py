@@ -1,0 +1,95 @@
+"""Synthetic workloads of BASELINE.json's configs, seeded numpy.
+
+Arrays are produced directly in the GPU layout: dense SoA ``[comps, I]``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .config import ChainDesc
+
+
+def quat_to_rot_rows(quat: np.ndarray) -> np.ndarray:
+    """[I,4] (w,x,y,z) unit quaternions -> [9, I] row-major rotation components."""
+    w, x, y, z = quat.T
+    return np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                     2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                     2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], axis=0)
+
+
+def random_batch(chain: ChainDesc, n_instances: int, n_obstacles: int, seed: int, dtype=np.float64,
+                 obst_comps: int = 4, slowdown: float = 0.05, order: float = 20.0, safe: float = 0.001,
+                 shoulder=None, box: float = 0.8):
+    """Configs 2-5: q ~ U(0.9 * limits); goal position ~ U(shell 0.3-0.8 m around the shoulder),
+    goal rotation ~ Haar (normalised Gaussian quaternion); obstacles ~ U(workspace box),
+    radius ~ U(0.03, 0.10); ``numpy.random.default_rng(seed)``.
+
+    Returns dict(q [N,I], goal [13,I], obst [M*comps, I]) of ``dtype``.
+    """
+    rng = np.random.default_rng(seed)
+    I, N, M = int(n_instances), chain.n_joints, int(n_obstacles)
+    if shoulder is None:
+        shoulder = chain.base[9:12]            # origin of the first joint
+    q = rng.uniform((0.9 * chain.q_lo)[:, None], (0.9 * chain.q_hi)[:, None], size=(N, I)).astype(dtype)
+    quat = rng.normal(size=(I, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    d = rng.normal(size=(I, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pg = d * rng.uniform(0.3, 0.8, size=(I, 1)) + np.asarray(shoulder)[None, :]
+    goal = np.concatenate([quat_to_rot_rows(quat), pg.T, np.full((1, I), slowdown)], axis=0).astype(dtype)
+    obst = np.empty((M, obst_comps, I), dtype=dtype)
+    sh = np.asarray(shoulder, dtype=np.float64)
+    for m in range(M):                       # per-obstacle draws keep peak memory at O(I)
+        obst[m, 0:3] = (rng.uniform(-box, box, size=(3, I)) + sh[:, None]).astype(dtype)
+        obst[m, 3] = rng.uniform(0.03, 0.10, size=I).astype(dtype)
+        if obst_comps == 6:
+            obst[m, 4] = safe
+            obst[m, 5] = order
+    return dict(q=q, goal=goal, obst=obst.reshape(M * obst_comps, I))
+
+
+def config1(chain: ChainDesc, config, seed: int = 0):
+    """BASELINE config 1: single LWR, start q and goal of old/system_start.sh.old:234,346,
+    three ObstacleP (radius 0.05, order 20: old/README.old:75) seeded between the start
+    end-effector position and the goal."""
+    rng = np.random.default_rng(seed)
+    g = np.asarray(config.initial_vf_pose[2], dtype=np.float64)
+    T = g[:16].reshape(4, 4)
+    goal = np.concatenate([T[:3, :3].reshape(9), T[:3, 3], [g[16] if g.size > 16 else 0.03]])[:, None]
+    q = np.asarray(config.initial_joint_pos, dtype=np.float64)[:, None]
+    start_ee = np.array([0.73, 0.28, 0.63])      # approximate EE at the start posture (offset seed only)
+    obst = np.zeros((3, 4, 1))
+    for m in range(3):
+        t = (m + 1) / 4.0
+        c = start_ee * (1 - t) + T[:3, 3] * t + rng.uniform(-0.08, 0.08, size=3)
+        obst[m, 0:3, 0] = c
+        obst[m, 3, 0] = 0.05
+    return dict(q=q, goal=goal, obst=obst.reshape(12, 1))
+
+
+def dual_arm_torso_chain() -> ChainDesc:
+    """BASELINE config 5: 3-DOF torso + 14 arm joints treated as one 17-joint serial chain
+    (6x17 Jacobian).  Synthetic geometry: a yaw-pitch-roll torso followed by two LWR-like
+    7-joint segments; only the shape (N = 17) matters for the benchmark."""
+    from . import kdl
+    from math import pi
+    segs = [
+        kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame(kdl.Rotation.RotX(pi / 2), kdl.Vector(0, 0, 0.20))),
+        kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame(kdl.Rotation.RotX(-pi / 2), kdl.Vector(0, 0, 0.0))),
+        kdl.Segment(kdl.Joint(kdl.Joint.RotX), kdl.Frame(kdl.Rotation.Identity(), kdl.Vector(0, 0, 0.25))),
+    ]
+    for _ in range(2):
+        segs += [
+            kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame.DH_Craig1989(0.0, pi / 2, 0.0, 0.0)),
+            kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame.DH_Craig1989(0.0, -pi / 2, 0.20, 0.0)),
+            kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame.DH_Craig1989(0.0, -pi / 2, 0.0, 0.0)),
+            kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame.DH_Craig1989(0.0, pi / 2, 0.195, 0.0)),
+            kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame.DH_Craig1989(0.0, pi / 2, 0.0, 0.0)),
+            kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame.DH_Craig1989(0.0, -pi / 2, 0.0, 0.0)),
+            kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame(kdl.Rotation.Identity(), kdl.Vector(0, 0, 0.05))),
+        ]
+    deg = pi / 180.0
+    limits = [[-60 * deg, 60 * deg], [-30 * deg, 60 * deg], [-30 * deg, 30 * deg]] + \
+             ([[-170 * deg, 170 * deg], [-120 * deg, 120 * deg]] * 3 + [[-170 * deg, 170 * deg]]) * 2
+    from .config import chain_from_segments
+    return chain_from_segments(segs, limits)
