@@ -55,49 +55,61 @@ def algorithmic_bytes(n_joints: int, n_obst: int, elem: int) -> int:
 # ----------------------------------------------------------------------------------------- clocks
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons through NVML (every ~2 ms) while the timed region runs."""
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.sm, self.reasons, self.power = gpu_index, [], set(), []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if visible:
+                try:
+                    phys = int(visible.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    phys = gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                   # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:                                    # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + self.err]}
+        self.stop_flag.set()
         self.thread.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, val in zip(names, r[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                "reasons": sorted(self.reasons), "source": "nvml, sampled during the timed region"}
 
 
 # ----------------------------------------------------------------------------------------- CPU arm (oracle)
@@ -114,7 +126,7 @@ def _cpu_worker(args):
     g = w["goal"][:, 0]
     g17 = [g[0], g[1], g[2], g[9], g[3], g[4], g[5], g[10], g[6], g[7], g[8], g[11], 0, 0, 0, 1, g[12]]
     prm = batch.Params(ns_mode=ns_mode, jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate)
-    loop = refshape.ControlLoop(chain, prm, w["q"][:, 0], g17, obstacles=w["obst"].reshape(n_obst, 4).tolist())
+    loop = refshape.ControlLoop(chain, prm, w["q"][:, 0], g17, obstacles=w["obst"][:, 0, :].tolist())
     t0 = time.perf_counter()
     loop.run(cycles)
     return cycles, time.perf_counter() - t0
@@ -152,7 +164,7 @@ def cpu_vectorised(n_obst: int, instances: int = 8192):
     chain = chain_from_config(cfg)
     w = workloads.random_batch(chain, instances, n_obst, seed=77)
     q, goal = w["q"].T.copy(), w["goal"].T.copy()
-    obst = w["obst"].reshape(n_obst, 4, instances).transpose(2, 0, 1).copy()
+    obst = w["obst"].transpose(1, 0, 2).copy()
     prm = batch.Params(jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate)
     batch.step(chain, prm, q[:256], goal[:256], obst[:256])
     t0 = time.perf_counter()
@@ -196,7 +208,7 @@ def run_reference_arm(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))

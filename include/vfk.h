@@ -21,10 +21,14 @@
  *
  * Data layout: every per-instance array is SoA, component-major: element
  * (component c, instance i) lives at base[c * ld + i], with ld >= n_instances the
- * leading dimension (in elements).  ld must be a multiple of 32 and every base
- * pointer 128-byte aligned so that warp loads are full 128-byte lines and the
- * obstacle tiles can be moved with cp.async.bulk (TMA).  Element type is float
- * (precision 32) or double (precision 64) as chosen at vfk_create().
+ * leading dimension (in instances).  The obstacle list is the one exception: it is
+ * [M][ld][4], one {x, y, z, radius} vector per (obstacle m, instance i) at
+ * base[(m * ld + i) * 4 + c], so that a thread fetches an obstacle with one 16/32-byte
+ * load and a tile of 128 instances is one contiguous row per obstacle (moved global ->
+ * shared by cp.async.bulk / TMA).  ld must be a multiple of 128 and every base pointer
+ * 128-byte aligned (the padding instances [n, ld) must be allocated; they are read
+ * but never written).  Element type is float (precision 32) or double (precision 64)
+ * as chosen at vfk_create().
  */
 #ifndef VFK_H_
 #define VFK_H_
@@ -90,8 +94,8 @@ typedef struct vfk_params {
     double rot_slowdown;         /* angle below which the rotational speed ramps down */
     double goal_force;           /* +1  (scripts/object_feeder:236) */
     double obst_force;           /* -10 (scripts/object_feeder:322) */
-    double obst_safe;            /* 0.001 (scripts/object_feeder:331), used when obst_comps == 4 */
-    double obst_order;           /* decay order, used when obst_comps == 4 */
+    double obst_safe;            /* 0.001 (scripts/object_feeder:331), used when vfk_buffers.obst_ext == NULL */
+    double obst_order;           /* decay order (> 0), used when vfk_buffers.obst_ext == NULL */
     double mixer_w[VFK_N_PORTS]; /* [vectorfield, nullspace, joint, mechanism, xtra1, xtra2] */
     double w_task[6];            /* diag of set_tweights (scripts/vf:296-305) */
     double w_joint[VFK_MAX_JOINTS]; /* diag of set_jweights (scripts/vf:306-309) */
@@ -108,7 +112,9 @@ typedef struct vfk_params {
 typedef struct vfk_buffers {
     void*       q;               /* [N][ld]  in; out when params.integrate                    */
     const void* goal;            /* [13][ld] attractor (vfl type 1) per instance                */
-    const void* obst;            /* [M][obst_comps][ld] decay repellers (vfl type 2): x,y,z,radius[,safe,order]; radius 0 = none */
+    const void* obst;            /* [M][ld][4] decay repellers (vfl type 2): x, y, z, radius; radius 0 = empty slot */
+    const void* obst_ext;        /* [M][ld][2] per-obstacle {safe distance, decay order} (wire-faithful,
+                                    scripts/object_feeder:326-333) or NULL -> params.obst_safe / obst_order */
     const void* jp_ref;          /* [N][ld]  joint reference (/jpctrl/ref) or NULL -> params.jp_ref */
     const void* ns_in;           /* PROJECTOR: qdot0 [N][ld] or NULL -> limit-avoidance gradient;
                                     CONTROL:   control [4][ld] or NULL -> params.ns_control      */
@@ -143,13 +149,13 @@ const char* vfk_last_error(vfk_handle h);   /* h may be NULL: last error of vfk_
  * Outputs hold the last cycle's values.  Returns the number of kernels launched
  * (>= 1) or a negative vfk_status. */
 int  vfk_step(vfk_handle h, const vfk_buffers* bufs, int64_t n_instances, int64_t ld,
-              int n_obstacles, int obst_comps, int k_cycles, void* stream);
+              int n_obstacles, int k_cycles, void* stream);
 
 /* Field visualisation query (scripts/vf:469-503): twist the composed field commands at
  * arbitrary tool poses pose_in[12][ld]; twist_out[6][ld].  Same goal/obst layout. */
 int  vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst,
-                    void* twist_out, int64_t n_instances, int64_t ld, int n_obstacles,
-                    int obst_comps, void* stream);
+                    const void* obst_ext, void* twist_out, int64_t n_instances, int64_t ld,
+                    int n_obstacles, void* stream);
 
 /* Weighted sum of command ports (src/command_mixer.py:78-82) on device buffers:
  * out[c][i] = sum_p w[p] * cmds[p][c][i]; cmds[p] may be NULL (skipped). */
@@ -158,13 +164,14 @@ int  vfk_mix(vfk_handle h, const void* const* cmds, const double* w, int n_ports
 
 /* ---- host-buffer sessions: the call a host-language plugin makes --------------
  * A session owns resident device copies of the scene (goal, obstacles) and state,
- * pinned staging buffers and a stream.  Host arrays are dense SoA [comps][n_instances]
- * (leading dimension n_instances) of the handle's precision.  vfk_session_cycle()
+ * pinned staging buffers and a stream.  Host arrays are dense (leading dimension
+ * n_instances, no padding) in the device layouts above, of the handle's precision.  vfk_session_cycle()
  * copies q host->device (if q_in != NULL), runs k_cycles fused cycles, copies the
  * requested outputs device->host and synchronises. */
-int  vfk_session_create(vfk_handle h, int64_t n_instances, int n_obstacles, int obst_comps, vfk_session* out);
+int  vfk_session_create(vfk_handle h, int64_t n_instances, int n_obstacles, int with_obst_ext, vfk_session* out);
 int  vfk_session_set_goal(vfk_session s, const void* goal_host);            /* [13][n] */
-int  vfk_session_set_obstacles(vfk_session s, const void* obst_host);       /* [M][comps][n] */
+int  vfk_session_set_obstacles(vfk_session s, const void* obst_host,         /* [M][n][4] */
+                               const void* obst_ext_host);                  /* [M][n][2] or NULL */
 int  vfk_session_set_q(vfk_session s, const void* q_host);                  /* [N][n] */
 int  vfk_session_set_jp_ref(vfk_session s, const void* ref_host);           /* [N][n] or NULL -> params.jp_ref */
 int  vfk_session_set_ns_input(vfk_session s, const void* ns_host);          /* [N|4][n] or NULL */

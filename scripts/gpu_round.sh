@@ -10,7 +10,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
 timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1
 echo "smoke exit $?" | tee -a $OUT/${TAG}_smoke.log
-timeout 600 python bench.py --steps 50 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 echo "bench exit $?"
 tail -c 3000 $OUT/${TAG}_bench.json
 SHORT="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras"

@@ -2,14 +2,15 @@
 import numpy as np
 
 
-def to_oracle(batch_arrays, n_obst, obst_comps=4):
-    """SoA [comps, I] -> the oracle's instance-major arrays."""
+def to_oracle(batch_arrays, n_obst):
+    """GPU layouts (q [N,I], goal [13,I], obst [M,I,4], obst_ext [M,I,2]) -> the oracle's instance-major arrays."""
     q = batch_arrays["q"].T.astype(np.float64)
     goal = batch_arrays["goal"].T.astype(np.float64)
-    I = q.shape[0]
     obst = None
     if n_obst > 0:
-        obst = batch_arrays["obst"].reshape(n_obst, obst_comps, I).transpose(2, 0, 1).astype(np.float64)
+        obst = batch_arrays["obst"].transpose(1, 0, 2).astype(np.float64)
+        if "obst_ext" in batch_arrays:
+            obst = np.concatenate([obst, batch_arrays["obst_ext"].transpose(1, 0, 2).astype(np.float64)], axis=2)
     return q, goal, obst
 
 

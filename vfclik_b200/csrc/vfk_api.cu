@@ -122,7 +122,7 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     c.jp_delta = (T)p.jp_delta;
     c.ns_gain = (T)p.ns_gain;
     c.ns_lookahead = (T)p.ns_lookahead;
-    c.rot_slowdown = (T)p.rot_slowdown;
+    c.rot_slowdown_inv = (T)(p.rot_slowdown > 0 ? 1.0 / p.rot_slowdown : INFINITY);
     c.goal_force = (T)p.goal_force;
     c.obst_force = (T)p.obst_force;
     c.obst_safe_inv = (T)(p.obst_safe > 0 ? 1.0 / p.obst_safe : INFINITY);
@@ -132,6 +132,7 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     c.integrate = p.integrate ? 1 : 0;
     c.unit_weights = unit ? 1 : 0;
     c.share_factor = (unit && p.ns_lambda == p.ik_lambda) ? 1 : 0;
+    c.need_jp = p.mixer_w[2] != 0.0 ? 1 : 0;
 }
 
 // -------------------------------------------------------------------------------- public: lifecycle
@@ -243,14 +244,28 @@ static int check_layout(vfk_ctx* h, const void* ptr, const char* name, bool requ
     return VFK_OK;
 }
 
-template <typename T, int N>
+// Shared-memory plan of one launch: ring of `n_stages` stages of kChunk obstacles each.
+template <typename T, bool EXT>
+static void plan_stages(int n_obst, int* n_chunks, int* n_stages, size_t* smem_bytes) {
+    const size_t stage = (size_t)kChunk * kBlock * (sizeof(Vec4<T>) + (EXT ? sizeof(Vec2<T>) : 0));
+    const size_t budget = sizeof(T) == 4 ? (64u << 10) : (96u << 10);      // per CTA: 3 (FP32) / 2 (FP64) CTAs per SM
+    int max_stages = (int)(budget / stage);
+    if (max_stages < 2) max_stages = 2;
+    if (max_stages > kMaxStages) max_stages = kMaxStages;
+    *n_chunks = (n_obst + kChunk - 1) / kChunk;
+    *n_stages = *n_chunks < max_stages ? *n_chunks : max_stages;
+    *smem_bytes = n_obst > 0 ? kSmemHeader + (size_t)(*n_stages) * stage : 0;
+}
+
+template <typename T, int N, bool EXT>
 static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
-                        int obst_comps, int k_cycles, cudaStream_t st) {
+                        int k_cycles, cudaStream_t st) {
     KArgs<T> a;
     memset(&a, 0, sizeof a);
     a.q = static_cast<T*>(b->q);
     a.goal = static_cast<const T*>(b->goal);
-    a.obst = static_cast<const T*>(b->obst);
+    a.obst = static_cast<const Vec4<T>*>(b->obst);
+    a.obst_ext = static_cast<const Vec2<T>*>(b->obst_ext);
     a.jp_ref = static_cast<const T*>(b->jp_ref);
     a.ns_in = static_cast<const T*>(b->ns_in);
     a.ns_lastvec = static_cast<T*>(b->ns_lastvec);
@@ -266,38 +281,54 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.n = n;
     a.ld = ld;
     a.n_obst = n_obst;
-    a.obst_comps = obst_comps;
     a.k_cycles = k_cycles;
+    size_t smem = 0;
+    plan_stages<T, EXT>(n_obst, &a.n_chunks, &a.n_stages, &smem);
+    constexpr int MINB = (sizeof(T) == 4) ? (N <= 10 ? 3 : 2) : (N <= 7 ? 2 : 1);
+    auto kern = vfk_cycle_kernel<T, N, EXT, MINB>;
+    static bool attr_set[8] = {false, false, false, false, false, false, false, false};   // per device
+    if (smem > (48u << 10) && h->device < 8 && !attr_set[h->device]) {
+        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        attr_set[h->device] = true;
+    } else if (smem > (48u << 10) && h->device >= 8) {
+        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+    }
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
-    vfk_cycle_kernel<T, N><<<grid, kBlock, 0, st>>>(c, a);
+    kern<<<grid, kBlock, smem, st>>>(c, a);
     VFK_CUDA(h, cudaGetLastError());
     return 1;
 }
 
+template <typename T, int N>
+static int dispatch_ext(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
+                        int k_cycles, cudaStream_t st) {
+    if (b->obst_ext && n_obst > 0) return launch_cycle<T, N, true>(h, c, b, n, ld, n_obst, k_cycles, st);
+    return launch_cycle<T, N, false>(h, c, b, n, ld, n_obst, k_cycles, st);
+}
+
 template <typename T>
 static int dispatch_n(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
-                      int obst_comps, int k_cycles, cudaStream_t st) {
+                      int k_cycles, cudaStream_t st) {
     switch (h->chain.n_joints) {
-        case 6: return launch_cycle<T, 6>(h, c, b, n, ld, n_obst, obst_comps, k_cycles, st);
-        case 7: return launch_cycle<T, 7>(h, c, b, n, ld, n_obst, obst_comps, k_cycles, st);
-        case 10: return launch_cycle<T, 10>(h, c, b, n, ld, n_obst, obst_comps, k_cycles, st);
-        case 17: return launch_cycle<T, 17>(h, c, b, n, ld, n_obst, obst_comps, k_cycles, st);
+        case 6: return dispatch_ext<T, 6>(h, c, b, n, ld, n_obst, k_cycles, st);
+        case 7: return dispatch_ext<T, 7>(h, c, b, n, ld, n_obst, k_cycles, st);
+        case 10: return dispatch_ext<T, 10>(h, c, b, n, ld, n_obst, k_cycles, st);
+        case 17: return dispatch_ext<T, 17>(h, c, b, n, ld, n_obst, k_cycles, st);
     }
     return fail(h, VFK_ERR_UNSUPPORTED, "no kernel for n_joints = %d", h->chain.n_joints);
 }
 
-extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst, int obst_comps,
-                        int k_cycles, void* stream) {
+extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst, int k_cycles,
+                        void* stream) {
     if (!h || !b) return fail(h, VFK_ERR_INVALID, "vfk_step: null argument");
     if (n < 0 || ld < n) return fail(h, VFK_ERR_INVALID, "need 0 <= n_instances <= ld (got n=%lld ld=%lld)", (long long)n, (long long)ld);
-    if (ld % 32) return fail(h, VFK_ERR_INVALID, "ld must be a multiple of 32 (got %lld)", (long long)ld);
+    if (ld % 128) return fail(h, VFK_ERR_INVALID, "ld must be a multiple of 128 (got %lld)", (long long)ld);
     if (n_obst < 0) return fail(h, VFK_ERR_INVALID, "n_obstacles must be >= 0");
-    if (obst_comps != 4 && obst_comps != 6) return fail(h, VFK_ERR_INVALID, "obst_comps must be 4 or 6");
     if (k_cycles < 1) return fail(h, VFK_ERR_INVALID, "k_cycles must be >= 1");
     int rc;
     if ((rc = check_layout(h, b->q, "q", true)) || (rc = check_layout(h, b->goal, "goal", true)) ||
-        (rc = check_layout(h, b->obst, "obst", n_obst > 0)) || (rc = check_layout(h, b->jp_ref, "jp_ref", false)) ||
-        (rc = check_layout(h, b->ns_in, "ns_in", false)) ||
+        (rc = check_layout(h, b->obst, "obst", n_obst > 0)) || (rc = check_layout(h, b->obst_ext, "obst_ext", false)) ||
+        (rc = check_layout(h, b->jp_ref, "jp_ref", false)) || (rc = check_layout(h, b->ns_in, "ns_in", false)) ||
         (rc = check_layout(h, b->ns_lastvec, "ns_lastvec", h->params.ns_mode == VFK_NS_CONTROL)) ||
         (rc = check_layout(h, b->q_cmded, "q_cmded", false)) || (rc = check_layout(h, b->qdot_vf, "qdot_vf", false)) ||
         (rc = check_layout(h, b->qdot_ns, "qdot_ns", false)) || (rc = check_layout(h, b->qdot_jp, "qdot_jp", false)) ||
@@ -309,26 +340,27 @@ extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int64_t l
     if (n == 0) return 0;
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (h->precision == 32) return dispatch_n<float>(h, h->cf, b, n, ld, n_obst, obst_comps, k_cycles, st);
-    return dispatch_n<double>(h, h->cd, b, n, ld, n_obst, obst_comps, k_cycles, st);
+    if (h->precision == 32) return dispatch_n<float>(h, h->cf, b, n, ld, n_obst, k_cycles, st);
+    return dispatch_n<double>(h, h->cd, b, n, ld, n_obst, k_cycles, st);
 }
 
-extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst, void* twist_out,
-                              int64_t n, int64_t ld, int n_obst, int obst_comps, void* stream) {
+extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst, const void* obst_ext,
+                              void* twist_out, int64_t n, int64_t ld, int n_obst, void* stream) {
     if (!h || !pose_in || !goal || !twist_out) return fail(h, VFK_ERR_INVALID, "vfk_field_eval: null argument");
-    if (n < 0 || ld < n || ld % 32) return fail(h, VFK_ERR_INVALID, "need 0 <= n <= ld, ld %% 32 == 0");
+    if (n < 0 || ld < n || ld % 128) return fail(h, VFK_ERR_INVALID, "need 0 <= n <= ld, ld %% 128 == 0");
     if (n_obst > 0 && !obst) return fail(h, VFK_ERR_INVALID, "obst is required when n_obstacles > 0");
-    if (obst_comps != 4 && obst_comps != 6) return fail(h, VFK_ERR_INVALID, "obst_comps must be 4 or 6");
     if (n == 0) return 0;
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     if (h->precision == 32)
-        vfk_field_kernel<float><<<grid, kBlock, 0, st>>>(h->cf, (const float*)pose_in, (const float*)goal, (const float*)obst,
-                                                         (float*)twist_out, n, ld, n_obst, obst_comps);
+        vfk_field_kernel<float><<<grid, kBlock, 0, st>>>(h->cf, (const float*)pose_in, (const float*)goal,
+                                                         (const Vec4<float>*)obst, (const Vec2<float>*)obst_ext,
+                                                         (float*)twist_out, n, ld, n_obst);
     else
         vfk_field_kernel<double><<<grid, kBlock, 0, st>>>(h->cd, (const double*)pose_in, (const double*)goal,
-                                                          (const double*)obst, (double*)twist_out, n, ld, n_obst, obst_comps);
+                                                          (const Vec4<double>*)obst, (const Vec2<double>*)obst_ext,
+                                                          (double*)twist_out, n, ld, n_obst);
     VFK_CUDA(h, cudaGetLastError());
     return 1;
 }
@@ -359,7 +391,7 @@ extern "C" int vfk_mix(vfk_handle h, const void* const* cmds, const double* w, i
 struct vfk_session_s {
     vfk_ctx* h;
     int64_t n, ld;
-    int n_obst, obst_comps, N;
+    int n_obst, has_ext, N;
     size_t es;                       // element size
     cudaStream_t stream;
     char* dev;                       // one device slab
@@ -374,11 +406,11 @@ struct vfk_session_s {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int obst_comps, vfk_session* out) {
+extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_obst_ext, vfk_session* out) {
     if (!h || !out) return fail(h, VFK_ERR_INVALID, "vfk_session_create: null argument");
     *out = nullptr;
     if (n < 1) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 1");
-    if (n_obst < 0 || (obst_comps != 4 && obst_comps != 6)) return fail(h, VFK_ERR_INVALID, "bad obstacle shape");
+    if (n_obst < 0) return fail(h, VFK_ERR_INVALID, "n_obstacles must be >= 0");
     VFK_CUDA(h, cudaSetDevice(h->device));
     vfk_session_s* s = new (std::nothrow) vfk_session_s();
     if (!s) return fail(h, VFK_ERR_INVALID, "out of host memory");
@@ -387,13 +419,13 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int obst_
     s->n = n;
     s->ld = (int64_t)align_up((size_t)n, 128);
     s->n_obst = n_obst;
-    s->obst_comps = obst_comps;
+    s->has_ext = with_obst_ext ? 1 : 0;
     s->N = h->chain.n_joints;
     s->es = h->precision == 32 ? 4 : 8;
     const size_t row = (size_t)s->ld * s->es;       // multiple of 512 bytes
     const int N = s->N;
-    // rows: q N, goal 13, obst M*comps, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, flags (int32: <= 1 row)
-    const size_t rows = (size_t)N * 9 + 13 + (size_t)n_obst * obst_comps + 12 + 1;
+    // rows: q N, goal 13, obst M*4 (+ M*2 ext), jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, flags (int32: <= 1 row)
+    const size_t rows = (size_t)N * 9 + 13 + (size_t)n_obst * (4 + (s->has_ext ? 2 : 0)) + 12 + 1;
     s->dev_bytes = rows * row;
     cudaError_t e = cudaMalloc((void**)&s->dev, s->dev_bytes);
     if (e != cudaSuccess) { delete s; return fail(h, VFK_ERR_CUDA, "cudaMalloc(%zu): %s", rows * row, cudaGetErrorString(e)); }
@@ -402,7 +434,8 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int obst_
     auto take = [&](size_t nrows) { char* r = p; p += nrows * row; return (void*)r; };
     s->b.q = take(N);
     s->b.goal = take(13);
-    s->b.obst = n_obst ? take((size_t)n_obst * obst_comps) : nullptr;
+    s->b.obst = n_obst ? take((size_t)n_obst * 4) : nullptr;
+    s->b.obst_ext = (n_obst && s->has_ext) ? take((size_t)n_obst * 2) : nullptr;
     s->d_jp_ref = take(N);
     s->d_ns_in = take(N);
     s->b.ns_lastvec = take(N);
@@ -444,12 +477,19 @@ extern "C" int vfk_session_set_goal(vfk_session s, const void* g) {
     VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
     return VFK_OK;
 }
-extern "C" int vfk_session_set_obstacles(vfk_session s, const void* o) {
+// host obstacles: dense [M][n][4] (x, y, z, radius per instance); ext: dense [M][n][2] (safe, order)
+extern "C" int vfk_session_set_obstacles(vfk_session s, const void* o, const void* ext) {
     if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_obstacles: null session");
     if (s->n_obst == 0) return VFK_OK;
     if (!o) return fail(s->h, VFK_ERR_INVALID, "vfk_session_set_obstacles: null argument");
+    if (s->has_ext && !ext) return fail(s->h, VFK_ERR_INVALID, "vfk_session_set_obstacles: session was created with obstacle ext rows");
     VFK_CUDA(s->h, cudaSetDevice(s->h->device));
-    VFK_CUDA(s->h, upload_rows(s, const_cast<void*>(s->b.obst), o, (size_t)s->n_obst * s->obst_comps));
+    VFK_CUDA(s->h, cudaMemcpy2DAsync(const_cast<void*>(s->b.obst), (size_t)s->ld * 4 * s->es, o, (size_t)s->n * 4 * s->es,
+                                     (size_t)s->n * 4 * s->es, (size_t)s->n_obst, cudaMemcpyHostToDevice, s->stream));
+    if (s->has_ext)
+        VFK_CUDA(s->h, cudaMemcpy2DAsync(const_cast<void*>(s->b.obst_ext), (size_t)s->ld * 2 * s->es, ext,
+                                         (size_t)s->n * 2 * s->es, (size_t)s->n * 2 * s->es, (size_t)s->n_obst,
+                                         cudaMemcpyHostToDevice, s->stream));
     VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
     return VFK_OK;
 }
@@ -511,7 +551,7 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
     if (!s->en_jp) b.qdot_jp = nullptr;
     if (!s->en_cmd) b.cmd = nullptr;
     if (!s->en_pose) b.pose = nullptr;
-    int rc = vfk_step(h, &b, s->n, s->ld, s->n_obst, s->obst_comps, k_cycles, s->stream);
+    int rc = vfk_step(h, &b, s->n, s->ld, s->n_obst, k_cycles, s->stream);
     if (rc < 0) return rc;
     const bool d_qd = qdot_out && pinned(qdot_out), d_qo = q_out && pinned(q_out), d_fl = flags_out && pinned(flags_out);
     if (qdot_out) VFK_CUDA(h, download_rows(s, d_qd ? qdot_out : (void*)pin_qd, s->b.qdot, s->N, s->es));

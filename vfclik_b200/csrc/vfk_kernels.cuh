@@ -1,15 +1,20 @@
 // vfk_kernels.cuh -- the fused vfclik control-cycle kernel for sm_100a.
 //
-// One thread = one manipulator instance; all per-instance state (q, frame, the 6xN
-// Jacobian, the 6x6 normal matrix) lives in registers across the K fused cycles.
-// Global arrays are SoA [component][ld]: a warp's access to one component is one
-// 128-byte (FP32) or 256-byte (FP64) contiguous line.  Robot constants (chain,
-// limits, gains) arrive as a __grid_constant__ kernel parameter, i.e. in the
-// constant bank, and are indexed at compile time only.
+// One thread = one manipulator instance; a CTA of 128 threads owns a tile of 128
+// consecutive instances.  All per-instance state (q, frame, the 6xN Jacobian, the 6x6
+// normal matrix) lives in registers across the K fused cycles.  Per-instance global
+// arrays are SoA [component][ld] (a warp's access to one component is one contiguous
+// 128-byte / 256-byte line); the obstacle list is [M][ld][4] = one {x,y,z,radius}
+// vector per (obstacle, instance), so the tile's obstacles are M contiguous rows of
+// 128 vectors.  Those rows are moved global -> shared with cp.async.bulk (TMA) into a
+// ring of stages guarded by mbarriers, issued before forward kinematics starts so the
+// copy overlaps the FK / Jacobian arithmetic; the repulsor loop then reads one
+// conflict-free LDS.128 per obstacle.  Robot constants (chain, limits, gains) arrive
+// as a __grid_constant__ kernel parameter (constant bank), indexed at compile time.
 //
 // Reference mapping (see include/vfk.h and SURVEY.md App. C.2):
 //   fk_jacobian()   scripts/vf:316-318, scripts/nullspace:175  (Lafik / KDL FK + Jacobian)
-//   field()         scripts/vf:276-293,344-347                 (vfl attractor + decay repellers)
+//   attractor/repulsor  scripts/vf:276-293,344-347              (vfl type 1 + type 2 fields)
 //   dls             scripts/vf:461                              (Lafik.getIKV)
 //   nullspace       scripts/nullspace:75-131,159-184
 //   jp controller   scripts/joint_p_controller:79-89,126-146
@@ -17,11 +22,15 @@
 #pragma once
 #include <stdint.h>
 #include "vfk_math.cuh"
+#include "vfk_tma.cuh"
 
 namespace vfk {
 
 constexpr int kMaxJ = 17;
 constexpr int kBlock = 128;          // threads (= instances) per CTA
+constexpr int kChunk = 8;            // obstacles per shared-memory stage
+constexpr int kMaxStages = 8;
+constexpr int kSmemHeader = 128;     // mbarriers live in the first 128 bytes of dynamic smem
 
 // Kernel-side constants in the kernel's arithmetic type.  Joints are canonicalised on
 // the host (vfk_api.cu: canonicalise_chain) so that every joint acts about / along its
@@ -40,7 +49,7 @@ struct KConst {
     T tool[12];
     T ns_control[4];
     T ik_lambda2, ns_lambda2, dt, speed_scale, max_vel, jp_kp, jp_delta;
-    T ns_gain, ns_lookahead, rot_slowdown, goal_force, obst_force, obst_safe_inv, obst_order;
+    T ns_gain, ns_lookahead, rot_slowdown_inv, goal_force, obst_force, obst_safe_inv, obst_order;
     int32_t prismatic_mask;    // bit j set: joint j is TransZ, else RotZ
     int32_t ns_mode;
     int32_t direct_control;    // resolved 0/1
@@ -48,13 +57,15 @@ struct KConst {
     int32_t unit_weights;      // w_task and w_joint are all ones
     int32_t share_factor;      // nullspace can reuse the IK Cholesky factor
     int32_t tool_identity;
+    int32_t need_jp;           // joint P controller observable (weight != 0 or an output wants it)
 };
 
 template <typename T>
 struct KArgs {
     T* q;
     const T* goal;
-    const T* obst;
+    const Vec4<T>* obst;       // [M][ld]
+    const Vec2<T>* obst_ext;   // [M][ld] {safe, order} or null
     const T* jp_ref;
     const T* ns_in;
     T* ns_lastvec;
@@ -70,7 +81,8 @@ struct KArgs {
     int64_t n;
     int64_t ld;
     int32_t n_obst;
-    int32_t obst_comps;
+    int32_t n_chunks;          // ceil(n_obst / kChunk)
+    int32_t n_stages;          // shared-memory stages (<= kMaxStages); >= n_chunks means resident
     int32_t k_cycles;
 };
 
@@ -127,26 +139,33 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
     }
 }
 
-// ------------------------------------------------------------------------------ field
-// Twist commanded by the composed field at tool frame (Rt, pt):
-//   V = normCart( goal_force * [unit(p_g - p); axis(R_g Rt^T)] + sum_k obst_force * decay_k ),
-//   v = speed * S0 * V_lin,  w = speed * S1 * V_rot.
-// goal_ptr / obst_ptr already point at this thread's instance column.
+// ------------------------------------------------------------------------------ field pieces
+// One decay repeller (vfl type 2): acc += (o - p)/d * (radius / max(d, safe))^order.
 template <typename T>
-__device__ __forceinline__ void field(const KConst<T>& c, const T (&Rt)[9], const T (&pt)[3],
-                                      const T* __restrict__ goal_ptr, const T* __restrict__ obst_ptr,
-                                      int64_t ld, int n_obst, int obst_comps, T (&v)[3], T (&w)[3]) {
-    T g[13];
-#pragma unroll
-    for (int k = 0; k < 13; ++k) g[k] = __ldg(goal_ptr + k * ld);
-    // attractor, linear part
+__device__ __forceinline__ void repel(const Vec4<T>& o, T safe_inv, T order, const T (&pt)[3], T (&acc)[3]) {
+    const T dx = o.x - pt[0], dy = o.y - pt[1], dz = o.z - pt[2];
+    const T dd = fma(dx, dx, fma(dy, dy, dz * dz));
+    const T inv = Prec<T>::fmin_(Prec<T>::rsqrt_pos(dd), Prec<T>::big());     // 1/d, finite at d = 0
+    const T ratio = o.w * Prec<T>::fmin_(inv, safe_inv);                        // radius / max(d, safe)
+    T decay = Prec<T>::pow_pos(ratio, order);
+    decay = o.w > T(0) ? decay : T(0);                                          // radius 0 = inactive slot
+    const T wgt = decay * inv;
+    acc[0] = fma(wgt, dx, acc[0]); acc[1] = fma(wgt, dy, acc[1]); acc[2] = fma(wgt, dz, acc[2]);
+}
+
+// Goal attractor (vfl type 1) at tool frame (Rt, pt): unit direction to the goal, unit rotation
+// axis of R_g Rt^T scaled by the rotational slowdown, and the translational slowdown scalar.
+template <typename T>
+__device__ __forceinline__ void attract(const KConst<T>& c, const T (&g)[13], const T (&Rt)[9], const T (&pt)[3],
+                                        T (&V)[3], T& S0, T (&w)[3]) {
     const T ex = g[9] - pt[0], ey = g[10] - pt[1], ez = g[11] - pt[2];
     const T d2 = fma(ex, ex, fma(ey, ey, ez * ez));
-    const T invd = d2 > T(0) ? Prec<T>::rsqrt_pos(d2) : T(0);
+    const T invd = Prec<T>::fmin_(Prec<T>::rsqrt_pos(d2), Prec<T>::big());
     const T dist = d2 * invd;
-    T V[3] = {c.goal_force * ex * invd, c.goal_force * ey * invd, c.goal_force * ez * invd};
-    // attractor, rotational part: R_err = R_g * Rt^T
-    T E[9];
+    const T gi = c.goal_force * invd;
+    V[0] = gi * ex; V[1] = gi * ey; V[2] = gi * ez;
+    S0 = g[12] > T(0) ? Prec<T>::fmin_(T(1), Prec<T>::div(dist, g[12])) : T(1);
+    T E[9];                                                     // R_err = R_g * Rt^T
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -157,54 +176,84 @@ __device__ __forceinline__ void field(const KConst<T>& c, const T (&Rt)[9], cons
     const T n2 = fma(qx, qx, fma(qy, qy, qz * qz));
     const T invn = n2 > T(0) ? Prec<T>::rsqrt_pos(n2) : T(0);
     const T angle = T(2) * Prec<T>::atan2_(n2 * invn, qw);
-    const T S1 = c.rot_slowdown > T(0) ? Prec<T>::fmin_(T(1), angle / c.rot_slowdown) : T(1);
-    const T S0 = g[12] > T(0) ? Prec<T>::fmin_(T(1), dist / g[12]) : T(1);
-    // decay repellers
-    T ax = T(0), ay = T(0), az = T(0);
-    for (int m = 0; m < n_obst; ++m) {
-        const T* o = obst_ptr + (int64_t)m * obst_comps * ld;
-        const T ox = __ldg(o), oy = __ldg(o + ld), oz = __ldg(o + 2 * ld), rad = __ldg(o + 3 * ld);
-        T safe_inv = c.obst_safe_inv, order = c.obst_order;
-        if (obst_comps >= 6) {
-            safe_inv = Prec<T>::rcp(__ldg(o + 4 * ld));
-            order = __ldg(o + 5 * ld);
-        }
-        const T dx = ox - pt[0], dy = oy - pt[1], dz = oz - pt[2];
-        const T dd = fma(dx, dx, fma(dy, dy, dz * dz));
-        const T inv = dd > T(0) ? Prec<T>::rsqrt_pos(dd) : T(0);
-        const T ratio = rad * Prec<T>::fmin_(inv, safe_inv);          // radius / max(d, safe)
-        const T decay = rad > T(0) ? Prec<T>::pow_pos(ratio, order) : T(0);
-        const T wgt = decay * inv;
-        ax = fma(wgt, dx, ax); ay = fma(wgt, dy, ay); az = fma(wgt, dz, az);
-    }
-    V[0] = fma(c.obst_force, ax, V[0]); V[1] = fma(c.obst_force, ay, V[1]); V[2] = fma(c.obst_force, az, V[2]);
-    // normCart: unit translational part (zero stays zero); pre-scale by the largest
-    // component so the squared norm cannot overflow in FP32.
-    const T big = Prec<T>::fmax_(Prec<T>::fabs_(V[0]), Prec<T>::fmax_(Prec<T>::fabs_(V[1]), Prec<T>::fabs_(V[2])));
-    if (big > T(0)) {
-        const T ib = Prec<T>::rcp(big);
-        V[0] *= ib; V[1] *= ib; V[2] *= ib;
-        const T nn = fma(V[0], V[0], fma(V[1], V[1], V[2] * V[2]));
-        const T inn = Prec<T>::rsqrt_pos(nn);
-        V[0] *= inn; V[1] *= inn; V[2] *= inn;
-    }
-    const T sl = c.speed_scale * S0;
-    v[0] = sl * V[0]; v[1] = sl * V[1]; v[2] = sl * V[2];
+    const T S1 = Prec<T>::fmin_(T(1), angle * c.rot_slowdown_inv);     // rot_slowdown_inv = +inf when off
     const T sr = c.speed_scale * S1 * c.goal_force * invn;
     w[0] = sr * qx; w[1] = sr * qy; w[2] = sr * qz;
 }
 
+// normCart + saturation: unit translational part (zero stays zero), pre-scaled by its largest
+// component so the squared norm cannot overflow in FP32; v = speed * S0 * V.
+template <typename T>
+__device__ __forceinline__ void saturate(const KConst<T>& c, T (&V)[3], T S0, T (&v)[3]) {
+    const T big = Prec<T>::fmax_(Prec<T>::fabs_(V[0]), Prec<T>::fmax_(Prec<T>::fabs_(V[1]), Prec<T>::fabs_(V[2])));
+    T scale = T(0);
+    if (big > T(0)) {
+        const T ib = Prec<T>::rcp(big);
+        V[0] *= ib; V[1] *= ib; V[2] *= ib;
+        scale = Prec<T>::rsqrt_pos(fma(V[0], V[0], fma(V[1], V[1], V[2] * V[2])));
+    }
+    const T sl = c.speed_scale * S0 * scale;
+    v[0] = sl * V[0]; v[1] = sl * V[1]; v[2] = sl * V[2];
+}
+
+// Issue the bulk copies of obstacle chunk `chunk` of this CTA's tile into stage `stage` (warp 0 only).
+template <typename T, bool EXT>
+__device__ __forceinline__ void issue_chunk(const KArgs<T>& a, int64_t tile0, int chunk, int stage, unsigned char* smem,
+                                            uint64_t* bars, int lane) {
+    constexpr uint32_t kRow = kBlock * sizeof(Vec4<T>);
+    constexpr uint32_t kRowExt = EXT ? kBlock * sizeof(Vec2<T>) : 0;
+    constexpr uint32_t kStage = kChunk * (kRow + kRowExt);
+    const int m0 = chunk * kChunk;
+    const int cnt = min(kChunk, a.n_obst - m0);
+    unsigned char* dst = smem + kSmemHeader + (size_t)stage * kStage;
+    if (lane == 0) mbar_arrive_expect_tx(&bars[stage], (uint32_t)cnt * (kRow + kRowExt));
+    __syncwarp();
+    if (lane < cnt) {
+        bulk_g2s(dst + lane * kRow, a.obst + (int64_t)(m0 + lane) * a.ld + tile0, kRow, &bars[stage]);
+        if (EXT)
+            bulk_g2s(dst + kChunk * kRow + lane * kRowExt, a.obst_ext + (int64_t)(m0 + lane) * a.ld + tile0, kRowExt,
+                     &bars[stage]);
+    }
+}
+
 // ------------------------------------------------------------------------------ the fused kernel
-template <typename T, int N>
-__global__ void __launch_bounds__(kBlock)
+template <typename T, int N, bool EXT, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KArgs<T> a) {
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= a.n) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    constexpr uint32_t kRow = kBlock * sizeof(Vec4<T>);
+    constexpr uint32_t kRowExt = EXT ? kBlock * sizeof(Vec2<T>) : 0;
+    constexpr uint32_t kStage = kChunk * (kRow + kRowExt);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int64_t tile0 = (int64_t)blockIdx.x * kBlock;
+    const bool active = tile0 + tid < a.n;
+    const int64_t i = active ? tile0 + tid : a.n - 1;      // idle lanes of the last tile shadow a valid instance
     const int64_t ld = a.ld;
+    const bool streaming = a.n_chunks > a.n_stages;
+    const int total_seq = a.n_chunks * (streaming ? a.k_cycles : 1);
+
+    // ---- stage the obstacle tile: all stages in flight before any arithmetic starts
+    if (a.n_obst > 0) {
+        if (tid == 0) {
+            for (int s = 0; s < a.n_stages; ++s) mbar_init(&bars[s], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int pre = min(a.n_stages, total_seq);
+            for (int s = 0; s < pre; ++s) issue_chunk<T, EXT>(a, tile0, s % a.n_chunks, s, smem, bars, lane);
+        }
+    }
 
     T q[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) q[j] = a.q[j * ld + i];
+    T g[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) g[k] = __ldg(a.goal + k * ld + i);
 
     T lastv[N];
     if (c.ns_mode == 2) {
@@ -212,6 +261,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         for (int j = 0; j < N; ++j) lastv[j] = a.ns_lastvec[j * ld + i];
     }
 
+    int seq = 0;                                            // obstacle chunks consumed so far (ring position)
     for (int cyc = 0; cyc < a.k_cycles; ++cyc) {
         const bool last = (cyc == a.k_cycles - 1);
         int flags = 0;
@@ -237,11 +287,45 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             }
         }
 
-        // 2-4. field, saturation, reference-point shift to the flange
+        // 2-4. field: attractor, repulsor sum over the staged obstacle tile, saturation, shift to the flange
         T tw[6];
         {
-            T v[3], w[3];
-            field<T>(c, Rt, pt, a.goal + i, a.obst + i, ld, a.n_obst, a.obst_comps, v, w);
+            T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)};
+            attract<T>(c, g, Rt, pt, V, S0, w);
+            for (int ch = 0; ch < a.n_chunks; ++ch) {
+                const int stage = streaming ? seq % a.n_stages : ch;
+                const uint32_t parity = streaming ? (uint32_t)(seq / a.n_stages) & 1u : 0u;
+                mbar_wait(&bars[stage], parity);
+                const unsigned char* sb = smem + kSmemHeader + (size_t)stage * kStage;
+                const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + tid;
+                const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * kRow) + tid;
+                const int cnt = min(kChunk, a.n_obst - ch * kChunk);
+                if (cnt == kChunk) {
+#pragma unroll
+                    for (int m = 0; m < kChunk; ++m) {
+                        const Vec4<T> o = so[m * kBlock];
+                        T safe_inv = c.obst_safe_inv, order = c.obst_order;
+                        if (EXT) { const Vec2<T> e = se[m * kBlock]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+                        repel<T>(o, safe_inv, order, pt, acc);
+                    }
+                } else {
+                    for (int m = 0; m < cnt; ++m) {
+                        const Vec4<T> o = so[m * kBlock];
+                        T safe_inv = c.obst_safe_inv, order = c.obst_order;
+                        if (EXT) { const Vec2<T> e = se[m * kBlock]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+                        repel<T>(o, safe_inv, order, pt, acc);
+                    }
+                }
+                if (streaming) {
+                    __syncthreads();                        // every thread is done with this stage
+                    if (tid < 32 && seq + a.n_stages < total_seq)
+                        issue_chunk<T, EXT>(a, tile0, (seq + a.n_stages) % a.n_chunks, stage, smem, bars, lane);
+                    ++seq;
+                }
+            }
+            V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
+            T v[3];
+            saturate<T>(c, V, S0, v);
             tw[0] = v[0] + (w[1] * dp[2] - w[2] * dp[1]);
             tw[1] = v[1] + (w[2] * dp[0] - w[0] * dp[2]);
             tw[2] = v[2] + (w[0] * dp[1] - w[1] * dp[0]);
@@ -385,9 +469,11 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             for (int j = 0; j < N; ++j) qd_ns[j] = bad ? T(0) : raw[j] * c.ns_gain;
         }
 
-        // 7. joint P controller
+        // 7. joint P controller (skipped when nothing can observe it)
         T qd_jp[N];
-        {
+#pragma unroll
+        for (int j = 0; j < N; ++j) qd_jp[j] = T(0);
+        if (c.need_jp || a.qdot_jp || a.flags) {
             bool all_reached = true;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
@@ -423,9 +509,9 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         }
         if (nan) flags |= 4;
         T ratio = T(1);
-        if (lead > c.max_vel) { ratio = c.max_vel / lead; flags |= 8; }
+        if (lead > c.max_vel) { ratio = Prec<T>::div(c.max_vel, lead); flags |= 8; }
 
-        if (last) {
+        if (last && active) {
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const T qd = mix[j] * ratio;
@@ -452,30 +538,44 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             for (int j = 0; j < N; ++j) q[j] = fma(c.dt, mix[j] * ratio, q[j]);
         }
     }
-    if (c.integrate) {
+    if (active) {
+        if (c.integrate) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) a.q[j * ld + i] = q[j];
-    }
-    if (c.ns_mode == 2) {
+            for (int j = 0; j < N; ++j) a.q[j * ld + i] = q[j];
+        }
+        if (c.ns_mode == 2) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) a.ns_lastvec[j * ld + i] = lastv[j];
+            for (int j = 0; j < N; ++j) a.ns_lastvec[j * ld + i] = lastv[j];
+        }
     }
 }
 
 // ------------------------------------------------------------------------------ small kernels
-// Field query at given poses (scripts/vf:469-503).
+// Field query at given tool poses (scripts/vf:469-503); low-rate visualisation path, plain loads.
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
 vfk_field_kernel(const __grid_constant__ KConst<T> c, const T* __restrict__ pose, const T* __restrict__ goal,
-                 const T* __restrict__ obst, T* __restrict__ twist, int64_t n, int64_t ld, int n_obst, int obst_comps) {
+                 const Vec4<T>* __restrict__ obst, const Vec2<T>* __restrict__ obst_ext, T* __restrict__ twist,
+                 int64_t n, int64_t ld, int n_obst) {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
-    T Rt[9], pt[3], v[3], w[3];
+    T Rt[9], pt[3], g[13];
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rt[k] = pose[k * ld + i];
 #pragma unroll
     for (int k = 0; k < 3; ++k) pt[k] = pose[(9 + k) * ld + i];
-    field<T>(c, Rt, pt, goal + i, obst + i, ld, n_obst, obst_comps, v, w);
+#pragma unroll
+    for (int k = 0; k < 13; ++k) g[k] = goal[k * ld + i];
+    T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)}, v[3];
+    attract<T>(c, g, Rt, pt, V, S0, w);
+    for (int m = 0; m < n_obst; ++m) {
+        const Vec4<T> o = obst[(int64_t)m * ld + i];
+        T safe_inv = c.obst_safe_inv, order = c.obst_order;
+        if (obst_ext) { const Vec2<T> e = obst_ext[(int64_t)m * ld + i]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+        repel<T>(o, safe_inv, order, pt, acc);
+    }
+    V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
+    saturate<T>(c, V, S0, v);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { twist[k * ld + i] = v[k]; twist[(3 + k) * ld + i] = w[k]; }
 }

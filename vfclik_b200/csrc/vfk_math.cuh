@@ -14,30 +14,62 @@ namespace vfk {
 
 template <typename T> struct Prec;
 
+// FP32: one MUFU instruction per transcendental (rsqrt / rcp / sqrt / lg2 / ex2 .approx.ftz,
+// max relative error ~2^-22), no IEEE division or sqrt subroutines in the hot path.
 template <> struct Prec<float> {
-    static __device__ __forceinline__ float rsqrt_pos(float x) { return rsqrtf(x); }
-    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
-    // x^y for x >= 0 through ex2(y * lg2(x)); x = 0 -> 0 for y > 0.
-    static __device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * __log2f(x)); }
+    static __device__ __forceinline__ float rsqrt_pos(float x) {
+        float r;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float sqrt_(float x) {
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float rcp(float x) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float div(float a, float b) { return a * rcp(b); }
+    // x^y for x >= 0, y > 0 through ex2(y * lg2(x)); x = 0 -> lg2 = -inf -> 0.
+    static __device__ __forceinline__ float pow_pos(float x, float y) {
+        float l, r;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+        l *= y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+        return r;
+    }
     static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
     static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
     static __device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
     static __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ float fabs_(float a) { return fabsf(a); }
+    static __device__ __forceinline__ float big() { return 1e18f; }
 };
 
 template <> struct Prec<double> {
     static __device__ __forceinline__ double rsqrt_pos(double x) { return 1.0 / sqrt(x); }
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
     static __device__ __forceinline__ double pow_pos(double x, double y) { return pow(x, y); }
     static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
     static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
     static __device__ __forceinline__ double fmin_(double a, double b) { return fmin(a, b); }
     static __device__ __forceinline__ double fmax_(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double fabs_(double a) { return fabs(a); }
+    static __device__ __forceinline__ double big() { return 1e150; }
 };
+
+// {x, y, z, radius} of one obstacle of one instance: one 16-byte (FP32) or 32-byte (FP64) vector.
+template <typename T> struct Vec4;
+template <> struct __align__(16) Vec4<float> { float x, y, z, w; };
+template <> struct __align__(32) Vec4<double> { double x, y, z, w; };
+template <typename T> struct Vec2;
+template <> struct __align__(8) Vec2<float> { float x, y; };
+template <> struct __align__(16) Vec2<double> { double x, y; };
 
 // ---- symmetric 6x6: packed lower triangle, index (i,j), i >= j -> i*(i+1)/2 + j
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }

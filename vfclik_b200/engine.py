@@ -92,7 +92,7 @@ def round_up(n: int, m: int = 128) -> int:
     return (int(n) + m - 1) // m * m
 
 
-_BUF_FIELDS = ("q", "goal", "obst", "jp_ref", "ns_in", "ns_lastvec", "q_cmded", "qdot_vf", "qdot_ns", "qdot_jp",
+_BUF_FIELDS = ("q", "goal", "obst", "obst_ext", "jp_ref", "ns_in", "ns_lastvec", "q_cmded", "qdot_vf", "qdot_ns", "qdot_jp",
                "qdot", "cmd", "pose", "flags")
 
 
@@ -160,7 +160,7 @@ class Engine:
         return torch.float32 if self.precision == 32 else torch.float64
 
     # -- device-buffer path
-    def step(self, bufs: Dict[str, object], n_instances: int, ld: int, n_obstacles: int, obst_comps: int = 4,
+    def step(self, bufs: Dict[str, object], n_instances: int, ld: int, n_obstacles: int,
              k_cycles: int = 1, stream: Optional[int] = None, ext_cmd=(None, None, None)) -> int:
         """K fused cycles on device buffers; returns the number of kernels launched."""
         b = BuffersC()
@@ -172,17 +172,17 @@ class Engine:
             import torch
             stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self._check(self._lib.vfk_step(self._h, C.byref(b), int(n_instances), int(ld), int(n_obstacles),
-                                            int(obst_comps), int(k_cycles), C.c_void_p(stream)))
+                                            int(k_cycles), C.c_void_p(stream)))
         self.launches += rc
         return rc
 
-    def field_eval(self, pose, goal, obst, twist_out, n_instances, ld, n_obstacles, obst_comps=4, stream=None) -> int:
+    def field_eval(self, pose, goal, obst, twist_out, n_instances, ld, n_obstacles, obst_ext=None, stream=None) -> int:
         if stream is None:
             import torch
             stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self._check(self._lib.vfk_field_eval(self._h, _dev_ptr(pose), _dev_ptr(goal), _dev_ptr(obst),
-                                                  _dev_ptr(twist_out), int(n_instances), int(ld), int(n_obstacles),
-                                                  int(obst_comps), C.c_void_p(stream)))
+                                                  _dev_ptr(obst_ext), _dev_ptr(twist_out), int(n_instances), int(ld),
+                                                  int(n_obstacles), C.c_void_p(stream)))
         self.launches += rc
         return rc
 
@@ -207,18 +207,19 @@ class Engine:
         return t
 
     # -- host-buffer path
-    def session(self, n_instances: int, n_obstacles: int, obst_comps: int = 4) -> "Session":
-        return Session(self, n_instances, n_obstacles, obst_comps)
+    def session(self, n_instances: int, n_obstacles: int, obst_ext: bool = False) -> "Session":
+        return Session(self, n_instances, n_obstacles, obst_ext)
 
 
 class Session:
-    """Resident scene + state on the GPU; numpy arrays in and out (dense SoA ``[comps, n]``)."""
+    """Resident scene + state on the GPU; numpy arrays in and out (dense SoA ``[comps, n]``;
+    obstacles ``[M, n, 4]`` and optionally ``[M, n, 2]`` {safe, order})."""
 
-    def __init__(self, engine: Engine, n_instances: int, n_obstacles: int, obst_comps: int = 4):
+    def __init__(self, engine: Engine, n_instances: int, n_obstacles: int, obst_ext: bool = False):
         self.e = engine
-        self.n, self.m, self.comps = int(n_instances), int(n_obstacles), int(obst_comps)
+        self.n, self.m, self.ext = int(n_instances), int(n_obstacles), bool(obst_ext)
         self._s = C.c_void_p()
-        engine._check(engine._lib.vfk_session_create(engine._h, self.n, self.m, self.comps, C.byref(self._s)))
+        engine._check(engine._lib.vfk_session_create(engine._h, self.n, self.m, int(self.ext), C.byref(self._s)))
 
     def close(self):
         if getattr(self, "_s", None) is not None and self._s:
@@ -241,12 +242,18 @@ class Session:
         a = self._arr(goal, 13)
         self.e._check(self.e._lib.vfk_session_set_goal(self._s, _lib.np_ptr(a)))
 
-    def set_obstacles(self, obst):
+    def set_obstacles(self, obst, obst_ext=None):
         if self.m == 0:
             return
-        a = np.ascontiguousarray(obst, dtype=self.e.np_dtype).reshape(self.m * self.comps, -1)
-        a = self._arr(a, self.m * self.comps)
-        self.e._check(self.e._lib.vfk_session_set_obstacles(self._s, _lib.np_ptr(a)))
+        a = np.ascontiguousarray(obst, dtype=self.e.np_dtype)
+        if a.shape != (self.m, self.n, 4):
+            raise ValueError("obstacles must be [M, n, 4], got %r" % (a.shape,))
+        x = None
+        if self.ext:
+            x = np.ascontiguousarray(obst_ext, dtype=self.e.np_dtype)
+            if x.shape != (self.m, self.n, 2):
+                raise ValueError("obstacle ext must be [M, n, 2], got %r" % (x.shape,))
+        self.e._check(self.e._lib.vfk_session_set_obstacles(self._s, _lib.np_ptr(a), None if x is None else _lib.np_ptr(x)))
 
     def set_q(self, q):
         a = self._arr(q, self.e.n_joints)
@@ -305,30 +312,31 @@ class Session:
 
 
 class DeviceBatch:
-    """Device-resident SoA buffers for one batch (torch CUDA tensors ``[comps, ld]``).
+    """Device-resident buffers for one batch (torch CUDA tensors, layouts of include/vfk.h).
 
     Convenience for callers that keep everything on the GPU (the benchmark's kernel-only
-    arm, the multi-GPU driver): ``upload`` copies dense numpy ``[comps, n]`` arrays in,
-    ``download`` copies them back; ``bufs`` is what ``Engine.step`` takes.
+    arm, the multi-GPU driver): ``upload`` copies dense numpy arrays in (``[comps, n]``;
+    obstacles ``[M, n, 4]``, ext ``[M, n, 2]``), ``download`` copies them back; ``bufs`` is what
+    ``Engine.step`` takes.
     """
 
     _ROWS = {"goal": 13, "pose": 12, "flags": 1}
 
-    def __init__(self, engine: Engine, n_instances: int, n_obstacles: int, obst_comps: int = 4,
+    def __init__(self, engine: Engine, n_instances: int, n_obstacles: int, obst_ext: bool = False,
                  outputs=("qdot",), inputs=()):
-        import torch
-        self.e, self.n, self.m, self.comps = engine, int(n_instances), int(n_obstacles), int(obst_comps)
+        self.e, self.n, self.m = engine, int(n_instances), int(n_obstacles)
         self.ld = round_up(self.n, 128)
         N = engine.n_joints
         self.t: Dict[str, object] = {}
         self.t["q"] = engine.alloc(N, self.ld)
         self.t["goal"] = engine.alloc(13, self.ld)
         if self.m:
-            self.t["obst"] = engine.alloc(self.m * self.comps, self.ld)
+            self.t["obst"] = engine.alloc(self.m, self.ld * 4).view(self.m, self.ld, 4)
+            if obst_ext:
+                self.t["obst_ext"] = engine.alloc(self.m, self.ld * 2).view(self.m, self.ld, 2)
         for name in tuple(outputs) + tuple(inputs):
             self._ensure(name)
         self.ext_cmd = [None, None, None]
-        self._torch = torch
 
     def _ensure(self, name):
         if name in self.t:
@@ -336,8 +344,8 @@ class DeviceBatch:
         import torch
         if name == "flags":
             self.t[name] = self.e.alloc(1, self.ld, dtype=torch.int32)
-        elif name == "ns_in":
-            self.t[name] = self.e.alloc(self.e.n_joints, self.ld)
+        elif name in ("obst", "obst_ext"):
+            raise KeyError("%s was not allocated (n_obstacles = 0 or obst_ext=False)" % name)
         else:
             self.t[name] = self.e.alloc(self._ROWS.get(name, self.e.n_joints), self.ld)
         return self.t[name]
@@ -345,6 +353,12 @@ class DeviceBatch:
     def upload(self, name: str, arr: np.ndarray):
         import torch
         t = self._ensure(name)
+        if name in ("obst", "obst_ext"):
+            a = np.ascontiguousarray(arr)
+            if a.shape != (self.m, self.n, t.shape[2]):
+                raise ValueError("%s must be [%d, %d, %d], got %r" % (name, self.m, self.n, t.shape[2], a.shape))
+            t[:, :self.n, :].copy_(torch.from_numpy(a).to(t.dtype))
+            return t
         a = np.ascontiguousarray(arr).reshape(-1, self.n)
         if a.shape[0] > t.shape[0]:
             raise ValueError("%s: %d rows do not fit %d" % (name, a.shape[0], t.shape[0]))
@@ -359,5 +373,4 @@ class DeviceBatch:
         return dict(self.t)
 
     def step(self, k_cycles: int = 1, stream=None) -> int:
-        return self.e.step(self.bufs, self.n, self.ld, self.m, self.comps, k_cycles, stream=stream,
-                           ext_cmd=tuple(self.ext_cmd))
+        return self.e.step(self.bufs, self.n, self.ld, self.m, k_cycles, stream=stream, ext_cmd=tuple(self.ext_cmd))

@@ -18,13 +18,13 @@ def quat_to_rot_rows(quat: np.ndarray) -> np.ndarray:
 
 
 def random_batch(chain: ChainDesc, n_instances: int, n_obstacles: int, seed: int, dtype=np.float64,
-                 obst_comps: int = 4, slowdown: float = 0.05, order: float = 20.0, safe: float = 0.001,
+                 obst_ext: bool = False, slowdown: float = 0.05, order: float = 20.0, safe: float = 0.001,
                  shoulder=None, box: float = 0.8):
     """Configs 2-5: q ~ U(0.9 * limits); goal position ~ U(shell 0.3-0.8 m around the shoulder),
     goal rotation ~ Haar (normalised Gaussian quaternion); obstacles ~ U(workspace box),
     radius ~ U(0.03, 0.10); ``numpy.random.default_rng(seed)``.
 
-    Returns dict(q [N,I], goal [13,I], obst [M*comps, I]) of ``dtype``.
+    Returns dict(q [N,I], goal [13,I], obst [M,I,4] {x,y,z,radius} [, obst_ext [M,I,2] {safe, order}]) of ``dtype``.
     """
     rng = np.random.default_rng(seed)
     I, N, M = int(n_instances), chain.n_joints, int(n_obstacles)
@@ -37,15 +37,18 @@ def random_batch(chain: ChainDesc, n_instances: int, n_obstacles: int, seed: int
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     pg = d * rng.uniform(0.3, 0.8, size=(I, 1)) + np.asarray(shoulder)[None, :]
     goal = np.concatenate([quat_to_rot_rows(quat), pg.T, np.full((1, I), slowdown)], axis=0).astype(dtype)
-    obst = np.empty((M, obst_comps, I), dtype=dtype)
+    obst = np.empty((M, I, 4), dtype=dtype)
     sh = np.asarray(shoulder, dtype=np.float64)
     for m in range(M):                       # per-obstacle draws keep peak memory at O(I)
-        obst[m, 0:3] = (rng.uniform(-box, box, size=(3, I)) + sh[:, None]).astype(dtype)
-        obst[m, 3] = rng.uniform(0.03, 0.10, size=I).astype(dtype)
-        if obst_comps == 6:
-            obst[m, 4] = safe
-            obst[m, 5] = order
-    return dict(q=q, goal=goal, obst=obst.reshape(M * obst_comps, I))
+        obst[m, :, 0:3] = (rng.uniform(-box, box, size=(I, 3)) + sh[None, :]).astype(dtype)
+        obst[m, :, 3] = rng.uniform(0.03, 0.10, size=I).astype(dtype)
+    out = dict(q=q, goal=goal, obst=obst)
+    if obst_ext:
+        ext = np.empty((M, I, 2), dtype=dtype)
+        ext[:, :, 0] = safe
+        ext[:, :, 1] = order
+        out["obst_ext"] = ext
+    return out
 
 
 def config1(chain: ChainDesc, config, seed: int = 0):
@@ -58,13 +61,13 @@ def config1(chain: ChainDesc, config, seed: int = 0):
     goal = np.concatenate([T[:3, :3].reshape(9), T[:3, 3], [g[16] if g.size > 16 else 0.03]])[:, None]
     q = np.asarray(config.initial_joint_pos, dtype=np.float64)[:, None]
     start_ee = np.array([0.73, 0.28, 0.63])      # approximate EE at the start posture (offset seed only)
-    obst = np.zeros((3, 4, 1))
+    obst = np.zeros((3, 1, 4))
     for m in range(3):
         t = (m + 1) / 4.0
         c = start_ee * (1 - t) + T[:3, 3] * t + rng.uniform(-0.08, 0.08, size=3)
-        obst[m, 0:3, 0] = c
-        obst[m, 3, 0] = 0.05
-    return dict(q=q, goal=goal, obst=obst.reshape(12, 1))
+        obst[m, 0, 0:3] = c
+        obst[m, 0, 3] = 0.05
+    return dict(q=q, goal=goal, obst=obst)
 
 
 def dual_arm_torso_chain() -> ChainDesc:
