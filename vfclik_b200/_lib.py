@@ -29,7 +29,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvfk.so")
 
 # every symbol include/vfk.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "vfk_version", "vfk_default_params", "vfk_create", "vfk_set_params", "vfk_get_params", "vfk_destroy",
+    "vfk_version", "vfk_default_params", "vfk_create", "vfk_set_params", "vfk_get_params", "vfk_chain_pattern",
+    "vfk_destroy",
     "vfk_last_error", "vfk_step", "vfk_field_eval", "vfk_mix", "vfk_session_create", "vfk_session_set_goal",
     "vfk_session_set_obstacles", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input",
     "vfk_session_cycle", "vfk_session_enable", "vfk_session_read", "vfk_session_buffers", "vfk_session_destroy",
@@ -102,6 +103,7 @@ def load():
     lib.vfk_create.argtypes = [C.POINTER(vp), C.POINTER(ChainDescC), i32, i32]
     lib.vfk_set_params.argtypes = [vp, C.POINTER(ParamsC)]
     lib.vfk_get_params.argtypes = [vp, C.POINTER(ParamsC)]
+    lib.vfk_chain_pattern.argtypes = [vp]
     lib.vfk_destroy.argtypes = [vp]
     lib.vfk_destroy.restype = None
     lib.vfk_last_error.argtypes = [vp]

@@ -24,6 +24,7 @@ struct vfk_ctx {
     int precision;
     int device;
     int sm_count;
+    int pattern;                // 0: GenericPattern, 1: LwrPattern (structure of the canonical chain)
     KConst<float> cf;
     KConst<double> cd;
     std::string err;
@@ -80,6 +81,26 @@ static void canonicalise_chain(const vfk_chain_desc& in, vfk_chain_desc& out) {
         }
         out.joint_type[j] = (t >= VFK_JOINT_TRANSX) ? VFK_JOINT_TRANSZ : VFK_JOINT_ROTZ;
     }
+}
+
+// Does the canonical chain have the structure PAT assumes (tip rotations = the pattern's signed
+// permutations, tip translations zero where the pattern drops them, identity base rotation)?
+template <class PAT>
+static bool chain_matches(const vfk_chain_desc& ch, int n_expected) {
+    if (ch.n_joints != n_expected) return false;
+    static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (PAT::base_identity && memcmp(ch.base, ident, sizeof ident) != 0) return false;
+    for (int j = 0; j < ch.n_joints; ++j) {
+        if (ch.joint_type[j] != VFK_JOINT_ROTZ) return false;
+        for (int k = 0; k < 3; ++k) {
+            for (int r = 0; r < 3; ++r) {            // column k of R_tip = sign * e_perm
+                const double want = (r == PAT::perm(j, k)) ? (double)PAT::sign(j, k) : 0.0;
+                if (ch.tip[j][3 * r + k] != want) return false;
+            }
+            if (!PAT::pnz(j, k) && ch.tip[j][9 + k] != 0.0) return false;
+        }
+    }
+    return true;
 }
 
 template <typename T>
@@ -207,6 +228,7 @@ extern "C" int vfk_create(vfk_handle* out, const vfk_chain_desc* chain, int prec
     if (!h) return fail(nullptr, VFK_ERR_INVALID, "out of host memory");
     h->chain = *chain;
     canonicalise_chain(h->chain, h->canon);
+    h->pattern = chain_matches<LwrPattern>(h->canon, 7) ? 1 : 0;
     h->precision = precision;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
@@ -233,6 +255,8 @@ extern "C" int vfk_get_params(vfk_handle h, vfk_params* out) {
     return VFK_OK;
 }
 
+extern "C" int vfk_chain_pattern(vfk_handle h) { return h ? h->pattern : VFK_ERR_INVALID; }
+
 extern "C" void vfk_destroy(vfk_handle h) { delete h; }
 
 extern "C" const char* vfk_last_error(vfk_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
@@ -257,7 +281,7 @@ static void plan_stages(int n_obst, int* n_chunks, int* n_stages, size_t* smem_b
     *smem_bytes = n_obst > 0 ? kSmemHeader + (size_t)(*n_stages) * stage : 0;
 }
 
-template <typename T, int N, bool EXT>
+template <typename T, int N, class PAT, bool EXT>
 static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
                         int k_cycles, cudaStream_t st) {
     KArgs<T> a;
@@ -285,7 +309,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     size_t smem = 0;
     plan_stages<T, EXT>(n_obst, &a.n_chunks, &a.n_stages, &smem);
     constexpr int MINB = (sizeof(T) == 4) ? (N <= 10 ? 3 : 2) : (N <= 7 ? 2 : 1);
-    auto kern = vfk_cycle_kernel<T, N, EXT, MINB>;
+    auto kern = vfk_cycle_kernel<T, N, PAT, EXT, MINB>;
     static bool attr_set[8] = {false, false, false, false, false, false, false, false};   // per device
     if (smem > (48u << 10) && h->device < 8 && !attr_set[h->device]) {
         VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
@@ -302,8 +326,14 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 template <typename T, int N>
 static int dispatch_ext(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
                         int k_cycles, cudaStream_t st) {
-    if (b->obst_ext && n_obst > 0) return launch_cycle<T, N, true>(h, c, b, n, ld, n_obst, k_cycles, st);
-    return launch_cycle<T, N, false>(h, c, b, n, ld, n_obst, k_cycles, st);
+    const bool ext = b->obst_ext && n_obst > 0;
+    if constexpr (N == 7) {
+        if (h->pattern == 1)
+            return ext ? launch_cycle<T, N, LwrPattern, true>(h, c, b, n, ld, n_obst, k_cycles, st)
+                       : launch_cycle<T, N, LwrPattern, false>(h, c, b, n, ld, n_obst, k_cycles, st);
+    }
+    return ext ? launch_cycle<T, N, GenericPattern, true>(h, c, b, n, ld, n_obst, k_cycles, st)
+               : launch_cycle<T, N, GenericPattern, false>(h, c, b, n, ld, n_obst, k_cycles, st);
 }
 
 template <typename T>

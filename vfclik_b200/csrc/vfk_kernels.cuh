@@ -86,21 +86,56 @@ struct KArgs {
     int32_t k_cycles;
 };
 
+// ------------------------------------------------------------------------------ chain patterns
+// A chain pattern fixes, at compile time, the *structure* of the tip frames: which tips have a
+// signed-permutation rotation (every DH chain with twists in {0, +-pi/2, pi}) and which tip
+// translation components are zero.  The numeric values still come from KConst; the pattern only
+// lets the compiler turn R * R_tip into register renaming and drop the multiplies by 0.
+// GenericPattern makes no assumption (full 3x3 products, runtime prismatic mask).
+struct GenericPattern {
+    static constexpr bool generic = true;
+    static constexpr bool base_identity = false;
+    __host__ __device__ static constexpr int perm(int, int) { return 0; }
+    __host__ __device__ static constexpr int sign(int, int) { return 1; }
+    __host__ __device__ static constexpr bool pnz(int, int) { return true; }
+};
+
+// KUKA LWR-style 7R chain: base rotation identity, tips RotX(+90), RotX(-90), RotX(-90), RotX(+90),
+// RotX(+90), RotX(-90), identity; translations only along y (tips 1, 3) and z (tip 6); all revolute.
+// new column k of (R * R_tip) = sign(j,k) * old column perm(j,k).
+struct LwrPattern {
+    static constexpr bool generic = false;
+    static constexpr bool base_identity = true;
+    __host__ __device__ static constexpr int kind(int j) {       // +1: RotX(+90), -1: RotX(-90), 0: identity
+        return (j == 0 || j == 3 || j == 4) ? 1 : (j == 6 ? 0 : -1);
+    }
+    __host__ __device__ static constexpr int perm(int j, int k) { return kind(j) == 0 ? k : (k == 0 ? 0 : (k == 1 ? 2 : 1)); }
+    __host__ __device__ static constexpr int sign(int j, int k) {
+        return kind(j) == 0 ? 1 : (k == 0 ? 1 : (k == 1 ? (kind(j) > 0 ? 1 : -1) : (kind(j) > 0 ? -1 : 1)));
+    }
+    __host__ __device__ static constexpr bool pnz(int j, int k) { return ((j == 1 || j == 3) && k == 1) || (j == 6 && k == 2); }
+};
+
 // ------------------------------------------------------------------------------ FK + J
 // T_{j+1} = T_j * RotZ(q_j) * tip_j.  Records the joint axis z_j = R_j[:,2] and origin
 // p_j before each joint, then forms J = [z x (p_e - p_j); z] (revolute) or [z; 0].
-template <typename T, int N>
+template <typename T, int N, class PAT>
 __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
                                             T (&R)[9], T (&p)[3], T (&Jl)[N][3], T (&Ja)[N][3]) {
+    if constexpr (PAT::base_identity) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = c.base[k];
+        for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? T(1) : T(0);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = c.base[k];
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) p[k] = c.base[9 + k];
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
+    static_for<0, N>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
         Ja[j][0] = R[2]; Ja[j][1] = R[5]; Ja[j][2] = R[8];
         Jl[j][0] = p[0]; Jl[j][1] = p[1]; Jl[j][2] = p[2];      // holds p_j until p_e is known
-        if (c.prismatic_mask & (1 << j)) {
+        if (PAT::generic && (c.prismatic_mask & (1 << j))) {
             p[0] = fma(R[2], q[j], p[0]); p[1] = fma(R[5], q[j], p[1]); p[2] = fma(R[8], q[j], p[2]);
         } else {
             T s, co;
@@ -113,21 +148,34 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
             }
         }
         const T* tp = c.tip[j];
+        static_for<0, 3>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            if constexpr (PAT::pnz(j, k)) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-            p[r] = fma(R[3 * r + 0], tp[9], fma(R[3 * r + 1], tp[10], fma(R[3 * r + 2], tp[11], p[r])));
+                for (int r = 0; r < 3; ++r) p[r] = fma(R[3 * r + k], tp[9 + k], p[r]);
+            }
+        });
         T Rn[9];
+        if constexpr (PAT::generic) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc)
-                Rn[3 * r + cc] = fma(R[3 * r + 0], tp[cc], fma(R[3 * r + 1], tp[3 + cc], R[3 * r + 2] * tp[6 + cc]));
+                for (int cc = 0; cc < 3; ++cc)
+                    Rn[3 * r + cc] = fma(R[3 * r + 0], tp[cc], fma(R[3 * r + 1], tp[3 + cc], R[3 * r + 2] * tp[6 + cc]));
+        } else {
+            static_for<0, 3>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    Rn[3 * r + k] = PAT::sign(j, k) > 0 ? R[3 * r + PAT::perm(j, k)] : -R[3 * r + PAT::perm(j, k)];
+            });
+        }
 #pragma unroll
         for (int k = 0; k < 9; ++k) R[k] = Rn[k];
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        if (c.prismatic_mask & (1 << j)) {
+    });
+    static_for<0, N>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        if (PAT::generic && (c.prismatic_mask & (1 << j))) {
             Jl[j][0] = Ja[j][0]; Jl[j][1] = Ja[j][1]; Jl[j][2] = Ja[j][2];
             Ja[j][0] = Ja[j][1] = Ja[j][2] = T(0);
         } else {
@@ -136,7 +184,7 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
             Jl[j][1] = Ja[j][2] * dx - Ja[j][0] * dz;
             Jl[j][2] = Ja[j][0] * dy - Ja[j][1] * dx;
         }
-    }
+    });
 }
 
 // ------------------------------------------------------------------------------ field pieces
@@ -217,7 +265,7 @@ __device__ __forceinline__ void issue_chunk(const KArgs<T>& a, int64_t tile0, in
 }
 
 // ------------------------------------------------------------------------------ the fused kernel
-template <typename T, int N, bool EXT, int MINB>
+template <typename T, int N, class PAT, bool EXT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KArgs<T> a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -268,7 +316,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 
         // 1. FK, Jacobian, tool frame
         T R[9], p[3], Jl[N][3], Ja[N][3];
-        fk_jacobian<T, N>(c, q, R, p, Jl, Ja);
+        fk_jacobian<T, N, PAT>(c, q, R, p, Jl, Ja);
         T Rt[9], pt[3], dp[3];
         if (c.tool_identity) {
 #pragma unroll
@@ -335,11 +383,30 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         // 5. weighted damped least squares: qdot = Wj Jw^T (Jw Jw^T + l^2 I)^-1 Wt t
         T A[21], invd[6];
         T qd_vf[N];
-        {
-            if (!c.unit_weights) {
+        if (c.unit_weights) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) tw[k] *= c.w_task[k];
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int s = 0; s <= r; ++s) {
+                    T acc = (r == s) ? c.ik_lambda2 : T(0);
+#pragma unroll
+                    for (int j = 0; j < N; ++j)
+                        acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], s < 3 ? Jl[j][s] : Ja[j][s - 3], acc);
+                    A[tri(r, s)] = acc;
+                }
+            chol6<T>(A, invd);
+            chol6_fwd<T>(A, invd, tw);
+            chol6_bwd<T>(A, invd, tw);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                T acc = T(0);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], tw[r], acc);
+                qd_vf[j] = acc;
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) tw[k] *= c.w_task[k];
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -347,13 +414,9 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                     T acc = (r == s) ? c.ik_lambda2 : T(0);
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        T jr = r < 3 ? Jl[j][r] : Ja[j][r - 3];
-                        T js = s < 3 ? Jl[j][s] : Ja[j][s - 3];
-                        if (!c.unit_weights) {
-                            const T wj2 = c.w_joint[j] * c.w_joint[j];
-                            jr *= c.w_task[r] * wj2;
-                            js *= c.w_task[s];
-                        }
+                        const T wj2 = c.w_joint[j] * c.w_joint[j];
+                        const T jr = (r < 3 ? Jl[j][r] : Ja[j][r - 3]) * (c.w_task[r] * wj2);
+                        const T js = (s < 3 ? Jl[j][s] : Ja[j][s - 3]) * c.w_task[s];
                         acc = fma(jr, js, acc);
                     }
                     A[tri(r, s)] = acc;
@@ -365,12 +428,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             for (int j = 0; j < N; ++j) {
                 T acc = T(0);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    T jr = r < 3 ? Jl[j][r] : Ja[j][r - 3];
-                    if (!c.unit_weights) jr *= c.w_task[r];
-                    acc = fma(jr, tw[r], acc);
-                }
-                qd_vf[j] = c.unit_weights ? acc : acc * c.w_joint[j] * c.w_joint[j];
+                for (int r = 0; r < 6; ++r) acc = fma((r < 3 ? Jl[j][r] : Ja[j][r - 3]) * c.w_task[r], tw[r], acc);
+                qd_vf[j] = acc * c.w_joint[j] * c.w_joint[j];
             }
         }
 
@@ -488,7 +547,6 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 
         // 8-9. mixer, clamp
         T mix[N];
-        T lead = T(0);
         bool nan = false;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -497,29 +555,46 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             m = fma(qd_ns[j], c.mixer_w[1], m);
             m = fma(qd_jp[j], c.mixer_w[2], m);
             nan = nan || (qd_vf[j] != qd_vf[j]) || (qd_ns[j] != qd_ns[j]) || (qd_jp[j] != qd_jp[j]);
+            mix[j] = m;
+        }
 #pragma unroll
-            for (int e = 0; e < 3; ++e)
-                if (a.ext_cmd[e]) {
+        for (int e = 0; e < 3; ++e)
+            if (a.ext_cmd[e]) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
                     const T x = __ldg(a.ext_cmd[e] + j * ld + i);
                     nan = nan || (x != x);
-                    m = fma(x, c.mixer_w[3 + e], m);
+                    mix[j] = fma(x, c.mixer_w[3 + e], mix[j]);
                 }
-            mix[j] = m;
-            lead = Prec<T>::fmax_(lead, Prec<T>::fabs_(m));
-        }
+            }
+        T lead = T(0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) lead = Prec<T>::fmax_(lead, Prec<T>::fabs_(mix[j]));
         if (nan) flags |= 4;
         T ratio = T(1);
         if (lead > c.max_vel) { ratio = Prec<T>::div(c.max_vel, lead); flags |= 8; }
 
         if (last && active) {
+            if (a.qdot_vf) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const T qd = mix[j] * ratio;
-                if (a.qdot_vf) a.qdot_vf[j * ld + i] = qd_vf[j];
-                if (a.qdot_ns) a.qdot_ns[j * ld + i] = qd_ns[j];
-                if (a.qdot_jp) a.qdot_jp[j * ld + i] = qd_jp[j];
-                if (a.qdot) a.qdot[j * ld + i] = qd;
-                if (a.cmd) {
+                for (int j = 0; j < N; ++j) a.qdot_vf[j * ld + i] = qd_vf[j];
+            }
+            if (a.qdot_ns) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) a.qdot_ns[j * ld + i] = qd_ns[j];
+            }
+            if (a.qdot_jp) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) a.qdot_jp[j * ld + i] = qd_jp[j];
+            }
+            if (a.qdot) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) a.qdot[j * ld + i] = mix[j] * ratio;
+            }
+            if (a.cmd) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const T qd = mix[j] * ratio;
                     const T qc = a.q_cmded ? __ldg(a.q_cmded + j * ld + i) : q[j];
                     a.cmd[j * ld + i] = c.direct_control ? qd : (-qc + q[j] + qd);
                 }

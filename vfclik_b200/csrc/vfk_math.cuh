@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <type_traits>
 
 namespace vfk {
 
@@ -74,49 +75,67 @@ template <> struct __align__(16) Vec2<double> { double x, y; };
 // ---- symmetric 6x6: packed lower triangle, index (i,j), i >= j -> i*(i+1)/2 + j
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
+// Compile-time loops: `#pragma unroll` left one of the nested Cholesky loops rolled, which
+// demoted the packed matrix to local memory; template recursion cannot be declined.
+template <int I, int END, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < END) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, END>(static_cast<F&&>(f));
+    }
+}
+
 // In-place Cholesky A = L L^T of a packed SPD 6x6.  On return a[] holds L's strict
 // lower part and inv_d[j] = 1 / L[j][j] (the diagonal is only ever needed inverted).
 template <typename T>
 __device__ __forceinline__ void chol6(T (&a)[21], T (&inv_d)[6]) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
+    static_for<0, 6>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
         T s = a[tri(j, j)];
-#pragma unroll
-        for (int k = 0; k < j; ++k) s = fma(-a[tri(j, k)], a[tri(j, k)], s);
+        static_for<0, j>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            s = fma(-a[tri(j, k)], a[tri(j, k)], s);
+        });
         const T id = Prec<T>::rsqrt_pos(s);
         inv_d[j] = id;
-#pragma unroll
-        for (int i = j + 1; i < 6; ++i) {
+        static_for<j + 1, 6>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
             T t = a[tri(i, j)];
-#pragma unroll
-            for (int k = 0; k < j; ++k) t = fma(-a[tri(i, k)], a[tri(j, k)], t);
+            static_for<0, j>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                t = fma(-a[tri(i, k)], a[tri(j, k)], t);
+            });
             a[tri(i, j)] = t * id;
-        }
-    }
+        });
+    });
 }
 
 // Solve L z = b (forward) in place.
 template <typename T>
 __device__ __forceinline__ void chol6_fwd(const T (&l)[21], const T (&inv_d)[6], T (&b)[6]) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    static_for<0, 6>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
         T t = b[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) t = fma(-l[tri(i, k)], b[k], t);
+        static_for<0, i>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            t = fma(-l[tri(i, k)], b[k], t);
+        });
         b[i] = t * inv_d[i];
-    }
+    });
 }
 
 // Solve L^T y = z (backward) in place.
 template <typename T>
 __device__ __forceinline__ void chol6_bwd(const T (&l)[21], const T (&inv_d)[6], T (&b)[6]) {
-#pragma unroll
-    for (int i = 5; i >= 0; --i) {
+    static_for<0, 6>([&](auto ic) {
+        constexpr int i = 5 - decltype(ic)::value;
         T t = b[i];
-#pragma unroll
-        for (int k = i + 1; k < 6; ++k) t = fma(-l[tri(k, i)], b[k], t);
+        static_for<i + 1, 6>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            t = fma(-l[tri(k, i)], b[k], t);
+        });
         b[i] = t * inv_d[i];
-    }
+    });
 }
 
 // Unit quaternion (w >= 0) of a rotation matrix given row-major m[9]; Shepperd's

@@ -124,6 +124,7 @@ class Engine:
         if rc != 0:
             raise VfkError(rc, self._lib.vfk_last_error(None).decode())
         self.launches = 0                       # kernels launched through this engine
+        self.chain_pattern = {0: "generic", 1: "lwr"}.get(self._lib.vfk_chain_pattern(self._h), "?")
         self.params = params if params is not None else Params()
         self.set_params(self.params)
 
