@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -268,17 +269,23 @@ static int check_layout(vfk_ctx* h, const void* ptr, const char* name, bool requ
     return VFK_OK;
 }
 
-// Shared-memory plan of one launch: ring of `n_stages` stages of kChunk obstacles each.
-template <typename T, bool EXT>
-static void plan_stages(int n_obst, int* n_chunks, int* n_stages, size_t* smem_bytes) {
-    const size_t stage = (size_t)kChunk * kBlock * (sizeof(Vec4<T>) + (EXT ? sizeof(Vec2<T>) : 0));
-    const size_t budget = sizeof(T) == 4 ? (64u << 10) : (96u << 10);      // per CTA: 3 (FP32) / 2 (FP64) CTAs per SM
-    int max_stages = (int)(budget / stage);
-    if (max_stages < 2) max_stages = 2;
-    if (max_stages > kMaxStages) max_stages = kMaxStages;
+// Launch plan: every warp is a persistent worker with its own obstacle ring (n_stages stages of kChunk
+// obstacles x 32 instances) and two q/goal buffers.  K = 1 streams through a 3-deep ring that runs one tile
+// ahead; K > 1 keeps the tile's obstacles resident across the fused cycles when they fit.
+template <typename T, int N, bool EXT>
+static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, size_t* smem_bytes) {
+    using WS = WarpStage<T, N, EXT>;
     *n_chunks = (n_obst + kChunk - 1) / kChunk;
-    *n_stages = *n_chunks < max_stages ? *n_chunks : max_stages;
-    *smem_bytes = n_obst > 0 ? kSmemHeader + (size_t)(*n_stages) * stage : 0;
+    int stages = sizeof(T) == 4 ? 3 : 2;
+    if (k_cycles > 1 && *n_chunks <= 4 && sizeof(T) == 4) stages = *n_chunks;      // resident across the K cycles
+    if (const char* e = getenv("VFK_STAGES")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxStages) stages = v;
+    }
+    if (*n_chunks > 0 && *n_chunks < stages) stages = *n_chunks;
+    if (*n_chunks == 0) stages = 0;
+    *n_stages = stages;
+    *smem_bytes = kSmemHeader + (size_t)(kBlock / 32) * WS::warp_bytes(stages);
 }
 
 template <typename T, int N, class PAT, bool EXT>
@@ -307,17 +314,17 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.n_obst = n_obst;
     a.k_cycles = k_cycles;
     size_t smem = 0;
-    plan_stages<T, EXT>(n_obst, &a.n_chunks, &a.n_stages, &smem);
+    plan_stages<T, N, EXT>(n_obst, k_cycles, &a.n_chunks, &a.n_stages, &smem);
     constexpr int MINB = (sizeof(T) == 4) ? (N <= 10 ? 3 : 2) : (N <= 7 ? 2 : 1);
     auto kern = vfk_cycle_kernel<T, N, PAT, EXT, MINB>;
-    static bool attr_set[8] = {false, false, false, false, false, false, false, false};   // per device
-    if (smem > (48u << 10) && h->device < 8 && !attr_set[h->device]) {
-        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-        attr_set[h->device] = true;
-    } else if (smem > (48u << 10) && h->device >= 8) {
-        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-    }
-    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+    int per_sm = 0;
+    VFK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+    if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "kernel does not fit an SM with %zu bytes of shared memory", smem);
+    const int64_t tiles = (n + 31) / 32;
+    const int64_t want = (tiles + kBlock / 32 - 1) / (kBlock / 32);
+    const int64_t cap = (int64_t)h->sm_count * per_sm;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     kern<<<grid, kBlock, smem, st>>>(c, a);
     VFK_CUDA(h, cudaGetLastError());
     return 1;

@@ -1,16 +1,17 @@
 // vfk_kernels.cuh -- the fused vfclik control-cycle kernel for sm_100a.
 //
-// One thread = one manipulator instance; a CTA of 128 threads owns a tile of 128
+// One thread = one manipulator instance; a warp is a persistent worker over tiles of 32
 // consecutive instances.  All per-instance state (q, frame, the 6xN Jacobian, the 6x6
 // normal matrix) lives in registers across the K fused cycles.  Per-instance global
 // arrays are SoA [component][ld] (a warp's access to one component is one contiguous
 // 128-byte / 256-byte line); the obstacle list is [M][ld][4] = one {x,y,z,radius}
-// vector per (obstacle, instance), so the tile's obstacles are M contiguous rows of
-// 128 vectors.  Those rows are moved global -> shared with cp.async.bulk (TMA) into a
-// ring of stages guarded by mbarriers, issued before forward kinematics starts so the
-// copy overlaps the FK / Jacobian arithmetic; the repulsor loop then reads one
-// conflict-free LDS.128 per obstacle.  Robot constants (chain, limits, gains) arrive
-// as a __grid_constant__ kernel parameter (constant bank), indexed at compile time.
+// vector per (obstacle, instance), so a tile's obstacles are M contiguous rows of 32
+// vectors.  q, goal and obstacle rows are moved global -> shared with cp.async.bulk
+// (TMA) into per-warp buffers guarded by mbarriers, one tile AHEAD of the arithmetic,
+// so HBM latency is hidden behind the previous tile's FK / Cholesky work; the repulsor
+// loop reads one conflict-free LDS.128 per obstacle.  Robot constants (chain, limits,
+// gains) arrive as a __grid_constant__ kernel parameter (constant bank), indexed at
+// compile time.
 //
 // Reference mapping (see include/vfk.h and SURVEY.md App. C.2):
 //   fk_jacobian()   scripts/vf:316-318, scripts/nullspace:175  (Lafik / KDL FK + Jacobian)
@@ -30,7 +31,7 @@ constexpr int kMaxJ = 17;
 constexpr int kBlock = 128;          // threads (= instances) per CTA
 constexpr int kChunk = 8;            // obstacles per shared-memory stage
 constexpr int kMaxStages = 8;
-constexpr int kSmemHeader = 128;     // mbarriers live in the first 128 bytes of dynamic smem
+constexpr int kSmemHeader = 512;     // per-warp mbarriers live in the first 512 bytes of dynamic smem
 
 // Kernel-side constants in the kernel's arithmetic type.  Joints are canonicalised on
 // the host (vfk_api.cu: canonicalise_chain) so that every joint acts about / along its
@@ -244,23 +245,52 @@ __device__ __forceinline__ void saturate(const KConst<T>& c, T (&V)[3], T S0, T 
     v[0] = sl * V[0]; v[1] = sl * V[1]; v[2] = sl * V[2];
 }
 
-// Issue the bulk copies of obstacle chunk `chunk` of this CTA's tile into stage `stage` (warp 0 only).
-template <typename T, bool EXT>
-__device__ __forceinline__ void issue_chunk(const KArgs<T>& a, int64_t tile0, int chunk, int stage, unsigned char* smem,
-                                            uint64_t* bars, int lane) {
-    constexpr uint32_t kRow = kBlock * sizeof(Vec4<T>);
-    constexpr uint32_t kRowExt = EXT ? kBlock * sizeof(Vec2<T>) : 0;
-    constexpr uint32_t kStage = kChunk * (kRow + kRowExt);
+// ------------------------------------------------------------------------------ per-warp staging
+// Every warp is an independent persistent worker over tiles of 32 consecutive instances.  It owns
+//   * a ring of `n_stages` obstacle stages (kChunk obstacles x 32 instances each), and
+//   * two q/goal buffers ((N + 13) rows x 32 instances),
+// each guarded by its own mbarrier and filled by cp.async.bulk (TMA).  The ring runs ahead of the
+// arithmetic across tile boundaries: while a warp works on tile t its lanes have already requested
+// q/goal of tile t+1 and, stage by stage, the obstacles of tile t+1.  No CTA-wide barrier exists.
+template <typename T, int N, bool EXT>
+struct WarpStage {
+    static constexpr uint32_t kRow = 32 * sizeof(Vec4<T>);                 // one obstacle, 32 instances
+    static constexpr uint32_t kRowExt = EXT ? 32 * sizeof(Vec2<T>) : 0;
+    static constexpr uint32_t kStage = kChunk * (kRow + kRowExt);
+    static constexpr uint32_t kQgRow = 32 * sizeof(T);
+    static constexpr uint32_t kQgRows = N + 13;
+    static constexpr uint32_t kQg = kQgRows * kQgRow;
+    static constexpr int kBars = kMaxStages + 2;                            // full[stage], qg[2]
+    __host__ __device__ static constexpr uint32_t warp_bytes(int n_stages) { return n_stages * kStage + 2 * kQg; }
+};
+
+template <typename T, int N, bool EXT>
+__device__ __forceinline__ void issue_obst(const KArgs<T>& a, int64_t tile0, int chunk, int stage, unsigned char* region,
+                                           uint64_t* bars, int lane) {
+    using WS = WarpStage<T, N, EXT>;
     const int m0 = chunk * kChunk;
     const int cnt = min(kChunk, a.n_obst - m0);
-    unsigned char* dst = smem + kSmemHeader + (size_t)stage * kStage;
-    if (lane == 0) mbar_arrive_expect_tx(&bars[stage], (uint32_t)cnt * (kRow + kRowExt));
+    unsigned char* dst = region + (size_t)stage * WS::kStage;
+    if (lane == 0) mbar_arrive_expect_tx(&bars[stage], (uint32_t)cnt * (WS::kRow + WS::kRowExt));
     __syncwarp();
     if (lane < cnt) {
-        bulk_g2s(dst + lane * kRow, a.obst + (int64_t)(m0 + lane) * a.ld + tile0, kRow, &bars[stage]);
+        bulk_g2s(dst + lane * WS::kRow, a.obst + (int64_t)(m0 + lane) * a.ld + tile0, WS::kRow, &bars[stage]);
         if (EXT)
-            bulk_g2s(dst + kChunk * kRow + lane * kRowExt, a.obst_ext + (int64_t)(m0 + lane) * a.ld + tile0, kRowExt,
-                     &bars[stage]);
+            bulk_g2s(dst + kChunk * WS::kRow + lane * WS::kRowExt, a.obst_ext + (int64_t)(m0 + lane) * a.ld + tile0,
+                     WS::kRowExt, &bars[stage]);
+    }
+}
+
+template <typename T, int N, bool EXT>
+__device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile0, int buf, unsigned char* region, uint64_t* bars,
+                                         int lane) {
+    using WS = WarpStage<T, N, EXT>;
+    unsigned char* dst = region + (size_t)a.n_stages * WS::kStage + (size_t)buf * WS::kQg;
+    if (lane == 0) mbar_arrive_expect_tx(&bars[kMaxStages + buf], WS::kQg);
+    __syncwarp();
+    if (lane < (int)WS::kQgRows) {
+        const T* src = lane < N ? a.q + (int64_t)lane * a.ld + tile0 : a.goal + (int64_t)(lane - N) * a.ld + tile0;
+        bulk_g2s(dst + lane * WS::kQgRow, src, WS::kQgRow, &bars[kMaxStages + buf]);
     }
 }
 
@@ -268,40 +298,47 @@ __device__ __forceinline__ void issue_chunk(const KArgs<T>& a, int64_t tile0, in
 template <typename T, int N, class PAT, bool EXT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KArgs<T> a) {
+    using WS = WarpStage<T, N, EXT>;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    constexpr uint32_t kRow = kBlock * sizeof(Vec4<T>);
-    constexpr uint32_t kRowExt = EXT ? kBlock * sizeof(Vec2<T>) : 0;
-    constexpr uint32_t kStage = kChunk * (kRow + kRowExt);
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int64_t tile0 = (int64_t)blockIdx.x * kBlock;
-    const bool active = tile0 + tid < a.n;
-    const int64_t i = active ? tile0 + tid : a.n - 1;      // idle lanes of the last tile shadow a valid instance
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * WS::kBars;
+    unsigned char* region = smem + kSmemHeader + (size_t)warp * WS::warp_bytes(a.n_stages);
     const int64_t ld = a.ld;
-    const bool streaming = a.n_chunks > a.n_stages;
-    const int total_seq = a.n_chunks * (streaming ? a.k_cycles : 1);
 
-    // ---- stage the obstacle tile: all stages in flight before any arithmetic starts
-    if (a.n_obst > 0) {
-        if (tid == 0) {
-            for (int s = 0; s < a.n_stages; ++s) mbar_init(&bars[s], 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-        if (tid < 32) {
-            const int pre = min(a.n_stages, total_seq);
-            for (int s = 0; s < pre; ++s) issue_chunk<T, EXT>(a, tile0, s % a.n_chunks, s, smem, bars, lane);
-        }
+    const int64_t n_tiles = (a.n + 31) >> 5;
+    const int64_t stride = (int64_t)gridDim.x * (kBlock / 32);
+    int64_t tile = (int64_t)blockIdx.x * (kBlock / 32) + warp;
+    if (tile >= n_tiles) return;
+
+    // ring bookkeeping: U chunk-uses per tile; S ring slots (resident: one slot per chunk, loaded once per tile)
+    const bool resident = a.n_chunks <= a.n_stages;
+    const int S = resident ? a.n_chunks : a.n_stages;
+    const int U = resident ? a.n_chunks : a.n_chunks * a.k_cycles;
+
+    if (lane == 0) {
+        for (int s = 0; s < kMaxStages + 2; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
     }
+    __syncwarp();
+    issue_qg<T, N, EXT>(a, tile << 5, 0, region, bars, lane);
+    for (int u = 0; u < S; ++u) issue_obst<T, N, EXT>(a, tile << 5, u % a.n_chunks, u, region, bars, lane);
+
+    int64_t seq = 0;                                        // chunk uses consumed so far by this warp
+    for (int it = 0; tile < n_tiles; tile += stride, ++it) {
+        const int64_t tile0 = tile << 5;
+        const bool active = tile0 + lane < a.n;
+        const int64_t i = tile0 + lane;                     // padding lanes compute on padding data, never store
+        if (tile + stride < n_tiles) issue_qg<T, N, EXT>(a, (tile + stride) << 5, (it + 1) & 1, region, bars, lane);
+        mbar_wait(&bars[kMaxStages + (it & 1)], (uint32_t)(it >> 1) & 1u);
+        const T* qg = reinterpret_cast<const T*>(region + (size_t)a.n_stages * WS::kStage + (size_t)(it & 1) * WS::kQg) + lane;
 
     T q[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) q[j] = a.q[j * ld + i];
+    for (int j = 0; j < N; ++j) q[j] = qg[j * 32];
     T g[13];
 #pragma unroll
-    for (int k = 0; k < 13; ++k) g[k] = __ldg(a.goal + k * ld + i);
+    for (int k = 0; k < 13; ++k) g[k] = qg[(N + k) * 32];
 
     T lastv[N];
     if (c.ns_mode == 2) {
@@ -309,7 +346,6 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         for (int j = 0; j < N; ++j) lastv[j] = a.ns_lastvec[j * ld + i];
     }
 
-    int seq = 0;                                            // obstacle chunks consumed so far (ring position)
     for (int cyc = 0; cyc < a.k_cycles; ++cyc) {
         const bool last = (cyc == a.k_cycles - 1);
         int flags = 0;
@@ -335,41 +371,43 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             }
         }
 
-        // 2-4. field: attractor, repulsor sum over the staged obstacle tile, saturation, shift to the flange
+        // 2-4. field: attractor, repulsor sum over the staged obstacles, saturation, shift to the flange
         T tw[6];
         {
             T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)};
             attract<T>(c, g, Rt, pt, V, S0, w);
             for (int ch = 0; ch < a.n_chunks; ++ch) {
-                const int stage = streaming ? seq % a.n_stages : ch;
-                const uint32_t parity = streaming ? (uint32_t)(seq / a.n_stages) & 1u : 0u;
-                mbar_wait(&bars[stage], parity);
-                const unsigned char* sb = smem + kSmemHeader + (size_t)stage * kStage;
-                const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + tid;
-                const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * kRow) + tid;
+                const int64_t use = resident ? (int64_t)it * U + ch : seq;
+                const int stage = (int)(use % S);
+                mbar_wait(&bars[stage], (uint32_t)(use / S) & 1u);
+                const unsigned char* sb = region + (size_t)stage * WS::kStage;
+                const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + lane;
+                const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * WS::kRow) + lane;
                 const int cnt = min(kChunk, a.n_obst - ch * kChunk);
                 if (cnt == kChunk) {
 #pragma unroll
                     for (int m = 0; m < kChunk; ++m) {
-                        const Vec4<T> o = so[m * kBlock];
+                        const Vec4<T> o = so[m * 32];
                         T safe_inv = c.obst_safe_inv, order = c.obst_order;
-                        if (EXT) { const Vec2<T> e = se[m * kBlock]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+                        if (EXT) { const Vec2<T> e = se[m * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
                         repel<T>(o, safe_inv, order, pt, acc);
                     }
                 } else {
                     for (int m = 0; m < cnt; ++m) {
-                        const Vec4<T> o = so[m * kBlock];
+                        const Vec4<T> o = so[m * 32];
                         T safe_inv = c.obst_safe_inv, order = c.obst_order;
-                        if (EXT) { const Vec2<T> e = se[m * kBlock]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+                        if (EXT) { const Vec2<T> e = se[m * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
                         repel<T>(o, safe_inv, order, pt, acc);
                     }
                 }
-                if (streaming) {
-                    __syncthreads();                        // every thread is done with this stage
-                    if (tid < 32 && seq + a.n_stages < total_seq)
-                        issue_chunk<T, EXT>(a, tile0, (seq + a.n_stages) % a.n_chunks, stage, smem, bars, lane);
-                    ++seq;
+                // this slot is free again: request the chunk that will occupy it S uses from now
+                if (!resident || last) {
+                    const int64_t nxt = use + S;
+                    const int64_t nt = tile + (nxt / U - it) * stride;
+                    __syncwarp();
+                    if (nt < n_tiles) issue_obst<T, N, EXT>(a, nt << 5, (int)((nxt % U) % a.n_chunks), stage, region, bars, lane);
                 }
+                ++seq;
             }
             V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
             T v[3];
@@ -623,6 +661,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             for (int j = 0; j < N; ++j) a.ns_lastvec[j * ld + i] = lastv[j];
         }
     }
+    }   // tile loop
 }
 
 // ------------------------------------------------------------------------------ small kernels
