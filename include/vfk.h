@@ -19,16 +19,22 @@
  *   velocity clamp + command     scripts/bridge:188-203
  *   plant integration            (external joint_sim; explicit Euler)
  *
- * Data layout: every per-instance array is SoA, component-major: element
- * (component c, instance i) lives at base[c * ld + i], with ld >= n_instances the
- * leading dimension (in instances).  The obstacle list is the one exception: it is
- * [M][ld][4], one {x, y, z, radius} vector per (obstacle m, instance i) at
- * base[(m * ld + i) * 4 + c], so that a thread fetches an obstacle with one 16/32-byte
- * load and a tile of 128 instances is one contiguous row per obstacle (moved global ->
- * shared by cp.async.bulk / TMA).  ld must be a multiple of 128 and every base pointer
- * 128-byte aligned (the padding instances [n, ld) must be allocated; they are read
- * but never written).  Element type is float (precision 32) or double (precision 64)
- * as chosen at vfk_create().
+ * Data layout ("tile-blocked SoA"): instances are grouped in tiles of VFK_TILE = 32
+ * (one warp).  A per-instance array with C components stores element (component c,
+ * instance i) at
+ *         base[ ((i / 32) * C + c) * 32 + i % 32 ]
+ * and the obstacle list stores obstacle m of instance i as one {x, y, z, radius}
+ * vector at
+ *         base[ (((i / 32) * M + m) * 32 + i % 32) * 4 + k ],  k = 0..3
+ * (obst_ext likewise with 2 scalars {safe distance, decay order}).  A warp's access to
+ * one component is one contiguous 128/256-byte line, and everything a warp needs for
+ * a tile -- q, goal, each chunk of 8 obstacles -- is one contiguous burst moved
+ * global -> shared by a single cp.async.bulk (TMA) copy.  Arrays cover
+ * ceil(n_instances / 32) whole tiles (the padding lanes of the last tile must be
+ * allocated; they are read, never written).  Base pointers must be 128-byte aligned.
+ * Element type is float (precision 32) or double (precision 64) as chosen at
+ * vfk_create().  vfk_pack()/vfk_unpack() convert dense SoA [C][n] device arrays to and
+ * from this layout; the host-buffer session API takes plain dense arrays.
  */
 #ifndef VFK_H_
 #define VFK_H_
@@ -41,6 +47,7 @@ extern "C" {
 
 #define VFK_VERSION 100          /* 0.1.0 */
 #define VFK_MAX_JOINTS 17
+#define VFK_TILE 32              /* instances per layout tile */
 #define VFK_N_PORTS 6            /* mixer inputs, order of scripts/bridge:593-596 */
 #define VFK_GOAL_COMPS 13        /* R_goal row-major (9), p_goal (3), slowdown distance (1) */
 #define VFK_POSE_COMPS 12        /* R row-major (9), p (3) */
@@ -108,26 +115,27 @@ typedef struct vfk_params {
     int32_t reserved;
 } vfk_params;
 
-/* Device buffers of one vfk_step() call.  NULL = not supplied / not wanted. */
+/* Device buffers of one vfk_step() call, all in the tile-blocked layout above
+ * ("[C]" = C components per instance).  NULL = not supplied / not wanted. */
 typedef struct vfk_buffers {
-    void*       q;               /* [N][ld]  in; out when params.integrate                    */
-    const void* goal;            /* [13][ld] attractor (vfl type 1) per instance                */
-    const void* obst;            /* [M][ld][4] decay repellers (vfl type 2): x, y, z, radius; radius 0 = empty slot */
-    const void* obst_ext;        /* [M][ld][2] per-obstacle {safe distance, decay order} (wire-faithful,
+    void*       q;               /* [N]  in; out when params.integrate                            */
+    const void* goal;            /* [13] attractor (vfl type 1) per instance                       */
+    const void* obst;            /* M obstacles x {x, y, z, radius}: decay repellers (vfl type 2); radius 0 = empty slot */
+    const void* obst_ext;        /* M obstacles x {safe distance, decay order} (wire-faithful,
                                     scripts/object_feeder:326-333) or NULL -> params.obst_safe / obst_order */
-    const void* jp_ref;          /* [N][ld]  joint reference (/jpctrl/ref) or NULL -> params.jp_ref */
-    const void* ns_in;           /* PROJECTOR: qdot0 [N][ld] or NULL -> limit-avoidance gradient;
-                                    CONTROL:   control [4][ld] or NULL -> params.ns_control      */
-    void*       ns_lastvec;      /* CONTROL: [N][ld] in/out sign-continuity state (scripts/nullspace:91-107) */
-    const void* q_cmded;         /* [N][ld]  last commanded q (scripts/bridge:169-172) or NULL -> q */
-    const void* ext_cmd[3];      /* mixer ports 3..5 [N][ld] each, or NULL -> 0 */
-    void*       qdot_vf;         /* out [N][ld]  /vectorField/qdotOut   */
-    void*       qdot_ns;         /* out [N][ld]  /nullspace/qdotout     */
-    void*       qdot_jp;         /* out [N][ld]  /jpctrl/out            */
-    void*       qdot;            /* out [N][ld]  clamped mixer output qdot_lim (scripts/bridge:196) */
-    void*       cmd;             /* out [N][ld]  command sent to the plant (scripts/bridge:198-203) */
-    void*       pose;            /* out [12][ld] tool frame (/vectorField/pose) */
-    int32_t*    flags;           /* out [ld]     VFK_FLAG_* */
+    const void* jp_ref;          /* [N]  joint reference (/jpctrl/ref) or NULL -> params.jp_ref   */
+    const void* ns_in;           /* PROJECTOR: qdot0 [N] or NULL -> limit-avoidance gradient;
+                                    CONTROL:   control [4] or NULL -> params.ns_control             */
+    void*       ns_lastvec;      /* CONTROL: [N] in/out sign-continuity state (scripts/nullspace:91-107) */
+    const void* q_cmded;         /* [N]  last commanded q (scripts/bridge:169-172) or NULL -> q     */
+    const void* ext_cmd[3];      /* mixer ports 3..5, [N] each, or NULL -> 0                        */
+    void*       qdot_vf;         /* out [N]  /vectorField/qdotOut                                  */
+    void*       qdot_ns;         /* out [N]  /nullspace/qdotout                                    */
+    void*       qdot_jp;         /* out [N]  /jpctrl/out                                           */
+    void*       qdot;            /* out [N]  clamped mixer output qdot_lim (scripts/bridge:196)    */
+    void*       cmd;             /* out [N]  command sent to the plant (scripts/bridge:198-203)    */
+    void*       pose;            /* out [12] tool frame (/vectorField/pose)                        */
+    int32_t*    flags;           /* out [1]  VFK_FLAG_*                                            */
 } vfk_buffers;
 
 typedef struct vfk_ctx* vfk_handle;
@@ -151,24 +159,30 @@ const char* vfk_last_error(vfk_handle h);   /* h may be NULL: last error of vfk_
  * (a cudaStream_t, may be NULL).  No allocation, no synchronisation.
  * Outputs hold the last cycle's values.  Returns the number of kernels launched
  * (>= 1) or a negative vfk_status. */
-int  vfk_step(vfk_handle h, const vfk_buffers* bufs, int64_t n_instances, int64_t ld,
-              int n_obstacles, int k_cycles, void* stream);
+int  vfk_step(vfk_handle h, const vfk_buffers* bufs, int64_t n_instances, int n_obstacles,
+              int k_cycles, void* stream);
 
 /* Field visualisation query (scripts/vf:469-503): twist the composed field commands at
- * arbitrary tool poses pose_in[12][ld]; twist_out[6][ld].  Same goal/obst layout. */
+ * arbitrary tool poses pose_in [12]; twist_out [6] (blocked layout).  Same goal/obst layout. */
 int  vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst,
-                    const void* obst_ext, void* twist_out, int64_t n_instances, int64_t ld,
-                    int n_obstacles, void* stream);
+                    const void* obst_ext, void* twist_out, int64_t n_instances, int n_obstacles,
+                    void* stream);
 
 /* Weighted sum of command ports (src/command_mixer.py:78-82) on device buffers:
- * out[c][i] = sum_p w[p] * cmds[p][c][i]; cmds[p] may be NULL (skipped). */
+ * out(c, i) = sum_p w[p] * cmds[p](c, i); cmds[p] may be NULL (skipped); nan_flags [1] optional. */
 int  vfk_mix(vfk_handle h, const void* const* cmds, const double* w, int n_ports, int n_channels,
-             void* out, int32_t* nan_flags, int64_t n_instances, int64_t ld, void* stream);
+             void* out, int32_t* nan_flags, int64_t n_instances, void* stream);
+
+/* Layout conversion on the device: dense SoA [comps][n] (width scalars per element: 1 for
+ * per-instance components, 4 for obstacles [M][n][4], 2 for obst_ext [M][n][2]) <-> tile-blocked. */
+int  vfk_pack(vfk_handle h, const void* dense, void* blocked, int comps, int width, int64_t n_instances, void* stream);
+int  vfk_unpack(vfk_handle h, const void* blocked, void* dense, int comps, int width, int64_t n_instances, void* stream);
 
 /* ---- host-buffer sessions: the call a host-language plugin makes --------------
  * A session owns resident device copies of the scene (goal, obstacles) and state,
- * pinned staging buffers and a stream.  Host arrays are dense (leading dimension
- * n_instances, no padding) in the device layouts above, of the handle's precision.  vfk_session_cycle()
+ * pinned staging buffers and a stream.  Host arrays are plain dense SoA of the handle's
+ * precision: [comps][n_instances] (obstacles [M][n][4], ext [M][n][2]); the session
+ * converts to / from the blocked layout on the GPU.  vfk_session_cycle()
  * copies q host->device (if q_in != NULL), runs k_cycles fused cycles, copies the
  * requested outputs device->host and synchronises. */
 int  vfk_session_create(vfk_handle h, int64_t n_instances, int n_obstacles, int with_obst_ext, vfk_session* out);
@@ -184,7 +198,7 @@ int  vfk_session_cycle(vfk_session s, const void* q_in_host, int k_cycles,
  * all off by default so the resident path only moves q in and qdot out. */
 int  vfk_session_enable(vfk_session s, const char* what, int on);
 int  vfk_session_read(vfk_session s, const char* what, void* out_host);     /* enabled outputs, "qdot", "q", "lastvec" */
-int  vfk_session_buffers(vfk_session s, vfk_buffers* out, int64_t* ld);     /* device view (for stream-ordered use) */
+int  vfk_session_buffers(vfk_session s, vfk_buffers* out);                  /* blocked device view (stream-ordered use) */
 void vfk_session_destroy(vfk_session s);
 
 #ifdef __cplusplus

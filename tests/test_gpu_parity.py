@@ -182,9 +182,7 @@ def test_per_instance_inputs_weights_tool_and_ext_ports(eng, lwr):
         db.upload("obst_ext", w["obst_ext"])
         db.upload("jp_ref", jp_ref); db.upload("ns_in", qd0); db.upload("q_cmded", q_cmded)
         for k in range(3):
-            db.ext_cmd[k] = e.alloc(7, db.ld)
-            import torch
-            db.ext_cmd[k][:, :n].copy_(torch.from_numpy(ext[k]))
+            db.ext_cmd[k] = db.to_blocked(ext[k])
         db.step(1)
         out = {k: db.download(k).T for k in ("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd")}
         ref = run_oracle(chain, e.params, w, M, jp_ref=jp_ref.T, ns_in=qd0.T, q_cmded=q_cmded.T,
@@ -287,7 +285,6 @@ def test_host_session_matches_device_path(eng, lwr):
 
 def test_field_eval_and_mix(eng, lwr):
     """/pose_in -> /vector_out query (scripts/vf:469-503) and the stand-alone mixer sum (src/command_mixer.py:78-82)."""
-    import torch
     from oracle import batch
     from vfclik_b200 import workloads
     from vfclik_b200.engine import DeviceBatch
@@ -305,32 +302,28 @@ def test_field_eval_and_mix(eng, lwr):
     db = DeviceBatch(e, n, M, outputs=())
     db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
     pose = db.upload("pose", np.concatenate([R.reshape(n, 9), p], axis=1).T)
-    tw = e.alloc(6, db.ld)
-    assert e.field_eval(pose, db.t["goal"], db.t["obst"], tw, n, db.ld, M) == 1
-    got = tw[:, :n].cpu().numpy().T
+    tw = db._ensure("twist")
+    assert e.field_eval(pose, db.t["goal"], db.t["obst"], tw, n, M) == 1
+    got = db.download("twist").T
     assert np.allclose(got, np.concatenate([v, om], axis=1), rtol=1e-9, atol=1e-12)
     # mixer
     rng = np.random.default_rng(12)
     cmds = [rng.normal(size=(7, n)) for _ in range(6)]
     cmds[4][3, 17] = np.nan
     wts = [1.0, 1.0, 0.3, 0.0, 0.25, -0.5]
-    dev = []
-    for c in cmds:
-        t = e.alloc(7, db.ld)
-        t[:, :n].copy_(torch.from_numpy(c))
-        dev.append(t)
+    dev = [db.to_blocked(c) for c in cmds]
     dev[3] = None                                            # an unconnected port
-    out = e.alloc(7, db.ld)
-    flags = e.alloc(1, db.ld, dtype=torch.int32)
-    e.mix(dev, wts, out, 7, n, db.ld, nan_flags=flags)
+    out = db._ensure("mix_out")
+    flags = db._ensure("flags")
+    e.mix(dev, wts, out, 7, n, nan_flags=flags)
     want = np.zeros((7, n))
     for c, wt, d in zip(cmds, wts, dev):
         if d is not None:
             want = want + c * wt
-    got = out[:, :n].cpu().numpy()
+    got = db.download("mix_out")
     ok = ~np.isnan(want)
     assert np.allclose(got[ok], want[ok], rtol=1e-12, atol=1e-14) and np.isnan(got[3, 17])
-    fl = flags[0, :n].cpu().numpy()
+    fl = db.download("flags")[0]
     assert fl[17] == 4 and fl.sum() == 4
 
 
@@ -340,12 +333,36 @@ def test_invalid_arguments_return_errors(eng, lwr):
     e = eng(32)
     db = DeviceBatch(e, 64, 2)
     with pytest.raises(VfkError):
-        e.step(db.bufs, 64, 96, 2)                  # ld not a multiple of 128
+        e.step(db.bufs, 64, -1)
     with pytest.raises(VfkError):
-        e.step(db.bufs, 64, db.ld, 2, k_cycles=0)
+        e.step(db.bufs, 64, 2, k_cycles=0)
     with pytest.raises(VfkError):
-        e.step({"q": db.t["q"]}, 64, db.ld, 0)      # goal missing
+        e.step({"q": db.t["q"]}, 64, 0)             # goal missing
+    with pytest.raises(VfkError):
+        e.step(dict(db.bufs, goal=db.t["goal"].data_ptr() + 4), 64, 2)     # misaligned base pointer
     with pytest.raises(VfkError):
         e.set_params(ns_mode=7)
     with pytest.raises(VfkError):
         e.set_params(ik_lambda=0.0)                 # outside the FP32 domain
+
+
+def test_pack_unpack_round_trip(eng, lwr):
+    """Dense SoA <-> tile-blocked conversion kernels: exact, for ragged n and every element width."""
+    from vfclik_b200.engine import DeviceBatch
+    e = eng(32)
+    rng = np.random.default_rng(13)
+    for n in (1, 31, 32, 33, 1000):
+        db = DeviceBatch(e, n, 3, obst_ext=True, outputs=("qdot",))
+        a = rng.normal(size=(7, n)).astype(np.float32)
+        o = rng.normal(size=(3, n, 4)).astype(np.float32)
+        x = rng.normal(size=(3, n, 2)).astype(np.float32)
+        db.upload("q", a); db.upload("obst", o); db.upload("obst_ext", x)
+        assert np.array_equal(db.download("q"), a)
+        assert np.array_equal(db.download("obst"), o)
+        assert np.array_equal(db.download("obst_ext"), x)
+        # the documented index formula: element (c, i) at ((i // 32) * C + c) * 32 + i % 32
+        flat = db.t["q"].reshape(-1).cpu().numpy()
+        i = n - 1
+        assert flat[((i // 32) * 7 + 3) * 32 + i % 32] == a[3, i]
+        oflat = db.t["obst"].reshape(-1).cpu().numpy()
+        assert oflat[(((i // 32) * 3 + 2) * 32 + i % 32) * 4 + 1] == o[2, i, 1]

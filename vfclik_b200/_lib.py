@@ -15,6 +15,7 @@ VFK_MAX_JOINTS = 17
 VFK_N_PORTS = 6
 VFK_GOAL_COMPS = 13
 VFK_POSE_COMPS = 12
+VFK_TILE = 32
 
 VFK_OK = 0
 VFK_ERR_INVALID = -1
@@ -31,7 +32,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvfk.so")
 EXPORTS = [
     "vfk_version", "vfk_default_params", "vfk_create", "vfk_set_params", "vfk_get_params", "vfk_chain_pattern",
     "vfk_destroy",
-    "vfk_last_error", "vfk_step", "vfk_field_eval", "vfk_mix", "vfk_session_create", "vfk_session_set_goal",
+    "vfk_last_error", "vfk_step", "vfk_field_eval", "vfk_mix", "vfk_pack", "vfk_unpack", "vfk_session_create", "vfk_session_set_goal",
     "vfk_session_set_obstacles", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input",
     "vfk_session_cycle", "vfk_session_enable", "vfk_session_read", "vfk_session_buffers", "vfk_session_destroy",
 ]
@@ -108,9 +109,11 @@ def load():
     lib.vfk_destroy.restype = None
     lib.vfk_last_error.argtypes = [vp]
     lib.vfk_last_error.restype = C.c_char_p
-    lib.vfk_step.argtypes = [vp, C.POINTER(BuffersC), i64, i64, i32, i32, vp]
-    lib.vfk_field_eval.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i32, vp]
-    lib.vfk_mix.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_double), i32, i32, vp, vp, i64, i64, vp]
+    lib.vfk_step.argtypes = [vp, C.POINTER(BuffersC), i64, i32, i32, vp]
+    lib.vfk_field_eval.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.vfk_mix.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_double), i32, i32, vp, vp, i64, vp]
+    lib.vfk_pack.argtypes = [vp, vp, vp, i32, i32, i64, vp]
+    lib.vfk_unpack.argtypes = [vp, vp, vp, i32, i32, i64, vp]
     lib.vfk_session_create.argtypes = [vp, i64, i32, i32, C.POINTER(vp)]
     for name in ("vfk_session_set_goal", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input"):
         getattr(lib, name).argtypes = [vp, vp]
@@ -118,7 +121,7 @@ def load():
     lib.vfk_session_cycle.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.vfk_session_read.argtypes = [vp, C.c_char_p, vp]
     lib.vfk_session_enable.argtypes = [vp, C.c_char_p, i32]
-    lib.vfk_session_buffers.argtypes = [vp, C.POINTER(BuffersC), C.POINTER(i64)]
+    lib.vfk_session_buffers.argtypes = [vp, C.POINTER(BuffersC)]
     lib.vfk_session_destroy.argtypes = [vp]
     lib.vfk_session_destroy.restype = None
     _lib = lib

@@ -289,8 +289,8 @@ static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, 
 }
 
 template <typename T, int N, class PAT, bool EXT>
-static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
-                        int k_cycles, cudaStream_t st) {
+static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
+                        cudaStream_t st) {
     KArgs<T> a;
     memset(&a, 0, sizeof a);
     a.q = static_cast<T*>(b->q);
@@ -310,7 +310,6 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.pose = static_cast<T*>(b->pose);
     a.flags = b->flags;
     a.n = n;
-    a.ld = ld;
     a.n_obst = n_obst;
     a.k_cycles = k_cycles;
     size_t smem = 0;
@@ -331,35 +330,33 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 }
 
 template <typename T, int N>
-static int dispatch_ext(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
-                        int k_cycles, cudaStream_t st) {
+static int dispatch_ext(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
+                        cudaStream_t st) {
     const bool ext = b->obst_ext && n_obst > 0;
     if constexpr (N == 7) {
         if (h->pattern == 1)
-            return ext ? launch_cycle<T, N, LwrPattern, true>(h, c, b, n, ld, n_obst, k_cycles, st)
-                       : launch_cycle<T, N, LwrPattern, false>(h, c, b, n, ld, n_obst, k_cycles, st);
+            return ext ? launch_cycle<T, N, LwrPattern, true>(h, c, b, n, n_obst, k_cycles, st)
+                       : launch_cycle<T, N, LwrPattern, false>(h, c, b, n, n_obst, k_cycles, st);
     }
-    return ext ? launch_cycle<T, N, GenericPattern, true>(h, c, b, n, ld, n_obst, k_cycles, st)
-               : launch_cycle<T, N, GenericPattern, false>(h, c, b, n, ld, n_obst, k_cycles, st);
+    return ext ? launch_cycle<T, N, GenericPattern, true>(h, c, b, n, n_obst, k_cycles, st)
+               : launch_cycle<T, N, GenericPattern, false>(h, c, b, n, n_obst, k_cycles, st);
 }
 
 template <typename T>
-static int dispatch_n(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst,
-                      int k_cycles, cudaStream_t st) {
+static int dispatch_n(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
+                      cudaStream_t st) {
     switch (h->chain.n_joints) {
-        case 6: return dispatch_ext<T, 6>(h, c, b, n, ld, n_obst, k_cycles, st);
-        case 7: return dispatch_ext<T, 7>(h, c, b, n, ld, n_obst, k_cycles, st);
-        case 10: return dispatch_ext<T, 10>(h, c, b, n, ld, n_obst, k_cycles, st);
-        case 17: return dispatch_ext<T, 17>(h, c, b, n, ld, n_obst, k_cycles, st);
+        case 6: return dispatch_ext<T, 6>(h, c, b, n, n_obst, k_cycles, st);
+        case 7: return dispatch_ext<T, 7>(h, c, b, n, n_obst, k_cycles, st);
+        case 10: return dispatch_ext<T, 10>(h, c, b, n, n_obst, k_cycles, st);
+        case 17: return dispatch_ext<T, 17>(h, c, b, n, n_obst, k_cycles, st);
     }
     return fail(h, VFK_ERR_UNSUPPORTED, "no kernel for n_joints = %d", h->chain.n_joints);
 }
 
-extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int64_t ld, int n_obst, int k_cycles,
-                        void* stream) {
+extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, void* stream) {
     if (!h || !b) return fail(h, VFK_ERR_INVALID, "vfk_step: null argument");
-    if (n < 0 || ld < n) return fail(h, VFK_ERR_INVALID, "need 0 <= n_instances <= ld (got n=%lld ld=%lld)", (long long)n, (long long)ld);
-    if (ld % 128) return fail(h, VFK_ERR_INVALID, "ld must be a multiple of 128 (got %lld)", (long long)ld);
+    if (n < 0) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 0 (got %lld)", (long long)n);
     if (n_obst < 0) return fail(h, VFK_ERR_INVALID, "n_obstacles must be >= 0");
     if (k_cycles < 1) return fail(h, VFK_ERR_INVALID, "k_cycles must be >= 1");
     int rc;
@@ -377,14 +374,14 @@ extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int64_t l
     if (n == 0) return 0;
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (h->precision == 32) return dispatch_n<float>(h, h->cf, b, n, ld, n_obst, k_cycles, st);
-    return dispatch_n<double>(h, h->cd, b, n, ld, n_obst, k_cycles, st);
+    if (h->precision == 32) return dispatch_n<float>(h, h->cf, b, n, n_obst, k_cycles, st);
+    return dispatch_n<double>(h, h->cd, b, n, n_obst, k_cycles, st);
 }
 
 extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst, const void* obst_ext,
-                              void* twist_out, int64_t n, int64_t ld, int n_obst, void* stream) {
+                              void* twist_out, int64_t n, int n_obst, void* stream) {
     if (!h || !pose_in || !goal || !twist_out) return fail(h, VFK_ERR_INVALID, "vfk_field_eval: null argument");
-    if (n < 0 || ld < n || ld % 128) return fail(h, VFK_ERR_INVALID, "need 0 <= n <= ld, ld %% 128 == 0");
+    if (n < 0) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 0");
     if (n_obst > 0 && !obst) return fail(h, VFK_ERR_INVALID, "obst is required when n_obstacles > 0");
     if (n == 0) return 0;
     VFK_CUDA(h, cudaSetDevice(h->device));
@@ -393,21 +390,21 @@ extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goa
     if (h->precision == 32)
         vfk_field_kernel<float><<<grid, kBlock, 0, st>>>(h->cf, (const float*)pose_in, (const float*)goal,
                                                          (const Vec4<float>*)obst, (const Vec2<float>*)obst_ext,
-                                                         (float*)twist_out, n, ld, n_obst);
+                                                         (float*)twist_out, n, n_obst);
     else
         vfk_field_kernel<double><<<grid, kBlock, 0, st>>>(h->cd, (const double*)pose_in, (const double*)goal,
                                                           (const Vec4<double>*)obst, (const Vec2<double>*)obst_ext,
-                                                          (double*)twist_out, n, ld, n_obst);
+                                                          (double*)twist_out, n, n_obst);
     VFK_CUDA(h, cudaGetLastError());
     return 1;
 }
 
 extern "C" int vfk_mix(vfk_handle h, const void* const* cmds, const double* w, int n_ports, int n_channels, void* out,
-                       int32_t* nan_flags, int64_t n, int64_t ld, void* stream) {
+                       int32_t* nan_flags, int64_t n, void* stream) {
     if (!h || !cmds || !w || !out) return fail(h, VFK_ERR_INVALID, "vfk_mix: null argument");
     if (n_ports < 0 || n_ports > 8) return fail(h, VFK_ERR_INVALID, "n_ports must be in 0..8");
     if (n_channels < 1) return fail(h, VFK_ERR_INVALID, "n_channels must be >= 1");
-    if (n < 0 || ld < n) return fail(h, VFK_ERR_INVALID, "need 0 <= n <= ld");
+    if (n < 0) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 0");
     if (n == 0) return 0;
     MixArgs m;
     memset(&m, 0, sizeof m);
@@ -415,30 +412,78 @@ extern "C" int vfk_mix(vfk_handle h, const void* const* cmds, const double* w, i
     for (int p = 0; p < n_ports; ++p) { m.cmds[p] = cmds[p]; m.w[p] = w[p]; }
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned grid = (unsigned)((n + 255) / 256);
+    const int64_t tiles = (n + 31) / 32;
+    int launches = 1;
+    if (nan_flags) { VFK_CUDA(h, cudaMemsetAsync(nan_flags, 0, (size_t)tiles * 32 * 4, st)); }
+    const unsigned grid = (unsigned)((tiles * n_channels * 32 + 255) / 256);
     if (h->precision == 32)
-        vfk_mix_kernel<float><<<grid, 256, 0, st>>>(m, (float*)out, nan_flags, n_channels, n, ld);
+        vfk_mix_kernel<float><<<grid, 256, 0, st>>>(m, (float*)out, nan_flags, n_channels, tiles);
     else
-        vfk_mix_kernel<double><<<grid, 256, 0, st>>>(m, (double*)out, nan_flags, n_channels, n, ld);
+        vfk_mix_kernel<double><<<grid, 256, 0, st>>>(m, (double*)out, nan_flags, n_channels, tiles);
     VFK_CUDA(h, cudaGetLastError());
+    return launches;
+}
+
+// -------------------------------------------------------------------------------- public: layout conversion
+template <typename V>
+static cudaError_t run_pack(const void* dense, void* blocked, int C, int64_t n, bool unpack, cudaStream_t st) {
+    const int64_t tiles = (n + 31) / 32;
+    const unsigned grid = (unsigned)((tiles * C * 32 + 255) / 256);
+    if (unpack)
+        vfk_unpack_kernel<V><<<grid, 256, 0, st>>>((const V*)blocked, (V*)const_cast<void*>(dense), C, n, tiles);
+    else
+        vfk_pack_kernel<V><<<grid, 256, 0, st>>>((const V*)dense, (V*)blocked, C, n, tiles);
+    return cudaGetLastError();
+}
+
+// width = scalars per element: 1 (per-instance components), 2 (obstacle ext) or 4 (obstacles)
+static int pack_dispatch(vfk_ctx* h, const void* dense, void* blocked, int C, int width, int64_t n, bool unpack,
+                         cudaStream_t st) {
+    if (!dense || !blocked) return fail(h, VFK_ERR_INVALID, "vfk_pack/unpack: null buffer");
+    if (C < 1 || n < 0) return fail(h, VFK_ERR_INVALID, "vfk_pack/unpack: bad shape");
+    if (n == 0) return 0;
+    cudaError_t e;
+    const bool f = h->precision == 32;
+    if (width == 1) e = f ? run_pack<float>(dense, blocked, C, n, unpack, st) : run_pack<double>(dense, blocked, C, n, unpack, st);
+    else if (width == 2) e = f ? run_pack<Vec2<float>>(dense, blocked, C, n, unpack, st) : run_pack<Vec2<double>>(dense, blocked, C, n, unpack, st);
+    else if (width == 4) e = f ? run_pack<Vec4<float>>(dense, blocked, C, n, unpack, st) : run_pack<Vec4<double>>(dense, blocked, C, n, unpack, st);
+    else return fail(h, VFK_ERR_INVALID, "vfk_pack/unpack: width must be 1, 2 or 4");
+    if (e != cudaSuccess) return fail(h, VFK_ERR_CUDA, "layout kernel: %s", cudaGetErrorString(e));
     return 1;
 }
 
+extern "C" int vfk_pack(vfk_handle h, const void* dense, void* blocked, int comps, int width, int64_t n, void* stream) {
+    if (!h) return fail(h, VFK_ERR_INVALID, "vfk_pack: null handle");
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    return pack_dispatch(h, dense, blocked, comps, width, n, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vfk_unpack(vfk_handle h, const void* blocked, void* dense, int comps, int width, int64_t n, void* stream) {
+    if (!h) return fail(h, VFK_ERR_INVALID, "vfk_unpack: null handle");
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    return pack_dispatch(h, dense, const_cast<void*>(blocked), comps, width, n, true, static_cast<cudaStream_t>(stream));
+}
+
 // -------------------------------------------------------------------------------- public: host-buffer sessions
+// Host arrays are dense SoA ([comps][n]; obstacles [M][n][4]); the session keeps a dense device staging
+// area and converts to / from the kernels' tile-blocked layout on the GPU (vfk_pack / vfk_unpack kernels).
 struct vfk_session_s {
     vfk_ctx* h;
-    int64_t n, ld;
+    int64_t n, tiles;
     int n_obst, has_ext, N;
     size_t es;                       // element size
     cudaStream_t stream;
     char* dev;                       // one device slab
     size_t dev_bytes;
-    vfk_buffers b;                   // device views into the slab
+    vfk_buffers b;                   // blocked device buffers
+    void* stage_in;                  // dense staging, big enough for the largest upload
+    void* stage_out;                 // dense staging for outputs (max(N, 12) rows)
     bool have_jp_ref, have_ns_in;
     bool en_vf, en_ns, en_jp, en_cmd, en_pose;   // optional per-controller outputs (off by default)
     void *d_jp_ref, *d_ns_in;
-    char* pin;                       // pinned staging: q in (N), qdot/q out (2N) + flags
+    char* pin;                       // pinned host staging: q in (N rows), qdot / q out (2N rows), flags
     size_t pin_bytes;
+    int launches;                    // kernels launched by the last call
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -454,18 +499,21 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     memset(&s->b, 0, sizeof s->b);
     s->h = h;
     s->n = n;
-    s->ld = (int64_t)align_up((size_t)n, 128);
+    s->tiles = (n + 31) / 32;
     s->n_obst = n_obst;
     s->has_ext = with_obst_ext ? 1 : 0;
     s->N = h->chain.n_joints;
     s->es = h->precision == 32 ? 4 : 8;
-    const size_t row = (size_t)s->ld * s->es;       // multiple of 512 bytes
     const int N = s->N;
-    // rows: q N, goal 13, obst M*4 (+ M*2 ext), jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, flags (int32: <= 1 row)
-    const size_t rows = (size_t)N * 9 + 13 + (size_t)n_obst * (4 + (s->has_ext ? 2 : 0)) + 12 + 1;
-    s->dev_bytes = rows * row;
+    const size_t row = align_up((size_t)s->tiles * 32 * s->es, 128);     // one component over all tiles
+    const size_t obst_rows = (size_t)n_obst * (4 + (s->has_ext ? 2 : 0));
+    // blocked: q N, goal 13, obst, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, flags 1
+    const size_t rows = (size_t)N * 9 + 13 + obst_rows + 12 + 1;
+    const size_t stage_in_rows = obst_rows > (size_t)(N > 13 ? N : 13) ? obst_rows : (size_t)(N > 13 ? N : 13);
+    const size_t stage_out_rows = (size_t)(N > 12 ? N : 12);
+    s->dev_bytes = (rows + stage_in_rows + stage_out_rows) * row;
     cudaError_t e = cudaMalloc((void**)&s->dev, s->dev_bytes);
-    if (e != cudaSuccess) { delete s; return fail(h, VFK_ERR_CUDA, "cudaMalloc(%zu): %s", rows * row, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { delete s; return fail(h, VFK_ERR_CUDA, "cudaMalloc(%zu): %s", s->dev_bytes, cudaGetErrorString(e)); }
     e = cudaMemset(s->dev, 0, s->dev_bytes);
     char* p = s->dev;
     auto take = [&](size_t nrows) { char* r = p; p += nrows * row; return (void*)r; };
@@ -483,8 +531,11 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->b.cmd = take(N);
     s->b.pose = take(12);
     s->b.flags = (int32_t*)take(1);
+    s->stage_in = take(stage_in_rows);
+    s->stage_out = take(stage_out_rows);
     s->have_jp_ref = s->have_ns_in = false;
     s->en_vf = s->en_ns = s->en_jp = s->en_cmd = s->en_pose = false;
+    s->launches = 0;
     s->pin_bytes = (size_t)N * 3 * (size_t)n * s->es + (size_t)n * 4;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->pin, s->pin_bytes);
@@ -497,64 +548,52 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     return VFK_OK;
 }
 
-// dense host [rows][n] -> device [rows][ld]
-static cudaError_t upload_rows(vfk_session_s* s, void* dst, const void* src, size_t rows) {
-    return cudaMemcpy2DAsync(dst, (size_t)s->ld * s->es, src, (size_t)s->n * s->es, (size_t)s->n * s->es, rows,
-                             cudaMemcpyHostToDevice, s->stream);
-}
-static cudaError_t download_rows(vfk_session_s* s, void* dst, const void* src, size_t rows, size_t es) {
-    return cudaMemcpy2DAsync(dst, (size_t)s->n * es, src, (size_t)s->ld * es, (size_t)s->n * es, rows,
-                             cudaMemcpyDeviceToHost, s->stream);
+// dense host [rows][n] (x width scalars) -> blocked device array
+static int upload_blocked(vfk_session_s* s, void* dst_blocked, const void* src_host, int comps, int width) {
+    vfk_ctx* h = s->h;
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    const size_t bytes = (size_t)comps * width * (size_t)s->n * s->es;
+    VFK_CUDA(h, cudaMemcpyAsync(s->stage_in, src_host, bytes, cudaMemcpyHostToDevice, s->stream));
+    int rc = pack_dispatch(h, s->stage_in, dst_blocked, comps, width, s->n, false, s->stream);
+    if (rc < 0) return rc;
+    s->launches += rc;
+    VFK_CUDA(h, cudaStreamSynchronize(s->stream));
+    return VFK_OK;
 }
 
 extern "C" int vfk_session_set_goal(vfk_session s, const void* g) {
     if (!s || !g) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_set_goal: null argument");
-    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
-    VFK_CUDA(s->h, upload_rows(s, const_cast<void*>(s->b.goal), g, 13));
-    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
-    return VFK_OK;
+    return upload_blocked(s, const_cast<void*>(s->b.goal), g, 13, 1);
 }
+
 // host obstacles: dense [M][n][4] (x, y, z, radius per instance); ext: dense [M][n][2] (safe, order)
 extern "C" int vfk_session_set_obstacles(vfk_session s, const void* o, const void* ext) {
     if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_obstacles: null session");
     if (s->n_obst == 0) return VFK_OK;
     if (!o) return fail(s->h, VFK_ERR_INVALID, "vfk_session_set_obstacles: null argument");
     if (s->has_ext && !ext) return fail(s->h, VFK_ERR_INVALID, "vfk_session_set_obstacles: session was created with obstacle ext rows");
-    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
-    VFK_CUDA(s->h, cudaMemcpy2DAsync(const_cast<void*>(s->b.obst), (size_t)s->ld * 4 * s->es, o, (size_t)s->n * 4 * s->es,
-                                     (size_t)s->n * 4 * s->es, (size_t)s->n_obst, cudaMemcpyHostToDevice, s->stream));
-    if (s->has_ext)
-        VFK_CUDA(s->h, cudaMemcpy2DAsync(const_cast<void*>(s->b.obst_ext), (size_t)s->ld * 2 * s->es, ext,
-                                         (size_t)s->n * 2 * s->es, (size_t)s->n * 2 * s->es, (size_t)s->n_obst,
-                                         cudaMemcpyHostToDevice, s->stream));
-    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
-    return VFK_OK;
+    int rc = upload_blocked(s, const_cast<void*>(s->b.obst), o, s->n_obst, 4);
+    if (rc == VFK_OK && s->has_ext) rc = upload_blocked(s, const_cast<void*>(s->b.obst_ext), ext, s->n_obst, 2);
+    return rc;
 }
+
 extern "C" int vfk_session_set_q(vfk_session s, const void* q) {
     if (!s || !q) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_set_q: null argument");
-    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
-    VFK_CUDA(s->h, upload_rows(s, s->b.q, q, s->N));
-    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
-    return VFK_OK;
+    return upload_blocked(s, s->b.q, q, s->N, 1);
 }
+
 extern "C" int vfk_session_set_jp_ref(vfk_session s, const void* r) {
     if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_jp_ref: null session");
     s->have_jp_ref = r != nullptr;
     if (!r) return VFK_OK;
-    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
-    VFK_CUDA(s->h, upload_rows(s, s->d_jp_ref, r, s->N));
-    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
-    return VFK_OK;
+    return upload_blocked(s, s->d_jp_ref, r, s->N, 1);
 }
+
 extern "C" int vfk_session_set_ns_input(vfk_session s, const void* x) {
     if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_ns_input: null session");
     s->have_ns_in = x != nullptr;
     if (!x) return VFK_OK;
-    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
-    const size_t rows = s->h->params.ns_mode == VFK_NS_CONTROL ? 4 : (size_t)s->N;
-    VFK_CUDA(s->h, upload_rows(s, s->d_ns_in, x, rows));
-    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
-    return VFK_OK;
+    return upload_blocked(s, s->d_ns_in, x, s->h->params.ns_mode == VFK_NS_CONTROL ? 4 : s->N, 1);
 }
 
 extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, void* qdot_out, void* q_out,
@@ -574,10 +613,13 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
         return at.type == cudaMemoryTypeHost;
     };
+    int launches = 0, rc;
     if (q_in) {
         const void* src = q_in;
         if (!pinned(q_in)) { memcpy(pin_q, q_in, blk); src = pin_q; }
-        VFK_CUDA(h, upload_rows(s, s->b.q, src, s->N));
+        VFK_CUDA(h, cudaMemcpyAsync(s->stage_in, src, blk, cudaMemcpyHostToDevice, s->stream));
+        if ((rc = pack_dispatch(h, s->stage_in, s->b.q, s->N, 1, s->n, false, s->stream)) < 0) return rc;
+        launches += rc;
     }
     vfk_buffers b = s->b;
     b.jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
@@ -588,17 +630,27 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
     if (!s->en_jp) b.qdot_jp = nullptr;
     if (!s->en_cmd) b.cmd = nullptr;
     if (!s->en_pose) b.pose = nullptr;
-    int rc = vfk_step(h, &b, s->n, s->ld, s->n_obst, k_cycles, s->stream);
-    if (rc < 0) return rc;
+    if ((rc = vfk_step(h, &b, s->n, s->n_obst, k_cycles, s->stream)) < 0) return rc;
+    launches += rc;
     const bool d_qd = qdot_out && pinned(qdot_out), d_qo = q_out && pinned(q_out), d_fl = flags_out && pinned(flags_out);
-    if (qdot_out) VFK_CUDA(h, download_rows(s, d_qd ? qdot_out : (void*)pin_qd, s->b.qdot, s->N, s->es));
-    if (q_out) VFK_CUDA(h, download_rows(s, d_qo ? q_out : (void*)pin_qo, s->b.q, s->N, s->es));
-    if (flags_out) VFK_CUDA(h, download_rows(s, d_fl ? (void*)flags_out : (void*)pin_fl, s->b.flags, 1, 4));
+    if (qdot_out) {
+        if ((rc = pack_dispatch(h, s->stage_out, s->b.qdot, s->N, 1, s->n, true, s->stream)) < 0) return rc;
+        launches += rc;
+        VFK_CUDA(h, cudaMemcpyAsync(d_qd ? qdot_out : (void*)pin_qd, s->stage_out, blk, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (q_out) {
+        if ((rc = pack_dispatch(h, s->stage_in, s->b.q, s->N, 1, s->n, true, s->stream)) < 0) return rc;
+        launches += rc;
+        VFK_CUDA(h, cudaMemcpyAsync(d_qo ? q_out : (void*)pin_qo, s->stage_in, blk, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (flags_out)      // one component: blocked == dense
+        VFK_CUDA(h, cudaMemcpyAsync(d_fl ? (void*)flags_out : (void*)pin_fl, s->b.flags, (size_t)s->n * 4,
+                                    cudaMemcpyDeviceToHost, s->stream));
     VFK_CUDA(h, cudaStreamSynchronize(s->stream));
     if (qdot_out && !d_qd) memcpy(qdot_out, pin_qd, blk);
     if (q_out && !d_qo) memcpy(q_out, pin_qo, blk);
     if (flags_out && !d_fl) memcpy(flags_out, pin_fl, (size_t)s->n * 4);
-    return rc;
+    return launches;
 }
 
 extern "C" int vfk_session_enable(vfk_session s, const char* what, int on) {
@@ -617,7 +669,7 @@ extern "C" int vfk_session_enable(vfk_session s, const char* what, int on) {
 extern "C" int vfk_session_read(vfk_session s, const char* what, void* out) {
     if (!s || !what || !out) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_read: null argument");
     const void* src = nullptr;
-    size_t rows = s->N;
+    int rows = s->N;
     if (!strcmp(what, "qdot_vf")) src = s->b.qdot_vf;
     else if (!strcmp(what, "qdot_ns")) src = s->b.qdot_ns;
     else if (!strcmp(what, "qdot_jp")) src = s->b.qdot_jp;
@@ -627,18 +679,20 @@ extern "C" int vfk_session_read(vfk_session s, const char* what, void* out) {
     else if (!strcmp(what, "lastvec")) src = s->b.ns_lastvec;
     else if (!strcmp(what, "pose")) { src = s->b.pose; rows = 12; }
     else return fail(s->h, VFK_ERR_INVALID, "vfk_session_read: unknown field '%s'", what);
-    VFK_CUDA(s->h, cudaSetDevice(s->h->device));
-    VFK_CUDA(s->h, download_rows(s, out, src, rows, s->es));
-    VFK_CUDA(s->h, cudaStreamSynchronize(s->stream));
+    vfk_ctx* h = s->h;
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    int rc = pack_dispatch(h, s->stage_out, const_cast<void*>(src), rows, 1, s->n, true, s->stream);
+    if (rc < 0) return rc;
+    VFK_CUDA(h, cudaMemcpyAsync(out, s->stage_out, (size_t)rows * s->n * s->es, cudaMemcpyDeviceToHost, s->stream));
+    VFK_CUDA(h, cudaStreamSynchronize(s->stream));
     return VFK_OK;
 }
 
-extern "C" int vfk_session_buffers(vfk_session s, vfk_buffers* out, int64_t* ld) {
+extern "C" int vfk_session_buffers(vfk_session s, vfk_buffers* out) {
     if (!s || !out) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_buffers: null argument");
     *out = s->b;
     out->jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
     out->ns_in = s->have_ns_in ? s->d_ns_in : nullptr;
-    if (ld) *ld = s->ld;
     return VFK_OK;
 }
 

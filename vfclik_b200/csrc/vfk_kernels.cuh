@@ -2,12 +2,13 @@
 //
 // One thread = one manipulator instance; a warp is a persistent worker over tiles of 32
 // consecutive instances.  All per-instance state (q, frame, the 6xN Jacobian, the 6x6
-// normal matrix) lives in registers across the K fused cycles.  Per-instance global
-// arrays are SoA [component][ld] (a warp's access to one component is one contiguous
-// 128-byte / 256-byte line); the obstacle list is [M][ld][4] = one {x,y,z,radius}
-// vector per (obstacle, instance), so a tile's obstacles are M contiguous rows of 32
-// vectors.  q, goal and obstacle rows are moved global -> shared with cp.async.bulk
-// (TMA) into per-warp buffers guarded by mbarriers, one tile AHEAD of the arithmetic,
+// normal matrix) lives in registers across the K fused cycles.  Global arrays are
+// tile-blocked SoA (include/vfk.h): element (component c, instance i) of a C-component
+// array lives at ((i/32)*C + c)*32 + i%32, obstacles at (((i/32)*M + m)*32 + i%32) as
+// one {x,y,z,radius} vector, so everything a warp needs for a tile -- q (N rows),
+// goal (13 rows), every chunk of 8 obstacles -- is ONE contiguous burst.  Those bursts
+// are moved global -> shared with cp.async.bulk (TMA), one copy each, into per-warp
+// buffers guarded by mbarriers, one tile AHEAD of the arithmetic,
 // so HBM latency is hidden behind the previous tile's FK / Cholesky work; the repulsor
 // loop reads one conflict-free LDS.128 per obstacle.  Robot constants (chain, limits,
 // gains) arrive as a __grid_constant__ kernel parameter (constant bank), indexed at
@@ -65,8 +66,8 @@ template <typename T>
 struct KArgs {
     T* q;
     const T* goal;
-    const Vec4<T>* obst;       // [M][ld]
-    const Vec2<T>* obst_ext;   // [M][ld] {safe, order} or null
+    const Vec4<T>* obst;       // blocked [tile][M][32]
+    const Vec2<T>* obst_ext;   // blocked [tile][M][32] {safe, order} or null
     const T* jp_ref;
     const T* ns_in;
     T* ns_lastvec;
@@ -80,7 +81,6 @@ struct KArgs {
     T* pose;
     int32_t* flags;
     int64_t n;
-    int64_t ld;
     int32_t n_obst;
     int32_t n_chunks;          // ceil(n_obst / kChunk)
     int32_t n_stages;          // shared-memory stages (<= kMaxStages); >= n_chunks means resident
@@ -264,33 +264,32 @@ struct WarpStage {
     __host__ __device__ static constexpr uint32_t warp_bytes(int n_stages) { return n_stages * kStage + 2 * kQg; }
 };
 
+// One bulk copy per obstacle chunk (and one for its ext rows): the chunk's kChunk x 32 vectors are contiguous.
+// Called by all lanes after a __syncwarp(); lane 0 issues.
 template <typename T, int N, bool EXT>
-__device__ __forceinline__ void issue_obst(const KArgs<T>& a, int64_t tile0, int chunk, int stage, unsigned char* region,
+__device__ __forceinline__ void issue_obst(const KArgs<T>& a, int64_t tile, int chunk, int stage, unsigned char* region,
                                            uint64_t* bars, int lane) {
     using WS = WarpStage<T, N, EXT>;
-    const int m0 = chunk * kChunk;
-    const int cnt = min(kChunk, a.n_obst - m0);
-    unsigned char* dst = region + (size_t)stage * WS::kStage;
-    if (lane == 0) mbar_arrive_expect_tx(&bars[stage], (uint32_t)cnt * (WS::kRow + WS::kRowExt));
-    __syncwarp();
-    if (lane < cnt) {
-        bulk_g2s(dst + lane * WS::kRow, a.obst + (int64_t)(m0 + lane) * a.ld + tile0, WS::kRow, &bars[stage]);
-        if (EXT)
-            bulk_g2s(dst + kChunk * WS::kRow + lane * WS::kRowExt, a.obst_ext + (int64_t)(m0 + lane) * a.ld + tile0,
-                     WS::kRowExt, &bars[stage]);
+    if (lane == 0) {
+        const int m0 = chunk * kChunk;
+        const uint32_t cnt = (uint32_t)min(kChunk, a.n_obst - m0);
+        unsigned char* dst = region + (size_t)stage * WS::kStage;
+        mbar_arrive_expect_tx(&bars[stage], cnt * (WS::kRow + WS::kRowExt));
+        bulk_g2s(dst, a.obst + (tile * a.n_obst + m0) * 32, cnt * WS::kRow, &bars[stage]);
+        if (EXT) bulk_g2s(dst + kChunk * WS::kRow, a.obst_ext + (tile * a.n_obst + m0) * 32, cnt * WS::kRowExt, &bars[stage]);
     }
 }
 
+// q tile (N rows) + goal tile (13 rows): two bulk copies into q/goal buffer `buf`.
 template <typename T, int N, bool EXT>
-__device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile0, int buf, unsigned char* region, uint64_t* bars,
+__device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile, int buf, unsigned char* region, uint64_t* bars,
                                          int lane) {
     using WS = WarpStage<T, N, EXT>;
-    unsigned char* dst = region + (size_t)a.n_stages * WS::kStage + (size_t)buf * WS::kQg;
-    if (lane == 0) mbar_arrive_expect_tx(&bars[kMaxStages + buf], WS::kQg);
-    __syncwarp();
-    if (lane < (int)WS::kQgRows) {
-        const T* src = lane < N ? a.q + (int64_t)lane * a.ld + tile0 : a.goal + (int64_t)(lane - N) * a.ld + tile0;
-        bulk_g2s(dst + lane * WS::kQgRow, src, WS::kQgRow, &bars[kMaxStages + buf]);
+    if (lane == 0) {
+        unsigned char* dst = region + (size_t)a.n_stages * WS::kStage + (size_t)buf * WS::kQg;
+        mbar_arrive_expect_tx(&bars[kMaxStages + buf], WS::kQg);
+        bulk_g2s(dst, a.q + tile * (N * 32), N * WS::kQgRow, &bars[kMaxStages + buf]);
+        bulk_g2s(dst + N * WS::kQgRow, a.goal + tile * (13 * 32), 13 * WS::kQgRow, &bars[kMaxStages + buf]);
     }
 }
 
@@ -304,14 +303,16 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     const int warp = threadIdx.x >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * WS::kBars;
     unsigned char* region = smem + kSmemHeader + (size_t)warp * WS::warp_bytes(a.n_stages);
-    const int64_t ld = a.ld;
-
     const int64_t n_tiles = (a.n + 31) >> 5;
     const int64_t stride = (int64_t)gridDim.x * (kBlock / 32);
     int64_t tile = (int64_t)blockIdx.x * (kBlock / 32) + warp;
     if (tile >= n_tiles) return;
 
-    // ring bookkeeping: U chunk-uses per tile; S ring slots (resident: one slot per chunk, loaded once per tile)
+    // Ring bookkeeping.  A "use" is one consumption of one chunk; a tile has U uses and the ring S slots.
+    // resident: S = n_chunks, every chunk is loaded once per tile and reused by all K cycles (U = n_chunks);
+    // streaming: S < n_chunks, chunks are re-requested every cycle (U = K * n_chunks).
+    // The producer cursor (p_*) is always exactly S uses ahead of the consumer, so a refill targets the slot
+    // the consumer has just finished with.  Everything advances by increments (no integer division).
     const bool resident = a.n_chunks <= a.n_stages;
     const int S = resident ? a.n_chunks : a.n_stages;
     const int U = resident ? a.n_chunks : a.n_chunks * a.k_cycles;
@@ -321,15 +322,22 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         mbar_fence_init();
     }
     __syncwarp();
-    issue_qg<T, N, EXT>(a, tile << 5, 0, region, bars, lane);
-    for (int u = 0; u < S; ++u) issue_obst<T, N, EXT>(a, tile << 5, u % a.n_chunks, u, region, bars, lane);
+    issue_qg<T, N, EXT>(a, tile, 0, region, bars, lane);
+    int64_t p_tile = tile;
+    int p_u = 0, p_chunk = 0;
+    for (int u = 0; u < S; ++u) {
+        issue_obst<T, N, EXT>(a, p_tile, p_chunk, u, region, bars, lane);
+        if (++p_chunk == a.n_chunks) p_chunk = 0;
+        if (++p_u == U) { p_u = 0; p_tile += stride; }
+    }
+    int c_stage = 0;
+    uint32_t c_phase = 0;
 
-    int64_t seq = 0;                                        // chunk uses consumed so far by this warp
     for (int it = 0; tile < n_tiles; tile += stride, ++it) {
-        const int64_t tile0 = tile << 5;
-        const bool active = tile0 + lane < a.n;
-        const int64_t i = tile0 + lane;                     // padding lanes compute on padding data, never store
-        if (tile + stride < n_tiles) issue_qg<T, N, EXT>(a, (tile + stride) << 5, (it + 1) & 1, region, bars, lane);
+        const bool active = (tile << 5) + lane < a.n;           // padding lanes compute on padding data, never store
+        const int64_t tN = tile * (N * 32) + lane;              // this lane's slot in an N-component blocked array
+        __syncwarp();
+        if (tile + stride < n_tiles) issue_qg<T, N, EXT>(a, tile + stride, (it + 1) & 1, region, bars, lane);
         mbar_wait(&bars[kMaxStages + (it & 1)], (uint32_t)(it >> 1) & 1u);
         const T* qg = reinterpret_cast<const T*>(region + (size_t)a.n_stages * WS::kStage + (size_t)(it & 1) * WS::kQg) + lane;
 
@@ -343,7 +351,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     T lastv[N];
     if (c.ns_mode == 2) {
 #pragma unroll
-        for (int j = 0; j < N; ++j) lastv[j] = a.ns_lastvec[j * ld + i];
+        for (int j = 0; j < N; ++j) lastv[j] = a.ns_lastvec[tN + j * 32];
     }
 
     for (int cyc = 0; cyc < a.k_cycles; ++cyc) {
@@ -377,9 +385,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)};
             attract<T>(c, g, Rt, pt, V, S0, w);
             for (int ch = 0; ch < a.n_chunks; ++ch) {
-                const int64_t use = resident ? (int64_t)it * U + ch : seq;
-                const int stage = (int)(use % S);
-                mbar_wait(&bars[stage], (uint32_t)(use / S) & 1u);
+                const int stage = resident ? ch : c_stage;
+                mbar_wait(&bars[stage], resident ? (uint32_t)(it & 1) : c_phase);
                 const unsigned char* sb = region + (size_t)stage * WS::kStage;
                 const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + lane;
                 const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * WS::kRow) + lane;
@@ -402,12 +409,12 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 }
                 // this slot is free again: request the chunk that will occupy it S uses from now
                 if (!resident || last) {
-                    const int64_t nxt = use + S;
-                    const int64_t nt = tile + (nxt / U - it) * stride;
                     __syncwarp();
-                    if (nt < n_tiles) issue_obst<T, N, EXT>(a, nt << 5, (int)((nxt % U) % a.n_chunks), stage, region, bars, lane);
+                    if (p_tile < n_tiles) issue_obst<T, N, EXT>(a, p_tile, p_chunk, stage, region, bars, lane);
+                    if (++p_chunk == a.n_chunks) p_chunk = 0;
+                    if (++p_u == U) { p_u = 0; p_tile += stride; }
                 }
-                ++seq;
+                if (!resident && ++c_stage == S) { c_stage = 0; c_phase ^= 1u; }
             }
             V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
             T v[3];
@@ -493,7 +500,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             if (c.ns_mode == 1) {
                 if (a.ns_in) {
 #pragma unroll
-                    for (int j = 0; j < N; ++j) x[j] = __ldg(a.ns_in + j * ld + i);
+                    for (int j = 0; j < N; ++j) x[j] = __ldg(a.ns_in + tN + j * 32);
                 } else {
 #pragma unroll
                     for (int j = 0; j < N; ++j) x[j] = c.ns_q0_scale[j] * (q[j] - c.ns_mid[j]);
@@ -547,7 +554,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 T sc = Prec<T>::rsqrt_pos(nn);
                 const bool neg = (l2 > T(0)) ? (dotl < T(0)) : (vmax < T(0));
                 if (neg) sc = -sc;
-                T c0 = a.ns_in ? __ldg(a.ns_in + i) : c.ns_control[0];
+                T c0 = a.ns_in ? __ldg(a.ns_in + tile * (4 * 32) + lane) : c.ns_control[0];
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     lastv[j] = raw[j] * sc;
@@ -574,7 +581,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             bool all_reached = true;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                T ref = a.jp_ref ? __ldg(a.jp_ref + j * ld + i) : c.jp_ref[j];
+                T ref = a.jp_ref ? __ldg(a.jp_ref + tN + j * 32) : c.jp_ref[j];
                 ref = ref < c.q_lo[j] ? c.q_lo[j] : (ref > c.q_hi[j] ? c.q_hi[j] : ref);
                 const T err = ref - q[j];
                 qd_jp[j] = err * c.jp_kp;
@@ -600,7 +607,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             if (a.ext_cmd[e]) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const T x = __ldg(a.ext_cmd[e] + j * ld + i);
+                    const T x = __ldg(a.ext_cmd[e] + tN + j * 32);
                     nan = nan || (x != x);
                     mix[j] = fma(x, c.mixer_w[3 + e], mix[j]);
                 }
@@ -615,35 +622,35 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         if (last && active) {
             if (a.qdot_vf) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) a.qdot_vf[j * ld + i] = qd_vf[j];
+                for (int j = 0; j < N; ++j) a.qdot_vf[tN + j * 32] = qd_vf[j];
             }
             if (a.qdot_ns) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) a.qdot_ns[j * ld + i] = qd_ns[j];
+                for (int j = 0; j < N; ++j) a.qdot_ns[tN + j * 32] = qd_ns[j];
             }
             if (a.qdot_jp) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) a.qdot_jp[j * ld + i] = qd_jp[j];
+                for (int j = 0; j < N; ++j) a.qdot_jp[tN + j * 32] = qd_jp[j];
             }
             if (a.qdot) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) a.qdot[j * ld + i] = mix[j] * ratio;
+                for (int j = 0; j < N; ++j) a.qdot[tN + j * 32] = mix[j] * ratio;
             }
             if (a.cmd) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const T qd = mix[j] * ratio;
-                    const T qc = a.q_cmded ? __ldg(a.q_cmded + j * ld + i) : q[j];
-                    a.cmd[j * ld + i] = c.direct_control ? qd : (-qc + q[j] + qd);
+                    const T qc = a.q_cmded ? __ldg(a.q_cmded + tN + j * 32) : q[j];
+                    a.cmd[tN + j * 32] = c.direct_control ? qd : (-qc + q[j] + qd);
                 }
             }
             if (a.pose) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) a.pose[k * ld + i] = Rt[k];
+                for (int k = 0; k < 9; ++k) a.pose[tile * (12 * 32) + k * 32 + lane] = Rt[k];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) a.pose[(9 + k) * ld + i] = pt[k];
+                for (int k = 0; k < 3; ++k) a.pose[tile * (12 * 32) + (9 + k) * 32 + lane] = pt[k];
             }
-            if (a.flags) a.flags[i] = flags;
+            if (a.flags) a.flags[(tile << 5) + lane] = flags;
         }
         // 10. plant
         if (c.integrate) {
@@ -654,11 +661,11 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     if (active) {
         if (c.integrate) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) a.q[j * ld + i] = q[j];
+            for (int j = 0; j < N; ++j) a.q[tN + j * 32] = q[j];
         }
         if (c.ns_mode == 2) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) a.ns_lastvec[j * ld + i] = lastv[j];
+            for (int j = 0; j < N; ++j) a.ns_lastvec[tN + j * 32] = lastv[j];
         }
     }
     }   // tile loop
@@ -670,28 +677,30 @@ template <typename T>
 __global__ void __launch_bounds__(kBlock)
 vfk_field_kernel(const __grid_constant__ KConst<T> c, const T* __restrict__ pose, const T* __restrict__ goal,
                  const Vec4<T>* __restrict__ obst, const Vec2<T>* __restrict__ obst_ext, T* __restrict__ twist,
-                 int64_t n, int64_t ld, int n_obst) {
+                 int64_t n, int n_obst) {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
+    const int64_t tile = i >> 5;
+    const int lane = (int)(i & 31);
     T Rt[9], pt[3], g[13];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Rt[k] = pose[k * ld + i];
+    for (int k = 0; k < 9; ++k) Rt[k] = pose[(tile * 12 + k) * 32 + lane];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) pt[k] = pose[(9 + k) * ld + i];
+    for (int k = 0; k < 3; ++k) pt[k] = pose[(tile * 12 + 9 + k) * 32 + lane];
 #pragma unroll
-    for (int k = 0; k < 13; ++k) g[k] = goal[k * ld + i];
+    for (int k = 0; k < 13; ++k) g[k] = goal[(tile * 13 + k) * 32 + lane];
     T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)}, v[3];
     attract<T>(c, g, Rt, pt, V, S0, w);
     for (int m = 0; m < n_obst; ++m) {
-        const Vec4<T> o = obst[(int64_t)m * ld + i];
+        const Vec4<T> o = obst[(tile * n_obst + m) * 32 + lane];
         T safe_inv = c.obst_safe_inv, order = c.obst_order;
-        if (obst_ext) { const Vec2<T> e = obst_ext[(int64_t)m * ld + i]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+        if (obst_ext) { const Vec2<T> e = obst_ext[(tile * n_obst + m) * 32 + lane]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
         repel<T>(o, safe_inv, order, pt, acc);
     }
     V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
     saturate<T>(c, V, S0, v);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { twist[k * ld + i] = v[k]; twist[(3 + k) * ld + i] = w[k]; }
+    for (int k = 0; k < 3; ++k) { twist[(tile * 6 + k) * 32 + lane] = v[k]; twist[(tile * 6 + 3 + k) * 32 + lane] = w[k]; }
 }
 
 struct MixArgs {
@@ -700,27 +709,59 @@ struct MixArgs {
     int n_ports;
 };
 
-// out[c][i] = sum_p w_p * cmds[p][c][i]  (src/command_mixer.py:78-82), NaN report (:71-75).
+// out(c, i) = sum_p w_p * cmds[p](c, i)  (src/command_mixer.py:78-82), NaN report (:71-75).  All arrays
+// share one blocked layout, so the sum is element-wise over the flat buffers (n_channels * 32 * tiles elements).
 template <typename T>
 __global__ void __launch_bounds__(256)
 vfk_mix_kernel(const __grid_constant__ MixArgs m, T* __restrict__ out, int32_t* __restrict__ nan_flags,
-               int n_channels, int64_t n, int64_t ld) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
+               int n_channels, int64_t n_tiles) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n_tiles * n_channels * 32) return;
+    T acc = T(0);
     bool nan = false;
-    for (int ch = 0; ch < n_channels; ++ch) {
-        T acc = T(0);
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            if (p < m.n_ports && m.cmds[p]) {
-                const T x = static_cast<const T*>(m.cmds[p])[(int64_t)ch * ld + i];
-                nan = nan || (x != x);
-                acc = fma(x, (T)m.w[p], acc);
-            }
+    for (int p = 0; p < 8; ++p) {
+        if (p < m.n_ports && m.cmds[p]) {
+            const T x = static_cast<const T*>(m.cmds[p])[e];
+            nan = nan || (x != x);
+            acc = fma(x, (T)m.w[p], acc);
         }
-        out[(int64_t)ch * ld + i] = acc;
     }
-    if (nan_flags) nan_flags[i] = nan ? 4 : 0;
+    out[e] = acc;
+    if (nan_flags && nan) {
+        const int64_t tile = e / (n_channels * 32);
+        atomicOr(&nan_flags[(tile << 5) + (e & 31)], 4);
+    }
+}
+
+// ------------------------------------------------------------------------------ layout conversion
+// dense SoA [C][n] (element size E bytes: scalar, Vec2 or Vec4 of T)  <->  tile-blocked [tile][C][32].
+template <typename V>
+__global__ void __launch_bounds__(256)
+vfk_pack_kernel(const V* __restrict__ dense, V* __restrict__ blocked, int C, int64_t n, int64_t n_tiles) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;          // index into the blocked array
+    if (e >= n_tiles * C * 32) return;
+    const int lane = (int)(e & 31);
+    const int64_t tc = e >> 5;
+    const int64_t tile = tc / C;
+    const int cidx = (int)(tc - tile * C);
+    const int64_t i = (tile << 5) + lane;
+    V zero;
+    memset(&zero, 0, sizeof zero);
+    blocked[e] = i < n ? dense[(int64_t)cidx * n + i] : zero;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+vfk_unpack_kernel(const V* __restrict__ blocked, V* __restrict__ dense, int C, int64_t n, int64_t n_tiles) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n_tiles * C * 32) return;
+    const int lane = (int)(e & 31);
+    const int64_t tc = e >> 5;
+    const int64_t tile = tc / C;
+    const int cidx = (int)(tc - tile * C);
+    const int64_t i = (tile << 5) + lane;
+    if (i < n) dense[(int64_t)cidx * n + i] = blocked[e];
 }
 
 }  // namespace vfk

@@ -1,7 +1,8 @@
 """Batch engine: Python face of the fused control-cycle kernel (``libvfk.so``).
 
 ``Engine`` wraps a ``vfk_handle`` (chain + per-robot constants); ``Engine.step`` runs K
-fused cycles on device buffers (torch CUDA tensors, SoA ``[comps, ld]``);
+fused cycles on device buffers (torch CUDA tensors in the tile-blocked layout of
+``include/vfk.h``; ``DeviceBatch`` allocates and converts them);
 ``Engine.session`` opens a host-buffer session (numpy in / numpy out) whose scene
 (goal, obstacles) stays resident on the GPU between cycles -- the call the
 reference-facing host modules (``vf``, ``nullspace``, ``joint_p_controller``, ``bridge``)
@@ -88,7 +89,7 @@ class Params:
         return p
 
 
-def round_up(n: int, m: int = 128) -> int:
+def round_up(n: int, m: int = 32) -> int:
     return (int(n) + m - 1) // m * m
 
 
@@ -161,49 +162,61 @@ class Engine:
         return torch.float32 if self.precision == 32 else torch.float64
 
     # -- device-buffer path
-    def step(self, bufs: Dict[str, object], n_instances: int, ld: int, n_obstacles: int,
-             k_cycles: int = 1, stream: Optional[int] = None, ext_cmd=(None, None, None)) -> int:
-        """K fused cycles on device buffers; returns the number of kernels launched."""
+    def _stream(self, stream):
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        return C.c_void_p(stream)
+
+    def step(self, bufs: Dict[str, object], n_instances: int, n_obstacles: int, k_cycles: int = 1,
+             stream: Optional[int] = None, ext_cmd=(None, None, None)) -> int:
+        """K fused cycles on blocked device buffers; returns the number of kernels launched."""
         b = BuffersC()
         for f in _BUF_FIELDS:
             setattr(b, f, _dev_ptr(bufs.get(f)))
         for e in range(3):
             b.ext_cmd[e] = _dev_ptr(ext_cmd[e])
-        if stream is None:
-            import torch
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-        rc = self._check(self._lib.vfk_step(self._h, C.byref(b), int(n_instances), int(ld), int(n_obstacles),
-                                            int(k_cycles), C.c_void_p(stream)))
+        rc = self._check(self._lib.vfk_step(self._h, C.byref(b), int(n_instances), int(n_obstacles), int(k_cycles),
+                                            self._stream(stream)))
         self.launches += rc
         return rc
 
-    def field_eval(self, pose, goal, obst, twist_out, n_instances, ld, n_obstacles, obst_ext=None, stream=None) -> int:
-        if stream is None:
-            import torch
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+    def field_eval(self, pose, goal, obst, twist_out, n_instances, n_obstacles, obst_ext=None, stream=None) -> int:
         rc = self._check(self._lib.vfk_field_eval(self._h, _dev_ptr(pose), _dev_ptr(goal), _dev_ptr(obst),
-                                                  _dev_ptr(obst_ext), _dev_ptr(twist_out), int(n_instances), int(ld),
-                                                  int(n_obstacles), C.c_void_p(stream)))
+                                                  _dev_ptr(obst_ext), _dev_ptr(twist_out), int(n_instances),
+                                                  int(n_obstacles), self._stream(stream)))
         self.launches += rc
         return rc
 
-    def mix(self, cmds, weights, out, n_channels, n_instances, ld, nan_flags=None, stream=None) -> int:
-        if stream is None:
-            import torch
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+    def mix(self, cmds, weights, out, n_channels, n_instances, nan_flags=None, stream=None) -> int:
         n_ports = len(cmds)
         arr = (C.c_void_p * n_ports)(*[_dev_ptr(c) for c in cmds])
         w = (C.c_double * n_ports)(*[float(x) for x in weights])
         rc = self._check(self._lib.vfk_mix(self._h, arr, w, n_ports, int(n_channels), _dev_ptr(out),
-                                           _dev_ptr(nan_flags), int(n_instances), int(ld), C.c_void_p(stream)))
+                                           _dev_ptr(nan_flags), int(n_instances), self._stream(stream)))
         self.launches += rc
         return rc
 
-    def alloc(self, comps: int, ld: int, dtype=None):
-        """Zeroed device tensor ``[comps, ld]`` (torch's allocator returns >= 256-byte aligned blocks;
-        with ld a multiple of 128 every row is 128-byte aligned)."""
+    def pack(self, dense, blocked, comps: int, width: int, n_instances: int, stream=None) -> int:
+        """dense SoA [comps][n] (x width scalars) -> tile-blocked, on the device."""
+        rc = self._check(self._lib.vfk_pack(self._h, _dev_ptr(dense), _dev_ptr(blocked), int(comps), int(width),
+                                            int(n_instances), self._stream(stream)))
+        self.launches += rc
+        return rc
+
+    def unpack(self, blocked, dense, comps: int, width: int, n_instances: int, stream=None) -> int:
+        rc = self._check(self._lib.vfk_unpack(self._h, _dev_ptr(blocked), _dev_ptr(dense), int(comps), int(width),
+                                              int(n_instances), self._stream(stream)))
+        self.launches += rc
+        return rc
+
+    def alloc(self, comps: int, n_instances: int, width: int = 1, dtype=None):
+        """Zeroed blocked device tensor ``[tiles, comps, 32(, width)]`` for ``n_instances`` instances
+        (torch's caching allocator returns >= 512-byte aligned blocks)."""
         import torch
-        t = torch.zeros((comps, ld), dtype=dtype or self.torch_dtype, device="cuda:%d" % self.device)
+        tiles = round_up(n_instances, 32) // 32
+        shape = (tiles, comps, 32) if width == 1 else (tiles, comps, 32, width)
+        t = torch.zeros(shape, dtype=dtype or self.torch_dtype, device="cuda:%d" % self.device)
         assert t.data_ptr() % 128 == 0
         return t
 
@@ -313,65 +326,87 @@ class Session:
 
 
 class DeviceBatch:
-    """Device-resident buffers for one batch (torch CUDA tensors, layouts of include/vfk.h).
+    """Device-resident buffers for one batch: torch CUDA tensors in the tile-blocked layout.
 
-    Convenience for callers that keep everything on the GPU (the benchmark's kernel-only
-    arm, the multi-GPU driver): ``upload`` copies dense numpy arrays in (``[comps, n]``;
-    obstacles ``[M, n, 4]``, ext ``[M, n, 2]``), ``download`` copies them back; ``bufs`` is what
-    ``Engine.step`` takes.
+    Convenience for callers that keep everything on the GPU (the benchmark's kernel-only arm,
+    the multi-GPU driver).  ``upload`` takes dense numpy arrays (``[comps, n]``; obstacles
+    ``[M, n, 4]``, ext ``[M, n, 2]``), moves them to the device and converts them with the
+    library's pack kernel; ``download`` converts back.  ``bufs`` is what ``Engine.step`` takes.
     """
 
-    _ROWS = {"goal": 13, "pose": 12, "flags": 1}
+    _ROWS = {"goal": 13, "pose": 12, "flags": 1, "twist": 6}
 
     def __init__(self, engine: Engine, n_instances: int, n_obstacles: int, obst_ext: bool = False,
                  outputs=("qdot",), inputs=()):
         self.e, self.n, self.m = engine, int(n_instances), int(n_obstacles)
-        self.ld = round_up(self.n, 128)
-        N = engine.n_joints
         self.t: Dict[str, object] = {}
-        self.t["q"] = engine.alloc(N, self.ld)
-        self.t["goal"] = engine.alloc(13, self.ld)
+        self.t["q"] = engine.alloc(engine.n_joints, self.n)
+        self.t["goal"] = engine.alloc(13, self.n)
         if self.m:
-            self.t["obst"] = engine.alloc(self.m, self.ld * 4).view(self.m, self.ld, 4)
+            self.t["obst"] = engine.alloc(self.m, self.n, width=4)
             if obst_ext:
-                self.t["obst_ext"] = engine.alloc(self.m, self.ld * 2).view(self.m, self.ld, 2)
+                self.t["obst_ext"] = engine.alloc(self.m, self.n, width=2)
         for name in tuple(outputs) + tuple(inputs):
             self._ensure(name)
         self.ext_cmd = [None, None, None]
+
+    def _comps(self, name):
+        if name == "ns_in":
+            return 4 if self.e.params.ns_mode == NS_CONTROL else self.e.n_joints
+        return self._ROWS.get(name, self.e.n_joints)
 
     def _ensure(self, name):
         if name in self.t:
             return self.t[name]
         import torch
         if name == "flags":
-            self.t[name] = self.e.alloc(1, self.ld, dtype=torch.int32)
+            self.t[name] = self.e.alloc(1, self.n, dtype=torch.int32)
         elif name in ("obst", "obst_ext"):
             raise KeyError("%s was not allocated (n_obstacles = 0 or obst_ext=False)" % name)
         else:
-            self.t[name] = self.e.alloc(self._ROWS.get(name, self.e.n_joints), self.ld)
+            self.t[name] = self.e.alloc(self._comps(name), self.n)
         return self.t[name]
 
-    def upload(self, name: str, arr: np.ndarray):
+    def to_blocked(self, arr: np.ndarray, out=None, width: int = 1):
+        """Dense numpy ``[comps, n]`` (or ``[comps, n, width]``) -> new (or given) blocked device tensor."""
         import torch
+        a = np.ascontiguousarray(arr, dtype=self.e.np_dtype)
+        comps = a.shape[0]
+        if a.shape[1] != self.n or (width > 1 and a.shape[2:] != (width,)):
+            raise ValueError("expected [%d, %d%s], got %r" % (comps, self.n, ", %d" % width if width > 1 else "", a.shape))
+        dense = torch.from_numpy(a).to("cuda:%d" % self.e.device)
+        if out is None:
+            out = self.e.alloc(comps, self.n, width=width)
+        self.e.pack(dense, out, comps, width, self.n)
+        torch.cuda.current_stream(self.e.device).synchronize()       # `dense` may be freed after return
+        return out
+
+    def upload(self, name: str, arr: np.ndarray):
         t = self._ensure(name)
-        if name in ("obst", "obst_ext"):
-            a = np.ascontiguousarray(arr)
-            if a.shape != (self.m, self.n, t.shape[2]):
-                raise ValueError("%s must be [%d, %d, %d], got %r" % (name, self.m, self.n, t.shape[2], a.shape))
-            t[:, :self.n, :].copy_(torch.from_numpy(a).to(t.dtype))
-            return t
-        a = np.ascontiguousarray(arr).reshape(-1, self.n)
-        if a.shape[0] > t.shape[0]:
-            raise ValueError("%s: %d rows do not fit %d" % (name, a.shape[0], t.shape[0]))
-        t[:a.shape[0], :self.n].copy_(torch.from_numpy(a).to(t.dtype))
-        return t
+        width = {"obst": 4, "obst_ext": 2}.get(name, 1)
+        a = np.asarray(arr)
+        if width == 1:
+            a = a.reshape(-1, self.n)
+        if a.shape[0] != t.shape[1]:
+            raise ValueError("%s: %d components given, buffer has %d" % (name, a.shape[0], t.shape[1]))
+        return self.to_blocked(a, out=t, width=width)
 
     def download(self, name: str) -> np.ndarray:
-        return self.t[name][:, :self.n].cpu().numpy()
+        """Blocked device tensor -> dense numpy ``[comps, n]`` (``[M, n, width]`` for obstacles)."""
+        import torch
+        t = self.t[name]
+        if t.dtype == torch.int32:                                   # flags: one component, blocked == dense
+            return t.reshape(-1)[:self.n].cpu().numpy().reshape(1, self.n)
+        comps = t.shape[1]
+        width = t.shape[3] if t.dim() == 4 else 1
+        shape = (comps, self.n) if width == 1 else (comps, self.n, width)
+        dense = torch.empty(shape, dtype=t.dtype, device=t.device)
+        self.e.unpack(t, dense, comps, width, self.n)
+        return dense.cpu().numpy()
 
     @property
     def bufs(self) -> Dict[str, object]:
         return dict(self.t)
 
     def step(self, k_cycles: int = 1, stream=None) -> int:
-        return self.e.step(self.bufs, self.n, self.ld, self.m, k_cycles, stream=stream, ext_cmd=tuple(self.ext_cmd))
+        return self.e.step(self.bufs, self.n, self.m, k_cycles, stream=stream, ext_cmd=tuple(self.ext_cmd))
