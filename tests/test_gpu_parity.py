@@ -270,7 +270,7 @@ def test_host_session_matches_device_path(eng, lwr):
         s.set_goal(w["goal"]); s.set_obstacles(w["obst"])
         s.enable("qdot_vf", "pose")
         qd = np.empty((7, n)); qo = np.empty((7, n)); fl = np.empty(n, dtype=np.int32)
-        assert s.cycle(q_in=w["q"], k_cycles=2, qdot_out=qd, q_out=qo, flags_out=fl) == 1
+        assert s.cycle(q_in=w["q"], k_cycles=2, qdot_out=qd, q_out=qo, flags_out=fl) == 4   # pack q, cycle kernel, unpack qdot, unpack q
         assert rel_err(qd.T, ref["qdot"]).max() <= FP64_RTOL
         assert np.max(np.abs(qo.T - ref["q"])) < 1e-12 and np.array_equal(fl, ref["flags"])
         assert rel_err(s.read("qdot_vf").T, ref["qdot_vf"]).max() <= FP64_RTOL

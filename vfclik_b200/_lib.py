@@ -26,7 +26,8 @@ VFK_ERR_NO_DEVICE = -4
 FLAG_AT_GOAL, FLAG_NS_LIMIT, FLAG_NAN, FLAG_CLAMPED = 1, 2, 4, 8
 NS_OFF, NS_PROJECTOR, NS_CONTROL = 0, 1, 2
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvfk.so")
+# VFK_LIB selects an alternative build of the same ABI (kernel tuning experiments); default = in-tree libvfk.so
+LIB_PATH = os.environ.get("VFK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvfk.so")
 
 # every symbol include/vfk.h declares (tests check the library exports all of them)
 EXPORTS = [

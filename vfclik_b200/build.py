@@ -31,17 +31,20 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: str = OUT) -> str:
+    if not force and out == OUT and up_to_date():
         return OUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed (%d): %s" % (res.returncode, " ".join(cmd)))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[len("--out="):] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv or bool(extra) or bool(outs), verbose="-v" in sys.argv, extra_flags=extra,
+                        out=outs[0] if outs else OUT))

@@ -155,6 +155,7 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     c.unit_weights = unit ? 1 : 0;
     c.share_factor = (unit && p.ns_lambda == p.ik_lambda) ? 1 : 0;
     c.need_jp = p.mixer_w[2] != 0.0 ? 1 : 0;
+    c.asin_series = (p.rot_slowdown > 0 && p.rot_slowdown <= 0.3) ? 1 : 0;
 }
 
 // -------------------------------------------------------------------------------- public: lifecycle
@@ -199,6 +200,7 @@ static int check_params(vfk_ctx* h, const vfk_params* p) {
         return fail(h, VFK_ERR_UNSUPPORTED, "VFK_NS_CONTROL needs a 1-D nullspace (n_joints = 7), got %d joints",
                     h->chain.n_joints);
     if (!(p->max_vel >= 0)) return fail(h, VFK_ERR_INVALID, "max_vel must be >= 0");
+    if (!(p->obst_order > 0)) return fail(h, VFK_ERR_INVALID, "obst_order must be > 0");
     return VFK_OK;
 }
 
@@ -314,7 +316,12 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.k_cycles = k_cycles;
     size_t smem = 0;
     plan_stages<T, N, EXT>(n_obst, k_cycles, &a.n_chunks, &a.n_stages, &smem);
-    constexpr int MINB = (sizeof(T) == 4) ? (N <= 10 ? 3 : 2) : (N <= 7 ? 2 : 1);
+    a.n_full = n_obst / kChunk;
+    a.n_rem = n_obst % kChunk;
+#ifndef VFK_MINB_F32
+#define VFK_MINB_F32 3
+#endif
+    constexpr int MINB = (sizeof(T) == 4) ? (N <= 10 ? VFK_MINB_F32 : 2) : (N <= 7 ? 2 : 1);
     auto kern = vfk_cycle_kernel<T, N, PAT, EXT, MINB>;
     VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
     int per_sm = 0;

@@ -60,6 +60,7 @@ struct KConst {
     int32_t share_factor;      // nullspace can reuse the IK Cholesky factor
     int32_t tool_identity;
     int32_t need_jp;           // joint P controller observable (weight != 0 or an output wants it)
+    int32_t asin_series;       // rot_slowdown <= 0.3 rad: small-angle series replaces atan2 in FP32
 };
 
 template <typename T>
@@ -83,6 +84,8 @@ struct KArgs {
     int64_t n;
     int32_t n_obst;
     int32_t n_chunks;          // ceil(n_obst / kChunk)
+    int32_t n_full;            // n_obst / kChunk (chunks with all kChunk obstacles)
+    int32_t n_rem;             // n_obst % kChunk
     int32_t n_stages;          // shared-memory stages (<= kMaxStages); >= n_chunks means resident
     int32_t k_cycles;
 };
@@ -190,15 +193,15 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
 
 // ------------------------------------------------------------------------------ field pieces
 // One decay repeller (vfl type 2): acc += (o - p)/d * (radius / max(d, safe))^order.
+// d^2 carries a 1e-30 (1e-300 in FP64) bias so that d = 0 gives a finite 1/d and a zero contribution
+// (0 * finite) without a branch; radius = 0 (empty slot) gives lg2(0) = -inf -> decay = 0 since order > 0.
 template <typename T>
 __device__ __forceinline__ void repel(const Vec4<T>& o, T safe_inv, T order, const T (&pt)[3], T (&acc)[3]) {
     const T dx = o.x - pt[0], dy = o.y - pt[1], dz = o.z - pt[2];
-    const T dd = fma(dx, dx, fma(dy, dy, dz * dz));
-    const T inv = Prec<T>::fmin_(Prec<T>::rsqrt_pos(dd), Prec<T>::big());     // 1/d, finite at d = 0
+    const T dd = fma(dx, dx, fma(dy, dy, fma(dz, dz, Prec<T>::tiny())));
+    const T inv = Prec<T>::rsqrt_pos(dd);                                       // 1/d
     const T ratio = o.w * Prec<T>::fmin_(inv, safe_inv);                        // radius / max(d, safe)
-    T decay = Prec<T>::pow_pos(ratio, order);
-    decay = o.w > T(0) ? decay : T(0);                                          // radius 0 = inactive slot
-    const T wgt = decay * inv;
+    const T wgt = Prec<T>::pow_pos(ratio, order) * inv;
     acc[0] = fma(wgt, dx, acc[0]); acc[1] = fma(wgt, dy, acc[1]); acc[2] = fma(wgt, dz, acc[2]);
 }
 
@@ -208,8 +211,8 @@ template <typename T>
 __device__ __forceinline__ void attract(const KConst<T>& c, const T (&g)[13], const T (&Rt)[9], const T (&pt)[3],
                                         T (&V)[3], T& S0, T (&w)[3]) {
     const T ex = g[9] - pt[0], ey = g[10] - pt[1], ez = g[11] - pt[2];
-    const T d2 = fma(ex, ex, fma(ey, ey, ez * ez));
-    const T invd = Prec<T>::fmin_(Prec<T>::rsqrt_pos(d2), Prec<T>::big());
+    const T d2 = fma(ex, ex, fma(ey, ey, fma(ez, ez, Prec<T>::tiny())));
+    const T invd = Prec<T>::rsqrt_pos(d2);
     const T dist = d2 * invd;
     const T gi = c.goal_force * invd;
     V[0] = gi * ex; V[1] = gi * ey; V[2] = gi * ez;
@@ -224,7 +227,17 @@ __device__ __forceinline__ void attract(const KConst<T>& c, const T (&g)[13], co
     rot_to_quat<T>(E, qw, qx, qy, qz);
     const T n2 = fma(qx, qx, fma(qy, qy, qz * qz));
     const T invn = n2 > T(0) ? Prec<T>::rsqrt_pos(n2) : T(0);
-    const T angle = T(2) * Prec<T>::atan2_(n2 * invn, qw);
+    // angle = 2 atan2(|xyz|, w) in [0, pi].  It only matters below rot_slowdown (above it S1 saturates at 1), so
+    // when the slowdown angle is small the FP32 path uses angle = 2 asin(n) through its series (error < 5e-7
+    // relative for n <= 0.15); larger n just has to stay above the threshold, which the series does.
+    const T nrm = n2 * invn;
+    T angle;
+    if (Prec<T>::kSeriesAsin && c.asin_series) {
+        const T n2c = Prec<T>::fmin_(n2, T(0.25));
+        angle = T(2) * nrm * fma(n2c, fma(n2c, T(0.075), T(1.0 / 6.0)), T(1));
+    } else {
+        angle = T(2) * Prec<T>::atan2_(nrm, qw);
+    }
     const T S1 = Prec<T>::fmin_(T(1), angle * c.rot_slowdown_inv);     // rot_slowdown_inv = +inf when off
     const T sr = c.speed_scale * S1 * c.goal_force * invn;
     w[0] = sr * qx; w[1] = sr * qy; w[2] = sr * qz;
@@ -390,8 +403,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 const unsigned char* sb = region + (size_t)stage * WS::kStage;
                 const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + lane;
                 const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * WS::kRow) + lane;
-                const int cnt = min(kChunk, a.n_obst - ch * kChunk);
-                if (cnt == kChunk) {
+                if (ch < a.n_full) {
 #pragma unroll
                     for (int m = 0; m < kChunk; ++m) {
                         const Vec4<T> o = so[m * 32];
@@ -400,7 +412,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                         repel<T>(o, safe_inv, order, pt, acc);
                     }
                 } else {
-                    for (int m = 0; m < cnt; ++m) {
+                    for (int m = 0; m < a.n_rem; ++m) {
                         const Vec4<T> o = so[m * 32];
                         T safe_inv = c.obst_safe_inv, order = c.obst_order;
                         if (EXT) { const Vec2<T> e = se[m * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }

@@ -42,12 +42,23 @@ template <> struct Prec<float> {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
         return r;
     }
-    static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+    // Joint angles are bounded by the joint limits (|q| <~ pi), where MUFU.SIN/COS are accurate to
+    // 2^-21.4 absolute -- the same order as the rounding of the FK products that consume them.
+    // -DVFK_ACCURATE_SINCOS=1 switches back to libdevice's sincosf.
+    static __device__ __forceinline__ void sincos_(float x, float* s, float* c) {
+#if defined(VFK_ACCURATE_SINCOS) && VFK_ACCURATE_SINCOS
+        sincosf(x, s, c);
+#else
+        __sincosf(x, s, c);
+#endif
+    }
     static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float tiny() { return 1e-30f; }
     static __device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
     static __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ float fabs_(float a) { return fabsf(a); }
     static __device__ __forceinline__ float big() { return 1e18f; }
+    static constexpr bool kSeriesAsin = true;
 };
 
 template <> struct Prec<double> {
@@ -62,6 +73,8 @@ template <> struct Prec<double> {
     static __device__ __forceinline__ double fmax_(double a, double b) { return fmax(a, b); }
     static __device__ __forceinline__ double fabs_(double a) { return fabs(a); }
     static __device__ __forceinline__ double big() { return 1e150; }
+    static __device__ __forceinline__ double tiny() { return 1e-300; }
+    static constexpr bool kSeriesAsin = false;
 };
 
 // {x, y, z, radius} of one obstacle of one instance: one 16-byte (FP32) or 32-byte (FP64) vector.
