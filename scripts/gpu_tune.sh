@@ -18,10 +18,7 @@ except Exception as e: print("$name failed", e)
 PY
 }
 run default A=1
-run stages2 VFK_STAGES=2
-run stages4 VFK_STAGES=4
-run minb4_s2 VFK_LIB=$PWD/build/libvfk_minb4.so VFK_STAGES=2
-run minb4_s3 VFK_LIB=$PWD/build/libvfk_minb4.so VFK_STAGES=3
-run accsincos VFK_LIB=$PWD/build/libvfk_accsincos.so
-timeout 200 python scripts/fp32_error.py 65536 2>&1 | tail -3
-VFK_LIB=$PWD/build/libvfk_accsincos.so timeout 200 python scripts/fp32_error.py 65536 2>&1 | tail -3
+run sincos_libdevice VFK_LIB=$PWD/build/libvfk_sincos1.so
+run sincos_mufu VFK_LIB=$PWD/build/libvfk_sincos2.so
+timeout 200 python scripts/fp32_error.py 262144 2>&1 | tail -3
+VFK_LIB=$PWD/build/libvfk_sincos1.so timeout 200 python scripts/fp32_error.py 262144 2>&1 | tail -3

@@ -42,14 +42,29 @@ template <> struct Prec<float> {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
         return r;
     }
-    // Joint angles are bounded by the joint limits (|q| <~ pi), where MUFU.SIN/COS are accurate to
-    // 2^-21.4 absolute -- the same order as the rounding of the FK products that consume them.
-    // -DVFK_ACCURATE_SINCOS=1 switches back to libdevice's sincosf.
+    // sin/cos of a joint angle.  Default: Cody-Waite reduction to [-pi/4, pi/4] (k = rint(2x/pi) taken from
+    // the mantissa of a magic-number add) + Cephes minimax polynomials, ~1 ulp, branch-free, valid for
+    // |x| < 1e4 rad.  -DVFK_SINCOS=1: libdevice sincosf.  -DVFK_SINCOS=2: MUFU.SIN/COS (2^-21.4 absolute; measured to
+    // push 5e-5 of random LWR instances past the 1e-4 qdot tolerance, so it is NOT the default).
     static __device__ __forceinline__ void sincos_(float x, float* s, float* c) {
-#if defined(VFK_ACCURATE_SINCOS) && VFK_ACCURATE_SINCOS
+#if defined(VFK_SINCOS) && VFK_SINCOS == 1
         sincosf(x, s, c);
-#else
+#elif defined(VFK_SINCOS) && VFK_SINCOS == 2
         __sincosf(x, s, c);
+#else
+        const float t = fmaf(x, 0.636619772367581343f, 12582912.0f);
+        const int ki = __float_as_int(t);
+        const float kf = t - 12582912.0f;
+        float r = fmaf(kf, -1.57079637050628662109375f, x);
+        r = fmaf(kf, 4.37113900018624283e-8f, r);
+        const float z = r * r;
+        const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * r, r);
+        const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
+                              z * z, fmaf(-0.5f, z, 1.0f));
+        const float ss = (ki & 1) ? cp : sp;
+        const float cs = (ki & 1) ? sp : cp;
+        *s = __int_as_float(__float_as_int(ss) ^ ((ki & 2) << 30));
+        *c = __int_as_float(__float_as_int(cs) ^ (((ki + 1) & 2) << 30));
 #endif
     }
     static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
