@@ -173,6 +173,11 @@ int  vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const v
 int  vfk_mix(vfk_handle h, const void* const* cmds, const double* w, int n_ports, int n_channels,
              void* out, int32_t* nan_flags, int64_t n_instances, void* stream);
 
+/* LWR_Bridge.set_vel (scripts/bridge:188-203) on device buffers [n_channels]: ratio = max_vel / max_c |qdot_c| when
+ * exceeded; cmd = qdot_lim if direct_control else -q_cmded + q + qdot_lim (q_cmded NULL -> q). qdot_lim_out optional. */
+int  vfk_set_vel(vfk_handle h, const void* qdot, const void* q, const void* q_cmded, double max_vel, int direct_control,
+                 void* cmd_out, void* qdot_lim_out, int n_channels, int64_t n_instances, void* stream);
+
 /* Layout conversion on the device: dense SoA [comps][n] (width scalars per element: 1 for
  * per-instance components, 4 for obstacles [M][n][4], 2 for obst_ext [M][n][2]) <-> tile-blocked. */
 int  vfk_pack(vfk_handle h, const void* dense, void* blocked, int comps, int width, int64_t n_instances, void* stream);

@@ -1,0 +1,162 @@
+"""GPU tests of the reference-shaped host modules (ports in, ports out) against the oracle's reference-shaped loop."""
+import io
+import time
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def fresh_ports():
+    from vfclik_b200 import ports as yarp
+    yarp.Network.reset()
+    yield yarp
+    yarp.Network.reset()
+
+
+def test_vfclik_app_config1_matches_reference_shaped_loop(lwr, built_lib, fresh_ports):
+    """BASELINE config 1 through the port-driven modules: single LWR, the reference's first goal, three ObstacleP,
+    simulation plant.  Every published qdot and the joint trajectory equal oracle/refshape.py's loop."""
+    from oracle import batch, refshape
+    from vfclik_b200 import workloads
+    from vfclik_b200.launcher import Vfclik
+    chain, cfg = lwr
+    w = workloads.config1(chain, cfg)
+    app = Vfclik(cfg, namespace="/0", sim=True, precision=64)
+    prm = batch.Params(jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate, max_vel=cfg.max_vel,
+                       jp_kp=cfg.jpctrl_kp, ik_lambda=cfg.ik_lambda, ns_lambda=cfg.ns_lambda)
+    try:
+        for m in range(3):
+            o = w["obst"][m, 0]
+            frame = [1, 0, 0, o[0], 0, 1, 0, o[1], 0, 0, 1, o[2], 0, 0, 0, 1]
+            app.set_obstacle_p(m, frame, o[3], 20)
+        assert sorted(app.runtime.vectorFields) == [1, 5, 6, 7]                    # ids of scripts/object_feeder:229-334
+        loop = refshape.ControlLoop(chain, prm, cfg.initial_joint_pos, cfg.initial_vf_pose[2],
+                                    obstacles=[list(w["obst"][m, 0]) for m in range(3)])
+        K = 60
+        for k in range(K):
+            cmd = app.step()
+            loop.cycle()
+            if k == 0:
+                continue            # first period: the command ports are still empty, exactly like a cold start
+            assert np.allclose(app.vf.last_qdot, loop.last["qdot_vf"], rtol=1e-9, atol=1e-12), k
+            assert np.allclose(app.nullspace.last_qdot, loop.last["qdot_ns"], rtol=1e-9, atol=1e-12), k
+        # the modular loop lags one period behind the synchronous oracle (cold start), so compare one step shifted
+        loop2 = refshape.ControlLoop(chain, prm, cfg.initial_joint_pos, cfg.initial_vf_pose[2],
+                                     obstacles=[list(w["obst"][m, 0]) for m in range(3)])
+        loop2.run(K - 1)
+        assert np.allclose(app.joint_sim.q, loop2.q, rtol=1e-9, atol=1e-11)
+        assert app.runtime.cycles == K and app.bridge.direct_control is False
+        # controller switching (src/handlers.py:189-211): joint mode [0,0,1,0,0,0]
+        fresh_ports.write_bottle_lists(_out_port(fresh_ports, "/0/test/w", app.bridge.weight_port.getName()), [0.0, 0.0, 1.0])
+        app.step(); app.step()
+        assert app.bridge.mixer.weights[:3] == [0.0, 0.0, 1.0]
+        q = np.asarray(app.bridge.last_q)
+        want = cfg.jpctrl_kp * (np.asarray(cfg.initial_joint_pos) - q)
+        assert np.allclose(app.bridge.last_cmd, want, rtol=1e-9, atol=1e-12)
+    finally:
+        app.close()
+
+
+def _out_port(yarp, name, dst):
+    p = yarp.BufferedPortBottle()
+    p.open(name)
+    yarp.Network.connect(name, dst)
+    return p
+
+
+def test_vf_module_protocol_edge_cases(lwr, built_lib, fresh_ports):
+    """Malformed messages are ignored with a warning, never raised (SURVEY.md section 8b error conventions)."""
+    from vfclik_b200.runtime import ControlRuntime
+    from vfclik_b200.vf import VectorFieldModule
+    yarp = fresh_ports
+    chain, cfg = lwr
+    rt = ControlRuntime(cfg, precision=64)
+    vf = VectorFieldModule(rt, "/0")
+    base = "/0" + cfg.robotarm_portbasename + "/vectorField"
+    param = _out_port(yarp, "/t/param", base + "/param")
+    weight = _out_port(yarp, "/t/weight", base + "/weight")
+    maxvel = _out_port(yarp, "/t/maxvel", base + "/max_vel")
+    qin = _out_port(yarp, "/t/q", base + "/qIn")
+    try:
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            yarp.write_bottle_lists(param, ["add", 1, 1.0, 1, list(cfg.initial_vf_pose[2])], strict=True)
+            yarp.write_bottle_lists(param, ["add", 9, -50.0, 4, [0.0] * 8], strict=True)     # hemisphere: not on the GPU yet
+            yarp.write_bottle_lists(param, ["add", 3, 1.0], strict=True)                      # wrong arity
+            yarp.write_bottle_lists(param, ["remove", 77], strict=True)                       # unknown id: silently nothing
+            yarp.write_bottle_lists(weight, ["t", 1.0, 1.0], strict=True)                     # wrong size
+            yarp.sendListPort(maxvel, [0.9])                                                  # above the 0.41 cap
+            vf.update()
+        out = buf.getvalue()
+        assert "Unknown vector field type, ignoring" in out and "expected 5" in out and "Wrong size" in out
+        assert "speedScale" in out and rt.params.speed_scale == cfg.speedScale
+        assert sorted(rt.vectorFields) == [1] and rt.params.w_task == (1.0,) * 6
+        yarp.sendListPort(maxvel, [0.3])
+        yarp.write_bottle_lists(weight, ["j", 1, 1, 0.5, 1, 1, 1, 1], strict=True)
+        yarp.sendListPort(qin, [0.1] * 6)                                                      # wrong length: ignored
+        vf.update()
+        assert rt.params.speed_scale == 0.3 and rt.params.w_joint[2] == 0.5 and vf.last_qdot is None
+        yarp.sendListPort(qin, cfg.initial_joint_pos)
+        vf.update()
+        assert vf.last_qdot is not None and np.all(np.isfinite(vf.last_qdot)) and np.max(np.abs(vf.last_qdot)) > 1e-3
+    finally:
+        vf.close()
+        rt.close()
+
+
+def test_command_mixer_class_reproduces_reference_golden_sequence(golden, built_lib, monkeypatch):
+    """The product CommandMixer (port logic on the host, sum in vfk_mix) on the scripted sequence recorded from the
+    real src/command_mixer.py."""
+    from vfclik_b200 import command_mixer, ports as yarp
+    ev, wev, short = golden["mixer_events"], golden["mixer_wevents"], golden["mixer_short"]
+    steps, n_ports, n = ev.shape
+    now = [1000.0]
+    monkeypatch.setattr(time, "time", lambda: now[0])
+    ports = [yarp.BufferedPortBottle() for _ in range(n_ports)]
+    wport = yarp.BufferedPortBottle()
+    mixer = command_mixer.CommandMixer(ports, wport, n, 2.0, [1.0, 1.0, 0.0, 0.0, 0.0, 0.0])
+    assert mixer.nChannels == n and mixer.guard_time == 2.0 and len(mixer.last_command) == n_ports
+    for s in range(steps):
+        now[0] += float(golden["mixer_dts"][s])
+        for p in range(n_ports):
+            if not np.isnan(ev[s, p, 0]):
+                ports[p]._deliver(yarp.Bottle(list(ev[s, p])))
+            elif short[s, p]:
+                ports[p]._deliver(yarp.Bottle([0.0] * (n - 2)))
+        wv = wev[s][~np.isnan(wev[s])]
+        if wv.size:
+            wport._deliver(yarp.Bottle(list(wv)))
+        with redirect_stdout(io.StringIO()):
+            out = mixer.read()
+        assert np.allclose(out, golden["mixer_out"][s], rtol=1e-14, atol=1e-15), s      # fma vs mul+add: <= 1 ulp
+        assert np.array_equal(np.asarray(mixer.weights), golden["mixer_weights_after"][s])
+    with redirect_stdout(io.StringIO()) as buf:
+        m2 = command_mixer.CommandMixer([yarp.BufferedPortBottle(), yarp.BufferedPortBottle()], None, 3, 1.0, [1.0])
+    assert m2.weights == [0.0, 0.0]
+
+
+def test_set_vel_kernel(lwr, built_lib):
+    """vfk_set_vel == LWR_Bridge.set_vel (scripts/bridge:188-203) on a batch, both command forms."""
+    from vfclik_b200.engine import DeviceBatch, Engine
+    chain, _ = lwr
+    e = Engine(chain, precision=64)
+    try:
+        n = 777
+        rng = np.random.default_rng(21)
+        qd = rng.normal(scale=0.8, size=(7, n)); q = rng.normal(size=(7, n)); qc = q + rng.normal(scale=0.01, size=(7, n))
+        db = DeviceBatch(e, n, 0, outputs=("cmd", "qdot"))
+        b_qd, b_q, b_qc = db.to_blocked(qd), db.to_blocked(q), db.to_blocked(qc)
+        lead = np.max(np.abs(qd), axis=0)
+        ratio = np.where(lead > 1.0, 1.0 / lead, 1.0)
+        for direct in (False, True):
+            e.set_vel(b_qd, b_q, db.t["cmd"], 1.0, direct, 7, n, q_cmded=b_qc, qdot_lim_out=db.t["qdot"])
+            want = qd * ratio if direct else (-qc + q + qd * ratio)
+            assert np.allclose(db.download("cmd"), want, rtol=1e-14, atol=1e-15)
+            assert np.allclose(db.download("qdot"), qd * ratio, rtol=1e-14, atol=1e-15)
+        assert np.any(ratio < 1) and np.any(ratio == 1)
+    finally:
+        e.close()

@@ -1,0 +1,139 @@
+"""CPU tests of the host-side logic: config loading, chain folding, ports, launcher CLI, sharding (gloo, world 2)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_chain_folds_fixed_segments(lwr):
+    chain, cfg = lwr
+    assert chain.n_joints == cfg.nJoints == 7
+    assert np.allclose(chain.base[9:12], [0.25, 0.0, 0.45 + 0.31])        # mounting * 0.31 m column
+    assert np.all(chain.joint_type == 3)                                  # all RotZ
+    assert np.allclose(chain.tip[1, 9:12], [0.0, 0.4, 0.0]) and np.allclose(chain.tip[6, 9:12], [0, 0, 0.078])
+    assert np.allclose(np.rad2deg(chain.q_hi), [170, 120, 170, 120, 170, 120, 170])
+
+
+def test_kdl_frame_algebra_matches_conventions():
+    from vfclik_b200 import kdl
+    a = kdl.Frame(kdl.Rotation.RotZ(0.3), kdl.Vector(1, 2, 3))
+    b = kdl.Frame(kdl.Rotation.RotX(-0.7), kdl.Vector(-1, 0.5, 0.25))
+    c = a * b
+    A = np.eye(4); A[:3, :3] = np.asarray(a.M.m).reshape(3, 3); A[:3, 3] = a.p.v
+    B = np.eye(4); B[:3, :3] = np.asarray(b.M.m).reshape(3, 3); B[:3, 3] = b.p.v
+    assert np.allclose(np.asarray(c.to_list16()).reshape(4, 4), A @ B)
+    assert kdl.Frame.from_list16(c.to_list16()).to_list12() == c.to_list12()
+    f = kdl.Frame.DH_Craig1989(0.1, np.pi / 2, 0.4, 0.0)
+    assert f.M.m == [1, 0, 0, 0, 0, -1, 0, 1, 0] and np.allclose(f.p.v, [0.1, -0.4, 0.0])
+
+
+def test_config_errors(tmp_path):
+    from vfclik_b200.config import load_config
+    with pytest.raises(FileNotFoundError):
+        load_config(str(tmp_path / "config-none-right.py"))
+    bad = tmp_path / "config-bad-right.py"
+    bad.write_text("nJoints = 7\n")
+    with pytest.raises(AttributeError):
+        load_config(str(bad))
+
+
+def test_ports_latest_value_and_strict_queue():
+    from vfclik_b200 import ports as yarp
+    yarp.Network.reset()
+    out = yarp.BufferedPortBottle(); out.open("/a/out")
+    latest = yarp.BufferedPortBottle(); latest.open("/b/in")
+    strict = yarp.BufferedPortBottle(); strict.open("/c/in"); strict.setStrict(True)
+    assert yarp.Network.connect("/a/out", "/b/in") and yarp.Network.connect("/a/out", "/c/in")
+    for k in range(3):
+        yarp.sendListPort(out, [k, k + 0.5])
+    assert yarp.readListPort(latest) == [2.0, 2.5] and latest.read(False) is None       # newest only, once
+    assert [yarp.readListPort(strict) for _ in range(3)] == [[0.0, 0.5], [1.0, 1.5], [2.0, 2.5]]
+    with pytest.raises(RuntimeError):
+        strict.read(True)                                                                # would block forever
+    # nested bottles: ("add", id, force, type, (params...))  scripts/vf:226-266
+    yarp.write_bottle_lists(out, ["add", 1, 1.0, 1, [0.0] * 17])
+    b = strict.read(False)
+    assert b.size() == 5 and b.get(0).toString() == "add" and b.get(1).asInt() == 1 and b.get(4).asList().size() == 17
+    assert b.get(2).isDouble() and b.get(3).isInt() and not b.get(0).isInt()
+    yarp.Network.reset()
+
+
+def test_arcosyarp_naming_and_readiness():
+    from vfclik_b200 import ports as yarp
+    yarp.Network.reset()
+    a = yarp.ArcosYarp(ports_name_prefix="/0", module_name_prefix="/lwr/right/vectorField")
+    b = yarp.ArcosYarp(ports_name_prefix="/0", module_name_prefix="/lwr/right/bridge")
+    qdot = a.create_yarp_port("/qdotOut", input_port=False)
+    assert qdot.getName() == "/0/lwr/right/vectorField/qdotOut"
+    a.connect(qdot, "/lwr/right/bridge", "/vectorfieldcmd")
+    assert not a.is_ready()                                  # remote port does not exist yet
+    cmd = b.create_yarp_port("/vectorfieldcmd", strict=False)
+    assert a.is_ready()
+    yarp.sendListPort(qdot, [1, 2, 3])
+    assert yarp.readListPort(cmd) == [1.0, 2.0, 3.0]
+    yarp.Network.reset()
+
+
+def test_weight_bottle_parsing():
+    from vfclik_b200 import ports as yarp
+    from vfclik_b200.vf import get_weight_matrix, list16_to_pose12, pose12_to_list16
+    b = yarp.Bottle.from_list(["t", 1.0, 1.0, 1.0, 0.5, 0.5, 0.5])
+    assert get_weight_matrix(b, 6) == [1.0, 1.0, 1.0, 0.5, 0.5, 0.5]
+    assert get_weight_matrix(b, 7) is None                   # wrong size -> ignored (scripts/vf:176-179)
+    p12 = list(range(12))
+    assert list16_to_pose12(pose12_to_list16(p12)) == p12
+
+
+def test_launcher_cli(tmp_path):
+    from vfclik_b200 import launcher
+    opts, _ = launcher.build_parser().parse_args([])
+    assert (opts.robot, opts.instance, opts.namespace, opts.config_dir, opts.sim, opts.no_nullspace) == \
+        ("lwr", "right", "/0", "../config_data/lwr/", False, False)
+    opts, _ = launcher.build_parser().parse_args(["-r", "icub", "-i", "left", "-n", "/1", "-d", "/x/", "-s", "--no_nullspace"])
+    assert (opts.robot, opts.instance, opts.namespace, opts.config_dir, opts.sim, opts.no_nullspace) == \
+        ("icub", "left", "/1", "/x/", True, True)
+    r = subprocess.run([sys.executable, "-m", "vfclik_b200.launcher", "-d", str(tmp_path) + "/", "-r", "nope"], cwd=ROOT,
+                       capture_output=True, text=True)
+    assert r.returncode == 255 and "not found, exiting" in r.stdout       # sys.exit(-1) (scripts/vfclik:83-85)
+
+
+def test_shard_range_partitions_exactly():
+    from vfclik_b200.distributed import shard_range
+    for n, w in ((16 << 20, 8), (1000, 3), (5, 8), (0, 2)):
+        ranges = [shard_range(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [e - b for b, e in ranges]
+        assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from vfclik_b200.distributed import reduce_stats, shard_range
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+b, e = shard_range(1000, r, w)
+stats = reduce_stats({"inst_cycles": float(e - b) * 10, "elapsed_ms_max": 1.0 + r, "err_max": 1e-9 * (r + 1), "t_min": 5.0 - r})
+if r == 0:
+    print("RESULT", stats["inst_cycles"], stats["elapsed_ms_max"], stats["err_max"], stats["t_min"])
+dist.destroy_process_group()
+"""
+
+
+def test_stats_reduction_world_size_2_gloo(tmp_path):
+    """The N > 1 host path (shard ranges + the final all_reduce) on CPU with the gloo backend."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", str(script), ROOT], capture_output=True, text=True, env=env,
+                       timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    assert [float(x) for x in line[1:]] == [10000.0, 2.0, 2e-9, 4.0]

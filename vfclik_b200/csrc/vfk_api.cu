@@ -431,6 +431,24 @@ extern "C" int vfk_mix(vfk_handle h, const void* const* cmds, const double* w, i
     return launches;
 }
 
+extern "C" int vfk_set_vel(vfk_handle h, const void* qdot, const void* q, const void* q_cmded, double max_vel, int direct_control,
+                           void* cmd_out, void* qdot_lim_out, int n_channels, int64_t n, void* stream) {
+    if (!h || !qdot || !q || !cmd_out) return fail(h, VFK_ERR_INVALID, "vfk_set_vel: null argument");
+    if (n_channels < 1 || n < 0 || !(max_vel >= 0)) return fail(h, VFK_ERR_INVALID, "vfk_set_vel: bad shape or max_vel");
+    if (n == 0) return 0;
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (h->precision == 32)
+        vfk_set_vel_kernel<float><<<grid, 256, 0, st>>>((const float*)qdot, (const float*)q, (const float*)q_cmded, (float*)cmd_out,
+                                                       (float*)qdot_lim_out, (float)max_vel, direct_control, n_channels, n);
+    else
+        vfk_set_vel_kernel<double><<<grid, 256, 0, st>>>((const double*)qdot, (const double*)q, (const double*)q_cmded,
+                                                        (double*)cmd_out, (double*)qdot_lim_out, max_vel, direct_control, n_channels, n);
+    VFK_CUDA(h, cudaGetLastError());
+    return 1;
+}
+
 // -------------------------------------------------------------------------------- public: layout conversion
 template <typename V>
 static cudaError_t run_pack(const void* dense, void* blocked, int C, int64_t n, bool unpack, cudaStream_t st) {

@@ -746,6 +746,25 @@ vfk_mix_kernel(const __grid_constant__ MixArgs m, T* __restrict__ out, int32_t* 
     }
 }
 
+// LWR_Bridge.set_vel (scripts/bridge:188-203) on blocked arrays: leading-joint clamp and command forming.
+template <typename T>
+__global__ void __launch_bounds__(256)
+vfk_set_vel_kernel(const T* __restrict__ qdot, const T* __restrict__ q, const T* __restrict__ q_cmded, T* __restrict__ cmd,
+                   T* __restrict__ qdot_lim, T max_vel, int direct, int n_channels, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int64_t base = (i >> 5) * (n_channels * 32) + (i & 31);
+    T lead = T(0);
+    for (int c = 0; c < n_channels; ++c) lead = Prec<T>::fmax_(lead, Prec<T>::fabs_(qdot[base + c * 32]));
+    const T ratio = lead > max_vel ? max_vel / lead : T(1);
+    for (int c = 0; c < n_channels; ++c) {
+        const T v = qdot[base + c * 32] * ratio;
+        if (qdot_lim) qdot_lim[base + c * 32] = v;
+        const T qc = q_cmded ? q_cmded[base + c * 32] : q[base + c * 32];
+        cmd[base + c * 32] = direct ? v : (-qc + q[base + c * 32] + v);
+    }
+}
+
 // ------------------------------------------------------------------------------ layout conversion
 // dense SoA [C][n] (element size E bytes: scalar, Vec2 or Vec4 of T)  <->  tile-blocked [tile][C][32].
 template <typename V>

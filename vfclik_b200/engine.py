@@ -197,6 +197,15 @@ class Engine:
         self.launches += rc
         return rc
 
+    def set_vel(self, qdot, q, cmd_out, max_vel: float, direct_control: bool, n_channels: int, n_instances: int,
+                q_cmded=None, qdot_lim_out=None, stream=None) -> int:
+        """``LWR_Bridge.set_vel`` arithmetic (``scripts/bridge:188-203``) on blocked device buffers."""
+        rc = self._check(self._lib.vfk_set_vel(self._h, _dev_ptr(qdot), _dev_ptr(q), _dev_ptr(q_cmded), float(max_vel),
+                                               int(bool(direct_control)), _dev_ptr(cmd_out), _dev_ptr(qdot_lim_out),
+                                               int(n_channels), int(n_instances), self._stream(stream)))
+        self.launches += rc
+        return rc
+
     def pack(self, dense, blocked, comps: int, width: int, n_instances: int, stream=None) -> int:
         """dense SoA [comps][n] (x width scalars) -> tile-blocked, on the device."""
         rc = self._check(self._lib.vfk_pack(self._h, _dev_ptr(dense), _dev_ptr(blocked), int(comps), int(width),
