@@ -366,3 +366,32 @@ def test_pack_unpack_round_trip(eng, lwr):
         assert flat[((i // 32) * 7 + 3) * 32 + i % 32] == a[3, i]
         oflat = db.t["obst"].reshape(-1).cpu().numpy()
         assert oflat[(((i // 32) * 3 + 2) * 32 + i % 32) * 4 + 1] == o[2, i, 1]
+
+
+@pytest.mark.parametrize("precision,m,k", [(64, 64, 3), (64, 100, 1), (32, 100, 2), (32, 256, 1), (64, 3, 1), (32, 9, 4)])
+def test_obstacle_ring_shapes(eng, lwr, precision, m, k):
+    """Streaming ring (more chunks than stages), ragged last chunk, K > 1 re-streaming, resident small lists."""
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(precision)
+    n = 1500
+    w = workloads.random_batch(chain, n, m, seed=30 + m, dtype=np.float32 if precision == 32 else np.float64)
+    out = run_gpu(e, w, m, k=k, outputs=("qdot_vf", "qdot"))
+    ref = run_oracle(chain, e.params, w, m, k=k)
+    tol = FP64_RTOL if precision == 64 else FP32_RTOL * (1 if k == 1 else 3)
+    check(out, ref, tol, keys=("qdot_vf", "qdot"))
+
+
+def test_config4_and_config5_shapes_fp32(eng, built_lib):
+    """BASELINE configs[3] (256 obstacles, repulsor-sum dominated) and configs[4] (17-DOF, 64 obstacles) at test size."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import Engine
+    chain = workloads.dual_arm_torso_chain()
+    e = Engine(chain, precision=32)
+    try:
+        w = workloads.random_batch(chain, 4096, 64, seed=41, dtype=np.float32)
+        out = run_gpu(e, w, 64, outputs=("qdot_vf", "qdot_ns", "qdot"))
+        ref = run_oracle(chain, e.params, w, 64)
+        check(out, ref, FP32_RTOL, keys=("qdot_vf", "qdot_ns", "qdot"))
+    finally:
+        e.close()
