@@ -395,3 +395,27 @@ def test_config4_and_config5_shapes_fp32(eng, built_lib):
         check(out, ref, FP32_RTOL, keys=("qdot_vf", "qdot_ns", "qdot"))
     finally:
         e.close()
+
+
+def test_host_session_chunk_pipeline(eng, lwr):
+    """Large sessions split the call into tile-aligned chunks on several streams (H2D / kernel / D2H overlap);
+    results must be identical to the single-launch device path, including a ragged last chunk."""
+    import torch
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(32)
+    n, M = 200_003, 4
+    w = workloads.random_batch(chain, n, M, seed=51, dtype=np.float32)
+    dev = run_gpu(e, w, M, k=2, outputs=("qdot", "flags"))
+    s = e.session(n, M)
+    try:
+        s.set_goal(w["goal"]); s.set_obstacles(w["obst"])
+        q_pin = torch.from_numpy(w["q"]).pin_memory()
+        qd = torch.empty((7, n), dtype=torch.float32).pin_memory()
+        qo = np.empty((7, n), dtype=np.float32)                      # pageable output goes through the staging copy
+        fl = np.empty(n, dtype=np.int32)
+        launches = s.cycle(q_in=q_pin.numpy(), k_cycles=2, qdot_out=qd.numpy(), q_out=qo, flags_out=fl)
+        assert launches == 3 * 4                                      # 3 chunks x (pack q, cycle, unpack qdot, unpack q)
+        assert np.array_equal(qd.numpy().T, dev["qdot"]) and np.array_equal(qo.T, dev["q"]) and np.array_equal(fl, dev["flags"])
+    finally:
+        s.close()

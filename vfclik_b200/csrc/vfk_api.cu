@@ -451,27 +451,29 @@ extern "C" int vfk_set_vel(vfk_handle h, const void* qdot, const void* q, const 
 
 // -------------------------------------------------------------------------------- public: layout conversion
 template <typename V>
-static cudaError_t run_pack(const void* dense, void* blocked, int C, int64_t n, bool unpack, cudaStream_t st) {
+static cudaError_t run_pack(const void* dense, int64_t dense_ld, void* blocked, int C, int64_t n, bool unpack, cudaStream_t st) {
     const int64_t tiles = (n + 31) / 32;
     const unsigned grid = (unsigned)((tiles * C * 32 + 255) / 256);
     if (unpack)
-        vfk_unpack_kernel<V><<<grid, 256, 0, st>>>((const V*)blocked, (V*)const_cast<void*>(dense), C, n, tiles);
+        vfk_unpack_kernel<V><<<grid, 256, 0, st>>>((const V*)blocked, (V*)const_cast<void*>(dense), dense_ld, C, n, tiles);
     else
-        vfk_pack_kernel<V><<<grid, 256, 0, st>>>((const V*)dense, (V*)blocked, C, n, tiles);
+        vfk_pack_kernel<V><<<grid, 256, 0, st>>>((const V*)dense, dense_ld, (V*)blocked, C, n, tiles);
     return cudaGetLastError();
 }
 
-// width = scalars per element: 1 (per-instance components), 2 (obstacle ext) or 4 (obstacles)
+// width = scalars per element: 1 (per-instance components), 2 (obstacle ext) or 4 (obstacles);
+// dense_ld = row pitch of the dense array in elements (>= n; lets a column range of a larger array be converted)
 static int pack_dispatch(vfk_ctx* h, const void* dense, void* blocked, int C, int width, int64_t n, bool unpack,
-                         cudaStream_t st) {
+                         cudaStream_t st, int64_t dense_ld = -1) {
     if (!dense || !blocked) return fail(h, VFK_ERR_INVALID, "vfk_pack/unpack: null buffer");
     if (C < 1 || n < 0) return fail(h, VFK_ERR_INVALID, "vfk_pack/unpack: bad shape");
     if (n == 0) return 0;
+    if (dense_ld < 0) dense_ld = n;
     cudaError_t e;
     const bool f = h->precision == 32;
-    if (width == 1) e = f ? run_pack<float>(dense, blocked, C, n, unpack, st) : run_pack<double>(dense, blocked, C, n, unpack, st);
-    else if (width == 2) e = f ? run_pack<Vec2<float>>(dense, blocked, C, n, unpack, st) : run_pack<Vec2<double>>(dense, blocked, C, n, unpack, st);
-    else if (width == 4) e = f ? run_pack<Vec4<float>>(dense, blocked, C, n, unpack, st) : run_pack<Vec4<double>>(dense, blocked, C, n, unpack, st);
+    if (width == 1) e = f ? run_pack<float>(dense, dense_ld, blocked, C, n, unpack, st) : run_pack<double>(dense, dense_ld, blocked, C, n, unpack, st);
+    else if (width == 2) e = f ? run_pack<Vec2<float>>(dense, dense_ld, blocked, C, n, unpack, st) : run_pack<Vec2<double>>(dense, dense_ld, blocked, C, n, unpack, st);
+    else if (width == 4) e = f ? run_pack<Vec4<float>>(dense, dense_ld, blocked, C, n, unpack, st) : run_pack<Vec4<double>>(dense, dense_ld, blocked, C, n, unpack, st);
     else return fail(h, VFK_ERR_INVALID, "vfk_pack/unpack: width must be 1, 2 or 4");
     if (e != cudaSuccess) return fail(h, VFK_ERR_CUDA, "layout kernel: %s", cudaGetErrorString(e));
     return 1;
@@ -498,6 +500,7 @@ struct vfk_session_s {
     int n_obst, has_ext, N;
     size_t es;                       // element size
     cudaStream_t stream;
+    cudaStream_t pipe[3];            // chunk pipeline of vfk_session_cycle (H2D / kernels / D2H overlap)
     char* dev;                       // one device slab
     size_t dev_bytes;
     vfk_buffers b;                   // blocked device buffers
@@ -535,7 +538,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     // blocked: q N, goal 13, obst, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, flags 1
     const size_t rows = (size_t)N * 9 + 13 + obst_rows + 12 + 1;
     const size_t stage_in_rows = obst_rows > (size_t)(N > 13 ? N : 13) ? obst_rows : (size_t)(N > 13 ? N : 13);
-    const size_t stage_out_rows = (size_t)(N > 12 ? N : 12);
+    const size_t stage_out_rows = (size_t)(N > 12 ? N : 12) + (size_t)N;      // qdot (or a read()) + q_out
     s->dev_bytes = (rows + stage_in_rows + stage_out_rows) * row;
     cudaError_t e = cudaMalloc((void**)&s->dev, s->dev_bytes);
     if (e != cudaSuccess) { delete s; return fail(h, VFK_ERR_CUDA, "cudaMalloc(%zu): %s", s->dev_bytes, cudaGetErrorString(e)); }
@@ -563,6 +566,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->launches = 0;
     s->pin_bytes = (size_t)N * 3 * (size_t)n * s->es + (size_t)n * 4;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&s->pipe[k], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->pin, s->pin_bytes);
     if (e != cudaSuccess) {
         cudaFree(s->dev);
@@ -621,12 +625,29 @@ extern "C" int vfk_session_set_ns_input(vfk_session s, const void* x) {
     return upload_blocked(s, s->d_ns_in, x, s->h->params.ns_mode == VFK_NS_CONTROL ? 4 : s->N, 1);
 }
 
+// Offset every buffer of a blocked view to the tile range starting at tile0.
+static vfk_buffers offset_view(const vfk_buffers& b, int64_t tile0, int N, int M, size_t es) {
+    vfk_buffers o = b;
+    auto off = [&](const void* p, size_t comps) -> void* {
+        return p ? (void*)((char*)const_cast<void*>(p) + (size_t)tile0 * comps * 32 * es) : nullptr;
+    };
+    o.q = off(b.q, N); o.goal = off(b.goal, 13); o.obst = off(b.obst, (size_t)M * 4); o.obst_ext = off(b.obst_ext, (size_t)M * 2);
+    o.jp_ref = off(b.jp_ref, N); o.ns_lastvec = off(b.ns_lastvec, N); o.q_cmded = off(b.q_cmded, N);
+    for (int e = 0; e < 3; ++e) o.ext_cmd[e] = off(b.ext_cmd[e], N);
+    o.qdot_vf = off(b.qdot_vf, N); o.qdot_ns = off(b.qdot_ns, N); o.qdot_jp = off(b.qdot_jp, N); o.qdot = off(b.qdot, N);
+    o.cmd = off(b.cmd, N); o.pose = off(b.pose, 12);
+    o.flags = b.flags ? b.flags + tile0 * 32 : nullptr;
+    return o;
+}
+
 extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, void* qdot_out, void* q_out,
                                  int32_t* flags_out) {
     if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_cycle: null session");
     vfk_ctx* h = s->h;
     VFK_CUDA(h, cudaSetDevice(h->device));
-    const size_t blk = (size_t)s->N * (size_t)s->n * s->es;
+    const int N = s->N;
+    const size_t es = s->es;
+    const size_t blk = (size_t)N * (size_t)s->n * es;
     char* pin_q = s->pin;
     char* pin_qd = s->pin + blk;
     char* pin_qo = s->pin + 2 * blk;
@@ -638,40 +659,75 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
         return at.type == cudaMemoryTypeHost;
     };
-    int launches = 0, rc;
+    const char* src_q = nullptr;
     if (q_in) {
-        const void* src = q_in;
-        if (!pinned(q_in)) { memcpy(pin_q, q_in, blk); src = pin_q; }
-        VFK_CUDA(h, cudaMemcpyAsync(s->stage_in, src, blk, cudaMemcpyHostToDevice, s->stream));
-        if ((rc = pack_dispatch(h, s->stage_in, s->b.q, s->N, 1, s->n, false, s->stream)) < 0) return rc;
-        launches += rc;
+        src_q = (const char*)q_in;
+        if (!pinned(q_in)) { memcpy(pin_q, q_in, blk); src_q = pin_q; }
     }
+    const bool d_qd = qdot_out && pinned(qdot_out), d_qo = q_out && pinned(q_out), d_fl = flags_out && pinned(flags_out);
+    char* dst_qd = qdot_out ? (d_qd ? (char*)qdot_out : pin_qd) : nullptr;
+    char* dst_qo = q_out ? (d_qo ? (char*)q_out : pin_qo) : nullptr;
+    char* dst_fl = flags_out ? (d_fl ? (char*)flags_out : pin_fl) : nullptr;
+
     vfk_buffers b = s->b;
     b.jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
-    b.ns_in = s->have_ns_in ? s->d_ns_in : nullptr;
+    b.ns_in = nullptr;                                          // offset separately below (4 or N components)
     if (!flags_out) b.flags = nullptr;
     if (!s->en_vf) b.qdot_vf = nullptr;
     if (!s->en_ns) b.qdot_ns = nullptr;
     if (!s->en_jp) b.qdot_jp = nullptr;
     if (!s->en_cmd) b.cmd = nullptr;
     if (!s->en_pose) b.pose = nullptr;
-    if ((rc = vfk_step(h, &b, s->n, s->n_obst, k_cycles, s->stream)) < 0) return rc;
-    launches += rc;
-    const bool d_qd = qdot_out && pinned(qdot_out), d_qo = q_out && pinned(q_out), d_fl = flags_out && pinned(flags_out);
-    if (qdot_out) {
-        if ((rc = pack_dispatch(h, s->stage_out, s->b.qdot, s->N, 1, s->n, true, s->stream)) < 0) return rc;
+    const int ns_comps = h->params.ns_mode == VFK_NS_CONTROL ? 4 : N;
+
+    // Chunk pipeline: with several chunks in flight on different streams the H2D copy of chunk c+1, the
+    // kernels of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex).  Chunks are whole tiles.
+    int n_chunks = (int)(s->n / 65536);
+    if (n_chunks > 8) n_chunks = 8;
+    if (n_chunks < 1) n_chunks = 1;
+    const int64_t tiles_per_chunk = (s->tiles + n_chunks - 1) / n_chunks;
+    char* stage_q = (char*)s->stage_in;                         // dense [N][n]
+    char* stage_qd = (char*)s->stage_out;                       // dense [N][n]
+    char* stage_qo = (char*)s->stage_out + (size_t)(N > 12 ? N : 12) * (align_up((size_t)s->tiles * 32 * es, 128));
+    const size_t pitch = (size_t)s->n * es;
+    int launches = 0, rc;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t t0 = (int64_t)c * tiles_per_chunk;
+        if (t0 >= s->tiles) break;
+        const int64_t t1 = t0 + tiles_per_chunk < s->tiles ? t0 + tiles_per_chunk : s->tiles;
+        const int64_t i0 = t0 * 32;
+        const int64_t cnt = (t1 * 32 < s->n ? t1 * 32 : s->n) - i0;
+        cudaStream_t st = n_chunks > 1 ? s->pipe[c % 3] : s->stream;
+        vfk_buffers v = offset_view(b, t0, N, s->n_obst, es);
+        if (s->have_ns_in) v.ns_in = (char*)s->d_ns_in + (size_t)t0 * ns_comps * 32 * es;
+        if (src_q) {
+            VFK_CUDA(h, cudaMemcpy2DAsync(stage_q + i0 * es, pitch, src_q + i0 * es, pitch, (size_t)cnt * es, N,
+                                          cudaMemcpyHostToDevice, st));
+            if ((rc = pack_dispatch(h, stage_q + i0 * es, v.q, N, 1, cnt, false, st, s->n)) < 0) return rc;
+            launches += rc;
+        }
+        if ((rc = vfk_step(h, &v, cnt, s->n_obst, k_cycles, st)) < 0) return rc;
         launches += rc;
-        VFK_CUDA(h, cudaMemcpyAsync(d_qd ? qdot_out : (void*)pin_qd, s->stage_out, blk, cudaMemcpyDeviceToHost, s->stream));
+        if (dst_qd) {
+            if ((rc = pack_dispatch(h, stage_qd + i0 * es, v.qdot, N, 1, cnt, true, st, s->n)) < 0) return rc;
+            launches += rc;
+            VFK_CUDA(h, cudaMemcpy2DAsync(dst_qd + i0 * es, pitch, stage_qd + i0 * es, pitch, (size_t)cnt * es, N,
+                                          cudaMemcpyDeviceToHost, st));
+        }
+        if (dst_qo) {
+            if ((rc = pack_dispatch(h, stage_qo + i0 * es, v.q, N, 1, cnt, true, st, s->n)) < 0) return rc;
+            launches += rc;
+            VFK_CUDA(h, cudaMemcpy2DAsync(dst_qo + i0 * es, pitch, stage_qo + i0 * es, pitch, (size_t)cnt * es, N,
+                                          cudaMemcpyDeviceToHost, st));
+        }
+        if (dst_fl)         // one component: blocked == dense
+            VFK_CUDA(h, cudaMemcpyAsync(dst_fl + i0 * 4, s->b.flags + i0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
     }
-    if (q_out) {
-        if ((rc = pack_dispatch(h, s->stage_in, s->b.q, s->N, 1, s->n, true, s->stream)) < 0) return rc;
-        launches += rc;
-        VFK_CUDA(h, cudaMemcpyAsync(d_qo ? q_out : (void*)pin_qo, s->stage_in, blk, cudaMemcpyDeviceToHost, s->stream));
+    if (n_chunks > 1) {
+        for (int k = 0; k < 3; ++k) VFK_CUDA(h, cudaStreamSynchronize(s->pipe[k]));
+    } else {
+        VFK_CUDA(h, cudaStreamSynchronize(s->stream));
     }
-    if (flags_out)      // one component: blocked == dense
-        VFK_CUDA(h, cudaMemcpyAsync(d_fl ? (void*)flags_out : (void*)pin_fl, s->b.flags, (size_t)s->n * 4,
-                                    cudaMemcpyDeviceToHost, s->stream));
-    VFK_CUDA(h, cudaStreamSynchronize(s->stream));
     if (qdot_out && !d_qd) memcpy(qdot_out, pin_qd, blk);
     if (q_out && !d_qo) memcpy(q_out, pin_qo, blk);
     if (flags_out && !d_fl) memcpy(flags_out, pin_fl, (size_t)s->n * 4);
@@ -728,5 +784,6 @@ extern "C" void vfk_session_destroy(vfk_session s) {
     cudaFreeHost(s->pin);
     cudaFree(s->dev);
     cudaStreamDestroy(s->stream);
+    for (int k = 0; k < 3; ++k) cudaStreamDestroy(s->pipe[k]);
     delete s;
 }

@@ -766,10 +766,10 @@ vfk_set_vel_kernel(const T* __restrict__ qdot, const T* __restrict__ q, const T*
 }
 
 // ------------------------------------------------------------------------------ layout conversion
-// dense SoA [C][n] (element size E bytes: scalar, Vec2 or Vec4 of T)  <->  tile-blocked [tile][C][32].
+// dense SoA [C][dense_ld >= n] (element: scalar, Vec2 or Vec4 of T)  <->  tile-blocked [tile][C][32].
 template <typename V>
 __global__ void __launch_bounds__(256)
-vfk_pack_kernel(const V* __restrict__ dense, V* __restrict__ blocked, int C, int64_t n, int64_t n_tiles) {
+vfk_pack_kernel(const V* __restrict__ dense, int64_t dense_ld, V* __restrict__ blocked, int C, int64_t n, int64_t n_tiles) {
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;          // index into the blocked array
     if (e >= n_tiles * C * 32) return;
     const int lane = (int)(e & 31);
@@ -779,12 +779,12 @@ vfk_pack_kernel(const V* __restrict__ dense, V* __restrict__ blocked, int C, int
     const int64_t i = (tile << 5) + lane;
     V zero;
     memset(&zero, 0, sizeof zero);
-    blocked[e] = i < n ? dense[(int64_t)cidx * n + i] : zero;
+    blocked[e] = i < n ? dense[(int64_t)cidx * dense_ld + i] : zero;
 }
 
 template <typename V>
 __global__ void __launch_bounds__(256)
-vfk_unpack_kernel(const V* __restrict__ blocked, V* __restrict__ dense, int C, int64_t n, int64_t n_tiles) {
+vfk_unpack_kernel(const V* __restrict__ blocked, V* __restrict__ dense, int64_t dense_ld, int C, int64_t n, int64_t n_tiles) {
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (e >= n_tiles * C * 32) return;
     const int lane = (int)(e & 31);
@@ -792,7 +792,7 @@ vfk_unpack_kernel(const V* __restrict__ blocked, V* __restrict__ dense, int C, i
     const int64_t tile = tc / C;
     const int cidx = (int)(tc - tile * C);
     const int64_t i = (tile << 5) + lane;
-    if (i < n) dense[(int64_t)cidx * n + i] = blocked[e];
+    if (i < n) dense[(int64_t)cidx * dense_ld + i] = blocked[e];
 }
 
 }  // namespace vfk
