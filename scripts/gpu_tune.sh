@@ -18,7 +18,8 @@ except Exception as e: print("$name failed", e)
 PY
 }
 run default A=1
-run sincos_libdevice VFK_LIB=$PWD/build/libvfk_sincos1.so
-run sincos_mufu VFK_LIB=$PWD/build/libvfk_sincos2.so
-timeout 200 python scripts/fp32_error.py 262144 2>&1 | tail -3
-VFK_LIB=$PWD/build/libvfk_sincos1.so timeout 200 python scripts/fp32_error.py 262144 2>&1 | tail -3
+run nolean VFK_NO_LEAN=1
+run lean4_s2 VFK_LIB=$PWD/build/libvfk_lean4.so VFK_STAGES=2
+run lean4_s3 VFK_LIB=$PWD/build/libvfk_lean4.so VFK_STAGES=3
+run lean3_s2 VFK_STAGES=2
+timeout 200 python scripts/fp32_error.py 65536 2>&1 | tail -3

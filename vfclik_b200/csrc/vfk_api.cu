@@ -290,7 +290,15 @@ static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, 
     *smem_bytes = kSmemHeader + (size_t)(kBlock / 32) * WS::warp_bytes(stages);
 }
 
-template <typename T, int N, class PAT, bool EXT>
+// The LEAN kernel's preconditions (see vfk_kernels.cuh).
+template <typename T>
+static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
+    return c.tool_identity && c.unit_weights && c.share_factor && c.ns_mode == VFK_NS_PROJECTOR && !c.need_jp && !b->ns_in &&
+           !b->jp_ref && !b->q_cmded && !b->ext_cmd[0] && !b->ext_cmd[1] && !b->ext_cmd[2] && !b->qdot_vf && !b->qdot_ns &&
+           !b->qdot_jp && !b->cmd && !b->pose && !b->flags && b->qdot && !getenv("VFK_NO_LEAN");
+}
+
+template <typename T, int N, class PAT, bool EXT, bool LEAN>
 static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
                         cudaStream_t st) {
     KArgs<T> a;
@@ -321,8 +329,11 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #ifndef VFK_MINB_F32
 #define VFK_MINB_F32 3
 #endif
-    constexpr int MINB = (sizeof(T) == 4) ? (N <= 10 ? VFK_MINB_F32 : 2) : (N <= 7 ? 2 : 1);
-    auto kern = vfk_cycle_kernel<T, N, PAT, EXT, MINB>;
+#ifndef VFK_MINB_LEAN
+#define VFK_MINB_LEAN 3
+#endif
+    constexpr int MINB = (sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? 2 : 1);
+    auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB>;
     VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
     int per_sm = 0;
     VFK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
@@ -336,17 +347,22 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     return 1;
 }
 
+template <typename T, int N, class PAT>
+static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
+                         cudaStream_t st) {
+    const bool ext = b->obst_ext && n_obst > 0;
+    if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st);
+    if (is_lean<T>(c, b)) return launch_cycle<T, N, PAT, false, true>(h, c, b, n, n_obst, k_cycles, st);
+    return launch_cycle<T, N, PAT, false, false>(h, c, b, n, n_obst, k_cycles, st);
+}
+
 template <typename T, int N>
 static int dispatch_ext(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
                         cudaStream_t st) {
-    const bool ext = b->obst_ext && n_obst > 0;
     if constexpr (N == 7) {
-        if (h->pattern == 1)
-            return ext ? launch_cycle<T, N, LwrPattern, true>(h, c, b, n, n_obst, k_cycles, st)
-                       : launch_cycle<T, N, LwrPattern, false>(h, c, b, n, n_obst, k_cycles, st);
+        if (h->pattern == 1) return dispatch_feat<T, N, LwrPattern>(h, c, b, n, n_obst, k_cycles, st);
     }
-    return ext ? launch_cycle<T, N, GenericPattern, true>(h, c, b, n, n_obst, k_cycles, st)
-               : launch_cycle<T, N, GenericPattern, false>(h, c, b, n, n_obst, k_cycles, st);
+    return dispatch_feat<T, N, GenericPattern>(h, c, b, n, n_obst, k_cycles, st);
 }
 
 template <typename T>

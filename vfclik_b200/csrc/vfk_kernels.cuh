@@ -307,7 +307,12 @@ __device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile, int bu
 }
 
 // ------------------------------------------------------------------------------ the fused kernel
-template <typename T, int N, class PAT, bool EXT, int MINB>
+// LEAN = compile-time promise of the common production shape (checked on the host, vfk_api.cu:is_lean): identity
+// tool frame and IK weights, projector-mode nullspace on the built-in limit-avoidance gradient sharing the IK
+// factor, joint P controller unobserved, no extra mixer ports, and q / qdot as the only outputs.  It removes every
+// runtime feature branch from the hot loop (fewer instructions, registers and I-cache lines); the general
+// instantiation keeps them all.
+template <typename T, int N, class PAT, bool EXT, bool LEAN, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KArgs<T> a) {
     using WS = WarpStage<T, N, EXT>;
@@ -362,7 +367,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     for (int k = 0; k < 13; ++k) g[k] = qg[(N + k) * 32];
 
     T lastv[N];
-    if (c.ns_mode == 2) {
+    if (!LEAN && c.ns_mode == 2) {
 #pragma unroll
         for (int j = 0; j < N; ++j) lastv[j] = a.ns_lastvec[tN + j * 32];
     }
@@ -375,7 +380,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         T R[9], p[3], Jl[N][3], Ja[N][3];
         fk_jacobian<T, N, PAT>(c, q, R, p, Jl, Ja);
         T Rt[9], pt[3], dp[3];
-        if (c.tool_identity) {
+        if (LEAN || c.tool_identity) {
 #pragma unroll
             for (int k = 0; k < 9; ++k) Rt[k] = R[k];
 #pragma unroll
@@ -440,7 +445,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         // 5. weighted damped least squares: qdot = Wj Jw^T (Jw Jw^T + l^2 I)^-1 Wt t
         T A[21], invd[6];
         T qd_vf[N];
-        if (c.unit_weights) {
+        if (LEAN || c.unit_weights) {
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -494,8 +499,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         T qd_ns[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) qd_ns[j] = T(0);
-        if (c.ns_mode != 0) {
-            if (!c.share_factor) {
+        if (LEAN || c.ns_mode != 0) {
+            if (!LEAN && !c.share_factor) {
 #pragma unroll
                 for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -509,8 +514,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 chol6<T>(A, invd);
             }
             T x[N];
-            if (c.ns_mode == 1) {
-                if (a.ns_in) {
+            if (LEAN || c.ns_mode == 1) {
+                if (!LEAN && a.ns_in) {
 #pragma unroll
                     for (int j = 0; j < N; ++j) x[j] = __ldg(a.ns_in + tN + j * 32);
                 } else {
@@ -554,7 +559,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 for (int r = 0; r < 6; ++r) acc = fma(-(r < 3 ? Jl[j][r] : Ja[j][r - 3]), y[r], acc);
                 raw[j] = acc;
             }
-            if (c.ns_mode == 2) {
+            if (!LEAN && c.ns_mode == 2) {
                 T nn = T(0), dotl = T(0), l2 = T(0), amax = T(-1), vmax = T(0);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
@@ -589,7 +594,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         T qd_jp[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) qd_jp[j] = T(0);
-        if (c.need_jp || a.qdot_jp || a.flags) {
+        if (!LEAN && (c.need_jp || a.qdot_jp || a.flags)) {
             bool all_reached = true;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
@@ -611,12 +616,12 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             m = fma(qd_vf[j], c.mixer_w[0], m);
             m = fma(qd_ns[j], c.mixer_w[1], m);
             m = fma(qd_jp[j], c.mixer_w[2], m);
-            nan = nan || (qd_vf[j] != qd_vf[j]) || (qd_ns[j] != qd_ns[j]) || (qd_jp[j] != qd_jp[j]);
+            if (!LEAN) nan = nan || (qd_vf[j] != qd_vf[j]) || (qd_ns[j] != qd_ns[j]) || (qd_jp[j] != qd_jp[j]);
             mix[j] = m;
         }
 #pragma unroll
         for (int e = 0; e < 3; ++e)
-            if (a.ext_cmd[e]) {
+            if (!LEAN && a.ext_cmd[e]) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const T x = __ldg(a.ext_cmd[e] + tN + j * 32);
@@ -632,23 +637,23 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         if (lead > c.max_vel) { ratio = Prec<T>::div(c.max_vel, lead); flags |= 8; }
 
         if (last && active) {
-            if (a.qdot_vf) {
+            if (!LEAN && a.qdot_vf) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) a.qdot_vf[tN + j * 32] = qd_vf[j];
             }
-            if (a.qdot_ns) {
+            if (!LEAN && a.qdot_ns) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) a.qdot_ns[tN + j * 32] = qd_ns[j];
             }
-            if (a.qdot_jp) {
+            if (!LEAN && a.qdot_jp) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) a.qdot_jp[tN + j * 32] = qd_jp[j];
             }
-            if (a.qdot) {
+            if (LEAN || a.qdot) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) a.qdot[tN + j * 32] = mix[j] * ratio;
             }
-            if (a.cmd) {
+            if (!LEAN && a.cmd) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const T qd = mix[j] * ratio;
@@ -656,13 +661,13 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                     a.cmd[tN + j * 32] = c.direct_control ? qd : (-qc + q[j] + qd);
                 }
             }
-            if (a.pose) {
+            if (!LEAN && a.pose) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) a.pose[tile * (12 * 32) + k * 32 + lane] = Rt[k];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) a.pose[tile * (12 * 32) + (9 + k) * 32 + lane] = pt[k];
             }
-            if (a.flags) a.flags[(tile << 5) + lane] = flags;
+            if (!LEAN && a.flags) a.flags[(tile << 5) + lane] = flags;
         }
         // 10. plant
         if (c.integrate) {
@@ -675,7 +680,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 #pragma unroll
             for (int j = 0; j < N; ++j) a.q[tN + j * 32] = q[j];
         }
-        if (c.ns_mode == 2) {
+        if (!LEAN && c.ns_mode == 2) {
 #pragma unroll
             for (int j = 0; j < N; ++j) a.ns_lastvec[tN + j * 32] = lastv[j];
         }
