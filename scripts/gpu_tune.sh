@@ -18,8 +18,7 @@ except Exception as e: print("$name failed", e)
 PY
 }
 run default A=1
-run nolean VFK_NO_LEAN=1
-run lean4_s2 VFK_LIB=$PWD/build/libvfk_lean4.so VFK_STAGES=2
-run lean4_s3 VFK_LIB=$PWD/build/libvfk_lean4.so VFK_STAGES=3
-run lean3_s2 VFK_STAGES=2
-timeout 200 python scripts/fp32_error.py 65536 2>&1 | tail -3
+run b32 VFK_LIB=$PWD/build/libvfk_b32.so
+run b64 VFK_LIB=$PWD/build/libvfk_b64.so
+run b32_s3 VFK_LIB=$PWD/build/libvfk_b32.so VFK_STAGES=3
+VFK_LIB=$PWD/build/libvfk_b32.so timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2

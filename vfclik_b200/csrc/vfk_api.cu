@@ -272,14 +272,15 @@ static int check_layout(vfk_ctx* h, const void* ptr, const char* name, bool requ
 }
 
 // Launch plan: every warp is a persistent worker with its own obstacle ring (n_stages stages of kChunk
-// obstacles x 32 instances) and two q/goal buffers.  K = 1 streams through a 3-deep ring that runs one tile
-// ahead; K > 1 keeps the tile's obstacles resident across the fused cycles when they fit.
+// obstacles x 32 instances) and two q/goal buffers.  Two stages measured best on B200 for both K = 1
+// (106 us vs 110 us with three at the headline shape) and K = 100 (streaming the ring from L2 every cycle at
+// full occupancy beats keeping four chunks resident at 2 CTAs/SM): gpurun_out t03, DESIGN.md section 4.1.
 template <typename T, int N, bool EXT>
 static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, size_t* smem_bytes) {
     using WS = WarpStage<T, N, EXT>;
+    (void)k_cycles;
     *n_chunks = (n_obst + kChunk - 1) / kChunk;
-    int stages = sizeof(T) == 4 ? 3 : 2;
-    if (k_cycles > 1 && *n_chunks <= 4 && sizeof(T) == 4) stages = *n_chunks;      // resident across the K cycles
+    int stages = 2;
     if (const char* e = getenv("VFK_STAGES")) {
         const int v = atoi(e);
         if (v >= 1 && v <= kMaxStages) stages = v;
@@ -332,7 +333,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #ifndef VFK_MINB_LEAN
 #define VFK_MINB_LEAN 3
 #endif
-    constexpr int MINB = (sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? 2 : 1);
+    constexpr int MINB = ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? 2 : 1)) * (128 / kBlock);
     auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB>;
     VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
     int per_sm = 0;
@@ -409,13 +410,13 @@ extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goa
     if (n == 0) return 0;
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    const unsigned grid = (unsigned)((n + kSmallBlock - 1) / kSmallBlock);
     if (h->precision == 32)
-        vfk_field_kernel<float><<<grid, kBlock, 0, st>>>(h->cf, (const float*)pose_in, (const float*)goal,
+        vfk_field_kernel<float><<<grid, kSmallBlock, 0, st>>>(h->cf, (const float*)pose_in, (const float*)goal,
                                                          (const Vec4<float>*)obst, (const Vec2<float>*)obst_ext,
                                                          (float*)twist_out, n, n_obst);
     else
-        vfk_field_kernel<double><<<grid, kBlock, 0, st>>>(h->cd, (const double*)pose_in, (const double*)goal,
+        vfk_field_kernel<double><<<grid, kSmallBlock, 0, st>>>(h->cd, (const double*)pose_in, (const double*)goal,
                                                           (const Vec4<double>*)obst, (const Vec2<double>*)obst_ext,
                                                           (double*)twist_out, n, n_obst);
     VFK_CUDA(h, cudaGetLastError());

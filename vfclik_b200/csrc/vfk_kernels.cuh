@@ -29,7 +29,11 @@
 namespace vfk {
 
 constexpr int kMaxJ = 17;
-constexpr int kBlock = 128;          // threads (= instances) per CTA
+#ifndef VFK_BLOCK
+#define VFK_BLOCK 128
+#endif
+constexpr int kBlock = VFK_BLOCK;    // threads per CTA of the cycle kernel (warps are independent workers)
+constexpr int kSmallBlock = 128;     // threads per CTA of the small one-element-per-thread kernels
 constexpr int kChunk = 8;            // obstacles per shared-memory stage
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 512;     // per-warp mbarriers live in the first 512 bytes of dynamic smem
@@ -691,11 +695,11 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 // ------------------------------------------------------------------------------ small kernels
 // Field query at given tool poses (scripts/vf:469-503); low-rate visualisation path, plain loads.
 template <typename T>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kSmallBlock)
 vfk_field_kernel(const __grid_constant__ KConst<T> c, const T* __restrict__ pose, const T* __restrict__ goal,
                  const Vec4<T>* __restrict__ obst, const Vec2<T>* __restrict__ obst_ext, T* __restrict__ twist,
                  int64_t n, int n_obst) {
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kSmallBlock + threadIdx.x;
     if (i >= n) return;
     const int64_t tile = i >> 5;
     const int lane = (int)(i & 31);
