@@ -51,6 +51,50 @@ def random_batch(chain: ChainDesc, n_instances: int, n_obstacles: int, seed: int
     return out
 
 
+def random_batch_device(engine, n_instances: int, n_obstacles: int, seed: int, slowdown: float = 0.05, box: float = 0.8):
+    """Same distributions as :func:`random_batch`, drawn on the GPU with torch's generator (large shapes:
+    config 4's 2M x 256 obstacles per GPU would take minutes and 8 GB of host memory through numpy).
+    Returns a ``DeviceBatch`` with q / goal / obst filled (blocked layout)."""
+    import torch
+    from .engine import DeviceBatch
+    chain = engine.chain
+    dev = "cuda:%d" % engine.device
+    dt = engine.torch_dtype
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    I, N, M = int(n_instances), chain.n_joints, int(n_obstacles)
+    lo = torch.tensor(0.9 * chain.q_lo, dtype=dt, device=dev)[:, None]
+    hi = torch.tensor(0.9 * chain.q_hi, dtype=dt, device=dev)[:, None]
+    q = lo + (hi - lo) * torch.rand((N, I), generator=g, dtype=dt, device=dev)
+    quat = torch.randn((4, I), generator=g, dtype=dt, device=dev)
+    quat = quat / quat.norm(dim=0, keepdim=True)
+    w, x, y, z = quat
+    rot = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                       2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                       2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=0)
+    d = torch.randn((3, I), generator=g, dtype=dt, device=dev)
+    d = d / d.norm(dim=0, keepdim=True)
+    sh = torch.tensor(chain.base[9:12], dtype=dt, device=dev)[:, None]
+    pg = d * (0.3 + 0.5 * torch.rand((1, I), generator=g, dtype=dt, device=dev)) + sh
+    goal = torch.cat([rot, pg, torch.full((1, I), slowdown, dtype=dt, device=dev)], dim=0)
+    db = DeviceBatch(engine, I, M, outputs=("qdot",))
+    engine.pack(q.contiguous(), db.t["q"], N, 1, I)
+    engine.pack(goal.contiguous(), db.t["goal"], 13, 1, I)
+    step = max(1, min(M, (1 << 26) // max(I, 1)))            # obstacles per slice: bound the dense temporary
+    tiles = db.t["obst"].shape[0]
+    for m0 in range(0, M, step):
+        m1 = min(M, m0 + step)
+        o = torch.empty((m1 - m0, I, 4), dtype=dt, device=dev)
+        o[:, :, 0:3] = (2 * box) * torch.rand((m1 - m0, I, 3), generator=g, dtype=dt, device=dev) - box + sh.T[None]
+        o[:, :, 3] = 0.03 + 0.07 * torch.rand((m1 - m0, I), generator=g, dtype=dt, device=dev)
+        blk = engine.alloc(m1 - m0, I, width=4)
+        engine.pack(o, blk, m1 - m0, 4, I)
+        db.t["obst"][:, m0:m1] = blk
+        del o, blk
+    torch.cuda.synchronize(engine.device)
+    return db
+
+
 def config1(chain: ChainDesc, config, seed: int = 0):
     """BASELINE config 1: single LWR, start q and goal of old/system_start.sh.old:234,346,
     three ObstacleP (radius 0.05, order 20: old/README.old:75) seeded between the start
