@@ -335,10 +335,20 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #endif
     constexpr int MINB = ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? 2 : 1)) * (128 / kBlock);
     auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB>;
-    VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+    // per (instantiation, device, smem size): opt in to > 48 KB of dynamic shared memory and ask the occupancy once
+    static int cached_per_sm[16];
+    static size_t cached_smem[16];
     int per_sm = 0;
-    VFK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
-    if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "kernel does not fit an SM with %zu bytes of shared memory", smem);
+    const int dslot = h->device & 15;
+    if (cached_per_sm[dslot] > 0 && cached_smem[dslot] == smem) {
+        per_sm = cached_per_sm[dslot];
+    } else {
+        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+        VFK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+        if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "kernel does not fit an SM with %zu bytes of shared memory", smem);
+        cached_per_sm[dslot] = per_sm;
+        cached_smem[dslot] = smem;
+    }
     const int64_t tiles = (n + 31) / 32;
     const int64_t want = (tiles + kBlock / 32 - 1) / (kBlock / 32);
     const int64_t cap = (int64_t)h->sm_count * per_sm;
