@@ -135,6 +135,7 @@ typedef struct vfk_buffers {
     void*       qdot;            /* out [N]  clamped mixer output qdot_lim (scripts/bridge:196)    */
     void*       cmd;             /* out [N]  command sent to the plant (scripts/bridge:198-203)    */
     void*       pose;            /* out [12] tool frame (/vectorField/pose)                        */
+    void*       twist;           /* out [6]  commanded tool twist velPos, velRot (/vectorField/vector_out, scripts/vf:346-347) */
     int32_t*    flags;           /* out [1]  VFK_FLAG_*                                            */
 } vfk_buffers;
 
@@ -178,6 +179,15 @@ int  vfk_mix(vfk_handle h, const void* const* cmds, const double* w, int n_ports
 int  vfk_set_vel(vfk_handle h, const void* qdot, const void* q, const void* q_cmded, double max_vel, int direct_control,
                  void* cmd_out, void* qdot_lim_out, int n_channels, int64_t n_instances, void* stream);
 
+/* Monitoring, one call per control cycle after vfk_step:
+ *   tracking-error diagnostics of scripts/vf:349-428 -> track_out [8] (the 7 doubles + arm_tracking of /vectorField/track_error),
+ *   distance monitor of scripts/monitor_distance:76-84,148-219 -> dist_out [2] (metres, degrees to the goal) and
+ *   tracking_state_out [2] int32 (majority over the last 20 cycles: 0 on goal, 1 follow, 2 not follow; -1 before 21 samples).
+ * pose [12] and twist [6] are vfk_step outputs; state_f [32] and state_i [6] (int32) carry the 5-frame / 4-command
+ * history between calls and must start zeroed.  Outputs may be NULL. */
+int  vfk_monitor(vfk_handle h, const void* pose, const void* twist, const void* goal, void* state_f, int32_t* state_i,
+                 void* track_out, void* dist_out, int32_t* tracking_state_out, int64_t n_instances, void* stream);
+
 /* Layout conversion on the device: dense SoA [comps][n] (width scalars per element: 1 for
  * per-instance components, 4 for obstacles [M][n][4], 2 for obst_ext [M][n][2]) <-> tile-blocked. */
 int  vfk_pack(vfk_handle h, const void* dense, void* blocked, int comps, int width, int64_t n_instances, void* stream);
@@ -199,7 +209,7 @@ int  vfk_session_set_jp_ref(vfk_session s, const void* ref_host);           /* [
 int  vfk_session_set_ns_input(vfk_session s, const void* ns_host);          /* [N|4][n] or NULL */
 int  vfk_session_cycle(vfk_session s, const void* q_in_host, int k_cycles,
                        void* qdot_out_host, void* q_out_host, int32_t* flags_out_host);
-/* Optional per-controller outputs the kernel writes each cycle ("qdot_vf","qdot_ns","qdot_jp","cmd","pose");
+/* Optional per-controller outputs the kernel writes each cycle ("qdot_vf","qdot_ns","qdot_jp","cmd","pose","twist");
  * all off by default so the resident path only moves q in and qdot out. */
 int  vfk_session_enable(vfk_session s, const char* what, int on);
 int  vfk_session_read(vfk_session s, const char* what, void* out_host);     /* enabled outputs, "qdot", "q", "lastvec" */

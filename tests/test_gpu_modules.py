@@ -160,3 +160,44 @@ def test_set_vel_kernel(lwr, built_lib):
         assert np.any(ratio < 1) and np.any(ratio == 1)
     finally:
         e.close()
+
+
+def test_monitor_kernel_matches_reference_shaped_monitor(lwr, built_lib):
+    """vfk_monitor (tracking diagnostics + distance monitor) over 40 cycles of 200 instances vs the
+    scalar restatement of scripts/vf:349-428 and scripts/monitor_distance:148-219."""
+    from oracle import monitor as omon
+    from oracle.refshape import KdlFrame
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch, Engine, Params
+    chain, cfg = lwr
+    e = Engine(chain, precision=64, params=Params.from_config(cfg, speed_scale=0.4, dt=0.02))
+    try:
+        n, M, K = 200, 4, 40
+        w = workloads.random_batch(chain, n, M, seed=61)
+        w["goal"][12] = 0.3                                   # wide slow-down ball: some instances reach "on goal"
+        db = DeviceBatch(e, n, M, outputs=("qdot", "pose", "twist"))
+        db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+        diag = [omon.TrackingDiagnostics() for _ in range(n)]
+        dmon = [omon.DistanceMonitor() for _ in range(n)]
+        goals = [KdlFrame(w["goal"][0:9, i].reshape(3, 3), w["goal"][9:12, i]) for i in range(n)]
+        seen_states = set()
+        for k in range(K):
+            db.step(1)
+            db.monitor()
+            pose, tw = db.download("pose"), db.download("twist")
+            track, dist, st = db.download("track"), db.download("dist"), db.download("tracking_state")
+            for i in range(0, n, 7):
+                f = KdlFrame(pose[0:9, i].reshape(3, 3), pose[9:12, i])
+                te = diag[i].update(f, tw[0:3, i], tw[3:6, i])
+                dx, dd, mx, mr = dmon[i].update(f, goals[i], te)
+                if te is None:
+                    assert np.all(track[:, i] == 0.0)
+                else:
+                    assert np.allclose(track[:, i], te, rtol=1e-6, atol=1e-7), (k, i, track[:, i], te)
+                assert np.isclose(dist[0, i], dx, rtol=1e-12, atol=1e-14) and np.isclose(dist[1, i], dd, rtol=1e-9, atol=1e-9)
+                want = (-1 if mx is None else omon.STATES.index(mx), -1 if mr is None else omon.STATES.index(mr))
+                assert (st[0, i], st[1, i]) == want, (k, i, st[:, i], want)
+                seen_states.update(want)
+        assert {-1, 1}.issubset(seen_states)
+    finally:
+        e.close()

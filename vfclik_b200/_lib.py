@@ -33,7 +33,7 @@ LIB_PATH = os.environ.get("VFK_LIB") or os.path.join(os.path.dirname(os.path.abs
 EXPORTS = [
     "vfk_version", "vfk_default_params", "vfk_create", "vfk_set_params", "vfk_get_params", "vfk_chain_pattern",
     "vfk_destroy",
-    "vfk_last_error", "vfk_step", "vfk_field_eval", "vfk_mix", "vfk_set_vel", "vfk_pack", "vfk_unpack", "vfk_session_create", "vfk_session_set_goal",
+    "vfk_last_error", "vfk_step", "vfk_field_eval", "vfk_mix", "vfk_set_vel", "vfk_monitor", "vfk_pack", "vfk_unpack", "vfk_session_create", "vfk_session_set_goal",
     "vfk_session_set_obstacles", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input",
     "vfk_session_cycle", "vfk_session_enable", "vfk_session_read", "vfk_session_buffers", "vfk_session_destroy",
 ]
@@ -78,7 +78,7 @@ class BuffersC(C.Structure):
         ("ns_in", C.c_void_p),
         ("ns_lastvec", C.c_void_p), ("q_cmded", C.c_void_p), ("ext_cmd", C.c_void_p * 3), ("qdot_vf", C.c_void_p),
         ("qdot_ns", C.c_void_p), ("qdot_jp", C.c_void_p), ("qdot", C.c_void_p), ("cmd", C.c_void_p),
-        ("pose", C.c_void_p), ("flags", C.c_void_p),
+        ("pose", C.c_void_p), ("twist", C.c_void_p), ("flags", C.c_void_p),
     ]
 
 
@@ -114,6 +114,7 @@ def load():
     lib.vfk_field_eval.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
     lib.vfk_mix.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_double), i32, i32, vp, vp, i64, vp]
     lib.vfk_set_vel.argtypes = [vp, vp, vp, vp, C.c_double, i32, vp, vp, i32, i64, vp]
+    lib.vfk_monitor.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.vfk_pack.argtypes = [vp, vp, vp, i32, i32, i64, vp]
     lib.vfk_unpack.argtypes = [vp, vp, vp, i32, i32, i64, vp]
     lib.vfk_session_create.argtypes = [vp, i64, i32, i32, C.POINTER(vp)]

@@ -296,7 +296,7 @@ template <typename T>
 static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
     return c.tool_identity && c.unit_weights && c.share_factor && c.ns_mode == VFK_NS_PROJECTOR && !c.need_jp && !b->ns_in &&
            !b->jp_ref && !b->q_cmded && !b->ext_cmd[0] && !b->ext_cmd[1] && !b->ext_cmd[2] && !b->qdot_vf && !b->qdot_ns &&
-           !b->qdot_jp && !b->cmd && !b->pose && !b->flags && b->qdot && !getenv("VFK_NO_LEAN");
+           !b->qdot_jp && !b->cmd && !b->pose && !b->twist && !b->flags && b->qdot && !getenv("VFK_NO_LEAN");
 }
 
 template <typename T, int N, class PAT, bool EXT, bool LEAN>
@@ -319,6 +319,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.qdot = static_cast<T*>(b->qdot);
     a.cmd = static_cast<T*>(b->cmd);
     a.pose = static_cast<T*>(b->pose);
+    a.twist = static_cast<T*>(b->twist);
     a.flags = b->flags;
     a.n = n;
     a.n_obst = n_obst;
@@ -401,7 +402,7 @@ extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int n_obs
         (rc = check_layout(h, b->q_cmded, "q_cmded", false)) || (rc = check_layout(h, b->qdot_vf, "qdot_vf", false)) ||
         (rc = check_layout(h, b->qdot_ns, "qdot_ns", false)) || (rc = check_layout(h, b->qdot_jp, "qdot_jp", false)) ||
         (rc = check_layout(h, b->qdot, "qdot", false)) || (rc = check_layout(h, b->cmd, "cmd", false)) ||
-        (rc = check_layout(h, b->pose, "pose", false)) || (rc = check_layout(h, b->flags, "flags", false)))
+        (rc = check_layout(h, b->pose, "pose", false)) || (rc = check_layout(h, b->twist, "twist", false)) || (rc = check_layout(h, b->flags, "flags", false)))
         return rc;
     for (int e = 0; e < 3; ++e)
         if ((rc = check_layout(h, b->ext_cmd[e], "ext_cmd", false))) return rc;
@@ -476,6 +477,26 @@ extern "C" int vfk_set_vel(vfk_handle h, const void* qdot, const void* q, const 
     return 1;
 }
 
+extern "C" int vfk_monitor(vfk_handle h, const void* pose, const void* twist, const void* goal, void* state_f, int32_t* state_i,
+                           void* track_out, void* dist_out, int32_t* tracking_state_out, int64_t n, void* stream) {
+    if (!h || !pose || !twist || !goal || !state_f || !state_i) return fail(h, VFK_ERR_INVALID, "vfk_monitor: null argument");
+    if (n < 0) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 0");
+    if (n == 0) return 0;
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((n + kSmallBlock - 1) / kSmallBlock);
+    if (h->precision == 32)
+        vfk_monitor_kernel<float><<<grid, kSmallBlock, 0, st>>>((const float*)pose, (const float*)twist, (const float*)goal,
+                                                               (float*)state_f, state_i, (float*)track_out, (float*)dist_out,
+                                                               tracking_state_out, n);
+    else
+        vfk_monitor_kernel<double><<<grid, kSmallBlock, 0, st>>>((const double*)pose, (const double*)twist, (const double*)goal,
+                                                                (double*)state_f, state_i, (double*)track_out, (double*)dist_out,
+                                                                tracking_state_out, n);
+    VFK_CUDA(h, cudaGetLastError());
+    return 1;
+}
+
 // -------------------------------------------------------------------------------- public: layout conversion
 template <typename V>
 static cudaError_t run_pack(const void* dense, int64_t dense_ld, void* blocked, int C, int64_t n, bool unpack, cudaStream_t st) {
@@ -534,7 +555,7 @@ struct vfk_session_s {
     void* stage_in;                  // dense staging, big enough for the largest upload
     void* stage_out;                 // dense staging for outputs (max(N, 12) rows)
     bool have_jp_ref, have_ns_in;
-    bool en_vf, en_ns, en_jp, en_cmd, en_pose;   // optional per-controller outputs (off by default)
+    bool en_vf, en_ns, en_jp, en_cmd, en_pose, en_twist;   // optional per-controller outputs (off by default)
     void *d_jp_ref, *d_ns_in;
     char* pin;                       // pinned host staging: q in (N rows), qdot / q out (2N rows), flags
     size_t pin_bytes;
@@ -562,8 +583,8 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     const int N = s->N;
     const size_t row = align_up((size_t)s->tiles * 32 * s->es, 128);     // one component over all tiles
     const size_t obst_rows = (size_t)n_obst * (4 + (s->has_ext ? 2 : 0));
-    // blocked: q N, goal 13, obst, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, flags 1
-    const size_t rows = (size_t)N * 9 + 13 + obst_rows + 12 + 1;
+    // blocked: q N, goal 13, obst, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, twist 6, flags 1
+    const size_t rows = (size_t)N * 9 + 13 + obst_rows + 12 + 6 + 1;
     const size_t stage_in_rows = obst_rows > (size_t)(N > 13 ? N : 13) ? obst_rows : (size_t)(N > 13 ? N : 13);
     const size_t stage_out_rows = (size_t)(N > 12 ? N : 12) + (size_t)N;      // qdot (or a read()) + q_out
     s->dev_bytes = (rows + stage_in_rows + stage_out_rows) * row;
@@ -585,11 +606,12 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->b.qdot = take(N);
     s->b.cmd = take(N);
     s->b.pose = take(12);
+    s->b.twist = take(6);
     s->b.flags = (int32_t*)take(1);
     s->stage_in = take(stage_in_rows);
     s->stage_out = take(stage_out_rows);
     s->have_jp_ref = s->have_ns_in = false;
-    s->en_vf = s->en_ns = s->en_jp = s->en_cmd = s->en_pose = false;
+    s->en_vf = s->en_ns = s->en_jp = s->en_cmd = s->en_pose = s->en_twist = false;
     s->launches = 0;
     s->pin_bytes = (size_t)N * 3 * (size_t)n * s->es + (size_t)n * 4;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
@@ -662,7 +684,7 @@ static vfk_buffers offset_view(const vfk_buffers& b, int64_t tile0, int N, int M
     o.jp_ref = off(b.jp_ref, N); o.ns_lastvec = off(b.ns_lastvec, N); o.q_cmded = off(b.q_cmded, N);
     for (int e = 0; e < 3; ++e) o.ext_cmd[e] = off(b.ext_cmd[e], N);
     o.qdot_vf = off(b.qdot_vf, N); o.qdot_ns = off(b.qdot_ns, N); o.qdot_jp = off(b.qdot_jp, N); o.qdot = off(b.qdot, N);
-    o.cmd = off(b.cmd, N); o.pose = off(b.pose, 12);
+    o.cmd = off(b.cmd, N); o.pose = off(b.pose, 12); o.twist = off(b.twist, 6);
     o.flags = b.flags ? b.flags + tile0 * 32 : nullptr;
     return o;
 }
@@ -705,6 +727,7 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
     if (!s->en_jp) b.qdot_jp = nullptr;
     if (!s->en_cmd) b.cmd = nullptr;
     if (!s->en_pose) b.pose = nullptr;
+    if (!s->en_twist) b.twist = nullptr;
     const int ns_comps = h->params.ns_mode == VFK_NS_CONTROL ? 4 : N;
 
     // Chunk pipeline: with several chunks in flight on different streams the H2D copy of chunk c+1, the
@@ -769,6 +792,7 @@ extern "C" int vfk_session_enable(vfk_session s, const char* what, int on) {
     else if (!strcmp(what, "qdot_jp")) f = &s->en_jp;
     else if (!strcmp(what, "cmd")) f = &s->en_cmd;
     else if (!strcmp(what, "pose")) f = &s->en_pose;
+    else if (!strcmp(what, "twist")) f = &s->en_twist;
     else return fail(s->h, VFK_ERR_INVALID, "vfk_session_enable: unknown output '%s'", what);
     *f = on != 0;
     return VFK_OK;
@@ -786,6 +810,7 @@ extern "C" int vfk_session_read(vfk_session s, const char* what, void* out) {
     else if (!strcmp(what, "q")) src = s->b.q;
     else if (!strcmp(what, "lastvec")) src = s->b.ns_lastvec;
     else if (!strcmp(what, "pose")) { src = s->b.pose; rows = 12; }
+    else if (!strcmp(what, "twist")) { src = s->b.twist; rows = 6; }
     else return fail(s->h, VFK_ERR_INVALID, "vfk_session_read: unknown field '%s'", what);
     vfk_ctx* h = s->h;
     VFK_CUDA(h, cudaSetDevice(h->device));

@@ -84,6 +84,7 @@ struct KArgs {
     T* qdot;
     T* cmd;
     T* pose;
+    T* twist;                  // [6] commanded tool twist (velPos, velRot of scripts/vf:346-347)
     int32_t* flags;
     int64_t n;
     int32_t n_obst;
@@ -440,6 +441,13 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
             T v[3];
             saturate<T>(c, V, S0, v);
+            if (!LEAN && last && active && a.twist) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    a.twist[tile * (6 * 32) + k * 32 + lane] = v[k];
+                    a.twist[tile * (6 * 32) + (3 + k) * 32 + lane] = w[k];
+                }
+            }
             tw[0] = v[0] + (w[1] * dp[2] - w[2] * dp[1]);
             tw[1] = v[1] + (w[2] * dp[0] - w[0] * dp[2]);
             tw[2] = v[2] + (w[0] * dp[1] - w[1] * dp[0]);
@@ -772,6 +780,158 @@ vfk_set_vel_kernel(const T* __restrict__ qdot, const T* __restrict__ q, const T*
         const T qc = q_cmded ? q_cmded[base + c * 32] : q[base + c * 32];
         cmd[base + c * 32] = direct ? v : (-qc + q[base + c * 32] + v);
     }
+}
+
+// ------------------------------------------------------------------------------ monitoring
+// Tracking-error diagnostics of scripts/vf:349-428 and the distance monitor of scripts/monitor_distance:76-84,148-219,
+// one thread per instance, state carried between calls in two blocked arrays:
+//   sf [32]: previous tool pose (12), the three previous commanded twists (3 x 6, oldest first), last track errors (2)
+//   si [6] : cycles seen, xyz state ring (2 x 32 bits), rot state ring (2 x 32 bits), votes in the ring
+// Outputs: track [8] = the 7 doubles + the arm_tracking int of /vectorField/track_error;
+//          dist [2]  = distance to the goal in metres and degrees (/dmonitor/distOut, object 0);
+//          state [2] = majority tracking state over the last 20 cycles (0 on goal, 1 follow, 2 not follow) for xyz / rot,
+//                      -1 until 21 samples have been seen.
+template <typename T>
+__device__ __forceinline__ void rotvec_between(const T (&Ra)[9], const T (&Rb)[9], T (&out)[3]) {
+    // KDL diff(Fa, Fb).rot = Ra * rotvec(Ra^T Rb)
+    T E[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+            E[3 * r + cc] = Ra[r] * Rb[cc] + Ra[3 + r] * Rb[3 + cc] + Ra[6 + r] * Rb[6 + cc];
+    T qw, qx, qy, qz;
+    rot_to_quat<T>(E, qw, qx, qy, qz);
+    const T n2 = qx * qx + qy * qy + qz * qz;
+    const T n = Prec<T>::sqrt_(n2);
+    const T ang = T(2) * Prec<T>::atan2_(n, qw);
+    const T sc = n > T(0) ? Prec<T>::div(ang, n) : T(0);
+    const T lx = qx * sc, ly = qy * sc, lz = qz * sc;
+    out[0] = Ra[0] * lx + Ra[1] * ly + Ra[2] * lz;
+    out[1] = Ra[3] * lx + Ra[4] * ly + Ra[5] * lz;
+    out[2] = Ra[6] * lx + Ra[7] * ly + Ra[8] * lz;
+}
+
+__device__ __forceinline__ int ring_majority(uint32_t lo, uint32_t hi) {
+    // 20 two-bit states packed from bit 0; first maximum in the order on goal, follow, not follow
+    int cnt[3] = {0, 0, 0};
+    uint64_t bits = ((uint64_t)hi << 32) | lo;
+#pragma unroll
+    for (int k = 0; k < 20; ++k) { const int s = (int)((bits >> (2 * k)) & 3u); if (s < 3) ++cnt[s]; }
+    int best = 0;
+    if (cnt[1] > cnt[best]) best = 1;
+    if (cnt[2] > cnt[best]) best = 2;
+    return best;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSmallBlock)
+vfk_monitor_kernel(const T* __restrict__ pose, const T* __restrict__ twist, const T* __restrict__ goal, T* __restrict__ sf,
+                   int32_t* __restrict__ si, T* __restrict__ track, T* __restrict__ dist, int32_t* __restrict__ state, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * kSmallBlock + threadIdx.x;
+    if (i >= n) return;
+    const int64_t tile = i >> 5;
+    const int lane = (int)(i & 31);
+    auto F = [&](const T* base, int comps, int c) -> const T& { return base[(tile * comps + c) * 32 + lane]; };
+    T R[9], p[3], cmd[6], g[13];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = F(pose, 12, k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = F(pose, 12, 9 + k);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cmd[k] = F(twist, 6, k);
+#pragma unroll
+    for (int k = 0; k < 13; ++k) g[k] = F(goal, 13, k);
+    T* sfi = sf + tile * (32 * 32) + lane;
+    int32_t* sii = si + tile * (6 * 32) + lane;
+    const int seen = sii[0] + 1;                       // frames appended so far, this one included (scripts/vf:354)
+
+    // ---- tracking diagnostics (scripts/vf:349-428): needs 6 frames and the command of 3 cycles ago
+    T te_xyz = T(0), te_rot = T(0);
+    bool have_te = false;
+    if (seen > 5) {
+        T Rp[9], pp[3], old[6];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rp[k] = sfi[k * 32];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pp[k] = sfi[(9 + k) * 32];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) old[k] = sfi[(12 + k) * 32];       // oldest of the 4 buffered commands
+        const T ev[3] = {p[0] - pp[0], p[1] - pp[1], p[2] - pp[2]};
+        T er[3];
+        rotvec_between<T>(Rp, R, er);
+        auto unit_dot = [&](const T (&a3)[3], const T* b3, T& amag, T& bmag) {
+            amag = Prec<T>::sqrt_(a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2]);
+            bmag = Prec<T>::sqrt_(b3[0] * b3[0] + b3[1] * b3[1] + b3[2] * b3[2]);
+            T ua[3] = {T(1), T(0), T(0)}, ub[3] = {T(1), T(0), T(0)};
+            if (amag > T(0)) { ua[0] = Prec<T>::div(a3[0], amag); ua[1] = Prec<T>::div(a3[1], amag); ua[2] = Prec<T>::div(a3[2], amag); }
+            if (bmag > T(0)) { ub[0] = Prec<T>::div(b3[0], bmag); ub[1] = Prec<T>::div(b3[1], bmag); ub[2] = Prec<T>::div(b3[2], bmag); }
+            T d = ub[0] * ua[0] + ub[1] * ua[1] + ub[2] * ua[2];
+            return Prec<T>::fmin_(T(1), Prec<T>::fmax_(T(-1), d));
+        };
+        T ext_vel_mag, cmd_vel_mag, ext_rot_mag, cmd_rot_mag;
+        const T vel_dot = unit_dot(ev, old, ext_vel_mag, cmd_vel_mag);
+        const T rot_dot = unit_dot(er, old + 3, ext_rot_mag, cmd_rot_mag);
+        te_xyz = Prec<T>::fabs_((T)acos((double)vel_dot));
+        te_rot = Prec<T>::fabs_((T)acos((double)rot_dot));
+        const T loop_freq = T(150), tracking_th = T(0.10);
+        const T ext_vel_corr = ext_vel_mag * loop_freq, ext_rot_corr = ext_rot_mag * loop_freq;
+        const T cmd_rot_corr = cmd_rot_mag / T(5), cmd_vel_corr = cmd_vel_mag;
+        const T ext_int_diff = Prec<T>::fabs_((cmd_vel_corr + cmd_rot_corr) - (ext_vel_corr + ext_rot_corr));
+        have_te = true;
+        if (track) {
+            T* t = track + tile * (8 * 32) + lane;
+            t[0] = te_xyz; t[32] = te_rot; t[64] = ext_vel_corr; t[96] = ext_rot_corr; t[128] = cmd_vel_corr;
+            t[160] = cmd_rot_corr; t[192] = ext_int_diff; t[224] = ext_int_diff < tracking_th ? T(1) : T(0);
+        }
+    } else if (track) {
+        T* t = track + tile * (8 * 32) + lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k * 32] = T(0);
+    }
+    // the monitor keeps the last track error it received (scripts/monitor_distance:156-159): carry it in sf[30..31]
+    if (have_te) { sfi[30 * 32] = te_xyz; sfi[31 * 32] = te_rot; } else { te_xyz = sfi[30 * 32]; te_rot = sfi[31 * 32]; }
+
+    // ---- distance monitor (scripts/monitor_distance:160-219), object 0 = the goal
+    const T dx = p[0] - g[9], dy = p[1] - g[10], dz = p[2] - g[11];
+    const T dxyz = Prec<T>::sqrt_(dx * dx + dy * dy + dz * dz);
+    T gr[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gr[k] = g[k];
+    T rv[3];
+    rotvec_between<T>(R, gr, rv);
+    const T ddeg = T(180.0 / 3.14159265358979323846) * Prec<T>::sqrt_(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+    if (dist) { dist[tile * (2 * 32) + lane] = dxyz; dist[tile * (2 * 32) + 32 + lane] = ddeg; }
+    int xs = 0, rs = 0;                                                // 0 on goal, 1 follow, 2 not follow
+    if (dxyz > T(0.02) && te_xyz > T(0.1)) xs = 2;
+    if (dxyz > T(0.02) && te_xyz < T(0.1)) xs = 1;
+    if (dxyz < T(0.02)) xs = 0;
+    if (ddeg > T(1.0) && te_rot > T(0.1)) rs = 2;
+    if (ddeg > T(1.0) && te_rot < T(0.1)) rs = 1;
+    if (ddeg < T(1.0)) rs = 0;
+    uint64_t xr = ((uint64_t)(uint32_t)sii[2 * 32] << 32) | (uint32_t)sii[1 * 32];
+    uint64_t rr = ((uint64_t)(uint32_t)sii[4 * 32] << 32) | (uint32_t)sii[3 * 32];
+    const uint64_t mask40 = (1ull << 40) - 1;
+    xr = ((xr << 2) | (uint64_t)xs) & mask40;                          // newest state in the low bits, 20 states kept
+    rr = ((rr << 2) | (uint64_t)rs) & mask40;
+    const int votes = sii[5 * 32] + 1;
+    if (state) {
+        int sx = -1, sr = -1;
+        if (votes > 20) { sx = ring_majority((uint32_t)xr, (uint32_t)(xr >> 32)); sr = ring_majority((uint32_t)rr, (uint32_t)(rr >> 32)); }
+        state[tile * (2 * 32) + lane] = sx;
+        state[tile * (2 * 32) + 32 + lane] = sr;
+    }
+    // ---- state update: shift the command ring, store the pose
+    sii[0] = seen; sii[1 * 32] = (int32_t)(uint32_t)xr; sii[2 * 32] = (int32_t)(uint32_t)(xr >> 32);
+    sii[3 * 32] = (int32_t)(uint32_t)rr; sii[4 * 32] = (int32_t)(uint32_t)(rr >> 32); sii[5 * 32] = votes;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sfi[k * 32] = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sfi[(9 + k) * 32] = p[k];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) sfi[(12 + k) * 32] = sfi[(18 + k) * 32];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sfi[(24 + k) * 32] = cmd[k];
 }
 
 // ------------------------------------------------------------------------------ layout conversion

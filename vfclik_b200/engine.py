@@ -94,7 +94,7 @@ def round_up(n: int, m: int = 32) -> int:
 
 
 _BUF_FIELDS = ("q", "goal", "obst", "obst_ext", "jp_ref", "ns_in", "ns_lastvec", "q_cmded", "qdot_vf", "qdot_ns", "qdot_jp",
-               "qdot", "cmd", "pose", "flags")
+               "qdot", "cmd", "pose", "twist", "flags")
 
 
 def _dev_ptr(x) -> Optional[int]:
@@ -203,6 +203,15 @@ class Engine:
         rc = self._check(self._lib.vfk_set_vel(self._h, _dev_ptr(qdot), _dev_ptr(q), _dev_ptr(q_cmded), float(max_vel),
                                                int(bool(direct_control)), _dev_ptr(cmd_out), _dev_ptr(qdot_lim_out),
                                                int(n_channels), int(n_instances), self._stream(stream)))
+        self.launches += rc
+        return rc
+
+    def monitor(self, pose, twist, goal, state_f, state_i, n_instances: int, track_out=None, dist_out=None,
+                tracking_state_out=None, stream=None) -> int:
+        """Tracking diagnostics + distance monitor (``scripts/vf:349-428``, ``scripts/monitor_distance:148-219``)."""
+        rc = self._check(self._lib.vfk_monitor(self._h, _dev_ptr(pose), _dev_ptr(twist), _dev_ptr(goal), _dev_ptr(state_f),
+                                               _dev_ptr(state_i), _dev_ptr(track_out), _dev_ptr(dist_out),
+                                               _dev_ptr(tracking_state_out), int(n_instances), self._stream(stream)))
         self.launches += rc
         return rc
 
@@ -343,7 +352,7 @@ class DeviceBatch:
     library's pack kernel; ``download`` converts back.  ``bufs`` is what ``Engine.step`` takes.
     """
 
-    _ROWS = {"goal": 13, "pose": 12, "flags": 1, "twist": 6}
+    _ROWS = {"goal": 13, "pose": 12, "flags": 1, "twist": 6, "track": 8, "dist": 2, "mon_f": 32}
 
     def __init__(self, engine: Engine, n_instances: int, n_obstacles: int, obst_ext: bool = False,
                  outputs=("qdot",), inputs=()):
@@ -368,8 +377,8 @@ class DeviceBatch:
         if name in self.t:
             return self.t[name]
         import torch
-        if name == "flags":
-            self.t[name] = self.e.alloc(1, self.n, dtype=torch.int32)
+        if name in ("flags", "mon_i", "tracking_state"):
+            self.t[name] = self.e.alloc({"flags": 1, "mon_i": 6, "tracking_state": 2}[name], self.n, dtype=torch.int32)
         elif name in ("obst", "obst_ext"):
             raise KeyError("%s was not allocated (n_obstacles = 0 or obst_ext=False)" % name)
         else:
@@ -404,8 +413,9 @@ class DeviceBatch:
         """Blocked device tensor -> dense numpy ``[comps, n]`` (``[M, n, width]`` for obstacles)."""
         import torch
         t = self.t[name]
-        if t.dtype == torch.int32:                                   # flags: one component, blocked == dense
-            return t.reshape(-1)[:self.n].cpu().numpy().reshape(1, self.n)
+        if t.dtype == torch.int32:                                   # int32 arrays: un-block on the host
+            a = t.cpu().numpy()                                      # [tiles, comps, 32]
+            return np.ascontiguousarray(a.transpose(1, 0, 2).reshape(a.shape[1], -1)[:, :self.n])
         comps = t.shape[1]
         width = t.shape[3] if t.dim() == 4 else 1
         shape = (comps, self.n) if width == 1 else (comps, self.n, width)
@@ -415,7 +425,15 @@ class DeviceBatch:
 
     @property
     def bufs(self) -> Dict[str, object]:
-        return dict(self.t)
+        return {k: v for k, v in self.t.items() if k in _BUF_FIELDS}
+
+    def monitor(self, stream=None) -> int:
+        """Run ``vfk_monitor`` on this batch's pose / twist / goal (allocates state and outputs on first use)."""
+        for name in ("mon_f", "mon_i", "track", "dist", "tracking_state"):
+            self._ensure(name)
+        return self.e.monitor(self.t["pose"], self.t["twist"], self.t["goal"], self.t["mon_f"], self.t["mon_i"], self.n,
+                              track_out=self.t["track"], dist_out=self.t["dist"], tracking_state_out=self.t["tracking_state"],
+                              stream=stream)
 
     def step(self, k_cycles: int = 1, stream=None) -> int:
         return self.e.step(self.bufs, self.n, self.m, k_cycles, stream=stream, ext_cmd=tuple(self.ext_cmd))
