@@ -51,6 +51,7 @@ extern "C" {
 #define VFK_N_PORTS 6            /* mixer inputs, order of scripts/bridge:593-596 */
 #define VFK_GOAL_COMPS 13        /* R_goal row-major (9), p_goal (3), slowdown distance (1) */
 #define VFK_POSE_COMPS 12        /* R row-major (9), p (3) */
+#define VFK_AUX_COMPS 12         /* auxiliary field record: type, force, 10 parameters */
 
 typedef enum vfk_status {
     VFK_OK = 0,
@@ -123,6 +124,10 @@ typedef struct vfk_buffers {
     const void* obst;            /* M obstacles x {x, y, z, radius}: decay repellers (vfl type 2); radius 0 = empty slot */
     const void* obst_ext;        /* M obstacles x {safe distance, decay order} (wire-faithful,
                                     scripts/object_feeder:326-333) or NULL -> params.obst_safe / obst_order */
+    const void* aux;             /* [n_aux * 12] auxiliary field records {type, force, p0..p9} or NULL:
+                                    type 4 hemisphere repeller {x,y,z, nx,ny,nz, safe, order} (scripts/object_feeder:335-354),
+                                    type 5 funnel attractor {x,y,z, ax,ay,az, cut angle, angle order, cut distance, distance order}
+                                    (scripts/object_feeder:262-280); other type codes = empty slot */
     const void* jp_ref;          /* [N]  joint reference (/jpctrl/ref) or NULL -> params.jp_ref   */
     const void* ns_in;           /* PROJECTOR: qdot0 [N] or NULL -> limit-avoidance gradient;
                                     CONTROL:   control [4] or NULL -> params.ns_control             */
@@ -137,6 +142,8 @@ typedef struct vfk_buffers {
     void*       pose;            /* out [12] tool frame (/vectorField/pose)                        */
     void*       twist;           /* out [6]  commanded tool twist velPos, velRot (/vectorField/vector_out, scripts/vf:346-347) */
     int32_t*    flags;           /* out [1]  VFK_FLAG_*                                            */
+    int32_t     n_aux;           /* slots in aux (0..64)                                           */
+    int32_t     reserved;
 } vfk_buffers;
 
 typedef struct vfk_ctx* vfk_handle;
@@ -166,8 +173,8 @@ int  vfk_step(vfk_handle h, const vfk_buffers* bufs, int64_t n_instances, int n_
 /* Field visualisation query (scripts/vf:469-503): twist the composed field commands at
  * arbitrary tool poses pose_in [12]; twist_out [6] (blocked layout).  Same goal/obst layout. */
 int  vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst,
-                    const void* obst_ext, void* twist_out, int64_t n_instances, int n_obstacles,
-                    void* stream);
+                    const void* obst_ext, const void* aux, int n_aux, void* twist_out,
+                    int64_t n_instances, int n_obstacles, void* stream);
 
 /* Weighted sum of command ports (src/command_mixer.py:78-82) on device buffers:
  * out(c, i) = sum_p w[p] * cmds[p](c, i); cmds[p] may be NULL (skipped); nan_flags [1] optional. */
@@ -204,6 +211,7 @@ int  vfk_session_create(vfk_handle h, int64_t n_instances, int n_obstacles, int 
 int  vfk_session_set_goal(vfk_session s, const void* goal_host);            /* [13][n] */
 int  vfk_session_set_obstacles(vfk_session s, const void* obst_host,         /* [M][n][4] */
                                const void* obst_ext_host);                  /* [M][n][2] or NULL */
+int  vfk_session_set_aux(vfk_session s, const void* aux_host, int n_aux);   /* [n_aux * 12][n] records, or NULL / 0 to clear */
 int  vfk_session_set_q(vfk_session s, const void* q_host);                  /* [N][n] */
 int  vfk_session_set_jp_ref(vfk_session s, const void* ref_host);           /* [N][n] or NULL -> params.jp_ref */
 int  vfk_session_set_ns_input(vfk_session s, const void* ns_host);          /* [N|4][n] or NULL */

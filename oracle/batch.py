@@ -30,6 +30,8 @@ ORACLE_CHOICES = [
     ("attractor rotational part", "unit rotation axis of R_goal * R_tool^T (base frame), extracted through the unit quaternion with w >= 0"),
     ("attractor scalars", "S0 = min(1, dist/slowdown) (1 if slowdown <= 0); S1 = min(1, angle/rot_slowdown)"),
     ("decay repeller (vfl type 2)", "V = (o - p)/d * (radius / max(d, safe))^order, zero rotational part, scalars (1, 1); force < 0 repels"),
+    ("hemisphere repeller (vfl type 4)", "n = normal/|normal|, h = (p - o).n; V = -n * (safe / max(h, safe))^order, zero rotational part, scalars (1, 1)"),
+    ("funnel attractor (vfl type 5)", "a = axis/|axis|, r = p - goal, s = r.a, r_perp = r - s a, theta = atan2(|r_perp|, s); V = -r_perp/|r_perp| * wa * wd with wa = 1 if theta <= cut_angle else (cut_angle/theta)^order_a and wd = 1 if |r| <= cut_dist else (cut_dist/|r|)^order_d"),
     ("normCart", "divides the translational part of the summed field by its Euclidean norm (zero stays zero); rotational part untouched"),
     ("velocity IK", "north_star closed form qdot = Wj Jw^T (Jw Jw^T + lambda^2 I)^-1 Wt t, Jw = Wt J Wj; lambda explicit"),
     ("nullspace projector", "B = I - J^T (J J^T + ns_lambda^2 I)^-1 J; ns_lambda = 0 is the reference's pinv form (scripts/nullspace:75-79)"),
@@ -173,7 +175,36 @@ def rot_axis_angle(Rerr: np.ndarray):
     return axis, angle
 
 
-def field_eval(prm: Params, Rt: np.ndarray, pt: np.ndarray, goal: np.ndarray, obst: Optional[np.ndarray]):
+def aux_field_eval(pt: np.ndarray, aux: np.ndarray) -> np.ndarray:
+    """Sum of force * V over the auxiliary field records aux[I, A, 12] = {type, force, p0..p9} (types 4 and 5, see
+    ORACLE_CHOICES; parameter layouts of ``scripts/object_feeder:262-280,335-354``).  Returns [I, 3]."""
+    I, A, _ = aux.shape
+    out = np.zeros((I, 3))
+    for s in range(A):
+        typ, force, p = aux[:, s, 0].astype(int), aux[:, s, 1], aux[:, s, 2:12]
+        r = pt - p[:, 0:3]
+        an = np.linalg.norm(p[:, 3:6], axis=1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            a = np.where(an[:, None] > 0, p[:, 3:6] / an[:, None], 0.0)
+            sa = np.einsum("ij,ij->i", r, a)
+            # type 4
+            v4 = -a * np.power(p[:, 6] / np.maximum(sa, p[:, 6]), p[:, 7])[:, None]
+            # type 5
+            rp = r - sa[:, None] * a
+            rho = np.linalg.norm(rp, axis=1)
+            theta = np.arctan2(rho, sa)
+            R = np.linalg.norm(r, axis=1)
+            wa = np.where(theta <= p[:, 6], 1.0, np.power(p[:, 6] / theta, p[:, 7]))
+            wd = np.where(R <= p[:, 8], 1.0, np.power(p[:, 8] / R, p[:, 9]))
+            v5 = np.where(rho[:, None] > 0, -rp / rho[:, None] * (wa * wd)[:, None], 0.0)
+        ok = an > 0
+        out += np.where(((typ == 4) & ok)[:, None], force[:, None] * v4, 0.0)
+        out += np.where(((typ == 5) & ok)[:, None], force[:, None] * v5, 0.0)
+    return out
+
+
+def field_eval(prm: Params, Rt: np.ndarray, pt: np.ndarray, goal: np.ndarray, obst: Optional[np.ndarray],
+               aux: Optional[np.ndarray] = None):
     """Composed vector field and scalar field at the tool frame (a3, a4).
 
     ``scripts/vf:276-293``: ``totalVF = normCart( null + sum_i force_i * V_i )``,
@@ -217,6 +248,8 @@ def field_eval(prm: Params, Rt: np.ndarray, pt: np.ndarray, goal: np.ndarray, ob
         # sequential accumulation in obstacle order, like the += chain of scripts/vf:280-290
         for k in range(obst.shape[1]):
             V[:, 0:3] += prm.obst_force * (w[:, k:k + 1] * dv[:, k, :])
+    if aux is not None and aux.shape[1] > 0:
+        V[:, 0:3] += aux_field_eval(pt, np.asarray(aux, dtype=np.float64))
     n = np.linalg.norm(V[:, 0:3], axis=1)
     with np.errstate(invalid="ignore", divide="ignore"):
         V[:, 0:3] = np.where(n[:, None] > 0.0, V[:, 0:3] / n[:, None], V[:, 0:3])
@@ -291,7 +324,7 @@ def ns_check_limits(prm: Params, chain, q: np.ndarray, qdot: np.ndarray):
 # --------------------------------------------------------------------------- full cycle
 
 def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastvec=None,
-         q_cmded=None, ext_cmd=(None, None, None), k_cycles: int = 1):
+         q_cmded=None, ext_cmd=(None, None, None), k_cycles: int = 1, aux=None):
     """K synchronous control cycles.
 
     Returns a dict with the last cycle's ``qdot_vf, qdot_ns, qdot_jp, qdot_mix, qdot`` (clamped),
@@ -316,7 +349,8 @@ def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastve
         pt = p + R @ ptool
         dp = p - pt                                   # PyKDL.diff(newkdlframe, kdlframe).vel
         # 2-3. field + saturation (scripts/vf:344-347)
-        v, om = field_eval(prm, Rt, pt, goal, obst)
+        v, om = field_eval(prm, Rt, pt, goal, obst, aux)
+        out_twist = np.concatenate([v, om], axis=1)
         # 4. Twist.RefPoint(dp): v' = v + w x dp (scripts/vf:456-459)
         tw = np.concatenate([v + np.cross(om, dp), om], axis=1)
         # 5. velocity IK (scripts/vf:461)
@@ -366,7 +400,7 @@ def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastve
         qc = q if q_cmded is None else np.asarray(q_cmded, dtype=np.float64)
         cmd = qd if direct else (-qc + q + qd)          # scripts/bridge:198-203
         out = dict(qdot_vf=qd_vf, qdot_ns=qd_ns, qdot_jp=qd_jp, qdot_mix=mix, qdot=qd, cmd=cmd,
-                   pose=np.concatenate([Rt.reshape(I, 9), pt], axis=1), flags=flags)
+                   pose=np.concatenate([Rt.reshape(I, 9), pt], axis=1), flags=flags, twist=out_twist)
         # 10. plant: explicit Euler (joint_sim is external to the reference)
         if prm.integrate:
             q = q + prm.dt * qd

@@ -286,9 +286,64 @@ class _DecayRepeller:
         return (1.0, 1.0)
 
 
+class _HemisphereRepeller:
+    """vfl type 4: params = xyz, normal, safe distance, decay order (scripts/object_feeder:335-354)."""
+
+    def setParams(self, params):
+        self.o = np.asarray(params[0:3], dtype=np.float64)
+        self.n = np.asarray(params[3:6], dtype=np.float64)
+        self.safe, self.order = float(params[6]), float(params[7])
+
+    def getVector(self, frame):
+        p = np.array([frame[3], frame[7], frame[11]], dtype=np.float64)
+        out = np.zeros(6)
+        nn = math.sqrt(float(self.n @ self.n))
+        if nn > 0.0:
+            nh = self.n / nn
+            h = float((p - self.o) @ nh)
+            out[:3] = -nh * (self.safe / max(h, self.safe)) ** self.order
+        return out
+
+    def getScalar(self, frame):
+        return (1.0, 1.0)
+
+
+class _FunnelAttractor:
+    """vfl type 5: params = goal xyz, axis, cut angle, angle-decay order, cut distance, distance-decay order
+    (scripts/object_feeder:262-280)."""
+
+    def setParams(self, params):
+        self.g = np.asarray(params[0:3], dtype=np.float64)
+        self.a = np.asarray(params[3:6], dtype=np.float64)
+        self.cut_a, self.ord_a, self.cut_d, self.ord_d = (float(x) for x in params[6:10])
+
+    def getVector(self, frame):
+        p = np.array([frame[3], frame[7], frame[11]], dtype=np.float64)
+        out = np.zeros(6)
+        an = math.sqrt(float(self.a @ self.a))
+        if an == 0.0:
+            return out
+        ah = self.a / an
+        r = p - self.g
+        s = float(r @ ah)
+        rp = r - s * ah
+        rho = math.sqrt(float(rp @ rp))
+        if rho == 0.0:
+            return out
+        theta = math.atan2(rho, s)
+        R = math.sqrt(float(r @ r))
+        wa = 1.0 if theta <= self.cut_a else (self.cut_a / theta) ** self.ord_a
+        wd = 1.0 if R <= self.cut_d else (self.cut_d / R) ** self.ord_d
+        out[:3] = -rp / rho * wa * wd
+        return out
+
+    def getScalar(self, frame):
+        return (1.0, 1.0)
+
+
 def vfl_library():
     """``vfl.vfl.vectorFieldLibrary()``: type id -> class (scripts/vf:146,238,283)."""
-    return {0: _NullField, 1: _PointAttractor, 2: _DecayRepeller}
+    return {0: _NullField, 1: _PointAttractor, 2: _DecayRepeller, 4: _HemisphereRepeller, 5: _FunnelAttractor}
 
 
 class VectorField:
@@ -444,7 +499,7 @@ class ControlLoop:
     SURVEY.md App. C.2 step 6); ``ns_mode`` 2 is the reference's 4-float control interface.
     """
 
-    def __init__(self, chain, prm: Params, q0, goal17, obstacles=(), jp_ref=None):
+    def __init__(self, chain, prm: Params, q0, goal17, obstacles=(), jp_ref=None, extra_fields=()):
         self.chain, self.prm = chain, prm
         N = chain.n_joints
         self.N = N
@@ -460,6 +515,8 @@ class ControlLoop:
             if len(ob) == 4:
                 ob = ob + [prm.obst_safe, prm.obst_order]
             self.vectorFields[5 + n] = [prm.obst_force, 2, ob]
+        for fid, force, vtype, params in extra_fields:
+            self.vectorFields[int(fid)] = [float(force), int(vtype), [float(x) for x in params]]
         self._compose()
         self.toolFrame = np.eye(4)
         t = np.asarray(prm.tool, dtype=np.float64)

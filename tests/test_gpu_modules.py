@@ -29,11 +29,11 @@ def test_vfclik_app_config1_matches_reference_shaped_loop(lwr, built_lib, fresh_
     prm = batch.Params(jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate, max_vel=cfg.max_vel,
                        jp_kp=cfg.jpctrl_kp, ik_lambda=cfg.ik_lambda, ns_lambda=cfg.ns_lambda)
     try:
-        for m in range(3):
+        obj = _out_port(fresh_ports, "/0/test/obj", app.ofeeder.objectPort.getName())
+        for m in range(3):                               # "set ObstacleP n (16 + radius + order)" (old/README.old:75)
             o = w["obst"][m, 0]
             frame = [1, 0, 0, o[0], 0, 1, 0, o[1], 0, 0, 1, o[2], 0, 0, 0, 1]
-            app.set_obstacle_p(m, frame, o[3], 20)
-        assert sorted(app.runtime.vectorFields) == [1, 5, 6, 7]                    # ids of scripts/object_feeder:229-334
+            fresh_ports.write_bottle_lists(obj, ["set", "ObstacleP", m, [float(v) for v in frame] + [float(o[3]), 20.0]], strict=True)
         loop = refshape.ControlLoop(chain, prm, cfg.initial_joint_pos, cfg.initial_vf_pose[2],
                                     obstacles=[list(w["obst"][m, 0]) for m in range(3)])
         K = 60
@@ -41,7 +41,8 @@ def test_vfclik_app_config1_matches_reference_shaped_loop(lwr, built_lib, fresh_
             cmd = app.step()
             loop.cycle()
             if k == 0:
-                continue            # first period: the command ports are still empty, exactly like a cold start
+                assert sorted(app.runtime.vectorFields) == [1, 5, 6, 7]            # ids of scripts/object_feeder:229-334
+                continue
             assert np.allclose(app.vf.last_qdot, loop.last["qdot_vf"], rtol=1e-9, atol=1e-12), k
             assert np.allclose(app.nullspace.last_qdot, loop.last["qdot_ns"], rtol=1e-9, atol=1e-12), k
         # the modular loop lags one period behind the synchronous oracle (cold start), so compare one step shifted
@@ -201,3 +202,77 @@ def test_monitor_kernel_matches_reference_shaped_monitor(lwr, built_lib):
         assert {-1, 1}.issubset(seen_states)
     finally:
         e.close()
+
+
+def test_handlers_drive_the_arm_through_ports(lwr, built_lib, fresh_ports):
+    """src/handlers.py surface: HandleArm.gotoFrame waits on /dmonitor/distOut, HandleBridge switches controllers,
+    HandleJController.set_ref_js waits on /bridge/encoders -- all through ports, spinning the single-process app."""
+    from vfclik_b200 import handlers
+    from vfclik_b200.launcher import Vfclik
+    chain, cfg = lwr
+    app = Vfclik(cfg, namespace="/0", sim=True, precision=64)
+    try:
+        prename = "/0" + cfg.robotarm_portbasename
+        arm = handlers.HandleArm(cfg.robotarm_portbasename, namespace="/0", spin=app.step)
+        bridge = handlers.HandleBridge(prename, spin=app.step, torso=False)
+        jctrl = handlers.HandleJController(prename, spin=app.step)
+        for _ in range(3):
+            app.step()
+        pose0 = arm.getPose()
+        assert len(pose0) == 16 and abs(pose0[15] - 1.0) < 1e-12
+        # a reachable Cartesian goal 12 cm from the start pose, same orientation
+        goal = list(pose0)
+        goal[3] += 0.08; goal[7] -= 0.06; goal[11] += 0.06
+        app.runtime.set_speed_scale(0.4)
+        arm.current_slowdown_distance = 0.05
+        ok, diff = arm.gotoFrame(goal, wait=60.0, goal_precision=[0.004, 0.02])
+        assert ok and diff[0] < 0.004 and diff[1] < 0.02, diff
+        assert app.dmonitor.last["dist"][0][0] == 0
+        # joint mode: go back to the initial posture
+        bridge.joint_controller()
+        ref = list(cfg.initial_joint_pos)
+        ok, diff = jctrl.set_ref_js(ref, wait=60.0, goal_precision=[0.01] * 7)
+        assert ok and np.max(np.abs(diff)) <= 0.01
+        assert app.bridge.mixer.weights[:4] == [0.0, 0.0, 1.0, 0.0] and app.jpctrl.at_goal == 1
+        bridge.cartesian_controller()
+        bridge.set_weights("task", [1, 1, 1, 0.5, 0.5, 0.5])
+        app.step(); app.step()
+        assert app.bridge.mixer.weights[:4] == [1.0, 1.0, 0.0, 0.0] and app.runtime.params.w_task[3] == 0.5
+        assert len(bridge.read_joint_angles()) == 7
+    finally:
+        app.close()
+
+
+def test_object_feeder_goal_and_normal_and_table(lwr, built_lib, fresh_ports):
+    """f2: "set goalAndNormal" (attractor + funnel type 5 + near-goal repeller) and "set ObstacleH" (hemisphere type 4)
+    through /ofeeder/object -> /vectorField/param -> the GPU's auxiliary-field slots, vs the reference-shaped loop."""
+    from oracle import batch, refshape
+    from vfclik_b200.launcher import Vfclik
+    chain, cfg = lwr
+    app = Vfclik(cfg, namespace="/0", sim=True, precision=64)
+    prm = batch.Params(jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate, max_vel=cfg.max_vel,
+                       jp_kp=cfg.jpctrl_kp, ik_lambda=cfg.ik_lambda, ns_lambda=cfg.ns_lambda)
+    try:
+        obj = _out_port(fresh_ports, "/0/test/obj", app.ofeeder.objectPort.getName())
+        g = list(cfg.initial_vf_pose[2][:16])
+        gan = g + [0.0, 0.3, -1.0, 0.5, 0.15, 0.04]                    # axis, cut angle, cut length, slowdown
+        table = [1, 0, 0, 0.7, 0, 1, 0, 0.1, 0, 0, 1, 0.9, 0, 0, 0, 1] + [0.0, 0.0, 1.0, 0.02, 3.0]   # normal, safe, order
+        fresh_ports.write_bottle_lists(obj, ["set", "goalAndNormal", [float(v) for v in gan]], strict=True)
+        fresh_ports.write_bottle_lists(obj, ["set", "ObstacleH", 0, [float(v) for v in table]], strict=True)
+        app.step()
+        vfields = app.runtime.vectorFields
+        assert sorted(vfields) == [1, 2, 3, 5] and [vfields[k][1] for k in (1, 2, 3, 5)] == [1, 5, 2, 4]
+        assert [vfields[k][0] for k in (1, 2, 3, 5)] == [1.0, 30.0, -10.0, -50.0]          # scripts/object_feeder:236,268,288,341
+        extra = [(k, vfields[k][0], vfields[k][1], vfields[k][2]) for k in (2, 3, 5)]
+        loop = refshape.ControlLoop(chain, prm, cfg.initial_joint_pos, vfields[1][2], extra_fields=extra)
+        loop.cycle()
+        assert np.allclose(app.vf.last_qdot, loop.last["qdot_vf"], rtol=1e-9, atol=1e-12)
+        for k in range(25):
+            app.step(); loop.cycle()
+            assert np.allclose(app.vf.last_qdot, loop.last["qdot_vf"], rtol=1e-8, atol=1e-11), k
+        # removing the table through the feeder frees the auxiliary slot again
+        fresh_ports.write_bottle_lists(obj, ["remove", 0], strict=True)
+        app.step()
+        assert 5 not in app.runtime.vectorFields
+    finally:
+        app.close()

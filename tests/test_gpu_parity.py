@@ -419,3 +419,38 @@ def test_host_session_chunk_pipeline(eng, lwr):
         assert np.array_equal(qd.numpy().T, dev["qdot"]) and np.array_equal(qo.T, dev["q"]) and np.array_equal(fl, dev["flags"])
     finally:
         s.close()
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_auxiliary_fields_types_4_and_5(eng, lwr, precision):
+    """Hemisphere repellers (vfl type 4) and funnel attractors (type 5) as per-instance auxiliary field records."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch
+    chain, _ = lwr
+    e = eng(precision)
+    n, M = 3000, 3
+    dt = np.float32 if precision == 32 else np.float64
+    rng = np.random.default_rng(71)
+    w = workloads.random_batch(chain, n, M, seed=70, dtype=dt)
+    aux = np.zeros((3, 12, n), dtype=dt)
+    aux[0, 0] = 4; aux[0, 1] = -50                                              # table below the workspace
+    aux[0, 2:5] = w["goal"][9:12] + rng.uniform(-0.3, 0.3, size=(3, n)); aux[0, 5:8] = rng.normal(size=(3, n))
+    aux[0, 8] = rng.uniform(0.01, 0.1, size=n); aux[0, 9] = rng.uniform(2, 6, size=n)
+    aux[1, 0] = 5; aux[1, 1] = 30                                               # funnel at the goal
+    aux[1, 2:5] = w["goal"][9:12]; aux[1, 5:8] = rng.normal(size=(3, n))
+    aux[1, 8] = rng.uniform(0.2, 0.8, size=n); aux[1, 9] = 10; aux[1, 10] = rng.uniform(0.1, 0.5, size=n); aux[1, 11] = 2
+    aux[2, 0] = np.where(rng.random(n) < 0.5, 0, 4); aux[2, 1] = -50            # half of the third slots are empty
+    aux[2, 2:5] = rng.uniform(-0.5, 0.5, size=(3, n)); aux[2, 5:8] = rng.normal(size=(3, n)); aux[2, 8] = 0.05; aux[2, 9] = 3
+    db = DeviceBatch(e, n, M, outputs=("qdot_vf", "qdot", "twist"))
+    db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+    db.set_aux(aux)
+    assert db.step(1) == 1
+    ref = run_oracle(chain, e.params, w, M, aux=aux.transpose(2, 0, 1).astype(np.float64))
+    tol = FP64_RTOL if precision == 64 else FP32_RTOL
+    for k in ("qdot_vf", "qdot"):
+        err = rel_err(db.download(k).T.astype(np.float64), ref[k])
+        assert err.max() <= tol, (k, float(err.max()))
+    assert np.max(np.abs(db.download("twist").T - ref["twist"])) <= (1e-12 if precision == 64 else 2e-6)
+    # and the fields change the answer
+    ref0 = run_oracle(chain, e.params, w, M)
+    assert np.max(np.abs(ref0["qdot_vf"] - ref["qdot_vf"])) > 1e-3

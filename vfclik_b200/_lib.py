@@ -15,6 +15,7 @@ VFK_MAX_JOINTS = 17
 VFK_N_PORTS = 6
 VFK_GOAL_COMPS = 13
 VFK_POSE_COMPS = 12
+VFK_AUX_COMPS = 12
 VFK_TILE = 32
 
 VFK_OK = 0
@@ -34,7 +35,7 @@ EXPORTS = [
     "vfk_version", "vfk_default_params", "vfk_create", "vfk_set_params", "vfk_get_params", "vfk_chain_pattern",
     "vfk_destroy",
     "vfk_last_error", "vfk_step", "vfk_field_eval", "vfk_mix", "vfk_set_vel", "vfk_monitor", "vfk_pack", "vfk_unpack", "vfk_session_create", "vfk_session_set_goal",
-    "vfk_session_set_obstacles", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input",
+    "vfk_session_set_obstacles", "vfk_session_set_aux", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input",
     "vfk_session_cycle", "vfk_session_enable", "vfk_session_read", "vfk_session_buffers", "vfk_session_destroy",
 ]
 
@@ -74,11 +75,12 @@ class ParamsC(C.Structure):
 
 class BuffersC(C.Structure):
     _fields_ = [
-        ("q", C.c_void_p), ("goal", C.c_void_p), ("obst", C.c_void_p), ("obst_ext", C.c_void_p), ("jp_ref", C.c_void_p),
+        ("q", C.c_void_p), ("goal", C.c_void_p), ("obst", C.c_void_p), ("obst_ext", C.c_void_p), ("aux", C.c_void_p),
+        ("jp_ref", C.c_void_p),
         ("ns_in", C.c_void_p),
         ("ns_lastvec", C.c_void_p), ("q_cmded", C.c_void_p), ("ext_cmd", C.c_void_p * 3), ("qdot_vf", C.c_void_p),
         ("qdot_ns", C.c_void_p), ("qdot_jp", C.c_void_p), ("qdot", C.c_void_p), ("cmd", C.c_void_p),
-        ("pose", C.c_void_p), ("twist", C.c_void_p), ("flags", C.c_void_p),
+        ("pose", C.c_void_p), ("twist", C.c_void_p), ("flags", C.c_void_p), ("n_aux", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -111,7 +113,7 @@ def load():
     lib.vfk_last_error.argtypes = [vp]
     lib.vfk_last_error.restype = C.c_char_p
     lib.vfk_step.argtypes = [vp, C.POINTER(BuffersC), i64, i32, i32, vp]
-    lib.vfk_field_eval.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.vfk_field_eval.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, vp]
     lib.vfk_mix.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_double), i32, i32, vp, vp, i64, vp]
     lib.vfk_set_vel.argtypes = [vp, vp, vp, vp, C.c_double, i32, vp, vp, i32, i64, vp]
     lib.vfk_monitor.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
@@ -121,6 +123,7 @@ def load():
     for name in ("vfk_session_set_goal", "vfk_session_set_q", "vfk_session_set_jp_ref", "vfk_session_set_ns_input"):
         getattr(lib, name).argtypes = [vp, vp]
     lib.vfk_session_set_obstacles.argtypes = [vp, vp, vp]
+    lib.vfk_session_set_aux.argtypes = [vp, vp, i32]
     lib.vfk_session_cycle.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.vfk_session_read.argtypes = [vp, C.c_char_p, vp]
     lib.vfk_session_enable.argtypes = [vp, C.c_char_p, i32]

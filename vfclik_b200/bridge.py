@@ -33,10 +33,14 @@ class JointSim:
         self.yarp_ctrl = yarp.ArcosYarp(ports_name_prefix=namespace, module_name_prefix=base + "/joint_sim")
         self.qvin = self.yarp_ctrl.create_yarp_port("/qvin", strict=False)
         self.qout = self.yarp_ctrl.create_yarp_port("/qout", input_port=False)
+        self.qin = self.yarp_ctrl.create_yarp_port("/qin", strict=False)       # teleport the simulated arm (HandleArmNew.set_sim_arm_q)
         self.q = [float(v) for v in config.initial_joint_pos]
         self.dt = float(config.rate)
 
     def update(self):
+        t = self.qin.read(False)
+        if t and t.size() == len(self.q):
+            self.q = [t.get(i).asDouble() for i in range(len(self.q))]
         b = self.qvin.read(False)
         if b and b.size() == len(self.q):
             self.q = [self.q[i] + self.dt * b.get(i).asDouble() for i in range(len(self.q))]

@@ -296,7 +296,7 @@ template <typename T>
 static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
     return c.tool_identity && c.unit_weights && c.share_factor && c.ns_mode == VFK_NS_PROJECTOR && !c.need_jp && !b->ns_in &&
            !b->jp_ref && !b->q_cmded && !b->ext_cmd[0] && !b->ext_cmd[1] && !b->ext_cmd[2] && !b->qdot_vf && !b->qdot_ns &&
-           !b->qdot_jp && !b->cmd && !b->pose && !b->twist && !b->flags && b->qdot && !getenv("VFK_NO_LEAN");
+           !b->qdot_jp && !b->cmd && !b->pose && !b->twist && !b->flags && !(b->aux && b->n_aux > 0) && b->qdot && !getenv("VFK_NO_LEAN");
 }
 
 template <typename T, int N, class PAT, bool EXT, bool LEAN>
@@ -308,6 +308,8 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.goal = static_cast<const T*>(b->goal);
     a.obst = static_cast<const Vec4<T>*>(b->obst);
     a.obst_ext = static_cast<const Vec2<T>*>(b->obst_ext);
+    a.aux = b->n_aux > 0 ? static_cast<const T*>(b->aux) : nullptr;
+    a.n_aux = a.aux ? b->n_aux : 0;
     a.jp_ref = static_cast<const T*>(b->jp_ref);
     a.ns_in = static_cast<const T*>(b->ns_in);
     a.ns_lastvec = static_cast<T*>(b->ns_lastvec);
@@ -394,9 +396,10 @@ extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int n_obs
     if (n < 0) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 0 (got %lld)", (long long)n);
     if (n_obst < 0) return fail(h, VFK_ERR_INVALID, "n_obstacles must be >= 0");
     if (k_cycles < 1) return fail(h, VFK_ERR_INVALID, "k_cycles must be >= 1");
+    if (b->n_aux < 0 || b->n_aux > 64) return fail(h, VFK_ERR_INVALID, "n_aux must be in 0..64");
     int rc;
     if ((rc = check_layout(h, b->q, "q", true)) || (rc = check_layout(h, b->goal, "goal", true)) ||
-        (rc = check_layout(h, b->obst, "obst", n_obst > 0)) || (rc = check_layout(h, b->obst_ext, "obst_ext", false)) ||
+        (rc = check_layout(h, b->obst, "obst", n_obst > 0)) || (rc = check_layout(h, b->obst_ext, "obst_ext", false)) || (rc = check_layout(h, b->aux, "aux", false)) ||
         (rc = check_layout(h, b->jp_ref, "jp_ref", false)) || (rc = check_layout(h, b->ns_in, "ns_in", false)) ||
         (rc = check_layout(h, b->ns_lastvec, "ns_lastvec", h->params.ns_mode == VFK_NS_CONTROL)) ||
         (rc = check_layout(h, b->q_cmded, "q_cmded", false)) || (rc = check_layout(h, b->qdot_vf, "qdot_vf", false)) ||
@@ -414,10 +417,12 @@ extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int n_obs
 }
 
 extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst, const void* obst_ext,
-                              void* twist_out, int64_t n, int n_obst, void* stream) {
+                              const void* aux, int n_aux, void* twist_out, int64_t n, int n_obst, void* stream) {
     if (!h || !pose_in || !goal || !twist_out) return fail(h, VFK_ERR_INVALID, "vfk_field_eval: null argument");
     if (n < 0) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 0");
     if (n_obst > 0 && !obst) return fail(h, VFK_ERR_INVALID, "obst is required when n_obstacles > 0");
+    if (n_aux < 0 || n_aux > 64) return fail(h, VFK_ERR_INVALID, "n_aux must be in 0..64");
+    if (n_aux == 0) aux = nullptr;
     if (n == 0) return 0;
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -425,11 +430,11 @@ extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goa
     if (h->precision == 32)
         vfk_field_kernel<float><<<grid, kSmallBlock, 0, st>>>(h->cf, (const float*)pose_in, (const float*)goal,
                                                          (const Vec4<float>*)obst, (const Vec2<float>*)obst_ext,
-                                                         (float*)twist_out, n, n_obst);
+                                                         (const float*)aux, n_aux, (float*)twist_out, n, n_obst);
     else
         vfk_field_kernel<double><<<grid, kSmallBlock, 0, st>>>(h->cd, (const double*)pose_in, (const double*)goal,
                                                           (const Vec4<double>*)obst, (const Vec2<double>*)obst_ext,
-                                                          (double*)twist_out, n, n_obst);
+                                                          (const double*)aux, n_aux, (double*)twist_out, n, n_obst);
     VFK_CUDA(h, cudaGetLastError());
     return 1;
 }
@@ -545,7 +550,7 @@ extern "C" int vfk_unpack(vfk_handle h, const void* blocked, void* dense, int co
 struct vfk_session_s {
     vfk_ctx* h;
     int64_t n, tiles;
-    int n_obst, has_ext, N;
+    int n_obst, has_ext, N, n_aux;
     size_t es;                       // element size
     cudaStream_t stream;
     cudaStream_t pipe[3];            // chunk pipeline of vfk_session_cycle (H2D / kernels / D2H overlap)
@@ -557,6 +562,7 @@ struct vfk_session_s {
     bool have_jp_ref, have_ns_in;
     bool en_vf, en_ns, en_jp, en_cmd, en_pose, en_twist;   // optional per-controller outputs (off by default)
     void *d_jp_ref, *d_ns_in;
+    char* aux_dev;                   // auxiliary field records (blocked + dense staging), grown on demand
     char* pin;                       // pinned host staging: q in (N rows), qdot / q out (2N rows), flags
     size_t pin_bytes;
     int launches;                    // kernels launched by the last call
@@ -613,6 +619,8 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->have_jp_ref = s->have_ns_in = false;
     s->en_vf = s->en_ns = s->en_jp = s->en_cmd = s->en_pose = s->en_twist = false;
     s->launches = 0;
+    s->n_aux = 0;
+    s->aux_dev = nullptr;
     s->pin_bytes = (size_t)N * 3 * (size_t)n * s->es + (size_t)n * 4;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     for (int k = 0; k < 3 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&s->pipe[k], cudaStreamNonBlocking);
@@ -655,6 +663,30 @@ extern "C" int vfk_session_set_obstacles(vfk_session s, const void* o, const voi
     return rc;
 }
 
+extern "C" int vfk_session_set_aux(vfk_session s, const void* aux, int n_aux) {
+    if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_aux: null session");
+    vfk_ctx* h = s->h;
+    if (n_aux < 0 || n_aux > 64) return fail(h, VFK_ERR_INVALID, "n_aux must be in 0..64");
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    if (!aux || n_aux == 0) { s->b.n_aux = 0; return VFK_OK; }
+    const size_t row = align_up((size_t)s->tiles * 32 * s->es, 128);
+    if (n_aux > s->n_aux) {                                   // grow the dedicated buffers (blocked + dense staging)
+        if (s->aux_dev) VFK_CUDA(h, cudaFree(s->aux_dev));
+        s->aux_dev = nullptr;
+        VFK_CUDA(h, cudaMalloc((void**)&s->aux_dev, 2 * (size_t)n_aux * 12 * row));
+        s->n_aux = n_aux;
+    }
+    char* blocked = s->aux_dev;
+    char* dense = s->aux_dev + (size_t)s->n_aux * 12 * row;
+    VFK_CUDA(h, cudaMemcpyAsync(dense, aux, (size_t)n_aux * 12 * s->n * s->es, cudaMemcpyHostToDevice, s->stream));
+    int rc = pack_dispatch(h, dense, blocked, n_aux * 12, 1, s->n, false, s->stream);
+    if (rc < 0) return rc;
+    VFK_CUDA(h, cudaStreamSynchronize(s->stream));
+    s->b.aux = blocked;
+    s->b.n_aux = n_aux;
+    return VFK_OK;
+}
+
 extern "C" int vfk_session_set_q(vfk_session s, const void* q) {
     if (!s || !q) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_set_q: null argument");
     return upload_blocked(s, s->b.q, q, s->N, 1);
@@ -681,6 +713,7 @@ static vfk_buffers offset_view(const vfk_buffers& b, int64_t tile0, int N, int M
         return p ? (void*)((char*)const_cast<void*>(p) + (size_t)tile0 * comps * 32 * es) : nullptr;
     };
     o.q = off(b.q, N); o.goal = off(b.goal, 13); o.obst = off(b.obst, (size_t)M * 4); o.obst_ext = off(b.obst_ext, (size_t)M * 2);
+    o.aux = off(b.aux, (size_t)b.n_aux * 12);
     o.jp_ref = off(b.jp_ref, N); o.ns_lastvec = off(b.ns_lastvec, N); o.q_cmded = off(b.q_cmded, N);
     for (int e = 0; e < 3; ++e) o.ext_cmd[e] = off(b.ext_cmd[e], N);
     o.qdot_vf = off(b.qdot_vf, N); o.qdot_ns = off(b.qdot_ns, N); o.qdot_jp = off(b.qdot_jp, N); o.qdot = off(b.qdot, N);
@@ -835,6 +868,7 @@ extern "C" void vfk_session_destroy(vfk_session s) {
     cudaStreamSynchronize(s->stream);
     cudaFreeHost(s->pin);
     cudaFree(s->dev);
+    if (s->aux_dev) cudaFree(s->aux_dev);
     cudaStreamDestroy(s->stream);
     for (int k = 0; k < 3; ++k) cudaStreamDestroy(s->pipe[k]);
     delete s;

@@ -73,6 +73,7 @@ struct KArgs {
     const T* goal;
     const Vec4<T>* obst;       // blocked [tile][M][32]
     const Vec2<T>* obst_ext;   // blocked [tile][M][32] {safe, order} or null
+    const T* aux;              // blocked [n_aux * 12] auxiliary field records or null
     const T* jp_ref;
     const T* ns_in;
     T* ns_lastvec;
@@ -93,6 +94,7 @@ struct KArgs {
     int32_t n_rem;             // n_obst % kChunk
     int32_t n_stages;          // shared-memory stages (<= kMaxStages); >= n_chunks means resident
     int32_t k_cycles;
+    int32_t n_aux;
 };
 
 // ------------------------------------------------------------------------------ chain patterns
@@ -246,6 +248,47 @@ __device__ __forceinline__ void attract(const KConst<T>& c, const T (&g)[13], co
     const T S1 = Prec<T>::fmin_(T(1), angle * c.rot_slowdown_inv);     // rot_slowdown_inv = +inf when off
     const T sr = c.speed_scale * S1 * c.goal_force * invn;
     w[0] = sr * qx; w[1] = sr * qy; w[2] = sr * qz;
+}
+
+// Auxiliary fields: records of VFK_AUX_COMPS = 12 scalars {type, force, p0..p9} in slots of a
+// blocked per-instance array.  type 4 = hemisphere repeller (scripts/object_feeder:335-354: xyz, normal, safe, order),
+// type 5 = funnel attractor (:262-280: goal xyz, axis, cut angle, angle-decay order, cut distance, distance-decay order);
+// any other type code = empty slot.  Functional forms: oracle.batch.ORACLE_CHOICES (vfl is un-vendored).
+template <typename T>
+__device__ __forceinline__ void aux_fields(const T* __restrict__ aux, int n_aux, int64_t tile, int lane, const T (&pt)[3], T (&V)[3]) {
+    for (int s = 0; s < n_aux; ++s) {
+        const T* r = aux + (tile * (n_aux * 12) + s * 12) * 32 + lane;
+        const int type = (int)__ldg(r);
+        if (type != 4 && type != 5) continue;
+        const T force = __ldg(r + 32);
+        T p[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) p[k] = __ldg(r + (2 + k) * 32);
+        const T rx = pt[0] - p[0], ry = pt[1] - p[1], rz = pt[2] - p[2];
+        const T an2 = p[3] * p[3] + p[4] * p[4] + p[5] * p[5];
+        if (!(an2 > T(0))) continue;
+        const T ian = Prec<T>::rsqrt_pos(an2);
+        const T ax = p[3] * ian, ay = p[4] * ian, az = p[5] * ian;
+        const T s_ax = rx * ax + ry * ay + rz * az;                       // height above the plane / distance along the axis
+        if (type == 4) {
+            const T safe = p[6], order = p[7];
+            const T ratio = Prec<T>::div(safe, Prec<T>::fmax_(s_ax, safe));
+            const T mag = -force * Prec<T>::pow_pos(ratio, order);        // field points toward the surface (-normal)
+            V[0] = fma(mag, ax, V[0]); V[1] = fma(mag, ay, V[1]); V[2] = fma(mag, az, V[2]);
+        } else {
+            const T cut_a = p[6], ord_a = p[7], cut_d = p[8], ord_d = p[9];
+            const T px = rx - s_ax * ax, py = ry - s_ax * ay, pz = rz - s_ax * az;   // radial offset from the approach axis
+            const T rho2 = px * px + py * py + pz * pz;
+            if (!(rho2 > T(0))) continue;
+            const T rho = Prec<T>::sqrt_(rho2);
+            const T theta = Prec<T>::atan2_(rho, s_ax);
+            const T R = Prec<T>::sqrt_(rx * rx + ry * ry + rz * rz);
+            const T wa = theta <= cut_a ? T(1) : Prec<T>::pow_pos(Prec<T>::div(cut_a, theta), ord_a);
+            const T wd = R <= cut_d ? T(1) : Prec<T>::pow_pos(Prec<T>::div(cut_d, R), ord_d);
+            const T mag = -force * wa * wd * Prec<T>::rcp(rho);           // unit vector toward the axis
+            V[0] = fma(mag, px, V[0]); V[1] = fma(mag, py, V[1]); V[2] = fma(mag, pz, V[2]);
+        }
+    }
 }
 
 // normCart + saturation: unit translational part (zero stays zero), pre-scaled by its largest
@@ -439,6 +482,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 if (!resident && ++c_stage == S) { c_stage = 0; c_phase ^= 1u; }
             }
             V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
+            if (!LEAN && a.aux) aux_fields<T>(a.aux, a.n_aux, tile, lane, pt, V);
             T v[3];
             saturate<T>(c, V, S0, v);
             if (!LEAN && last && active && a.twist) {
@@ -705,8 +749,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 template <typename T>
 __global__ void __launch_bounds__(kSmallBlock)
 vfk_field_kernel(const __grid_constant__ KConst<T> c, const T* __restrict__ pose, const T* __restrict__ goal,
-                 const Vec4<T>* __restrict__ obst, const Vec2<T>* __restrict__ obst_ext, T* __restrict__ twist,
-                 int64_t n, int n_obst) {
+                 const Vec4<T>* __restrict__ obst, const Vec2<T>* __restrict__ obst_ext, const T* __restrict__ aux, int n_aux,
+                 T* __restrict__ twist, int64_t n, int n_obst) {
     const int64_t i = (int64_t)blockIdx.x * kSmallBlock + threadIdx.x;
     if (i >= n) return;
     const int64_t tile = i >> 5;
@@ -727,6 +771,7 @@ vfk_field_kernel(const __grid_constant__ KConst<T> c, const T* __restrict__ pose
         repel<T>(o, safe_inv, order, pt, acc);
     }
     V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
+    if (aux) aux_fields<T>(aux, n_aux, tile, lane, pt, V);
     saturate<T>(c, V, S0, v);
 #pragma unroll
     for (int k = 0; k < 3; ++k) { twist[(tile * 6 + k) * 32 + lane] = v[k]; twist[(tile * 6 + 3 + k) * 32 + lane] = w[k]; }

@@ -93,7 +93,7 @@ def round_up(n: int, m: int = 32) -> int:
     return (int(n) + m - 1) // m * m
 
 
-_BUF_FIELDS = ("q", "goal", "obst", "obst_ext", "jp_ref", "ns_in", "ns_lastvec", "q_cmded", "qdot_vf", "qdot_ns", "qdot_jp",
+_BUF_FIELDS = ("q", "goal", "obst", "obst_ext", "aux", "jp_ref", "ns_in", "ns_lastvec", "q_cmded", "qdot_vf", "qdot_ns", "qdot_jp",
                "qdot", "cmd", "pose", "twist", "flags")
 
 
@@ -176,15 +176,18 @@ class Engine:
             setattr(b, f, _dev_ptr(bufs.get(f)))
         for e in range(3):
             b.ext_cmd[e] = _dev_ptr(ext_cmd[e])
+        aux = bufs.get("aux")
+        b.n_aux = 0 if aux is None else int(aux.shape[1]) // 12
         rc = self._check(self._lib.vfk_step(self._h, C.byref(b), int(n_instances), int(n_obstacles), int(k_cycles),
                                             self._stream(stream)))
         self.launches += rc
         return rc
 
-    def field_eval(self, pose, goal, obst, twist_out, n_instances, n_obstacles, obst_ext=None, stream=None) -> int:
+    def field_eval(self, pose, goal, obst, twist_out, n_instances, n_obstacles, obst_ext=None, aux=None, n_aux=0,
+                   stream=None) -> int:
         rc = self._check(self._lib.vfk_field_eval(self._h, _dev_ptr(pose), _dev_ptr(goal), _dev_ptr(obst),
-                                                  _dev_ptr(obst_ext), _dev_ptr(twist_out), int(n_instances),
-                                                  int(n_obstacles), self._stream(stream)))
+                                                  _dev_ptr(obst_ext), _dev_ptr(aux), int(n_aux), _dev_ptr(twist_out),
+                                                  int(n_instances), int(n_obstacles), self._stream(stream)))
         self.launches += rc
         return rc
 
@@ -287,6 +290,16 @@ class Session:
                 raise ValueError("obstacle ext must be [M, n, 2], got %r" % (x.shape,))
         self.e._check(self.e._lib.vfk_session_set_obstacles(self._s, _lib.np_ptr(a), None if x is None else _lib.np_ptr(x)))
 
+    def set_aux(self, aux):
+        """Auxiliary field records ``[n_aux, 12, n]`` ({type, force, 10 params}; types 4 and 5), or None to clear."""
+        if aux is None:
+            self.e._check(self.e._lib.vfk_session_set_aux(self._s, None, 0))
+            return
+        a = np.ascontiguousarray(aux, dtype=self.e.np_dtype)
+        if a.ndim != 3 or a.shape[1:] != (12, self.n):
+            raise ValueError("aux must be [n_aux, 12, n], got %r" % (a.shape,))
+        self.e._check(self.e._lib.vfk_session_set_aux(self._s, _lib.np_ptr(a), int(a.shape[0])))
+
     def set_q(self, q):
         a = self._arr(q, self.e.n_joints)
         self.e._check(self.e._lib.vfk_session_set_q(self._s, _lib.np_ptr(a)))
@@ -337,7 +350,7 @@ class Session:
             self.e._check(self.e._lib.vfk_session_enable(self._s, w.encode(), int(on)))
 
     def read(self, what: str) -> np.ndarray:
-        rows = 12 if what == "pose" else self.e.n_joints
+        rows = {"pose": 12, "twist": 6}.get(what, self.e.n_joints)
         out = np.empty((rows, self.n), dtype=self.e.np_dtype)
         self.e._check(self.e._lib.vfk_session_read(self._s, what.encode(), _lib.np_ptr(out)))
         return out
@@ -398,6 +411,14 @@ class DeviceBatch:
         self.e.pack(dense, out, comps, width, self.n)
         torch.cuda.current_stream(self.e.device).synchronize()       # `dense` may be freed after return
         return out
+
+    def set_aux(self, aux: np.ndarray):
+        """Auxiliary field records ``[n_aux, 12, n]`` -> blocked ``aux`` buffer of this batch."""
+        a = np.ascontiguousarray(aux, dtype=self.e.np_dtype)
+        if a.ndim != 3 or a.shape[1:] != (12, self.n):
+            raise ValueError("aux must be [n_aux, 12, n], got %r" % (a.shape,))
+        self.t["aux"] = self.to_blocked(a.reshape(a.shape[0] * 12, self.n))
+        return self.t["aux"]
 
     def upload(self, name: str, arr: np.ndarray):
         t = self._ensure(name)

@@ -38,22 +38,24 @@ class Vfclik:
     def __init__(self, config, namespace="/0", sim=True, no_nullspace=False, precision=64, device=0):
         from .bridge import BridgeModule, JointSim
         from .joint_p_controller import JointPControllerModule
+        from .monitor_distance import MonitorDistanceModule
         from .nullspace import NullspaceModule
+        from .object_feeder import ObjectFeederModule
         from .runtime import ControlRuntime, NS_OFF, NS_PROJECTOR
         from .vf import VectorFieldModule
         self.config = config
         self.runtime = ControlRuntime(config, n_instances=1, precision=precision, device=device)
         self.runtime.set_params(ns_mode=NS_OFF if no_nullspace else NS_PROJECTOR)
         self.vf = VectorFieldModule(self.runtime, namespace)
+        self.ofeeder = ObjectFeederModule(config, namespace)
+        self.dmonitor = MonitorDistanceModule(self.runtime, namespace)
         self.jpctrl = JointPControllerModule(self.runtime, namespace)
         self.nullspace = None if no_nullspace else NullspaceModule(self.runtime, namespace)
         self.joint_sim = JointSim(config, namespace) if sim else None
         self.bridge = BridgeModule(self.runtime, namespace, sim=sim)
         self.namespace = namespace
         self.cycles = 0
-        # object_feeder's first message (scripts/object_feeder:102-108): config.initial_vf_pose
-        if hasattr(config, "initial_vf_pose"):
-            self.set_goal(config.initial_vf_pose[2])
+        # the first goal comes from object_feeder's own first message (scripts/object_feeder:102-108): config.initial_vf_pose
 
     def _param_port(self):
         return self.vf.paramPort
@@ -80,16 +82,19 @@ class Vfclik:
         if self.joint_sim is not None:
             self.joint_sim.update()
         self.bridge.update()
+        while self.ofeeder.update():
+            pass
         self.vf.update()
         if self.nullspace is not None:
             self.nullspace.update()
         self.jpctrl.update()
+        self.dmonitor.update()
         cmd = self.bridge.finish()
         self.cycles += 1
         return cmd
 
     def close(self):
-        for m in (self.vf, self.jpctrl, self.nullspace, self.joint_sim, self.bridge):
+        for m in (self.vf, self.ofeeder, self.dmonitor, self.jpctrl, self.nullspace, self.joint_sim, self.bridge):
             if m is not None:
                 m.close()
         self.runtime.close()

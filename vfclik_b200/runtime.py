@@ -10,9 +10,9 @@ outputs (the synchronous idealisation of DESIGN.md section 1).
 
 Scene protocol = ``scripts/vf:210-293``: fields are ``{id: [force, type, params]}``;
 type 1 (point attractor, 16 frame floats + slowdown) becomes the instance's goal, type 2
-(decay repeller: x, y, z, radius, safe, order) takes an obstacle slot.  Types 4 / 5
-(hemisphere / funnel) are not on the GPU yet and are ignored with the
-reference's own "Unknown vector field type, ignoring" warning.
+(decay repeller: x, y, z, radius, safe, order) takes an obstacle slot, types 4 / 5
+(hemisphere repeller / funnel attractor) take an auxiliary-field
+slot.  Any other type gets the reference's "Unknown vector field type, ignoring" warning.
 """
 from __future__ import annotations
 
@@ -24,7 +24,8 @@ import numpy as np
 from .config import chain_from_config
 from .engine import Engine, Params, NS_CONTROL, NS_OFF, NS_PROJECTOR  # noqa: F401
 
-SUPPORTED_FIELD_TYPES = (0, 1, 2)
+SUPPORTED_FIELD_TYPES = (0, 1, 2, 4, 5)
+MAX_AUX_SLOTS = 4
 CONFIG_MAX_SPEED_SCALE = 0.41          # scripts/vf:134
 
 
@@ -44,7 +45,7 @@ class ControlRuntime:
         prm = dataclasses.replace(prm, integrate=1 if simulate_plant else 0, goal_force=0.0)
         self.engine = Engine(self.chain, precision=precision, device=device, params=prm)
         self.session = self.engine.session(self.I, self.M, obst_ext=True)
-        self.session.enable("qdot_vf", "qdot_ns", "qdot_jp", "cmd", "pose")
+        self.session.enable("qdot_vf", "qdot_ns", "qdot_jp", "cmd", "pose", "twist")
         dt = self.engine.np_dtype
         self.goal = np.zeros((13, self.I), dtype=dt)
         self.goal[0] = self.goal[4] = self.goal[8] = 1.0
@@ -52,6 +53,7 @@ class ControlRuntime:
         self.obst_ext = np.zeros((self.M, self.I, 2), dtype=dt)
         self.obst_ext[:, :, 0] = prm.obst_safe
         self.obst_ext[:, :, 1] = prm.obst_order
+        self.aux = np.zeros((MAX_AUX_SLOTS, 12, self.I), dtype=dt)       # type 0 = empty slot
         self.vectorFields: Dict[int, list] = {}                         # scripts/vf:145
         self._slot_of: Dict[int, int] = {}
         self._scene_dirty = True
@@ -109,8 +111,10 @@ class ControlRuntime:
         prm = self.params
         goal_force = 0.0
         self.obst[:, 0, :] = 0.0
+        self.aux[:, :, 0] = 0.0
         self._slot_of.clear()
         slot = 0
+        aslot = 0
         have_goal = False
         for fid in sorted(self.vectorFields):
             force, vtype, p = self.vectorFields[fid]
@@ -149,6 +153,18 @@ class ControlRuntime:
                 self.obst_ext[slot, 0, 1] = order
                 self._slot_of[fid] = slot
                 slot += 1
+            elif vtype in (4, 5):
+                want = 8 if vtype == 4 else 10
+                if len(p) < want:
+                    dprint("Wrong number of values for field type %d, ignoring" % vtype)
+                    continue
+                if aslot >= MAX_AUX_SLOTS:
+                    dprint("No free auxiliary field slot (%d), ignoring field %d" % (MAX_AUX_SLOTS, fid))
+                    continue
+                self.aux[aslot, 0, 0] = vtype
+                self.aux[aslot, 1, 0] = force
+                self.aux[aslot, 2:2 + want, 0] = p[:want]
+                aslot += 1
         if goal_force != prm.goal_force:
             self.engine.set_params(goal_force=goal_force)
         self._scene_dirty = True
@@ -192,19 +208,24 @@ class ControlRuntime:
         if self._q_cached is not None and np.array_equal(self._q_cached, q) and k_cycles == 1:
             return self._out
         if self._scene_dirty:
-            self.session.set_goal(self.goal)
-            self.session.set_obstacles(self.obst, self.obst_ext)
-            self._scene_dirty = False
+            self._upload_scene()
         qdot = np.empty((self.N, self.I), dtype=dt)
         q_out = np.empty((self.N, self.I), dtype=dt)
         flags = np.empty(self.I, dtype=np.int32)
         self.session.cycle(q_in=q, k_cycles=k_cycles, qdot_out=qdot, q_out=q_out, flags_out=flags)
         self._out = dict(qdot=qdot, q=q_out, flags=flags, qdot_vf=self.session.read("qdot_vf"),
                          qdot_ns=self.session.read("qdot_ns"), qdot_jp=self.session.read("qdot_jp"),
-                         cmd=self.session.read("cmd"), pose=self.session.read("pose"))
+                         cmd=self.session.read("cmd"), pose=self.session.read("pose"), twist=self.session.read("twist"))
         self._q_cached = q.copy()
         self.cycles += k_cycles
         return self._out
+
+    def _upload_scene(self):
+        self.session.set_goal(self.goal)
+        self.session.set_obstacles(self.obst, self.obst_ext)
+        used = int(np.any(self.aux[:, 0, :] != 0, axis=1).sum())
+        self.session.set_aux(self.aux[:used] if used else None)
+        self._scene_dirty = False
 
     def close(self):
         self.session.close()
@@ -228,9 +249,7 @@ def field_query(runtime: "ControlRuntime", pose12: np.ndarray) -> np.ndarray:
     import torch
     e = runtime.engine
     if runtime._scene_dirty:
-        runtime.session.set_goal(runtime.goal)
-        runtime.session.set_obstacles(runtime.obst, runtime.obst_ext)
-        runtime._scene_dirty = False
+        runtime._upload_scene()
     b = _session_device_view(runtime)
     dev = "cuda:%d" % e.device
     dense = torch.from_numpy(np.ascontiguousarray(pose12, dtype=e.np_dtype)).to(dev)
@@ -239,6 +258,6 @@ def field_query(runtime: "ControlRuntime", pose12: np.ndarray) -> np.ndarray:
     tw_d = torch.empty((6, runtime.I), dtype=e.torch_dtype, device=dev)
     e.pack(dense, pose_b, 12, 1, runtime.I)
     e.field_eval(pose_b, int(b.goal), int(b.obst) if b.obst else None, tw_b, runtime.I, runtime.M,
-                 obst_ext=int(b.obst_ext) if b.obst_ext else None)
+                 obst_ext=int(b.obst_ext) if b.obst_ext else None, aux=int(b.aux) if b.aux else None, n_aux=int(b.n_aux))
     e.unpack(tw_b, tw_d, 6, 1, runtime.I)
     return tw_d.cpu().numpy()
