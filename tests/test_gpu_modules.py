@@ -30,6 +30,9 @@ def test_vfclik_app_config1_matches_reference_shaped_loop(lwr, built_lib, fresh_
                        jp_kp=cfg.jpctrl_kp, ik_lambda=cfg.ik_lambda, ns_lambda=cfg.ns_lambda)
     try:
         obj = _out_port(fresh_ports, "/0/test/obj", app.ofeeder.objectPort.getName())
+        # the feeder's first iteration replaces whatever it read by config.initial_vf_pose (scripts/object_feeder:98-103),
+        # so let it publish its first goal before the obstacles are sent
+        assert app.ofeeder.update() and sorted(app.ofeeder.objects) == [0]
         for m in range(3):                               # "set ObstacleP n (16 + radius + order)" (old/README.old:75)
             o = w["obst"][m, 0]
             frame = [1, 0, 0, o[0], 0, 1, 0, o[1], 0, 0, 1, o[2], 0, 0, 0, 1]
@@ -254,6 +257,7 @@ def test_object_feeder_goal_and_normal_and_table(lwr, built_lib, fresh_ports):
                        jp_kp=cfg.jpctrl_kp, ik_lambda=cfg.ik_lambda, ns_lambda=cfg.ns_lambda)
     try:
         obj = _out_port(fresh_ports, "/0/test/obj", app.ofeeder.objectPort.getName())
+        app.ofeeder.update()                                             # first goal from config.initial_vf_pose
         g = list(cfg.initial_vf_pose[2][:16])
         gan = g + [0.0, 0.3, -1.0, 0.5, 0.15, 0.04]                    # axis, cut angle, cut length, slowdown
         table = [1, 0, 0, 0.7, 0, 1, 0, 0.1, 0, 0, 1, 0.9, 0, 0, 0, 1] + [0.0, 0.0, 1.0, 0.02, 3.0]   # normal, safe, order
