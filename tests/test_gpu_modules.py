@@ -89,7 +89,7 @@ def test_vf_module_protocol_edge_cases(lwr, built_lib, fresh_ports):
         buf = io.StringIO()
         with redirect_stdout(buf):
             yarp.write_bottle_lists(param, ["add", 1, 1.0, 1, list(cfg.initial_vf_pose[2])], strict=True)
-            yarp.write_bottle_lists(param, ["add", 9, -50.0, 4, [0.0] * 8], strict=True)     # hemisphere: not on the GPU yet
+            yarp.write_bottle_lists(param, ["add", 9, -50.0, 7, [0.0] * 8], strict=True)     # a type vfl does not have
             yarp.write_bottle_lists(param, ["add", 3, 1.0], strict=True)                      # wrong arity
             yarp.write_bottle_lists(param, ["remove", 77], strict=True)                       # unknown id: silently nothing
             yarp.write_bottle_lists(weight, ["t", 1.0, 1.0], strict=True)                     # wrong size
