@@ -114,9 +114,9 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------- CPU arm (oracle)
 
-def _cpu_worker(args):
-    """Reference-shaped scalar loop (oracle/refshape.py) on one core: `cycles` control cycles of one instance."""
-    seed, n_obst, cycles, ns_mode = args
+def _cpu_worker_main(conn, seed, n_obst, ns_mode):
+    """One host core: builds its own reference-shaped control loop (oracle/refshape.py) once, then advances it by the
+    number of control cycles the parent asks for and reports the time the cycles took."""
     from oracle import batch, refshape
     from vfclik_b200 import workloads
     from vfclik_b200.config import PACKAGE_CONFIG_DIR, chain_from_config, config_filename, load_config
@@ -127,9 +127,14 @@ def _cpu_worker(args):
     g17 = [g[0], g[1], g[2], g[9], g[3], g[4], g[5], g[10], g[6], g[7], g[8], g[11], 0, 0, 0, 1, g[12]]
     prm = batch.Params(ns_mode=ns_mode, jp_ref=tuple(cfg.initial_joint_pos), speed_scale=cfg.speedScale, dt=cfg.rate)
     loop = refshape.ControlLoop(chain, prm, w["q"][:, 0], g17, obstacles=w["obst"][:, 0, :].tolist())
-    t0 = time.perf_counter()
-    loop.run(cycles)
-    return cycles, time.perf_counter() - t0
+    conn.send("ready")
+    while True:
+        cycles = conn.recv()
+        if cycles is None:
+            break
+        t0 = time.perf_counter()
+        loop.run(cycles)
+        conn.send((cycles, time.perf_counter() - t0))
 
 
 class CpuArm:
@@ -137,22 +142,32 @@ class CpuArm:
 
     def __init__(self, n_obst: int, ns_mode: int = 1):
         import multiprocessing as mp
+        ctx = mp.get_context("spawn")
         self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         self.n_obst, self.ns_mode = n_obst, ns_mode
-        self.pool = mp.get_context("spawn").Pool(self.cores)
-        self.seed = 1000
+        self.workers = []
+        for c in range(self.cores):
+            parent, child = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker_main, args=(child, 1000 + c, n_obst, ns_mode), daemon=True)
+            p.start()
+            self.workers.append((p, parent))
+        for _, conn in self.workers:
+            assert conn.recv() == "ready"
 
     def step(self, cycles_per_core: int):
-        jobs = [(self.seed + c, self.n_obst, cycles_per_core, self.ns_mode) for c in range(self.cores)]
-        self.seed += self.cores
+        """Every core advances its instance by `cycles_per_core` control cycles; returns (total cycles, wall seconds)."""
         t0 = time.perf_counter()
-        res = self.pool.map(_cpu_worker, jobs)
+        for _, conn in self.workers:
+            conn.send(cycles_per_core)
+        res = [conn.recv() for _, conn in self.workers]
         wall = time.perf_counter() - t0
         return sum(r[0] for r in res), wall
 
     def close(self):
-        self.pool.close()
-        self.pool.join()
+        for p, conn in self.workers:
+            conn.send(None)
+        for p, _ in self.workers:
+            p.join(timeout=5)
 
 
 def cpu_vectorised(n_obst: int, instances: int = 8192):
@@ -179,8 +194,13 @@ def run_reference_arm(args, rank: int):
     n_inst, n_obst, precision, desc = WORKLOADS[args.workload]
     arm = CpuArm(n_obst)
     cycles_per_core = args.cpu_cycles
-    for _ in range(args.warmup):
-        arm.step(max(1, cycles_per_core // 4))
+    rate = None
+    for _ in range(max(args.warmup, 1)):
+        c, t = arm.step(max(1, cycles_per_core // 4))
+        rate = c / t / arm.cores                       # control cycles per second per core
+    # bound the whole timed run to about a minute whatever --steps is: a step is a fixed number of cycles per core
+    budget_s = 60.0
+    cycles_per_core = max(1, min(cycles_per_core, int(budget_s * rate / max(args.steps, 1))))
     total, wall = 0, 0.0
     for _ in range(args.steps):
         c, t = arm.step(cycles_per_core)

@@ -547,13 +547,16 @@ extern "C" int vfk_unpack(vfk_handle h, const void* blocked, void* dense, int co
 // -------------------------------------------------------------------------------- public: host-buffer sessions
 // Host arrays are dense SoA ([comps][n]; obstacles [M][n][4]); the session keeps a dense device staging
 // area and converts to / from the kernels' tile-blocked layout on the GPU (vfk_pack / vfk_unpack kernels).
+constexpr int kMaxSessionChunks = 32;
+
 struct vfk_session_s {
     vfk_ctx* h;
     int64_t n, tiles;
     int n_obst, has_ext, N, n_aux;
     size_t es;                       // element size
     cudaStream_t stream;
-    cudaStream_t pipe[3];            // chunk pipeline of vfk_session_cycle (H2D / kernels / D2H overlap)
+    cudaStream_t pipe[3];            // chunk pipeline of vfk_session_cycle: [0] H2D, [1] kernels, [2] D2H
+    cudaEvent_t ev_up[kMaxSessionChunks], ev_done[kMaxSessionChunks];
     char* dev;                       // one device slab
     size_t dev_bytes;
     vfk_buffers b;                   // blocked device buffers
@@ -624,6 +627,10 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->pin_bytes = (size_t)N * 3 * (size_t)n * s->es + (size_t)n * 4;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     for (int k = 0; k < 3 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&s->pipe[k], cudaStreamNonBlocking);
+    for (int k = 0; k < kMaxSessionChunks && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&s->ev_up[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done[k], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->pin, s->pin_bytes);
     if (e != cudaSuccess) {
         cudaFree(s->dev);
@@ -763,11 +770,17 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
     if (!s->en_twist) b.twist = nullptr;
     const int ns_comps = h->params.ns_mode == VFK_NS_CONTROL ? 4 : N;
 
-    // Chunk pipeline: with several chunks in flight on different streams the H2D copy of chunk c+1, the
-    // kernels of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex).  Chunks are whole tiles.
+    // Chunk pipeline: a three-stage software pipeline over tile-aligned chunks.  All uploads go back to back on the
+    // H2D stream, the kernels of chunk c wait for its upload on the compute stream, and its downloads wait for the
+    // kernels on the D2H stream, so the two DMA engines (PCIe is full duplex) and the SMs all stay busy.
     int n_chunks = (int)(s->n / 65536);
-    if (n_chunks > 8) n_chunks = 8;
+    if (n_chunks > 16) n_chunks = 16;
+    if (const char* e = getenv("VFK_SESSION_CHUNKS")) n_chunks = atoi(e);
+    if (n_chunks > kMaxSessionChunks) n_chunks = kMaxSessionChunks;
     if (n_chunks < 1) n_chunks = 1;
+    if ((int64_t)n_chunks > s->tiles) n_chunks = (int)s->tiles;
+    const bool piped = n_chunks > 1;
+    cudaStream_t st_up = piped ? s->pipe[0] : s->stream, st_k = piped ? s->pipe[1] : s->stream, st_dn = piped ? s->pipe[2] : s->stream;
     const int64_t tiles_per_chunk = (s->tiles + n_chunks - 1) / n_chunks;
     char* stage_q = (char*)s->stage_in;                         // dense [N][n]
     char* stage_qd = (char*)s->stage_out;                       // dense [N][n]
@@ -780,33 +793,42 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
         const int64_t t1 = t0 + tiles_per_chunk < s->tiles ? t0 + tiles_per_chunk : s->tiles;
         const int64_t i0 = t0 * 32;
         const int64_t cnt = (t1 * 32 < s->n ? t1 * 32 : s->n) - i0;
-        cudaStream_t st = n_chunks > 1 ? s->pipe[c % 3] : s->stream;
         vfk_buffers v = offset_view(b, t0, N, s->n_obst, es);
         if (s->have_ns_in) v.ns_in = (char*)s->d_ns_in + (size_t)t0 * ns_comps * 32 * es;
         if (src_q) {
             VFK_CUDA(h, cudaMemcpy2DAsync(stage_q + i0 * es, pitch, src_q + i0 * es, pitch, (size_t)cnt * es, N,
-                                          cudaMemcpyHostToDevice, st));
-            if ((rc = pack_dispatch(h, stage_q + i0 * es, v.q, N, 1, cnt, false, st, s->n)) < 0) return rc;
+                                          cudaMemcpyHostToDevice, st_up));
+            if (piped) {
+                VFK_CUDA(h, cudaEventRecord(s->ev_up[c], st_up));
+                VFK_CUDA(h, cudaStreamWaitEvent(st_k, s->ev_up[c], 0));
+            }
+            if ((rc = pack_dispatch(h, stage_q + i0 * es, v.q, N, 1, cnt, false, st_k, s->n)) < 0) return rc;
             launches += rc;
         }
-        if ((rc = vfk_step(h, &v, cnt, s->n_obst, k_cycles, st)) < 0) return rc;
+        if ((rc = vfk_step(h, &v, cnt, s->n_obst, k_cycles, st_k)) < 0) return rc;
         launches += rc;
         if (dst_qd) {
-            if ((rc = pack_dispatch(h, stage_qd + i0 * es, v.qdot, N, 1, cnt, true, st, s->n)) < 0) return rc;
+            if ((rc = pack_dispatch(h, stage_qd + i0 * es, v.qdot, N, 1, cnt, true, st_k, s->n)) < 0) return rc;
             launches += rc;
-            VFK_CUDA(h, cudaMemcpy2DAsync(dst_qd + i0 * es, pitch, stage_qd + i0 * es, pitch, (size_t)cnt * es, N,
-                                          cudaMemcpyDeviceToHost, st));
         }
         if (dst_qo) {
-            if ((rc = pack_dispatch(h, stage_qo + i0 * es, v.q, N, 1, cnt, true, st, s->n)) < 0) return rc;
+            if ((rc = pack_dispatch(h, stage_qo + i0 * es, v.q, N, 1, cnt, true, st_k, s->n)) < 0) return rc;
             launches += rc;
-            VFK_CUDA(h, cudaMemcpy2DAsync(dst_qo + i0 * es, pitch, stage_qo + i0 * es, pitch, (size_t)cnt * es, N,
-                                          cudaMemcpyDeviceToHost, st));
         }
+        if (piped) {
+            VFK_CUDA(h, cudaEventRecord(s->ev_done[c], st_k));
+            VFK_CUDA(h, cudaStreamWaitEvent(st_dn, s->ev_done[c], 0));
+        }
+        if (dst_qd)
+            VFK_CUDA(h, cudaMemcpy2DAsync(dst_qd + i0 * es, pitch, stage_qd + i0 * es, pitch, (size_t)cnt * es, N,
+                                          cudaMemcpyDeviceToHost, st_dn));
+        if (dst_qo)
+            VFK_CUDA(h, cudaMemcpy2DAsync(dst_qo + i0 * es, pitch, stage_qo + i0 * es, pitch, (size_t)cnt * es, N,
+                                          cudaMemcpyDeviceToHost, st_dn));
         if (dst_fl)         // one component: blocked == dense
-            VFK_CUDA(h, cudaMemcpyAsync(dst_fl + i0 * 4, s->b.flags + i0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+            VFK_CUDA(h, cudaMemcpyAsync(dst_fl + i0 * 4, s->b.flags + i0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st_dn));
     }
-    if (n_chunks > 1) {
+    if (piped) {
         for (int k = 0; k < 3; ++k) VFK_CUDA(h, cudaStreamSynchronize(s->pipe[k]));
     } else {
         VFK_CUDA(h, cudaStreamSynchronize(s->stream));
@@ -871,5 +893,6 @@ extern "C" void vfk_session_destroy(vfk_session s) {
     if (s->aux_dev) cudaFree(s->aux_dev);
     cudaStreamDestroy(s->stream);
     for (int k = 0; k < 3; ++k) cudaStreamDestroy(s->pipe[k]);
+    for (int k = 0; k < kMaxSessionChunks; ++k) { cudaEventDestroy(s->ev_up[k]); cudaEventDestroy(s->ev_done[k]); }
     delete s;
 }
