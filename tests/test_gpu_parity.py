@@ -417,6 +417,21 @@ def test_host_session_chunk_pipeline(eng, lwr):
         launches = s.cycle(q_in=q_pin.numpy(), k_cycles=2, qdot_out=qd.numpy(), q_out=qo, flags_out=fl)
         assert launches == 3 * 4                                      # 3 chunks x (pack q, cycle, unpack qdot, unpack q)
         assert np.array_equal(qd.numpy().T, dev["qdot"]) and np.array_equal(qo.T, dev["q"]) and np.array_equal(fl, dev["flags"])
+        # same buffers again: the second call captures the pipeline into a CUDA graph, later calls replay it
+        for _ in range(3):
+            qd.zero_(); qo[:] = 0; fl[:] = -1
+            assert s.cycle(q_in=q_pin.numpy(), k_cycles=2, qdot_out=qd.numpy(), q_out=qo, flags_out=fl) == 12
+            assert np.array_equal(qd.numpy().T, dev["qdot"]) and np.array_equal(qo.T, dev["q"]) and np.array_equal(fl, dev["flags"])
+        # a parameter change invalidates the captured graph (the constants are baked into the kernel nodes)
+        old = e.params
+        e.set_params(speed_scale=0.1)
+        s.cycle(q_in=q_pin.numpy(), k_cycles=2, qdot_out=qd.numpy())
+        s.cycle(q_in=q_pin.numpy(), k_cycles=2, qdot_out=qd.numpy())
+        slow = qd.numpy().copy()
+        e.set_params(old)
+        assert not np.array_equal(slow.T, dev["qdot"])
+        s.cycle(q_in=q_pin.numpy(), k_cycles=2, qdot_out=qd.numpy())
+        assert np.array_equal(qd.numpy().T, dev["qdot"])
     finally:
         s.close()
 

@@ -26,6 +26,7 @@ struct vfk_ctx {
     int device;
     int sm_count;
     int pattern;                // 0: GenericPattern, 1: LwrPattern (structure of the canonical chain)
+    uint64_t generation;        // bumped by vfk_set_params: captured CUDA graphs bake the constants in
     KConst<float> cf;
     KConst<double> cd;
     std::string err;
@@ -235,6 +236,7 @@ extern "C" int vfk_create(vfk_handle* out, const vfk_chain_desc* chain, int prec
     h->precision = precision;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    h->generation = 1;
     vfk_default_params(&h->params, n);
     build_const(*h, h->cf);
     build_const(*h, h->cd);
@@ -247,6 +249,7 @@ extern "C" int vfk_set_params(vfk_handle h, const vfk_params* p) {
     int rc = check_params(h, p);
     if (rc != VFK_OK) return rc;
     h->params = *p;
+    h->generation++;
     build_const(*h, h->cf);
     build_const(*h, h->cd);
     return VFK_OK;
@@ -556,7 +559,7 @@ struct vfk_session_s {
     size_t es;                       // element size
     cudaStream_t stream;
     cudaStream_t pipe[3];            // chunk pipeline of vfk_session_cycle: [0] H2D, [1] kernels, [2] D2H
-    cudaEvent_t ev_up[kMaxSessionChunks], ev_done[kMaxSessionChunks];
+    cudaEvent_t ev_up[kMaxSessionChunks], ev_done[kMaxSessionChunks], ev_fork, ev_join[2];
     char* dev;                       // one device slab
     size_t dev_bytes;
     vfk_buffers b;                   // blocked device buffers
@@ -569,6 +572,11 @@ struct vfk_session_s {
     char* pin;                       // pinned host staging: q in (N rows), qdot / q out (2N rows), flags
     size_t pin_bytes;
     int launches;                    // kernels launched by the last call
+    uint64_t generation;             // bumped by every setter that changes what a cycle does
+    // cached CUDA graph of one vfk_session_cycle (the pipeline is ~30-100 API calls; one graph launch replaces them)
+    cudaGraphExec_t graph_exec;
+    int graph_launches;
+    struct { const void *src_q, *dst_qd, *dst_qo, *dst_fl; int k; uint64_t hgen, sgen; } graph_key;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -624,6 +632,10 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->launches = 0;
     s->n_aux = 0;
     s->aux_dev = nullptr;
+    s->generation = 1;
+    s->graph_exec = nullptr;
+    s->graph_launches = 0;
+    memset(&s->graph_key, 0, sizeof s->graph_key);
     s->pin_bytes = (size_t)N * 3 * (size_t)n * s->es + (size_t)n * 4;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     for (int k = 0; k < 3 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&s->pipe[k], cudaStreamNonBlocking);
@@ -631,6 +643,8 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
         e = cudaEventCreateWithFlags(&s->ev_up[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done[k], cudaEventDisableTiming);
     }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&s->ev_join[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->pin, s->pin_bytes);
     if (e != cudaSuccess) {
         cudaFree(s->dev);
@@ -675,6 +689,7 @@ extern "C" int vfk_session_set_aux(vfk_session s, const void* aux, int n_aux) {
     vfk_ctx* h = s->h;
     if (n_aux < 0 || n_aux > 64) return fail(h, VFK_ERR_INVALID, "n_aux must be in 0..64");
     VFK_CUDA(h, cudaSetDevice(h->device));
+    s->generation++;
     if (!aux || n_aux == 0) { s->b.n_aux = 0; return VFK_OK; }
     const size_t row = align_up((size_t)s->tiles * 32 * s->es, 128);
     if (n_aux > s->n_aux) {                                   // grow the dedicated buffers (blocked + dense staging)
@@ -702,6 +717,7 @@ extern "C" int vfk_session_set_q(vfk_session s, const void* q) {
 extern "C" int vfk_session_set_jp_ref(vfk_session s, const void* r) {
     if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_jp_ref: null session");
     s->have_jp_ref = r != nullptr;
+    s->generation++;
     if (!r) return VFK_OK;
     return upload_blocked(s, s->d_jp_ref, r, s->N, 1);
 }
@@ -709,6 +725,7 @@ extern "C" int vfk_session_set_jp_ref(vfk_session s, const void* r) {
 extern "C" int vfk_session_set_ns_input(vfk_session s, const void* x) {
     if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_ns_input: null session");
     s->have_ns_in = x != nullptr;
+    s->generation++;
     if (!x) return VFK_OK;
     return upload_blocked(s, s->d_ns_in, x, s->h->params.ns_mode == VFK_NS_CONTROL ? 4 : s->N, 1);
 }
@@ -729,39 +746,17 @@ static vfk_buffers offset_view(const vfk_buffers& b, int64_t tile0, int N, int M
     return o;
 }
 
-extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, void* qdot_out, void* q_out,
-                                 int32_t* flags_out) {
-    if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_cycle: null session");
+// Enqueue one cycle's pipeline (uploads, layout kernels, cycle kernels, downloads) on the session's streams.
+// Used eagerly and under stream capture; returns the number of kernels enqueued.
+static int enqueue_cycle(vfk_session_s* s, const char* src_q, int k_cycles, char* dst_qd, char* dst_qo, char* dst_fl,
+                         bool want_flags, int n_chunks) {
     vfk_ctx* h = s->h;
-    VFK_CUDA(h, cudaSetDevice(h->device));
     const int N = s->N;
     const size_t es = s->es;
-    const size_t blk = (size_t)N * (size_t)s->n * es;
-    char* pin_q = s->pin;
-    char* pin_qd = s->pin + blk;
-    char* pin_qo = s->pin + 2 * blk;
-    char* pin_fl = s->pin + 3 * blk;
-    // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pinned
-    // memory) are used directly; pageable ones go through the session's pinned staging area.
-    auto pinned = [](const void* p) {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-        return at.type == cudaMemoryTypeHost;
-    };
-    const char* src_q = nullptr;
-    if (q_in) {
-        src_q = (const char*)q_in;
-        if (!pinned(q_in)) { memcpy(pin_q, q_in, blk); src_q = pin_q; }
-    }
-    const bool d_qd = qdot_out && pinned(qdot_out), d_qo = q_out && pinned(q_out), d_fl = flags_out && pinned(flags_out);
-    char* dst_qd = qdot_out ? (d_qd ? (char*)qdot_out : pin_qd) : nullptr;
-    char* dst_qo = q_out ? (d_qo ? (char*)q_out : pin_qo) : nullptr;
-    char* dst_fl = flags_out ? (d_fl ? (char*)flags_out : pin_fl) : nullptr;
-
     vfk_buffers b = s->b;
     b.jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
     b.ns_in = nullptr;                                          // offset separately below (4 or N components)
-    if (!flags_out) b.flags = nullptr;
+    if (!want_flags) b.flags = nullptr;
     if (!s->en_vf) b.qdot_vf = nullptr;
     if (!s->en_ns) b.qdot_ns = nullptr;
     if (!s->en_jp) b.qdot_jp = nullptr;
@@ -769,18 +764,8 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
     if (!s->en_pose) b.pose = nullptr;
     if (!s->en_twist) b.twist = nullptr;
     const int ns_comps = h->params.ns_mode == VFK_NS_CONTROL ? 4 : N;
-
-    // Chunk pipeline: a three-stage software pipeline over tile-aligned chunks.  All uploads go back to back on the
-    // H2D stream, the kernels of chunk c wait for its upload on the compute stream, and its downloads wait for the
-    // kernels on the D2H stream, so the two DMA engines (PCIe is full duplex) and the SMs all stay busy.
-    int n_chunks = (int)(s->n / 65536);
-    if (n_chunks > 16) n_chunks = 16;
-    if (const char* e = getenv("VFK_SESSION_CHUNKS")) n_chunks = atoi(e);
-    if (n_chunks > kMaxSessionChunks) n_chunks = kMaxSessionChunks;
-    if (n_chunks < 1) n_chunks = 1;
-    if ((int64_t)n_chunks > s->tiles) n_chunks = (int)s->tiles;
     const bool piped = n_chunks > 1;
-    cudaStream_t st_up = piped ? s->pipe[0] : s->stream, st_k = piped ? s->pipe[1] : s->stream, st_dn = piped ? s->pipe[2] : s->stream;
+    cudaStream_t st_up = piped ? s->pipe[0] : s->pipe[1], st_k = s->pipe[1], st_dn = piped ? s->pipe[2] : s->pipe[1];
     const int64_t tiles_per_chunk = (s->tiles + n_chunks - 1) / n_chunks;
     char* stage_q = (char*)s->stage_in;                         // dense [N][n]
     char* stage_qd = (char*)s->stage_out;                       // dense [N][n]
@@ -828,11 +813,93 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
         if (dst_fl)         // one component: blocked == dense
             VFK_CUDA(h, cudaMemcpyAsync(dst_fl + i0 * 4, s->b.flags + i0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st_dn));
     }
-    if (piped) {
-        for (int k = 0; k < 3; ++k) VFK_CUDA(h, cudaStreamSynchronize(s->pipe[k]));
-    } else {
-        VFK_CUDA(h, cudaStreamSynchronize(s->stream));
+    return launches;
+}
+
+extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, void* qdot_out, void* q_out,
+                                 int32_t* flags_out) {
+    if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_cycle: null session");
+    vfk_ctx* h = s->h;
+    if (k_cycles < 1) return fail(h, VFK_ERR_INVALID, "k_cycles must be >= 1");
+    VFK_CUDA(h, cudaSetDevice(h->device));
+    const size_t blk = (size_t)s->N * (size_t)s->n * s->es;
+    char* pin_q = s->pin;
+    char* pin_qd = s->pin + blk;
+    char* pin_qo = s->pin + 2 * blk;
+    char* pin_fl = s->pin + 3 * blk;
+    // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pinned
+    // memory) are used directly; pageable ones go through the session's pinned staging area.
+    auto pinned = [](const void* p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const char* src_q = nullptr;
+    if (q_in) {
+        src_q = (const char*)q_in;
+        if (!pinned(q_in)) { memcpy(pin_q, q_in, blk); src_q = pin_q; }
     }
+    const bool d_qd = qdot_out && pinned(qdot_out), d_qo = q_out && pinned(q_out), d_fl = flags_out && pinned(flags_out);
+    char* dst_qd = qdot_out ? (d_qd ? (char*)qdot_out : pin_qd) : nullptr;
+    char* dst_qo = q_out ? (d_qo ? (char*)q_out : pin_qo) : nullptr;
+    char* dst_fl = flags_out ? (d_fl ? (char*)flags_out : pin_fl) : nullptr;
+
+    // Chunk pipeline: a three-stage software pipeline over tile-aligned chunks.  All uploads go back to back on the
+    // H2D stream, the kernels of chunk c wait for its upload on the compute stream, and its downloads wait for the
+    // kernels on the D2H stream, so the two DMA engines (PCIe is full duplex) and the SMs all stay busy.
+    int n_chunks = (int)(s->n / 65536);
+    if (n_chunks > 8) n_chunks = 8;
+    if (const char* e = getenv("VFK_SESSION_CHUNKS")) n_chunks = atoi(e);
+    if (n_chunks > kMaxSessionChunks) n_chunks = kMaxSessionChunks;
+    if (n_chunks < 1) n_chunks = 1;
+    if ((int64_t)n_chunks > s->tiles) n_chunks = (int)s->tiles;
+
+    // The pipeline is dozens of API calls; repeated calls with the same buffers replay ONE captured CUDA graph.
+    // The first call with a given (buffers, K, parameter generation) runs eagerly (it also warms the launch-plan
+    // caches), the second captures, later ones only launch the graph.
+    const bool use_graph = n_chunks > 1 && !getenv("VFK_NO_GRAPH");
+    auto& key = s->graph_key;
+    const bool same = key.src_q == src_q && key.dst_qd == dst_qd && key.dst_qo == dst_qo && key.dst_fl == dst_fl &&
+                      key.k == k_cycles && key.hgen == h->generation && key.sgen == s->generation;
+    int launches = 0;
+    cudaStream_t origin = s->pipe[1];
+    if (use_graph && same && s->graph_exec) {
+        VFK_CUDA(h, cudaGraphLaunch(s->graph_exec, origin));
+        launches = s->graph_launches;
+    } else if (use_graph && same) {
+        cudaGraph_t graph = nullptr;
+        VFK_CUDA(h, cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
+        cudaError_t ce = cudaEventRecord(s->ev_fork, origin);                       // fork the two DMA streams
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s->pipe[0], s->ev_fork, 0);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s->pipe[2], s->ev_fork, 0);
+        int rc = ce == cudaSuccess ? enqueue_cycle(s, src_q, k_cycles, dst_qd, dst_qo, dst_fl, flags_out != nullptr, n_chunks) : -1;
+        if (ce == cudaSuccess) ce = cudaEventRecord(s->ev_join[0], s->pipe[0]);     // join them back
+        if (ce == cudaSuccess) ce = cudaEventRecord(s->ev_join[1], s->pipe[2]);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(origin, s->ev_join[0], 0);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(origin, s->ev_join[1], 0);
+        cudaError_t ee = cudaStreamEndCapture(origin, &graph);
+        if (rc < 0 || ce != cudaSuccess || ee != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc < 0 && ce == cudaSuccess) return rc;
+            return fail(h, VFK_ERR_CUDA, "graph capture of the session pipeline failed: %s",
+                        cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+        }
+        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+        cudaError_t ie = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { s->graph_exec = nullptr; return fail(h, VFK_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+        s->graph_launches = rc;
+        VFK_CUDA(h, cudaGraphLaunch(s->graph_exec, origin));
+        launches = rc;
+    } else {
+        if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+        key.src_q = src_q; key.dst_qd = dst_qd; key.dst_qo = dst_qo; key.dst_fl = dst_fl;
+        key.k = k_cycles; key.hgen = h->generation; key.sgen = s->generation;
+        launches = enqueue_cycle(s, src_q, k_cycles, dst_qd, dst_qo, dst_fl, flags_out != nullptr, n_chunks);
+        if (launches < 0) return launches;
+    }
+    for (int k = 0; k < 3; ++k) VFK_CUDA(h, cudaStreamSynchronize(s->pipe[k]));
     if (qdot_out && !d_qd) memcpy(qdot_out, pin_qd, blk);
     if (q_out && !d_qo) memcpy(q_out, pin_qo, blk);
     if (flags_out && !d_fl) memcpy(flags_out, pin_fl, (size_t)s->n * 4);
@@ -850,6 +917,7 @@ extern "C" int vfk_session_enable(vfk_session s, const char* what, int on) {
     else if (!strcmp(what, "twist")) f = &s->en_twist;
     else return fail(s->h, VFK_ERR_INVALID, "vfk_session_enable: unknown output '%s'", what);
     *f = on != 0;
+    s->generation++;
     return VFK_OK;
 }
 
@@ -891,8 +959,10 @@ extern "C" void vfk_session_destroy(vfk_session s) {
     cudaFreeHost(s->pin);
     cudaFree(s->dev);
     if (s->aux_dev) cudaFree(s->aux_dev);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     cudaStreamDestroy(s->stream);
     for (int k = 0; k < 3; ++k) cudaStreamDestroy(s->pipe[k]);
     for (int k = 0; k < kMaxSessionChunks; ++k) { cudaEventDestroy(s->ev_up[k]); cudaEventDestroy(s->ev_done[k]); }
+    cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join[0]); cudaEventDestroy(s->ev_join[1]);
     delete s;
 }
