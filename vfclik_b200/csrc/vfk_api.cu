@@ -847,8 +847,10 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
     // Chunk pipeline: a three-stage software pipeline over tile-aligned chunks.  All uploads go back to back on the
     // H2D stream, the kernels of chunk c wait for its upload on the compute stream, and its downloads wait for the
     // kernels on the D2H stream, so the two DMA engines (PCIe is full duplex) and the SMs all stay busy.
+    // (measured on B200, 1 M instances: 1 chunk 1.26 ms, 4 chunks 0.90 ms, 8 chunks 0.96 ms, 16 chunks 1.05 ms per call;
+    //  the floor set by the two concurrent 29 MB PCIe transfers is 0.62 ms)
     int n_chunks = (int)(s->n / 65536);
-    if (n_chunks > 8) n_chunks = 8;
+    if (n_chunks > 4) n_chunks = 4;
     if (const char* e = getenv("VFK_SESSION_CHUNKS")) n_chunks = atoi(e);
     if (n_chunks > kMaxSessionChunks) n_chunks = kMaxSessionChunks;
     if (n_chunks < 1) n_chunks = 1;
