@@ -77,11 +77,24 @@ template <> struct Prec<float> {
 };
 
 template <> struct Prec<double> {
-    static __device__ __forceinline__ double rsqrt_pos(double x) { return 1.0 / sqrt(x); }
+    static __device__ __forceinline__ double rsqrt_pos(double x) { return rsqrt(x); }      // <= 2 ulp, no IEEE div + sqrt
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double div(double a, double b) { return a / b; }
-    static __device__ __forceinline__ double pow_pos(double x, double y) { return pow(x, y); }
+    // x^y for x >= 0, y > 0.  Decay orders are small integers in practice (20, 5, 3, 2: scripts/object_feeder:274-333):
+    // square-and-multiply costs ~2 log2(y) DMULs instead of libdevice pow's ~100 instructions and is exact to a few ulp.
+    static __device__ __forceinline__ double pow_pos(double x, double y) {
+        const int n = (int)y;
+        if ((double)n == y && n <= 64) {
+            double r = 1.0, b = x;
+            for (int k = n; k > 0; k >>= 1) {
+                if (k & 1) r *= b;
+                b *= b;
+            }
+            return r;
+        }
+        return pow(x, y);
+    }
     static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
     static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
     static __device__ __forceinline__ double fmin_(double a, double b) { return fmin(a, b); }
