@@ -157,6 +157,7 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     c.share_factor = (unit && p.ns_lambda == p.ik_lambda) ? 1 : 0;
     c.need_jp = p.mixer_w[2] != 0.0 ? 1 : 0;
     c.asin_series = (p.rot_slowdown > 0 && p.rot_slowdown <= 0.3) ? 1 : 0;
+    c.order_int = (p.obst_order == std::floor(p.obst_order) && p.obst_order >= 1 && p.obst_order <= 64) ? (int)p.obst_order : 0;
 }
 
 // -------------------------------------------------------------------------------- public: lifecycle

@@ -65,6 +65,7 @@ struct KConst {
     int32_t tool_identity;
     int32_t need_jp;           // joint P controller observable (weight != 0 or an output wants it)
     int32_t asin_series;       // rot_slowdown <= 0.3 rad: small-angle series replaces atan2 in FP32
+    int32_t order_int;         // obst_order when it is a small integer, else 0
 };
 
 template <typename T>
@@ -202,13 +203,13 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
 // One decay repeller (vfl type 2): acc += (o - p)/d * (radius / max(d, safe))^order.
 // d^2 carries a 1e-30 (1e-300 in FP64) bias so that d = 0 gives a finite 1/d and a zero contribution
 // (0 * finite) without a branch; radius = 0 (empty slot) gives lg2(0) = -inf -> decay = 0 since order > 0.
-template <typename T>
+template <typename T, int ORDER = 0>
 __device__ __forceinline__ void repel(const Vec4<T>& o, T safe_inv, T order, const T (&pt)[3], T (&acc)[3]) {
     const T dx = o.x - pt[0], dy = o.y - pt[1], dz = o.z - pt[2];
     const T dd = fma(dx, dx, fma(dy, dy, fma(dz, dz, Prec<T>::tiny())));
     const T inv = Prec<T>::rsqrt_pos(dd);                                       // 1/d
     const T ratio = o.w * Prec<T>::fmin_(inv, safe_inv);                        // radius / max(d, safe)
-    const T wgt = Prec<T>::pow_pos(ratio, order) * inv;
+    const T wgt = pow_fixed<ORDER, T>(ratio, order) * inv;
     acc[0] = fma(wgt, dx, acc[0]); acc[1] = fma(wgt, dy, acc[1]); acc[2] = fma(wgt, dz, acc[2]);
 }
 
@@ -457,13 +458,21 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + lane;
                 const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * WS::kRow) + lane;
                 if (ch < a.n_full) {
+                    // FP64 with a uniform small-integer decay order: fixed multiplication chain instead of pow()
+                    auto full_chunk = [&](auto order_c) {
+                        constexpr int ORD = decltype(order_c)::value;
 #pragma unroll
-                    for (int m = 0; m < kChunk; ++m) {
-                        const Vec4<T> o = so[m * 32];
-                        T safe_inv = c.obst_safe_inv, order = c.obst_order;
-                        if (EXT) { const Vec2<T> e = se[m * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
-                        repel<T>(o, safe_inv, order, pt, acc);
-                    }
+                        for (int m = 0; m < kChunk; ++m) {
+                            const Vec4<T> o = so[m * 32];
+                            T safe_inv = c.obst_safe_inv, order = c.obst_order;
+                            if (EXT) { const Vec2<T> e = se[m * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+                            repel<T, ORD>(o, safe_inv, order, pt, acc);
+                        }
+                    };
+                    if (sizeof(T) == 8 && !EXT && c.order_int == 20) full_chunk(std::integral_constant<int, 20>{});
+                    else if (sizeof(T) == 8 && !EXT && c.order_int == 5) full_chunk(std::integral_constant<int, 5>{});
+                    else if (sizeof(T) == 8 && !EXT && c.order_int == 2) full_chunk(std::integral_constant<int, 2>{});
+                    else full_chunk(std::integral_constant<int, 0>{});
                 } else {
                     for (int m = 0; m < a.n_rem; ++m) {
                         const Vec4<T> o = so[m * 32];

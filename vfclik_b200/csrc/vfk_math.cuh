@@ -105,6 +105,17 @@ template <> struct Prec<double> {
     static constexpr bool kSeriesAsin = false;
 };
 
+// x^ORDER by a fixed multiplication chain (FP64 repeller fast path; ORDER = 0 means "use Prec<T>::pow_pos").
+template <int ORDER, typename T>
+__device__ __forceinline__ T pow_fixed(T x, T y) {
+    if constexpr (ORDER == 2) { return x * x; }
+    else if constexpr (ORDER == 3) { return x * x * x; }
+    else if constexpr (ORDER == 5) { const T x2 = x * x; return x2 * x2 * x; }
+    else if constexpr (ORDER == 10) { const T x2 = x * x, x5 = x2 * x2 * x; return x5 * x5; }
+    else if constexpr (ORDER == 20) { const T x2 = x * x, x5 = x2 * x2 * x, x10 = x5 * x5; return x10 * x10; }
+    else { return Prec<T>::pow_pos(x, y); }
+}
+
 // {x, y, z, radius} of one obstacle of one instance: one 16-byte (FP32) or 32-byte (FP64) vector.
 template <typename T> struct Vec4;
 template <> struct __align__(16) Vec4<float> { float x, y, z, w; };
