@@ -404,6 +404,19 @@ def main():
                                       "ms_per_launch": tot / 10, "l2": "flushed between launches (256 MiB write)"}
             e64.close()
 
+        if world == 1 and args.workload == "config3":
+            # BASELINE configs[0] on the GPU: ONE LWR, the reference's first goal, 3 obstacles, 1000 control cycles fused
+            # into one launch (the latency-bound opposite corner of the design space; the CPU reference loop does ~10^3/s)
+            e1 = Engine(chain, precision=64, device=local_rank, params=params)
+            w1 = workloads.config1(chain, cfg)
+            d1 = DeviceBatch(e1, 1, 3, outputs=("qdot",))
+            d1.upload("q", w1["q"]); d1.upload("goal", w1["goal"]); d1.upload("obst", w1["obst"])
+            d1.step(1000)
+            ms1 = timed(lambda: d1.step(1000), 3) / 3
+            extras["config1_single_robot_fp64"] = {"instances": 1, "kcycles": 1000, "value": 1000 / (ms1 * 1e-3), "unit": UNIT,
+                                                   "us_per_cycle": ms1}
+            e1.close()
+
     # ---- final stats gather (the only collective: NCCL all_reduce of a few scalars)
     stats = torch.tensor([float(n_inst * args.kcycles * args.steps), float(gpu_launches + e2e_launches)],
                          device="cuda", dtype=torch.float64)

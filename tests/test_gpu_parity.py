@@ -469,3 +469,59 @@ def test_auxiliary_fields_types_4_and_5(eng, lwr, precision):
     # and the fields change the answer
     ref0 = run_oracle(chain, e.params, w, M)
     assert np.max(np.abs(ref0["qdot_vf"] - ref["qdot_vf"])) > 1e-3
+
+
+def test_full_size_config3_properties_and_sampled_oracle(lwr, built_lib):
+    """BASELINE configs[2] at full size (1,048,576 instances, 32 obstacles, FP32, nullspace on): the oracle on a
+    random sample of 16,384 instances plus size-independent properties on the whole batch -- permutation equivariance,
+    an empty obstacle slot changes nothing, K launches == one launch of K cycles, output finiteness and the clamp bound."""
+    import torch
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch, Engine, Params
+    chain, cfg = lwr
+    e = Engine(chain, precision=32, params=Params.from_config(cfg))
+    try:
+        n, M = 1 << 20, 32
+        w = workloads.random_batch(chain, n, M, seed=1, dtype=np.float32)
+        db = DeviceBatch(e, n, M, outputs=("qdot",))
+        db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+        q_before = db.t["q"].clone()
+        assert db.step(1) == 1
+        qd = db.download("qdot")                                   # [7, n]
+        q1 = db.download("q")
+        assert np.all(np.isfinite(qd)) and np.max(np.abs(qd)) <= cfg.max_vel * (1 + 1e-6)
+        assert np.allclose(q1, w["q"] + np.float32(cfg.rate) * qd, rtol=0, atol=2e-7)      # explicit Euler
+        # sampled oracle parity
+        rng = np.random.default_rng(5)
+        idx = np.sort(rng.choice(n, size=16384, replace=False))
+        sub = dict(q=w["q"][:, idx], goal=w["goal"][:, idx], obst=np.ascontiguousarray(w["obst"][:, idx]))
+        ref = run_oracle(chain, e.params, sub, M)
+        err = rel_err(qd[:, idx].T.astype(np.float64), ref["qdot"])
+        assert err.max() <= FP32_RTOL, float(err.max())
+        # permutation equivariance (bit-exact): instance order carries no information
+        perm = rng.permutation(n)
+        dbp = DeviceBatch(e, n, M, outputs=("qdot",))
+        dbp.upload("q", w["q"][:, perm]); dbp.upload("goal", w["goal"][:, perm])
+        dbp.upload("obst", np.ascontiguousarray(w["obst"][:, perm]))
+        dbp.step(1)
+        assert np.array_equal(dbp.download("qdot"), qd[:, perm])
+        del dbp
+        # an extra empty slot (radius 0) is a no-op (bit-exact), and 33 obstacles exercise the ragged last chunk
+        obst33 = np.concatenate([w["obst"], np.zeros((1, n, 4), dtype=np.float32)], axis=0)
+        obst33[32, :, 0:3] = 0.5
+        db33 = DeviceBatch(e, n, M + 1, outputs=("qdot",))
+        db33.upload("q", w["q"]); db33.upload("goal", w["goal"]); db33.upload("obst", obst33)
+        db33.step(1)
+        assert np.array_equal(db33.download("qdot"), qd)
+        del db33, obst33
+        # K fused cycles == K single-cycle launches (state round-trips HBM bit-exactly)
+        db.t["q"].copy_(q_before)
+        for _ in range(5):
+            db.step(1)
+        q_loop, qd_loop = db.download("q"), db.download("qdot")
+        db.t["q"].copy_(q_before)
+        db.step(5)
+        assert np.array_equal(db.download("q"), q_loop) and np.array_equal(db.download("qdot"), qd_loop)
+        torch.cuda.synchronize()
+    finally:
+        e.close()
