@@ -490,7 +490,7 @@ def test_full_size_config3_properties_and_sampled_oracle(lwr, built_lib):
         qd = db.download("qdot")                                   # [7, n]
         q1 = db.download("q")
         assert np.all(np.isfinite(qd)) and np.max(np.abs(qd)) <= cfg.max_vel * (1 + 1e-6)
-        assert np.allclose(q1, w["q"] + np.float32(cfg.rate) * qd, rtol=0, atol=2e-7)      # explicit Euler
+        assert np.allclose(q1, w["q"] + np.float32(cfg.rate) * qd, rtol=0, atol=5e-7)      # explicit Euler (fma vs mul+add: 1 ulp at |q| ~ 3)
         # sampled oracle parity
         rng = np.random.default_rng(5)
         idx = np.sort(rng.choice(n, size=16384, replace=False))
