@@ -18,7 +18,6 @@ except Exception as e: print("$name failed", e)
 PY
 }
 run default A=1
-run b32 VFK_LIB=$PWD/build/libvfk_b32.so
-run b64 VFK_LIB=$PWD/build/libvfk_b64.so
-run b32_s3 VFK_LIB=$PWD/build/libvfk_b32.so VFK_STAGES=3
-VFK_LIB=$PWD/build/libvfk_b32.so timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+run pure_fp32 VFK_LIB=$PWD/build/libvfk_pure32.so
+timeout 300 python scripts/fp32_error.py 1048576 2>&1 | grep -E "twist|qdot_vf|qdot_ns"
+VFK_LIB=$PWD/build/libvfk_pure32.so timeout 300 python scripts/fp32_error.py 1048576 2>&1 | grep -E "twist|qdot_vf|qdot_ns"

@@ -111,10 +111,11 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     const vfk_chain_desc& ch = h.canon;
     const vfk_params& p = h.params;
     const int n = ch.n_joints;
-    for (int k = 0; k < 12; ++k) c.base[k] = (T)ch.base[k];
+    using W = typename KConst<T>::W;
+    for (int k = 0; k < 12; ++k) c.base[k] = (W)ch.base[k];
     bool unit = true;
     for (int j = 0; j < n; ++j) {
-        for (int k = 0; k < 12; ++k) c.tip[j][k] = (T)ch.tip[j][k];
+        for (int k = 0; k < 12; ++k) c.tip[j][k] = (W)ch.tip[j][k];
         c.q_lo[j] = (T)ch.q_lo[j];
         c.q_hi[j] = (T)ch.q_hi[j];
         const double rng = ch.q_hi[j] - ch.q_lo[j];
@@ -136,8 +137,8 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     c.tool_identity = memcmp(p.tool, ident, sizeof ident) == 0;
     for (int k = 0; k < 12; ++k) c.tool[k] = (T)p.tool[k];
     for (int k = 0; k < 4; ++k) c.ns_control[k] = (T)p.ns_control[k];
-    c.ik_lambda2 = (T)(p.ik_lambda * p.ik_lambda);
-    c.ns_lambda2 = (T)(p.ns_lambda * p.ns_lambda);
+    c.ik_lambda2 = (W)(p.ik_lambda * p.ik_lambda);
+    c.ns_lambda2 = (W)(p.ns_lambda * p.ns_lambda);
     c.dt = (T)p.dt;
     c.speed_scale = (T)p.speed_scale;
     c.max_vel = (T)p.max_vel;

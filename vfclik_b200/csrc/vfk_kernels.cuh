@@ -43,8 +43,9 @@ constexpr int kSmemHeader = 512;     // per-warp mbarriers live in the first 512
 // local Z axis: RotX/RotY/TransX/TransY are conjugated into the neighbouring tips.
 template <typename T>
 struct KConst {
-    T base[12];
-    T tip[kMaxJ][12];
+    using W = typename WideOf<T>::type;
+    W base[12];
+    W tip[kMaxJ][12];
     T q_lo[kMaxJ], q_hi[kMaxJ];
     T ns_q0_scale[kMaxJ];      // -k / (hi - lo)^2
     T ns_mid[kMaxJ];
@@ -54,7 +55,8 @@ struct KConst {
     T mixer_w[6];
     T tool[12];
     T ns_control[4];
-    T ik_lambda2, ns_lambda2, dt, speed_scale, max_vel, jp_kp, jp_delta;
+    W ik_lambda2, ns_lambda2;
+    T dt, speed_scale, max_vel, jp_kp, jp_delta;
     T ns_gain, ns_lookahead, rot_slowdown_inv, goal_force, obst_force, obst_safe_inv, obst_order;
     int32_t prismatic_mask;    // bit j set: joint j is TransZ, else RotZ
     int32_t ns_mode;
@@ -129,14 +131,17 @@ struct LwrPattern {
 };
 
 // ------------------------------------------------------------------------------ FK + J
-// T_{j+1} = T_j * RotZ(q_j) * tip_j.  Records the joint axis z_j = R_j[:,2] and origin
-// p_j before each joint, then forms J = [z x (p_e - p_j); z] (revolute) or [z; 0].
+// T_{j+1} = T_j * RotZ(q_j) * tip_j, carried in the wide type W (double in both modes: an FP32 chain leaves ~1e-7 m in the
+// tool position, which the order-20 repeller decay turns into 1e-4 relative field errors near obstacles).  Records the
+// joint axis z_j = R_j[:,2] and origin p_j before each joint, then forms J = [z x (p_e - p_j); z] (revolute) or [z; 0]
+// in T.  Outputs: R, and the tool-less flange position as hi + lo parts in T (lo = 0 when T is already wide).
 template <typename T, int N, class PAT>
-__device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
-                                            T (&R)[9], T (&p)[3], T (&Jl)[N][3], T (&Ja)[N][3]) {
+__device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N], typename WideOf<T>::type (&R)[9],
+                                            typename WideOf<T>::type (&p)[3], T (&Jl)[N][3], T (&Ja)[N][3]) {
+    using W = typename WideOf<T>::type;
     if constexpr (PAT::base_identity) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? T(1) : T(0);
+        for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? W(1) : W(0);
     } else {
 #pragma unroll
         for (int k = 0; k < 9; ++k) R[k] = c.base[k];
@@ -145,21 +150,22 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
     for (int k = 0; k < 3; ++k) p[k] = c.base[9 + k];
     static_for<0, N>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
-        Ja[j][0] = R[2]; Ja[j][1] = R[5]; Ja[j][2] = R[8];
-        Jl[j][0] = p[0]; Jl[j][1] = p[1]; Jl[j][2] = p[2];      // holds p_j until p_e is known
+        Ja[j][0] = (T)R[2]; Ja[j][1] = (T)R[5]; Ja[j][2] = (T)R[8];
+        Jl[j][0] = (T)p[0]; Jl[j][1] = (T)p[1]; Jl[j][2] = (T)p[2];      // holds p_j until p_e is known
+        const W qj = (W)q[j];
         if (PAT::generic && (c.prismatic_mask & (1 << j))) {
-            p[0] = fma(R[2], q[j], p[0]); p[1] = fma(R[5], q[j], p[1]); p[2] = fma(R[8], q[j], p[2]);
+            p[0] = fma(R[2], qj, p[0]); p[1] = fma(R[5], qj, p[1]); p[2] = fma(R[8], qj, p[2]);
         } else {
-            T s, co;
-            Prec<T>::sincos_(q[j], &s, &co);
+            W s, co;
+            sincos_wide(qj, &s, &co);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const T a = R[3 * r + 0], b = R[3 * r + 1];
+                const W a = R[3 * r + 0], b = R[3 * r + 1];
                 R[3 * r + 0] = fma(co, a, s * b);
                 R[3 * r + 1] = fma(co, b, -s * a);
             }
         }
-        const T* tp = c.tip[j];
+        const W* tp = c.tip[j];
         static_for<0, 3>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             if constexpr (PAT::pnz(j, k)) {
@@ -167,7 +173,7 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
                 for (int r = 0; r < 3; ++r) p[r] = fma(R[3 * r + k], tp[9 + k], p[r]);
             }
         });
-        T Rn[9];
+        W Rn[9];
         if constexpr (PAT::generic) {
 #pragma unroll
             for (int r = 0; r < 3; ++r)
@@ -185,13 +191,15 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
 #pragma unroll
         for (int k = 0; k < 9; ++k) R[k] = Rn[k];
     });
+    const T pe[3] = {(T)p[0], (T)p[1], (T)p[2]};
+    const T pel[3] = {(T)(p[0] - (W)pe[0]), (T)(p[1] - (W)pe[1]), (T)(p[2] - (W)pe[2])};
     static_for<0, N>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         if (PAT::generic && (c.prismatic_mask & (1 << j))) {
             Jl[j][0] = Ja[j][0]; Jl[j][1] = Ja[j][1]; Jl[j][2] = Ja[j][2];
             Ja[j][0] = Ja[j][1] = Ja[j][2] = T(0);
         } else {
-            const T dx = p[0] - Jl[j][0], dy = p[1] - Jl[j][1], dz = p[2] - Jl[j][2];
+            const T dx = (pe[0] - Jl[j][0]) + pel[0], dy = (pe[1] - Jl[j][1]) + pel[1], dz = (pe[2] - Jl[j][2]) + pel[2];
             Jl[j][0] = Ja[j][1] * dz - Ja[j][2] * dy;
             Jl[j][1] = Ja[j][2] * dx - Ja[j][0] * dz;
             Jl[j][2] = Ja[j][0] * dy - Ja[j][1] * dx;
@@ -199,13 +207,30 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
     });
 }
 
+// Tool position as a sum of two T values (hi + lo): differences against it are accurate to an ulp of the difference
+// even though T alone cannot represent the position to better than 6e-8 m.  lo is identically zero when T is wide.
+template <typename T>
+struct Pos {
+    T hi[3], lo[3];
+    template <typename W>
+    __device__ __forceinline__ void set(const W (&p)[3]) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { hi[k] = (T)p[k]; lo[k] = (T)(p[k] - (W)hi[k]); }
+    }
+    // x - position_k
+    __device__ __forceinline__ T from(T x, int k) const {
+        if constexpr (sizeof(T) == sizeof(typename WideOf<T>::type)) return x - hi[k];
+        else return (x - hi[k]) - lo[k];
+    }
+};
+
 // ------------------------------------------------------------------------------ field pieces
 // One decay repeller (vfl type 2): acc += (o - p)/d * (radius / max(d, safe))^order.
 // d^2 carries a 1e-30 (1e-300 in FP64) bias so that d = 0 gives a finite 1/d and a zero contribution
 // (0 * finite) without a branch; radius = 0 (empty slot) gives lg2(0) = -inf -> decay = 0 since order > 0.
 template <typename T, int ORDER = 0>
-__device__ __forceinline__ void repel(const Vec4<T>& o, T safe_inv, T order, const T (&pt)[3], T (&acc)[3]) {
-    const T dx = o.x - pt[0], dy = o.y - pt[1], dz = o.z - pt[2];
+__device__ __forceinline__ void repel(const Vec4<T>& o, T safe_inv, T order, const Pos<T>& pt, T (&acc)[3]) {
+    const T dx = pt.from(o.x, 0), dy = pt.from(o.y, 1), dz = pt.from(o.z, 2);
     const T dd = fma(dx, dx, fma(dy, dy, fma(dz, dz, Prec<T>::tiny())));
     const T inv = Prec<T>::rsqrt_pos(dd);                                       // 1/d
     const T ratio = o.w * Prec<T>::fmin_(inv, safe_inv);                        // radius / max(d, safe)
@@ -216,9 +241,9 @@ __device__ __forceinline__ void repel(const Vec4<T>& o, T safe_inv, T order, con
 // Goal attractor (vfl type 1) at tool frame (Rt, pt): unit direction to the goal, unit rotation
 // axis of R_g Rt^T scaled by the rotational slowdown, and the translational slowdown scalar.
 template <typename T>
-__device__ __forceinline__ void attract(const KConst<T>& c, const T (&g)[13], const T (&Rt)[9], const T (&pt)[3],
+__device__ __forceinline__ void attract(const KConst<T>& c, const T (&g)[13], const T (&Rt)[9], const Pos<T>& pt,
                                         T (&V)[3], T& S0, T (&w)[3]) {
-    const T ex = g[9] - pt[0], ey = g[10] - pt[1], ez = g[11] - pt[2];
+    const T ex = pt.from(g[9], 0), ey = pt.from(g[10], 1), ez = pt.from(g[11], 2);
     const T d2 = fma(ex, ex, fma(ey, ey, fma(ez, ez, Prec<T>::tiny())));
     const T invd = Prec<T>::rsqrt_pos(d2);
     const T dist = d2 * invd;
@@ -256,7 +281,7 @@ __device__ __forceinline__ void attract(const KConst<T>& c, const T (&g)[13], co
 // type 5 = funnel attractor (:262-280: goal xyz, axis, cut angle, angle-decay order, cut distance, distance-decay order);
 // any other type code = empty slot.  Functional forms: oracle.batch.ORACLE_CHOICES (vfl is un-vendored).
 template <typename T>
-__device__ __forceinline__ void aux_fields(const T* __restrict__ aux, int n_aux, int64_t tile, int lane, const T (&pt)[3], T (&V)[3]) {
+__device__ __forceinline__ void aux_fields(const T* __restrict__ aux, int n_aux, int64_t tile, int lane, const Pos<T>& pt, T (&V)[3]) {
     for (int s = 0; s < n_aux; ++s) {
         const T* r = aux + (tile * (n_aux * 12) + s * 12) * 32 + lane;
         const int type = (int)__ldg(r);
@@ -265,7 +290,7 @@ __device__ __forceinline__ void aux_fields(const T* __restrict__ aux, int n_aux,
         T p[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) p[k] = __ldg(r + (2 + k) * 32);
-        const T rx = pt[0] - p[0], ry = pt[1] - p[1], rz = pt[2] - p[2];
+        const T rx = -pt.from(p[0], 0), ry = -pt.from(p[1], 1), rz = -pt.from(p[2], 2);
         const T an2 = p[3] * p[3] + p[4] * p[4] + p[5] * p[5];
         if (!(an2 > T(0))) continue;
         const T ian = Prec<T>::rsqrt_pos(an2);
@@ -426,23 +451,31 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         int flags = 0;
 
         // 1. FK, Jacobian, tool frame
-        T R[9], p[3], Jl[N][3], Ja[N][3];
-        fk_jacobian<T, N, PAT>(c, q, R, p, Jl, Ja);
-        T Rt[9], pt[3], dp[3];
-        if (LEAN || c.tool_identity) {
+        using W = typename WideOf<T>::type;
+        T Jl[N][3], Ja[N][3];
+        T Rt[9], dp[3];
+        Pos<T> pt;
+        {
+            W Rw[9], pw[3];
+            fk_jacobian<T, N, PAT>(c, q, Rw, pw, Jl, Ja);
+            if (LEAN || c.tool_identity) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) Rt[k] = R[k];
+                for (int k = 0; k < 9; ++k) Rt[k] = (T)Rw[k];
+                pt.set(pw);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { pt[k] = p[k]; dp[k] = T(0); }
-        } else {
+                for (int k = 0; k < 3; ++k) dp[k] = T(0);
+            } else {
+                W ptw[3];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const T off = fma(R[3 * r + 0], c.tool[9], fma(R[3 * r + 1], c.tool[10], R[3 * r + 2] * c.tool[11]));
-                pt[r] = p[r] + off;
-                dp[r] = p[r] - pt[r];
+                for (int r = 0; r < 3; ++r) {
+                    const W off = fma(Rw[3 * r + 0], (W)c.tool[9], fma(Rw[3 * r + 1], (W)c.tool[10], Rw[3 * r + 2] * (W)c.tool[11]));
+                    ptw[r] = pw[r] + off;
+                    dp[r] = (T)(-off);
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc)
-                    Rt[3 * r + cc] = fma(R[3 * r + 0], c.tool[cc], fma(R[3 * r + 1], c.tool[3 + cc], R[3 * r + 2] * c.tool[6 + cc]));
+                    for (int cc = 0; cc < 3; ++cc)
+                        Rt[3 * r + cc] = (T)fma(Rw[3 * r + 0], (W)c.tool[cc], fma(Rw[3 * r + 1], (W)c.tool[3 + cc], Rw[3 * r + 2] * (W)c.tool[6 + cc]));
+                }
+                pt.set(ptw);
             }
         }
 
@@ -507,56 +540,63 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             tw[3] = w[0]; tw[4] = w[1]; tw[5] = w[2];
         }
 
-        // 5. weighted damped least squares: qdot = Wj Jw^T (Jw Jw^T + l^2 I)^-1 Wt t
-        T A[21], invd[6];
-        T qd_vf[N];
-        if (LEAN || c.unit_weights) {
+        // 5. weighted damped least squares: qdot = Wj Jw^T (Jw Jw^T + l^2 I)^-1 Wt t.  The normal matrix, its Cholesky
+        // factor and the triangular solves are carried in W: formed in FP32, A's rounding error (~1e-6 absolute) is 1e-4
+        // of lambda^2 = 0.01 and lands directly in the joints' weakest direction.  J itself stays in T.
+        const bool unitw = LEAN || c.unit_weights;
+        const bool ns_on = LEAN || c.ns_mode != 0;
+        const bool ns_proj = LEAN || c.ns_mode == 1;
+        const bool share = LEAN || c.share_factor;
+        T x[N];                                             // nullspace input (projector mode): known before the factorisation
+        if (ns_proj) {
+            if (!LEAN && a.ns_in) {
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
+                for (int j = 0; j < N; ++j) x[j] = __ldg(a.ns_in + tN + j * 32);
+            } else {
 #pragma unroll
-                for (int s = 0; s <= r; ++s) {
-                    T acc = (r == s) ? c.ik_lambda2 : T(0);
-#pragma unroll
-                    for (int j = 0; j < N; ++j)
-                        acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], s < 3 ? Jl[j][s] : Ja[j][s - 3], acc);
-                    A[tri(r, s)] = acc;
-                }
-            chol6<T>(A, invd);
-            chol6_fwd<T>(A, invd, tw);
-            chol6_bwd<T>(A, invd, tw);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                T acc = T(0);
-#pragma unroll
-                for (int r = 0; r < 6; ++r) acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], tw[r], acc);
-                qd_vf[j] = acc;
+                for (int j = 0; j < N; ++j) x[j] = c.ns_q0_scale[j] * (q[j] - c.ns_mid[j]);
             }
-        } else {
+        }
+        W A[21], invd[6], Jx[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) tw[k] *= c.w_task[k];
+        for (int r = 0; r < 6; ++r) {
+            Jx[r] = W(0);
+#pragma unroll
+            for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ik_lambda2 : W(0);
+        }
+        static_for<0, N>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            W col[6] = {(W)Jl[j][0], (W)Jl[j][1], (W)Jl[j][2], (W)Ja[j][0], (W)Ja[j][1], (W)Ja[j][2]};
+            if (ns_proj && share) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (W)x[j], Jx[r]);
+            }
+            if (!unitw) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) col[r] *= (W)c.w_task[r] * (W)c.w_joint[j];
+            }
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int s = 0; s <= r; ++s) {
-                    T acc = (r == s) ? c.ik_lambda2 : T(0);
+                for (int s = 0; s <= r; ++s) A[tri(r, s)] = fma(col[r], col[s], A[tri(r, s)]);
+        });
+        chol6<W>(A, invd);
+        T qd_vf[N];
+        {
+            W y[6];
 #pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        const T wj2 = c.w_joint[j] * c.w_joint[j];
-                        const T jr = (r < 3 ? Jl[j][r] : Ja[j][r - 3]) * (c.w_task[r] * wj2);
-                        const T js = (s < 3 ? Jl[j][s] : Ja[j][s - 3]) * c.w_task[s];
-                        acc = fma(jr, js, acc);
-                    }
-                    A[tri(r, s)] = acc;
-                }
-            chol6<T>(A, invd);
-            chol6_fwd<T>(A, invd, tw);
-            chol6_bwd<T>(A, invd, tw);
+            for (int r = 0; r < 6; ++r) y[r] = unitw ? (W)tw[r] : (W)tw[r] * (W)c.w_task[r];
+            chol6_fwd<W>(A, invd, y);
+            chol6_bwd<W>(A, invd, y);
+            T yt[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) yt[r] = unitw ? (T)y[r] : (T)(y[r] * (W)c.w_task[r]);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 T acc = T(0);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) acc = fma((r < 3 ? Jl[j][r] : Ja[j][r - 3]) * c.w_task[r], tw[r], acc);
-                qd_vf[j] = acc * c.w_joint[j] * c.w_joint[j];
+                for (int r = 0; r < 6; ++r) acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], yt[r], acc);
+                qd_vf[j] = unitw ? acc : acc * c.w_joint[j] * c.w_joint[j];
             }
         }
 
@@ -564,67 +604,69 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         T qd_ns[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) qd_ns[j] = T(0);
-        if (LEAN || c.ns_mode != 0) {
-            if (!LEAN && !c.share_factor) {
+        if (ns_on) {
+            if (!share) {                                   // own damping or weighted IK: factor J J^T + ns_lambda^2 I
 #pragma unroll
-                for (int r = 0; r < 6; ++r)
+                for (int r = 0; r < 6; ++r) {
+                    Jx[r] = W(0);
 #pragma unroll
-                    for (int s = 0; s <= r; ++s) {
-                        T acc = (r == s) ? c.ns_lambda2 : T(0);
-#pragma unroll
-                        for (int j = 0; j < N; ++j)
-                            acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], s < 3 ? Jl[j][s] : Ja[j][s - 3], acc);
-                        A[tri(r, s)] = acc;
-                    }
-                chol6<T>(A, invd);
-            }
-            T x[N];
-            if (LEAN || c.ns_mode == 1) {
-                if (!LEAN && a.ns_in) {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) x[j] = __ldg(a.ns_in + tN + j * 32);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) x[j] = c.ns_q0_scale[j] * (q[j] - c.ns_mid[j]);
+                    for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ns_lambda2 : W(0);
                 }
-            } else {
+                static_for<0, N>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    const W col[6] = {(W)Jl[j][0], (W)Jl[j][1], (W)Jl[j][2], (W)Ja[j][0], (W)Ja[j][1], (W)Ja[j][2]};
+                    if (ns_proj) {
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (W)x[j], Jx[r]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int s = 0; s <= r; ++s) A[tri(r, s)] = fma(col[r], col[s], A[tri(r, s)]);
+                });
+                chol6<W>(A, invd);
+            }
+            if (!ns_proj) {
                 // 1-D nullspace: pick the column of B = I - J^T A^-1 J with the largest
                 // diagonal entry B_jj = 1 - |L^-1 J[:,j]|^2 (first maximum wins).
                 int jstar = 0;
-                T best = T(-1);
+                W best = W(-1);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    T col[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
-                    chol6_fwd<T>(A, invd, col);
-                    T s2 = T(0);
+                    W col[6] = {(W)Jl[j][0], (W)Jl[j][1], (W)Jl[j][2], (W)Ja[j][0], (W)Ja[j][1], (W)Ja[j][2]};
+                    chol6_fwd<W>(A, invd, col);
+                    W s2 = W(0);
 #pragma unroll
                     for (int r = 0; r < 6; ++r) s2 = fma(col[r], col[r], s2);
-                    const T bjj = T(1) - s2;
+                    const W bjj = W(1) - s2;
                     if (bjj > best) { best = bjj; jstar = j; }
                 }
 #pragma unroll
-                for (int j = 0; j < N; ++j) x[j] = (j == jstar) ? T(1) : T(0);
+                for (int r = 0; r < 6; ++r) Jx[r] = W(0);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    x[j] = (j == jstar) ? T(1) : T(0);
+                    if (j == jstar) {
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) Jx[r] = (W)(r < 3 ? Jl[j][r] : Ja[j][r - 3]);
+                    }
+                }
             }
             // raw = x - J^T A^-1 (J x)
-            T y[6];
+            chol6_fwd<W>(A, invd, Jx);
+            chol6_bwd<W>(A, invd, Jx);
+            T yt[6];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) {
-                T acc = T(0);
-#pragma unroll
-                for (int j = 0; j < N; ++j) acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], x[j], acc);
-                y[r] = acc;
-            }
-            chol6_fwd<T>(A, invd, y);
-            chol6_bwd<T>(A, invd, y);
+            for (int r = 0; r < 6; ++r) yt[r] = (T)Jx[r];
             T raw[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 T acc = x[j];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) acc = fma(-(r < 3 ? Jl[j][r] : Ja[j][r - 3]), y[r], acc);
+                for (int r = 0; r < 6; ++r) acc = fma(-(r < 3 ? Jl[j][r] : Ja[j][r - 3]), yt[r], acc);
                 raw[j] = acc;
             }
-            if (!LEAN && c.ns_mode == 2) {
+            if (!ns_proj) {
                 T nn = T(0), dotl = T(0), l2 = T(0), amax = T(-1), vmax = T(0);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
@@ -730,7 +772,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 #pragma unroll
                 for (int k = 0; k < 9; ++k) a.pose[tile * (12 * 32) + k * 32 + lane] = Rt[k];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) a.pose[tile * (12 * 32) + (9 + k) * 32 + lane] = pt[k];
+                for (int k = 0; k < 3; ++k) a.pose[tile * (12 * 32) + (9 + k) * 32 + lane] = pt.hi[k];
             }
             if (!LEAN && a.flags) a.flags[(tile << 5) + lane] = flags;
         }
@@ -764,11 +806,12 @@ vfk_field_kernel(const __grid_constant__ KConst<T> c, const T* __restrict__ pose
     if (i >= n) return;
     const int64_t tile = i >> 5;
     const int lane = (int)(i & 31);
-    T Rt[9], pt[3], g[13];
+    T Rt[9], g[13];
+    Pos<T> pt;
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rt[k] = pose[(tile * 12 + k) * 32 + lane];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) pt[k] = pose[(tile * 12 + 9 + k) * 32 + lane];
+    for (int k = 0; k < 3; ++k) { pt.hi[k] = pose[(tile * 12 + 9 + k) * 32 + lane]; pt.lo[k] = T(0); }
 #pragma unroll
     for (int k = 0; k < 13; ++k) g[k] = goal[(tile * 13 + k) * 32 + lane];
     T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)}, v[3];

@@ -105,6 +105,48 @@ template <> struct Prec<double> {
     static constexpr bool kSeriesAsin = false;
 };
 
+// Working type of the two ill-conditioned stages (forward kinematics, normal equations): double in both modes.  In the
+// FP32 mode everything that touches HBM and the whole field stays FP32; -DVFK_PURE_FP32 makes those stages FP32 too
+// (measured: max qdot error over 1 M random instances 1.2e-4 instead of ~1e-6).
+#if defined(VFK_PURE_FP32)
+template <typename T> struct WideOf { using type = T; };
+#else
+template <typename T> struct WideOf { using type = double; };
+#endif
+
+// sin / cos in double for joint angles: Cody-Waite reduction to [-pi/4, pi/4] with k taken from the mantissa of a
+// magic-number add, Taylor polynomials to x^15 / x^16 (truncation < 5e-17), branch-free quadrant selection.
+__device__ __forceinline__ void sincos_wide(double x, double* s, double* c) {
+    const double t = fma(x, 0.63661977236758134308, 6755399441055744.0);
+    const int ki = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -1.57079632679489655800e+00, x);
+    r = fma(kf, -6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double sp = -7.64716373181981647590e-13;                 // -1/15!
+    sp = fma(sp, z, 1.60590438368216145994e-10);              //  1/13!
+    sp = fma(sp, z, -2.50521083854417187751e-08);             // -1/11!
+    sp = fma(sp, z, 2.75573192239858906526e-06);              //  1/9!
+    sp = fma(sp, z, -1.98412698412698412698e-04);             // -1/7!
+    sp = fma(sp, z, 8.33333333333333333333e-03);              //  1/5!
+    sp = fma(sp, z, -1.66666666666666666667e-01);             // -1/3!
+    sp = fma(sp * z, r, r);
+    double cp = 4.77947733238738529744e-14;                   //  1/16!
+    cp = fma(cp, z, -1.14707455977297247139e-11);             // -1/14!
+    cp = fma(cp, z, 2.08767569878680989792e-09);              //  1/12!
+    cp = fma(cp, z, -2.75573192239858906526e-07);             // -1/10!
+    cp = fma(cp, z, 2.48015873015873015873e-05);              //  1/8!
+    cp = fma(cp, z, -1.38888888888888888889e-03);             // -1/6!
+    cp = fma(cp, z, 4.16666666666666666667e-02);              //  1/4!
+    cp = fma(cp, z, -0.5);
+    cp = fma(cp, z, 1.0);
+    const double ss = (ki & 1) ? cp : sp;
+    const double cs = (ki & 1) ? sp : cp;
+    *s = (ki & 2) ? -ss : ss;
+    *c = ((ki + 1) & 2) ? -cs : cs;
+}
+__device__ __forceinline__ void sincos_wide(float x, float* s, float* c) { Prec<float>::sincos_(x, s, c); }
+
 // x^ORDER by a fixed multiplication chain (FP64 repeller fast path; ORDER = 0 means "use Prec<T>::pow_pos").
 template <int ORDER, typename T>
 __device__ __forceinline__ T pow_fixed(T x, T y) {
