@@ -18,6 +18,6 @@ except Exception as e: print("$name failed", e)
 PY
 }
 run default A=1
-run pure_fp32 VFK_LIB=$PWD/build/libvfk_pure32.so
-timeout 300 python scripts/fp32_error.py 1048576 2>&1 | grep -E "twist|qdot_vf|qdot_ns"
-VFK_LIB=$PWD/build/libvfk_pure32.so timeout 300 python scripts/fp32_error.py 1048576 2>&1 | grep -E "twist|qdot_vf|qdot_ns"
+run ne_only VFK_LIB=$PWD/build/libvfk_ne.so
+run fk_only VFK_LIB=$PWD/build/libvfk_fk.so
+for l in ne fk; do VFK_LIB=$PWD/build/libvfk_$l.so timeout 300 python scripts/fp32_error.py 1048576 2>&1 | grep -E "twist|qdot_vf"; done

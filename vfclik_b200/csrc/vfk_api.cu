@@ -137,8 +137,8 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     c.tool_identity = memcmp(p.tool, ident, sizeof ident) == 0;
     for (int k = 0; k < 12; ++k) c.tool[k] = (T)p.tool[k];
     for (int k = 0; k < 4; ++k) c.ns_control[k] = (T)p.ns_control[k];
-    c.ik_lambda2 = (W)(p.ik_lambda * p.ik_lambda);
-    c.ns_lambda2 = (W)(p.ns_lambda * p.ns_lambda);
+    c.ik_lambda2 = (typename WideNE<T>::type)(p.ik_lambda * p.ik_lambda);
+    c.ns_lambda2 = (typename WideNE<T>::type)(p.ns_lambda * p.ns_lambda);
     c.dt = (T)p.dt;
     c.speed_scale = (T)p.speed_scale;
     c.max_vel = (T)p.max_vel;

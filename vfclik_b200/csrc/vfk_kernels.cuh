@@ -55,7 +55,7 @@ struct KConst {
     T mixer_w[6];
     T tool[12];
     T ns_control[4];
-    W ik_lambda2, ns_lambda2;
+    typename WideNE<T>::type ik_lambda2, ns_lambda2;
     T dt, speed_scale, max_vel, jp_kp, jp_delta;
     T ns_gain, ns_lookahead, rot_slowdown_inv, goal_force, obst_force, obst_safe_inv, obst_order;
     int32_t prismatic_mask;    // bit j set: joint j is TransZ, else RotZ
@@ -543,6 +543,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         // 5. weighted damped least squares: qdot = Wj Jw^T (Jw Jw^T + l^2 I)^-1 Wt t.  The normal matrix, its Cholesky
         // factor and the triangular solves are carried in W: formed in FP32, A's rounding error (~1e-6 absolute) is 1e-4
         // of lambda^2 = 0.01 and lands directly in the joints' weakest direction.  J itself stays in T.
+        using WN = typename WideNE<T>::type;
         const bool unitw = LEAN || c.unit_weights;
         const bool ns_on = LEAN || c.ns_mode != 0;
         const bool ns_proj = LEAN || c.ns_mode == 1;
@@ -557,40 +558,40 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 for (int j = 0; j < N; ++j) x[j] = c.ns_q0_scale[j] * (q[j] - c.ns_mid[j]);
             }
         }
-        W A[21], invd[6], Jx[6];
+        WN A[21], invd[6], Jx[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-            Jx[r] = W(0);
+            Jx[r] = WN(0);
 #pragma unroll
-            for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ik_lambda2 : W(0);
+            for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ik_lambda2 : WN(0);
         }
         static_for<0, N>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
-            W col[6] = {(W)Jl[j][0], (W)Jl[j][1], (W)Jl[j][2], (W)Ja[j][0], (W)Ja[j][1], (W)Ja[j][2]};
+            WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
             if (ns_proj && share) {
 #pragma unroll
-                for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (W)x[j], Jx[r]);
+                for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (WN)x[j], Jx[r]);
             }
             if (!unitw) {
 #pragma unroll
-                for (int r = 0; r < 6; ++r) col[r] *= (W)c.w_task[r] * (W)c.w_joint[j];
+                for (int r = 0; r < 6; ++r) col[r] *= (WN)c.w_task[r] * (WN)c.w_joint[j];
             }
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int s = 0; s <= r; ++s) A[tri(r, s)] = fma(col[r], col[s], A[tri(r, s)]);
         });
-        chol6<W>(A, invd);
+        chol6<WN>(A, invd);
         T qd_vf[N];
         {
-            W y[6];
+            WN y[6];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) y[r] = unitw ? (W)tw[r] : (W)tw[r] * (W)c.w_task[r];
-            chol6_fwd<W>(A, invd, y);
-            chol6_bwd<W>(A, invd, y);
+            for (int r = 0; r < 6; ++r) y[r] = unitw ? (WN)tw[r] : (WN)tw[r] * (WN)c.w_task[r];
+            chol6_fwd<WN>(A, invd, y);
+            chol6_bwd<WN>(A, invd, y);
             T yt[6];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) yt[r] = unitw ? (T)y[r] : (T)(y[r] * (W)c.w_task[r]);
+            for (int r = 0; r < 6; ++r) yt[r] = unitw ? (T)y[r] : (T)(y[r] * (WN)c.w_task[r]);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 T acc = T(0);
@@ -608,53 +609,53 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             if (!share) {                                   // own damping or weighted IK: factor J J^T + ns_lambda^2 I
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
-                    Jx[r] = W(0);
+                    Jx[r] = WN(0);
 #pragma unroll
-                    for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ns_lambda2 : W(0);
+                    for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ns_lambda2 : WN(0);
                 }
                 static_for<0, N>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    const W col[6] = {(W)Jl[j][0], (W)Jl[j][1], (W)Jl[j][2], (W)Ja[j][0], (W)Ja[j][1], (W)Ja[j][2]};
+                    const WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
                     if (ns_proj) {
 #pragma unroll
-                        for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (W)x[j], Jx[r]);
+                        for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (WN)x[j], Jx[r]);
                     }
 #pragma unroll
                     for (int r = 0; r < 6; ++r)
 #pragma unroll
                         for (int s = 0; s <= r; ++s) A[tri(r, s)] = fma(col[r], col[s], A[tri(r, s)]);
                 });
-                chol6<W>(A, invd);
+                chol6<WN>(A, invd);
             }
             if (!ns_proj) {
                 // 1-D nullspace: pick the column of B = I - J^T A^-1 J with the largest
                 // diagonal entry B_jj = 1 - |L^-1 J[:,j]|^2 (first maximum wins).
                 int jstar = 0;
-                W best = W(-1);
+                WN best = WN(-1);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    W col[6] = {(W)Jl[j][0], (W)Jl[j][1], (W)Jl[j][2], (W)Ja[j][0], (W)Ja[j][1], (W)Ja[j][2]};
-                    chol6_fwd<W>(A, invd, col);
-                    W s2 = W(0);
+                    WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
+                    chol6_fwd<WN>(A, invd, col);
+                    WN s2 = WN(0);
 #pragma unroll
                     for (int r = 0; r < 6; ++r) s2 = fma(col[r], col[r], s2);
-                    const W bjj = W(1) - s2;
+                    const WN bjj = WN(1) - s2;
                     if (bjj > best) { best = bjj; jstar = j; }
                 }
 #pragma unroll
-                for (int r = 0; r < 6; ++r) Jx[r] = W(0);
+                for (int r = 0; r < 6; ++r) Jx[r] = WN(0);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     x[j] = (j == jstar) ? T(1) : T(0);
                     if (j == jstar) {
 #pragma unroll
-                        for (int r = 0; r < 6; ++r) Jx[r] = (W)(r < 3 ? Jl[j][r] : Ja[j][r - 3]);
+                        for (int r = 0; r < 6; ++r) Jx[r] = (WN)(r < 3 ? Jl[j][r] : Ja[j][r - 3]);
                     }
                 }
             }
             // raw = x - J^T A^-1 (J x)
-            chol6_fwd<W>(A, invd, Jx);
-            chol6_bwd<W>(A, invd, Jx);
+            chol6_fwd<WN>(A, invd, Jx);
+            chol6_bwd<WN>(A, invd, Jx);
             T yt[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) yt[r] = (T)Jx[r];

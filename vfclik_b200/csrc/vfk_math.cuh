@@ -105,13 +105,27 @@ template <> struct Prec<double> {
     static constexpr bool kSeriesAsin = false;
 };
 
-// Working type of the two ill-conditioned stages (forward kinematics, normal equations): double in both modes.  In the
-// FP32 mode everything that touches HBM and the whole field stays FP32; -DVFK_PURE_FP32 makes those stages FP32 too
-// (measured: max qdot error over 1 M random instances 1.2e-4 instead of ~1e-6).
+// Working types of the two ill-conditioned stages.  Measured on B200 over 1,048,576 random LWR instances with 32
+// obstacles (scripts/fp32_error.py, FP32 mode, max relative qdot error / launch time):
+//     pure FP32                         1.2e-4   106 us     (-DVFK_PURE_FP32)  -- 2 instances in 10^6 beyond 1e-4
+//     FK in double, normal eq. FP32     6.3e-5   111 us     (default)
+//     FK in FP32, normal eq. double     1.2e-4   115 us     (-DVFK_WIDE_NE_ONLY)
+//     both in double                    1.6e-5   127 us     (-DVFK_WIDE_NE)
+// An FP32 kinematic chain leaves ~1e-7 m in the tool position, which the order-20 repeller decay turns into up to 1e-4
+// of relative field error next to an obstacle -- the dominant tail.  Forming J J^T + lambda^2 I in FP32 perturbs its
+// smallest eigenvalues (~lambda^2 = 0.01) by ~1e-6, the second, smaller tail.  Everything that touches HBM stays T.
 #if defined(VFK_PURE_FP32)
 template <typename T> struct WideOf { using type = T; };
-#else
+template <typename T> struct WideNE { using type = T; };
+#elif defined(VFK_WIDE_NE_ONLY)
+template <typename T> struct WideOf { using type = T; };
+template <typename T> struct WideNE { using type = double; };
+#elif defined(VFK_WIDE_NE)
 template <typename T> struct WideOf { using type = double; };
+template <typename T> struct WideNE { using type = double; };
+#else
+template <typename T> struct WideOf { using type = double; };      // forward kinematics
+template <typename T> struct WideNE { using type = T; };           // normal equations
 #endif
 
 // sin / cos in double for joint angles: Cody-Waite reduction to [-pi/4, pi/4] with k taken from the mantissa of a
