@@ -296,6 +296,8 @@ static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, 
     *smem_bytes = kSmemHeader + (size_t)(kBlock / 32) * WS::warp_bytes(stages);
 }
 
+constexpr int64_t kCoopMaxInstances = 4096;      // <= 128 tiles: 1024 cooperative warps instead of 128 solo ones
+
 // The LEAN kernel's preconditions (see vfk_kernels.cuh).
 template <typename T>
 static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
@@ -304,7 +306,7 @@ static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
            !b->qdot_jp && !b->cmd && !b->pose && !b->twist && !b->flags && !(b->aux && b->n_aux > 0) && b->qdot && !getenv("VFK_NO_LEAN");
 }
 
-template <typename T, int N, class PAT, bool EXT, bool LEAN>
+template <typename T, int N, class PAT, bool EXT, bool LEAN, int G = 1>
 static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
                         cudaStream_t st) {
     KArgs<T> a;
@@ -342,7 +344,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #define VFK_MINB_LEAN 3
 #endif
     constexpr int MINB = ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? 2 : 1)) * (128 / kBlock);
-    auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB>;
+    auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB, G>;
     // per (instantiation, device, smem size): opt in to > 48 KB of dynamic shared memory and ask the occupancy once
     static int cached_per_sm[16];
     static size_t cached_smem[16];
@@ -357,8 +359,8 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
         cached_per_sm[dslot] = per_sm;
         cached_smem[dslot] = smem;
     }
-    const int64_t tiles = (n + 31) / 32;
-    const int64_t want = (tiles + kBlock / 32 - 1) / (kBlock / 32);
+    const int64_t units = (n + 31) / 32 * G;                 // G = 8: a tile is spread over 8 warps (4 instances each)
+    const int64_t want = (units + kBlock / 32 - 1) / (kBlock / 32);
     const int64_t cap = (int64_t)h->sm_count * per_sm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     kern<<<grid, kBlock, smem, st>>>(c, a);
@@ -370,6 +372,10 @@ template <typename T, int N, class PAT>
 static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
                          cudaStream_t st) {
     const bool ext = b->obst_ext && n_obst > 0;
+    // small batches cannot fill the GPU with one thread per instance: switch to the cooperative latency shape
+    const bool coop = n <= kCoopMaxInstances && n_obst >= kChunk && !getenv("VFK_NO_COOP");
+    if (coop) return ext ? launch_cycle<T, N, PAT, true, false, kChunk>(h, c, b, n, n_obst, k_cycles, st)
+                         : launch_cycle<T, N, PAT, false, false, kChunk>(h, c, b, n, n_obst, k_cycles, st);
     if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st);
     if (is_lean<T>(c, b)) return launch_cycle<T, N, PAT, false, true>(h, c, b, n, n_obst, k_cycles, st);
     return launch_cycle<T, N, PAT, false, false>(h, c, b, n, n_obst, k_cycles, st);

@@ -386,7 +386,11 @@ __device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile, int bu
 // factor, joint P controller unobserved, no extra mixer ports, and q / qdot as the only outputs.  It removes every
 // runtime feature branch from the hot loop (fewer instructions, registers and I-cache lines); the general
 // instantiation keeps them all.
-template <typename T, int N, class PAT, bool EXT, bool LEAN, int MINB>
+// G = lanes cooperating on one instance.  G = 1: one thread per instance (throughput shape).  G = 8: latency shape for
+// small batches -- a warp takes 4 instances of a tile, the 8 lanes of a group split each chunk of 8 obstacles between
+// them and combine their partial repulsor sums with __shfl_xor_sync; the rest of the cycle is computed redundantly by
+// the group and lane 0 of the group stores.  A tile is then spread over 8 warps instead of one.
+template <typename T, int N, class PAT, bool EXT, bool LEAN, int MINB, int G = 1>
 __global__ void __launch_bounds__(kBlock, MINB)
 vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KArgs<T> a) {
     using WS = WarpStage<T, N, EXT>;
@@ -395,10 +399,14 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     const int warp = threadIdx.x >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * WS::kBars;
     unsigned char* region = smem + kSmemHeader + (size_t)warp * WS::warp_bytes(a.n_stages);
+    static_assert(G == 1 || G == kChunk, "a cooperative group takes one obstacle of a chunk per lane");
+    constexpr int kSub = G == 1 ? 1 : G;                        // work units per tile (G == 8: 8 units of 4 instances)
     const int64_t n_tiles = (a.n + 31) >> 5;
+    const int64_t n_units = n_tiles * kSub;
     const int64_t stride = (int64_t)gridDim.x * (kBlock / 32);
-    int64_t tile = (int64_t)blockIdx.x * (kBlock / 32) + warp;
-    if (tile >= n_tiles) return;
+    int64_t unit = (int64_t)blockIdx.x * (kBlock / 32) + warp;
+    if (unit >= n_units) return;
+    const int ol = lane & (G - 1);                              // obstacle lane within the group
 
     // Ring bookkeeping.  A "use" is one consumption of one chunk; a tile has U uses and the ring S slots.
     // resident: S = n_chunks, every chunk is loaded once per tile and reused by all K cycles (U = n_chunks);
@@ -414,24 +422,26 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         mbar_fence_init();
     }
     __syncwarp();
-    issue_qg<T, N, EXT>(a, tile, 0, region, bars, lane);
-    int64_t p_tile = tile;
+    issue_qg<T, N, EXT>(a, unit / kSub, 0, region, bars, lane);
+    int64_t p_unit = unit;
     int p_u = 0, p_chunk = 0;
     for (int u = 0; u < S; ++u) {
-        issue_obst<T, N, EXT>(a, p_tile, p_chunk, u, region, bars, lane);
+        issue_obst<T, N, EXT>(a, p_unit / kSub, p_chunk, u, region, bars, lane);
         if (++p_chunk == a.n_chunks) p_chunk = 0;
-        if (++p_u == U) { p_u = 0; p_tile += stride; }
+        if (++p_u == U) { p_u = 0; p_unit += stride; }
     }
     int c_stage = 0;
     uint32_t c_phase = 0;
 
-    for (int it = 0; tile < n_tiles; tile += stride, ++it) {
-        const bool active = (tile << 5) + lane < a.n;           // padding lanes compute on padding data, never store
-        const int64_t tN = tile * (N * 32) + lane;              // this lane's slot in an N-component blocked array
+    for (int it = 0; unit < n_units; unit += stride, ++it) {
+        const int64_t tile = unit / kSub;
+        const int slot = G == 1 ? lane : (int)(unit % kSub) * (32 / G) + (lane / G);     // instance within the tile
+        const bool active = (tile << 5) + slot < a.n && ol == 0;     // padding / helper lanes compute, never store
+        const int64_t tN = tile * (N * 32) + slot;              // this instance's slot in an N-component blocked array
         __syncwarp();
-        if (tile + stride < n_tiles) issue_qg<T, N, EXT>(a, tile + stride, (it + 1) & 1, region, bars, lane);
+        if (unit + stride < n_units) issue_qg<T, N, EXT>(a, (unit + stride) / kSub, (it + 1) & 1, region, bars, lane);
         mbar_wait(&bars[kMaxStages + (it & 1)], (uint32_t)(it >> 1) & 1u);
-        const T* qg = reinterpret_cast<const T*>(region + (size_t)a.n_stages * WS::kStage + (size_t)(it & 1) * WS::kQg) + lane;
+        const T* qg = reinterpret_cast<const T*>(region + (size_t)a.n_stages * WS::kStage + (size_t)(it & 1) * WS::kQg) + slot;
 
     T q[N];
 #pragma unroll
@@ -488,9 +498,17 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 const int stage = resident ? ch : c_stage;
                 mbar_wait(&bars[stage], resident ? (uint32_t)(it & 1) : c_phase);
                 const unsigned char* sb = region + (size_t)stage * WS::kStage;
-                const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + lane;
-                const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * WS::kRow) + lane;
-                if (ch < a.n_full) {
+                const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + slot;
+                const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * WS::kRow) + slot;
+                if constexpr (G > 1) {
+                    // cooperative shape: lane ol of the group takes obstacle ol of this chunk
+                    if (ol < (ch < a.n_full ? kChunk : a.n_rem)) {
+                        const Vec4<T> o = so[ol * 32];
+                        T safe_inv = c.obst_safe_inv, order = c.obst_order;
+                        if (EXT) { const Vec2<T> e = se[ol * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+                        repel<T>(o, safe_inv, order, pt, acc);
+                    }
+                } else if (ch < a.n_full) {
                     // FP64 with a uniform small-integer decay order: fixed multiplication chain instead of pow()
                     auto full_chunk = [&](auto order_c) {
                         constexpr int ORD = decltype(order_c)::value;
@@ -517,21 +535,28 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 // this slot is free again: request the chunk that will occupy it S uses from now
                 if (!resident || last) {
                     __syncwarp();
-                    if (p_tile < n_tiles) issue_obst<T, N, EXT>(a, p_tile, p_chunk, stage, region, bars, lane);
+                    if (p_unit < n_units) issue_obst<T, N, EXT>(a, p_unit / kSub, p_chunk, stage, region, bars, lane);
                     if (++p_chunk == a.n_chunks) p_chunk = 0;
-                    if (++p_u == U) { p_u = 0; p_tile += stride; }
+                    if (++p_u == U) { p_u = 0; p_unit += stride; }
                 }
                 if (!resident && ++c_stage == S) { c_stage = 0; c_phase ^= 1u; }
             }
+            if constexpr (G > 1) {                          // combine the group's partial repulsor sums
+#pragma unroll
+                for (int off = 1; off < G; off <<= 1) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+                }
+            }
             V[0] = fma(c.obst_force, acc[0], V[0]); V[1] = fma(c.obst_force, acc[1], V[1]); V[2] = fma(c.obst_force, acc[2], V[2]);
-            if (!LEAN && a.aux) aux_fields<T>(a.aux, a.n_aux, tile, lane, pt, V);
+            if (!LEAN && a.aux) aux_fields<T>(a.aux, a.n_aux, tile, slot, pt, V);
             T v[3];
             saturate<T>(c, V, S0, v);
             if (!LEAN && last && active && a.twist) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    a.twist[tile * (6 * 32) + k * 32 + lane] = v[k];
-                    a.twist[tile * (6 * 32) + (3 + k) * 32 + lane] = w[k];
+                    a.twist[tile * (6 * 32) + k * 32 + slot] = v[k];
+                    a.twist[tile * (6 * 32) + (3 + k) * 32 + slot] = w[k];
                 }
             }
             tw[0] = v[0] + (w[1] * dp[2] - w[2] * dp[1]);
@@ -679,7 +704,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 T sc = Prec<T>::rsqrt_pos(nn);
                 const bool neg = (l2 > T(0)) ? (dotl < T(0)) : (vmax < T(0));
                 if (neg) sc = -sc;
-                T c0 = a.ns_in ? __ldg(a.ns_in + tile * (4 * 32) + lane) : c.ns_control[0];
+                T c0 = a.ns_in ? __ldg(a.ns_in + tile * (4 * 32) + slot) : c.ns_control[0];
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     lastv[j] = raw[j] * sc;
@@ -771,11 +796,11 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             }
             if (!LEAN && a.pose) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) a.pose[tile * (12 * 32) + k * 32 + lane] = Rt[k];
+                for (int k = 0; k < 9; ++k) a.pose[tile * (12 * 32) + k * 32 + slot] = Rt[k];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) a.pose[tile * (12 * 32) + (9 + k) * 32 + lane] = pt.hi[k];
+                for (int k = 0; k < 3; ++k) a.pose[tile * (12 * 32) + (9 + k) * 32 + slot] = pt.hi[k];
             }
-            if (!LEAN && a.flags) a.flags[(tile << 5) + lane] = flags;
+            if (!LEAN && a.flags) a.flags[(tile << 5) + slot] = flags;
         }
         // 10. plant
         if (c.integrate) {
