@@ -1,0 +1,128 @@
+// vfk_launch.cuh -- launch plan and feature dispatch of the fused cycle kernel (included by vfk_cycle_*.cu).
+#pragma once
+#include <cstdlib>
+#include <cstring>
+
+#include "vfk_ctx.cuh"
+
+using namespace vfk;
+
+// Launch plan: every warp is a persistent worker with its own obstacle ring (n_stages stages of kChunk
+// obstacles x 32 instances) and two q/goal buffers.  Two stages measured best on B200 for both K = 1
+// (106 us vs 110 us with three at the headline shape) and K = 100 (streaming the ring from L2 every cycle at
+// full occupancy beats keeping four chunks resident at 2 CTAs/SM): gpurun_out t03, DESIGN.md section 4.1.
+template <typename T, int N, bool EXT>
+static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, size_t* smem_bytes) {
+    using WS = WarpStage<T, N, EXT>;
+    (void)k_cycles;
+    *n_chunks = (n_obst + kChunk - 1) / kChunk;
+    int stages = 2;
+    if (const char* e = getenv("VFK_STAGES")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxStages) stages = v;
+    }
+    if (*n_chunks > 0 && *n_chunks < stages) stages = *n_chunks;
+    if (*n_chunks == 0) stages = 0;
+    *n_stages = stages;
+    *smem_bytes = kSmemHeader + (size_t)(kBlock / 32) * WS::warp_bytes(stages);
+}
+
+constexpr int64_t kCoopMaxInstances = 4096;      // <= 128 tiles: 1024 cooperative warps instead of 128 solo ones
+
+// The LEAN kernel's preconditions (see vfk_kernels.cuh).
+template <typename T>
+static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
+    return c.tool_identity && c.unit_weights && c.share_factor && c.ns_mode == VFK_NS_PROJECTOR && !c.need_jp && !b->ns_in &&
+           !b->jp_ref && !b->q_cmded && !b->ext_cmd[0] && !b->ext_cmd[1] && !b->ext_cmd[2] && !b->qdot_vf && !b->qdot_ns &&
+           !b->qdot_jp && !b->cmd && !b->pose && !b->twist && !b->flags && !(b->aux && b->n_aux > 0) && b->qdot && !getenv("VFK_NO_LEAN");
+}
+
+template <typename T, int N, class PAT, bool EXT, bool LEAN, int G = 1>
+static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
+                        cudaStream_t st) {
+    KArgs<T> a;
+    memset(&a, 0, sizeof a);
+    a.q = static_cast<T*>(b->q);
+    a.goal = static_cast<const T*>(b->goal);
+    a.obst = static_cast<const Vec4<T>*>(b->obst);
+    a.obst_ext = static_cast<const Vec2<T>*>(b->obst_ext);
+    a.aux = b->n_aux > 0 ? static_cast<const T*>(b->aux) : nullptr;
+    a.n_aux = a.aux ? b->n_aux : 0;
+    a.jp_ref = static_cast<const T*>(b->jp_ref);
+    a.ns_in = static_cast<const T*>(b->ns_in);
+    a.ns_lastvec = static_cast<T*>(b->ns_lastvec);
+    a.q_cmded = static_cast<const T*>(b->q_cmded);
+    for (int e = 0; e < 3; ++e) a.ext_cmd[e] = static_cast<const T*>(b->ext_cmd[e]);
+    a.qdot_vf = static_cast<T*>(b->qdot_vf);
+    a.qdot_ns = static_cast<T*>(b->qdot_ns);
+    a.qdot_jp = static_cast<T*>(b->qdot_jp);
+    a.qdot = static_cast<T*>(b->qdot);
+    a.cmd = static_cast<T*>(b->cmd);
+    a.pose = static_cast<T*>(b->pose);
+    a.twist = static_cast<T*>(b->twist);
+    a.flags = b->flags;
+    a.n = n;
+    a.n_obst = n_obst;
+    a.k_cycles = k_cycles;
+    size_t smem = 0;
+    plan_stages<T, N, EXT>(n_obst, k_cycles, &a.n_chunks, &a.n_stages, &smem);
+    a.n_full = n_obst / kChunk;
+    a.n_rem = n_obst % kChunk;
+#ifndef VFK_MINB_F32
+#define VFK_MINB_F32 3
+#endif
+#ifndef VFK_MINB_LEAN
+#define VFK_MINB_LEAN 3
+#endif
+    constexpr int MINB = ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? 2 : 1)) * (128 / kBlock);
+    auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB, G>;
+    // per (instantiation, device, smem size): opt in to > 48 KB of dynamic shared memory and ask the occupancy once
+    static int cached_per_sm[16];
+    static size_t cached_smem[16];
+    int per_sm = 0;
+    const int dslot = h->device & 15;
+    if (cached_per_sm[dslot] > 0 && cached_smem[dslot] == smem) {
+        per_sm = cached_per_sm[dslot];
+    } else {
+        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+        VFK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+        if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "kernel does not fit an SM with %zu bytes of shared memory", smem);
+        cached_per_sm[dslot] = per_sm;
+        cached_smem[dslot] = smem;
+    }
+    const int64_t units = (n + 31) / 32 * G;                 // G = 8: a tile is spread over 8 warps (4 instances each)
+    const int64_t want = (units + kBlock / 32 - 1) / (kBlock / 32);
+    const int64_t cap = (int64_t)h->sm_count * per_sm;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    kern<<<grid, kBlock, smem, st>>>(c, a);
+    VFK_CUDA(h, cudaGetLastError());
+    return 1;
+}
+
+template <typename T, int N, class PAT>
+static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
+                         cudaStream_t st) {
+    const bool ext = b->obst_ext && n_obst > 0;
+    // Small FP64 batches cannot fill the GPU with one thread per instance: switch to the cooperative latency shape.
+    // Measured (scripts/latency.py, one robot, 1000 fused cycles): FP64 M = 32: 6.4 vs 7.1 us per cycle, M = 256: 23.6 vs
+    // 36.3 us.  In FP32 the repeller is three MUFU instructions and the shape only adds ring overhead (3.7 vs 2.7 us),
+    // so it is neither selected nor instantiated there.
+    if constexpr (sizeof(T) == 8) {
+        const bool coop = n <= kCoopMaxInstances && n_obst >= 2 * kChunk && !getenv("VFK_NO_COOP");
+        if (coop) return ext ? launch_cycle<T, N, PAT, true, false, kChunk>(h, c, b, n, n_obst, k_cycles, st)
+                             : launch_cycle<T, N, PAT, false, false, kChunk>(h, c, b, n, n_obst, k_cycles, st);
+    }
+    if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st);
+    if (is_lean<T>(c, b)) return launch_cycle<T, N, PAT, false, true>(h, c, b, n, n_obst, k_cycles, st);
+    return launch_cycle<T, N, PAT, false, false>(h, c, b, n, n_obst, k_cycles, st);
+}
+
+template <typename T, int N>
+static int dispatch_ext(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
+                        cudaStream_t st) {
+    if constexpr (N == 7) {
+        if (h->pattern == 1) return dispatch_feat<T, N, LwrPattern>(h, c, b, n, n_obst, k_cycles, st);
+    }
+    return dispatch_feat<T, N, GenericPattern>(h, c, b, n, n_obst, k_cycles, st);
+}
+
