@@ -85,6 +85,11 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
         c.jp_ref[j] = (T)p.jp_ref[j];
         if (p.w_joint[j] != 1.0) unit = false;
         if (ch.joint_type[j] == VFK_JOINT_TRANSZ) c.prismatic_mask |= (1 << j);
+        // structure of the tip rotation (exact tests: the fast paths must give the general product's value)
+        const double* r = ch.tip[j];
+        const bool xtwist = r[0] == 1.0 && r[1] == 0.0 && r[2] == 0.0 && r[3] == 0.0 && r[6] == 0.0 && r[4] == r[8] && r[5] == -r[7];
+        if (xtwist && r[4] == 1.0 && r[7] == 0.0) c.tipident_mask |= (1 << j);
+        else if (xtwist) c.xtwist_mask |= (1 << j);
     }
     bool all_zero = true;
     for (int k = 0; k < 6; ++k) {

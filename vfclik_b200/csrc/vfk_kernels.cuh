@@ -59,6 +59,8 @@ struct KConst {
     T dt, speed_scale, max_vel, jp_kp, jp_delta;
     T ns_gain, ns_lookahead, rot_slowdown_inv, goal_force, obst_force, obst_safe_inv, obst_order;
     int32_t prismatic_mask;    // bit j set: joint j is TransZ, else RotZ
+    int32_t xtwist_mask;       // bit j set: tip j's rotation is RotX(alpha) (every DH-specified chain), alpha in tip[j][4], [7]
+    int32_t tipident_mask;     // bit j set: tip j's rotation is the identity
     int32_t ns_mode;
     int32_t direct_control;    // resolved 0/1
     int32_t integrate;
@@ -157,7 +159,7 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
             p[0] = fma(R[2], qj, p[0]); p[1] = fma(R[5], qj, p[1]); p[2] = fma(R[8], qj, p[2]);
         } else {
             W s, co;
-            sincos_wide(qj, &s, &co);
+            sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(qj, &s, &co);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const W a = R[3 * r + 0], b = R[3 * r + 1];
@@ -175,11 +177,26 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
         });
         W Rn[9];
         if constexpr (PAT::generic) {
+            // warp-uniform choice on the robot's constants: identity tip (nothing), X-twist tip (12 ops), general (27)
+            if (c.tipident_mask & (1 << j)) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+                for (int k = 0; k < 9; ++k) Rn[k] = R[k];
+            } else if (c.xtwist_mask & (1 << j)) {
+                const W ca = tp[4], sa = tp[7];
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc)
-                    Rn[3 * r + cc] = fma(R[3 * r + 0], tp[cc], fma(R[3 * r + 1], tp[3 + cc], R[3 * r + 2] * tp[6 + cc]));
+                for (int r = 0; r < 3; ++r) {
+                    const W a = R[3 * r + 1], b = R[3 * r + 2];
+                    Rn[3 * r + 0] = R[3 * r + 0];
+                    Rn[3 * r + 1] = fma(ca, a, sa * b);
+                    Rn[3 * r + 2] = fma(ca, b, -sa * a);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+                        Rn[3 * r + cc] = fma(R[3 * r + 0], tp[cc], fma(R[3 * r + 1], tp[3 + cc], R[3 * r + 2] * tp[6 + cc]));
+            }
         } else {
             static_for<0, 3>([&](auto kc) {
                 constexpr int k = decltype(kc)::value;

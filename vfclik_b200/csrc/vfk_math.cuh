@@ -129,29 +129,38 @@ template <typename T> struct WideNE { using type = T; };           // normal equ
 #endif
 
 // sin / cos in double for joint angles: Cody-Waite reduction to [-pi/4, pi/4] with k taken from the mantissa of a
-// magic-number add, Taylor polynomials to x^15 / x^16 (truncation < 5e-17), branch-free quadrant selection.
+// magic-number add, Taylor polynomials, branch-free quadrant selection.  The FP32 mode's wide kinematic chain stops at
+// x^11 / x^12 (truncation < 7e-12 and < 4e-13 at pi/4: four decades below an FP32 ulp, which is all its consumer keeps).  The coefficients sit in constant memory so every DFMA takes its coefficient as a
+// constant-bank operand; as immediates they cost two UMOV per use in the 10- and 17-joint kernels.
+struct SinCosTab {
+    double two_over_pi, magic, pio2_hi, pio2_lo;
+    double s[7];     // -1/3!, 1/5!, -1/7!, 1/9!, -1/11!, 1/13!, -1/15!
+    double c[7];     // 1/4!, -1/6!, 1/8!, -1/10!, 1/12!, -1/14!, 1/16!
+};
+static __device__ __constant__ SinCosTab kSinCos = {
+    0.63661977236758134308, 6755399441055744.0, 1.57079632679489655800e+00, 6.12323399573676603587e-17,
+    {-1.66666666666666666667e-01, 8.33333333333333333333e-03, -1.98412698412698412698e-04, 2.75573192239858906526e-06,
+     -2.50521083854417187751e-08, 1.60590438368216145994e-10, -7.64716373181981647590e-13},
+    {4.16666666666666666667e-02, -1.38888888888888888889e-03, 2.48015873015873015873e-05, -2.75573192239858906526e-07,
+     2.08767569878680989792e-09, -1.14707455977297247139e-11, 4.77947733238738529744e-14}};
+
+// TERMS = 5: x^11 / x^12 (the FP32 mode's wide chain); TERMS = 7: x^15 / x^16, truncation < 5e-17 (FP64 mode).
+template <int TERMS>
 __device__ __forceinline__ void sincos_wide(double x, double* s, double* c) {
-    const double t = fma(x, 0.63661977236758134308, 6755399441055744.0);
+    const SinCosTab& k = kSinCos;
+    const double t = fma(x, k.two_over_pi, k.magic);
     const int ki = __double2loint(t);
-    const double kf = t - 6755399441055744.0;
-    double r = fma(kf, -1.57079632679489655800e+00, x);
-    r = fma(kf, -6.12323399573676603587e-17, r);
+    const double kf = t - k.magic;
+    double r = fma(kf, -k.pio2_hi, x);
+    r = fma(kf, -k.pio2_lo, r);
     const double z = r * r;
-    double sp = -7.64716373181981647590e-13;                 // -1/15!
-    sp = fma(sp, z, 1.60590438368216145994e-10);              //  1/13!
-    sp = fma(sp, z, -2.50521083854417187751e-08);             // -1/11!
-    sp = fma(sp, z, 2.75573192239858906526e-06);              //  1/9!
-    sp = fma(sp, z, -1.98412698412698412698e-04);             // -1/7!
-    sp = fma(sp, z, 8.33333333333333333333e-03);              //  1/5!
-    sp = fma(sp, z, -1.66666666666666666667e-01);             // -1/3!
+    double sp = k.s[TERMS - 1], cp = k.c[TERMS - 1];
+#pragma unroll
+    for (int i = TERMS - 2; i >= 0; --i) {
+        sp = fma(sp, z, k.s[i]);
+        cp = fma(cp, z, k.c[i]);
+    }
     sp = fma(sp * z, r, r);
-    double cp = 4.77947733238738529744e-14;                   //  1/16!
-    cp = fma(cp, z, -1.14707455977297247139e-11);             // -1/14!
-    cp = fma(cp, z, 2.08767569878680989792e-09);              //  1/12!
-    cp = fma(cp, z, -2.75573192239858906526e-07);             // -1/10!
-    cp = fma(cp, z, 2.48015873015873015873e-05);              //  1/8!
-    cp = fma(cp, z, -1.38888888888888888889e-03);             // -1/6!
-    cp = fma(cp, z, 4.16666666666666666667e-02);              //  1/4!
     cp = fma(cp, z, -0.5);
     cp = fma(cp, z, 1.0);
     const double ss = (ki & 1) ? cp : sp;
@@ -159,6 +168,7 @@ __device__ __forceinline__ void sincos_wide(double x, double* s, double* c) {
     *s = (ki & 2) ? -ss : ss;
     *c = ((ki + 1) & 2) ? -cs : cs;
 }
+template <int TERMS>
 __device__ __forceinline__ void sincos_wide(float x, float* s, float* c) { Prec<float>::sincos_(x, s, c); }
 
 // x^ORDER by a fixed multiplication chain (FP64 repeller fast path; ORDER = 0 means "use Prec<T>::pow_pos").
