@@ -387,6 +387,19 @@ def main():
         ms_k = timed(lambda: db.step(kf), 3)
         extras["k_fused"] = {"kcycles": kf, "value": world * n_inst * kf * 3 / (ms_k * 1e-3), "unit": UNIT,
                              "ms_per_launch": ms_k / 3}
+        try:
+            # compute-bound shape: algorithmic FLOPs (frozen exact count, workloads.ALGORITHMIC_OPS) against the FFMA /
+            # DFMA rate measured on this pool's B200 by scripts/peaks.cu (profiles/r01_pipe_peaks.json)
+            flops = workloads.algorithmic_flops(N, n_obst)
+            pk = json.load(open(os.path.join(ROOT, "profiles", "r01_pipe_peaks.json")))
+            peak_tf = float(pk["fp32_ffma_tflops" if precision == 32 else "fp64_dfma_tflops"])
+            ach = flops * n_inst * kf * 3 / (ms_k * 1e-3) / 1e12
+            extras["k_fused"]["roofline"] = {"bound": "fp32 pipe" if precision == 32 else "fp64 pipe", "achieved": ach,
+                                             "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                                             "algorithmic_flops_per_instance_cycle": flops,
+                                             "peak_source": "profiles/r01_pipe_peaks.json (scripts/peaks.cu)"}
+        except Exception as exc:      # the headline line must not depend on a side measurement
+            extras["k_fused"]["roofline"] = {"error": str(exc)}
         if args.workload == "config3" and world == 1:
             n2, m2 = WORKLOADS["config2"][0], WORKLOADS["config2"][1]
             e64 = Engine(chain, precision=64, device=local_rank, params=params)

@@ -19,7 +19,7 @@ hdr, units, data = rows[0], rows[1], rows[2:]
 keys = ("Kernel Name", "gpu__time_duration", "dram__bytes", "dram_throughput", "registers_per_thread", "occupancy",
         "inst_executed.sum", "issue_active", "warps_active", "stalled", "pipe_fma", "pipe_xu", "pipe_alu", "pipe_lsu",
         "lts__t_bytes.sum", "sm__throughput", "thread_inst_executed_per_inst", "shared_mem", "l1tex__t_bytes.sum",
-        "Grid Size", "Block Size")
+        "Grid Size", "Block Size", "sass_thread_inst_executed_op", "cycles_elapsed.avg.per_second", "pipe_fp64")
 keep = [i for i, h in enumerate(hdr) if any(k in h for k in keys)]
 with open(os.path.join(pr, tag + "_ncu_full_summary.csv"), "w") as f:
     w = csv.writer(f)
@@ -40,3 +40,25 @@ d[workload + "_source"] = "%s_ncu_full_summary.csv: dram__bytes_read.sum + dram_
 json.dump(d, open(tj, "w"), indent=1)
 dur, _ = col("gpu__time_duration.sum")
 print("traffic per launch %.1f MB, duration %s us" % (traffic / 1e6, dur))
+
+
+# executed FLOP/s from the SASS op counters ("achieved FLOP/s ... from ncu against both peaks")
+def rate(op):
+    name = "smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op
+    return col(name)[0] if name in hdr else [0.0] * len(data)
+try:
+    clk, cu = col("smsp__cycles_elapsed.avg.per_second")
+    clk = [c * {"Ghz": 1e9, "Mhz": 1e6, "hz": 1.0}.get(cu, 1e9) for c in clk]
+    f32 = [(a + m + 2 * f) * c / 1e12 for a, m, f, c in zip(rate("fadd"), rate("fmul"), rate("ffma"), clk)]
+    f64 = [(a + m + 2 * f) * c / 1e12 for a, m, f, c in zip(rate("dadd"), rate("dmul"), rate("dfma"), clk)]
+    pk = json.load(open(os.path.join(pr, "r01_pipe_peaks.json")))
+    d[workload + "_executed_flops"] = {
+        "fp32_tflops": sum(f32) / len(f32), "fp64_tflops": sum(f64) / len(f64),
+        "fp32_frac_of_measured_ffma_peak": sum(f32) / len(f32) / pk["fp32_ffma_tflops"],
+        "fp64_frac_of_measured_dfma_peak": sum(f64) / len(f64) / pk["fp64_dfma_tflops"],
+        "hbm_tbs": traffic / (sum(dur) / len(dur) * 1e-6) / 1e12,
+        "source": "%s_ncu_full_summary.csv: smsp__sass_thread_inst_executed_op_{f,d}{add,mul,fma}_pred_on (FMA = 2)" % tag}
+    json.dump(d, open(tj, "w"), indent=1)
+    print("executed: FP32 %.2f TFLOP/s, FP64 %.2f TFLOP/s" % (sum(f32) / len(f32), sum(f64) / len(f64)))
+except Exception as exc:
+    print("no executed-FLOP summary:", exc)

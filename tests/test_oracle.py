@@ -217,3 +217,24 @@ def test_golden_is_reproducible_from_reference(golden):
     for k, v in data.items():
         assert np.allclose(np.asarray(v, dtype=np.float64), np.asarray(golden[k], dtype=np.float64), equal_nan=True,
                            atol=1e-12), k
+
+
+def test_operation_count_is_frozen_and_counts_the_oracle(lwr):
+    """the FLOP constants bench.py computes the K-fused roofline from are an exact count of the oracle's
+    cycle -- the counting implementation must reproduce oracle.batch.step, and its counts must equal the frozen table."""
+    from oracle import opcount
+    chain, _ = lwr
+    prm = batch.Params()
+    rng = np.random.default_rng(5)
+    w = workloads.random_batch(chain, 4, 32, seed=11)
+    for i in range(4):
+        q, goal, obst = w["q"][:, i], w["goal"][:, i], w["obst"][:, i, :]
+        out, _ = opcount.cycle(chain, prm, q, goal, obst)
+        ref = batch.step(chain, prm, q[None, :], goal[None, :], obst[None, :, :])
+        assert np.allclose(out["qdot"], ref["qdot"][0], rtol=1e-10, atol=1e-13)
+        assert np.allclose(out["q"], ref["q"][0], rtol=1e-12, atol=1e-13)
+    for (n, m), (flops, trans) in workloads.ALGORITHMIC_OPS.items():
+        ch = chain if n == 7 else workloads.dual_arm_torso_chain()
+        c = opcount.count(ch, m, samples=3)
+        assert (c.flops, c.transcendentals) == (flops, trans), ((n, m), c.flops, c.transcendentals)
+    assert workloads.algorithmic_flops(7, 64) == workloads.ALGORITHMIC_OPS[(7, 32)][0] + 20 * 32

@@ -17,6 +17,24 @@ def quat_to_rot_rows(quat: np.ndarray) -> np.ndarray:
                      2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], axis=0)
 
 
+# Exact arithmetic of one instance-cycle: {(N, M): (FLOPs, transcendentals)}, counted by executing the
+# oracle's cycle on a counting scalar type (oracle/opcount.py; add / sub / mul / div / sqrt = 1 FLOP, FMA = 2; sin, cos,
+# atan2, pow counted apart; constant folding and structural 0 / 1 entries free).  Frozen here; tests/test_oracle.py
+# re-derives them.  The K-fused roofline (FP32 pipe) in bench.py is computed from these.
+ALGORITHMIC_OPS = {(7, 3): (1064, 18), (7, 32): (1644, 47), (7, 256): (6124, 271), (17, 64): (3443, 99)}
+
+
+def algorithmic_flops(n_joints: int, n_obst: int) -> int:
+    """FLOPs per instance-cycle; shapes other than the frozen ones use the per-obstacle slope (20 FLOPs) of the nearest."""
+    if (n_joints, n_obst) in ALGORITHMIC_OPS:
+        return ALGORITHMIC_OPS[(n_joints, n_obst)][0]
+    same = [(abs(m - n_obst), m) for (n, m) in ALGORITHMIC_OPS if n == n_joints]
+    if not same:
+        raise KeyError("no frozen operation count for %d joints" % n_joints)
+    m0 = min(same)[1]
+    return ALGORITHMIC_OPS[(n_joints, m0)][0] + 20 * (n_obst - m0)
+
+
 def random_batch(chain: ChainDesc, n_instances: int, n_obstacles: int, seed: int, dtype=np.float64,
                  obst_ext: bool = False, slowdown: float = 0.05, order: float = 20.0, safe: float = 0.001,
                  shoulder=None, box: float = 0.8):
