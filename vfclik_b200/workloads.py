@@ -18,7 +18,7 @@ def quat_to_rot_rows(quat: np.ndarray) -> np.ndarray:
 
 
 # Exact arithmetic of one instance-cycle: {(N, M): (FLOPs, transcendentals)}, counted by executing the
-# oracle's cycle on a counting scalar type (oracle/opcount.py; add / sub / mul / div / sqrt = 1 FLOP, FMA = 2; sin, cos,
+# oracle's cycle on a counting scalar type (the `opcount` module of the test oracle; add / sub / mul / div / sqrt = 1 FLOP, FMA = 2; sin, cos,
 # atan2, pow counted apart; constant folding and structural 0 / 1 entries free).  Frozen here; tests/test_oracle.py
 # re-derives them.  The K-fused roofline (FP32 pipe) in bench.py is computed from these.
 ALGORITHMIC_OPS = {(7, 3): (1064, 18), (7, 32): (1644, 47), (7, 256): (6124, 271), (17, 64): (3443, 99)}
