@@ -75,6 +75,15 @@ enum { VFK_NS_OFF = 0,           /* --no_nullspace (scripts/vfclik:73-79) */
        VFK_NS_PROJECTOR = 1,     /* qdot_ns = gain * check((I - J^+ J) qdot0) */
        VFK_NS_CONTROL = 2 };     /* reference 4-float control interface, 1-D nullspace (N = 7) */
 
+/* Robot back-end whose set_vel() the clamp / command step restates:
+ *   LWR       leading-joint clamp; cmd = qdot_lim (direct) or -q_cmded + q + qdot_lim      (scripts/bridge:182-210)
+ *   POWERCUBE leading-joint clamp, then the shoulder-speed clamp of joint 0.  Bug-compatible: the reference reuses one
+ *             `ratio` variable, so when the shoulder limit is NOT hit the leading ratio is applied a second time
+ *             (scripts/bridge:288-305); cmd = qdot_lim
+ *   ICUB      leading-joint clamp; cmd = qdot_lim (scripts/bridge:507-530; inactive torso joints are handled through the
+ *             joint weights the bridge sends to the vector field, :470-500) */
+enum { VFK_BRIDGE_LWR = 0, VFK_BRIDGE_POWERCUBE = 1, VFK_BRIDGE_ICUB = 2 };
+
 /* Serial chain: flange = base * prod_i ( Joint_i(q_i) * tip_i ).  Frames are 12
  * doubles: R row-major (9) then p (3).  Replaces the PyKDL chain Lafik builds from
  * config.segments (scripts/vf:153). */
@@ -110,10 +119,12 @@ typedef struct vfk_params {
     double tool[12];             /* tool frame in the flange frame (scripts/vf:321-330) */
     double jp_ref[VFK_MAX_JOINTS];  /* used when vfk_buffers.jp_ref == NULL (config.initial_joint_pos) */
     double ns_control[4];        /* used in VFK_NS_CONTROL when vfk_buffers.ns_in == NULL */
+    double shoulder_vel[2];      /* VFK_BRIDGE_POWERCUBE: config.max_vel_shoulder_pos (> 0), max_vel_shoulder_neg (< 0)
+                                    (scripts/bridge:296-303) */
     int32_t ns_mode;             /* VFK_NS_* */
     int32_t direct_control;      /* -1: auto = all mixer weights zero (scripts/bridge:604); 0 / 1 force */
     int32_t integrate;           /* 1: q += dt * qdot_lim after every cycle (simulation plant) */
-    int32_t reserved;
+    int32_t bridge_kind;         /* VFK_BRIDGE_*: which set_vel the clamp / command step follows */
 } vfk_params;
 
 /* Device buffers of one vfk_step() call, all in the tile-blocked layout above
@@ -182,7 +193,9 @@ int  vfk_mix(vfk_handle h, const void* const* cmds, const double* w, int n_ports
              void* out, int32_t* nan_flags, int64_t n_instances, void* stream);
 
 /* LWR_Bridge.set_vel (scripts/bridge:188-203) on device buffers [n_channels]: ratio = max_vel / max_c |qdot_c| when
- * exceeded; cmd = qdot_lim if direct_control else -q_cmded + q + qdot_lim (q_cmded NULL -> q). qdot_lim_out optional. */
+ * exceeded; cmd = qdot_lim if direct_control else -q_cmded + q + qdot_lim (q_cmded NULL -> q). qdot_lim_out optional.
+ * params.bridge_kind selects the back-end: VFK_BRIDGE_POWERCUBE adds the shoulder clamp of Powercube_Bridge.set_vel
+ * (scripts/bridge:288-305), and it and VFK_BRIDGE_ICUB (:507-530) always command qdot_lim itself. */
 int  vfk_set_vel(vfk_handle h, const void* qdot, const void* q, const void* q_cmded, double max_vel, int direct_control,
                  void* cmd_out, void* qdot_lim_out, int n_channels, int64_t n_instances, void* stream);
 

@@ -76,6 +76,8 @@ class Params:
     ns_mode: int = 1                   # 0 off, 1 projector, 2 control (reference interface)
     direct_control: int = -1           # -1 auto: all mixer weights zero (scripts/bridge:604)
     integrate: int = 1
+    bridge_kind: int = 0               # 0 LWR_Bridge, 1 Powercube_Bridge, 2 ICUB_Bridge (scripts/bridge:102-111)
+    shoulder_vel: tuple = (0.0, 0.0)   # Powercube: config.max_vel_shoulder_pos (> 0), max_vel_shoulder_neg (< 0)
 
 
 # --------------------------------------------------------------------------- FK / J
@@ -397,8 +399,17 @@ def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastve
             ratio = np.where(lead > prm.max_vel, prm.max_vel / lead, 1.0)
         flags |= np.where(lead > prm.max_vel, FLAG_CLAMPED, 0).astype(np.int32)
         qd = mix * ratio[:, None]
+        if prm.bridge_kind == 1:
+            # Powercube_Bridge.set_vel (scripts/bridge:288-305).  One `ratio` variable serves both clamps, so when the
+            # shoulder limit is not hit the leading ratio is applied a second time (kept: bug-compatible).
+            sh = qd[:, 0]
+            with np.errstate(invalid="ignore", divide="ignore"):
+                r2 = np.where(sh > prm.shoulder_vel[0], np.abs(prm.shoulder_vel[0] / sh),
+                              np.where(sh < prm.shoulder_vel[1], np.abs(prm.shoulder_vel[1] / sh), ratio))
+            qd = qd * r2[:, None]
         qc = q if q_cmded is None else np.asarray(q_cmded, dtype=np.float64)
-        cmd = qd if direct else (-qc + q + qd)          # scripts/bridge:198-203
+        # scripts/bridge:198-203 (LWR offset form); the Powercube and iCub back-ends command qdot_lim itself (:304-312,:517-530)
+        cmd = qd if (direct or prm.bridge_kind != 0) else (-qc + q + qd)
         out = dict(qdot_vf=qd_vf, qdot_ns=qd_ns, qdot_jp=qd_jp, qdot_mix=mix, qdot=qd, cmd=cmd,
                    pose=np.concatenate([Rt.reshape(I, 9), pt], axis=1), flags=flags, twist=out_twist)
         # 10. plant: explicit Euler (joint_sim is external to the reference)

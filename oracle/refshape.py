@@ -610,7 +610,15 @@ class ControlLoop:
         else:
             ratio = 1.0
         qdot_lim = [v * ratio for v in mix]
-        cmd = [qdot_lim[i] if direct else (-q[i] + q[i] + qdot_lim[i]) for i in range(N)]
+        if prm.bridge_kind == 1:
+            # Powercube_Bridge.set_vel, scripts/bridge:295-303 (statement for statement; `ratio` is the variable above)
+            shoulder_vel = qdot_lim[0]
+            if shoulder_vel > prm.shoulder_vel[0]:
+                ratio = abs(prm.shoulder_vel[0] / shoulder_vel)
+            elif shoulder_vel < prm.shoulder_vel[1]:
+                ratio = abs(prm.shoulder_vel[1] / shoulder_vel)
+            qdot_lim = [i * ratio for i in qdot_lim]
+        cmd = [qdot_lim[i] if (direct or prm.bridge_kind != 0) else (-q[i] + q[i] + qdot_lim[i]) for i in range(N)]
         # ---- plant (external joint_sim): explicit Euler
         if prm.integrate:
             self.q = [q[i] + prm.dt * qdot_lim[i] for i in range(N)]

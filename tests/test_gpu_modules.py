@@ -280,3 +280,80 @@ def test_object_feeder_goal_and_normal_and_table(lwr, built_lib, fresh_ports):
         assert 5 not in app.runtime.vectorFields
     finally:
         app.close()
+
+
+def test_bridge_backends_powercube_icub_and_torso_sharing(lwr, built_lib, fresh_ports):
+    """SURVEY.md 8 row f4 through the port-driven bridge module: Powercube shoulder clamp, iCub torso (de)activation
+    weights, and the LWR bridge taking its torso joints from the other arm's plant (scripts/bridge:140-147,174-178)."""
+    import copy
+    from vfclik_b200.launcher import Vfclik
+    _, cfg = lwr
+
+    # --- Powercube: leading clamp + shoulder clamp, command = qdot_lim (scripts/bridge:288-312)
+    c1 = copy.copy(cfg)
+    c1.arm_type, c1.max_vel_shoulder_pos, c1.max_vel_shoulder_neg, c1.speedScale, c1.max_vel = "powercube", 0.004, -0.004, 0.41, 0.05
+    app = Vfclik(c1, namespace="/1", sim=True, precision=64)
+    try:
+        hit = 0
+        for _ in range(6):
+            cmd = app.step()
+        for _ in range(10):
+            cmd = app.step()
+            mix = [a + b for a, b in zip(app.vf.last_qdot, app.nullspace.last_qdot)]      # mixer weights [1,1,0,0,0,0]
+            leading_vel = max(map(abs, mix))
+            ratio = c1.max_vel / leading_vel if leading_vel > c1.max_vel else 1.0
+            qdot_lim = [v * ratio for v in mix]
+            shoulder_vel = qdot_lim[0]
+            if shoulder_vel > c1.max_vel_shoulder_pos:
+                ratio = abs(c1.max_vel_shoulder_pos / shoulder_vel); hit += 1
+            elif shoulder_vel < c1.max_vel_shoulder_neg:
+                ratio = abs(c1.max_vel_shoulder_neg / shoulder_vel); hit += 1
+            qdot_lim = [i * ratio for i in qdot_lim]
+            assert np.allclose(cmd, qdot_lim, rtol=1e-9, atol=1e-13)
+        assert hit > 0
+        assert app.bridge.qin_port.getName() == "/1" + cfg.robotarm_portbasename + "/bridge/qin"
+    finally:
+        app.close()
+    fresh_ports.Network.reset()
+
+    # --- iCub: torso_cjoints -> ['j', w0..w9] on /control_weights:o (scripts/bridge:470-506)
+    c2 = copy.copy(cfg)
+    c2.arm_type, c2.icub_torso_cjoints = "icub", [True, True, True]
+    app = Vfclik(c2, namespace="/2", sim=True, precision=64)
+    try:
+        base = "/2" + cfg.robotarm_portbasename + "/bridge"
+        probe = fresh_ports.BufferedPortBottle(); probe.open("/2/test/weights_probe")
+        fresh_ports.Network.connect(base + "/control_weights:o", "/2/test/weights_probe")
+        tc = _out_port(fresh_ports, "/2/test/tc", base + "/torso_cjoints:i")
+        fresh_ports.write_bottle_lists(tc, [1, 0, 1], strict=True)
+        with redirect_stdout(io.StringIO()) as log:
+            app.step()
+        b = probe.read(False)
+        assert b is not None and b.get(0).asString() == "j"
+        assert [b.get(i).asDouble() for i in range(1, b.size())] == [1.0, 0.0, 1.0] + [1.0] * 7
+        assert app.bridge.icub_torso_cjoints == [True, False, True]
+        assert "Received a torso_joints bottle" in log.getvalue()
+        fresh_ports.write_bottle_lists(tc, [1, 0], strict=True)
+        with redirect_stdout(io.StringIO()) as log:
+            cmd = app.step()
+        assert "wrong length" in log.getvalue() and probe.read(False) is None
+        # the iCub bridge commands qdot_lim itself, never the LWR offset form
+        mix = np.asarray(app.vf.last_qdot) + np.asarray(app.nullspace.last_qdot)
+        lead = np.max(np.abs(mix))
+        assert np.allclose(cmd, mix * (min(1.0, cfg.max_vel / lead)), rtol=1e-9, atol=1e-13)
+    finally:
+        app.close()
+    fresh_ports.Network.reset()
+
+    # --- LWR with the torso on the other arm's plant
+    c3 = copy.copy(cfg)
+    c3.torso_joints, c3.torso_instance, c3.torso_qin_portname = [0, 1], "left", "/torso_qin"
+    other = fresh_ports.BufferedPortBottle(); other.open("/3/lwr/left/joint_sim/qout")
+    app = Vfclik(c3, namespace="/3", sim=True, precision=64)
+    try:
+        fresh_ports.write_bottle_lists(other, [0.11, -0.22, 9, 9, 9, 9, 9], strict=True)
+        app.step()
+        assert app.bridge.last_q[:2] == [0.11, -0.22]                     # torso joints: the other arm's plant
+        assert np.allclose(app.bridge.last_q[2:], cfg.initial_joint_pos[2:])   # the rest: this arm's own joint_sim
+    finally:
+        app.close()

@@ -525,3 +525,35 @@ def test_full_size_config3_properties_and_sampled_oracle(lwr, built_lib):
         torch.cuda.synchronize()
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_powercube_and_icub_bridge_backends(lwr, built_lib, precision):
+    """Powercube_Bridge.set_vel's shoulder clamp (scripts/bridge:288-305, incl. the reference's
+    double application of the leading ratio) and the iCub / Powercube command form, fused in the cycle kernel."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import BRIDGE_ICUB, BRIDGE_POWERCUBE, Engine, Params
+    chain, cfg = lwr
+    dt = np.float32 if precision == 32 else np.float64
+    w = workloads.random_batch(chain, 3000, 8, seed=17, dtype=dt)
+    # fast enough that all three cases occur: no clamp, leading clamp only, shoulder clamp
+    base = dataclasses.replace(Params.from_config(cfg), speed_scale=0.41, max_vel=0.3)
+    for kind, shoulder in ((BRIDGE_POWERCUBE, (0.05, -0.08)), (BRIDGE_ICUB, (0.0, 0.0))):
+        prm = dataclasses.replace(base, bridge_kind=kind, shoulder_vel=shoulder)
+        e = Engine(chain, precision=precision, params=prm)
+        try:
+            out = run_gpu(e, w, 8)
+            ref = run_oracle(chain, prm, w, 8)
+            check(out, ref, FP64_RTOL if precision == 64 else FP32_RTOL)
+            assert np.allclose(out["cmd"], out["qdot"])               # both back-ends command qdot_lim itself
+            if kind == BRIDGE_POWERCUBE:
+                sh = ref["qdot"][:, 0]
+                assert np.all(sh <= shoulder[0] * (1 + 1e-12)) and np.all(sh >= shoulder[1] * (1 + 1e-12))
+                lwr_like = run_oracle(chain, dataclasses.replace(prm, bridge_kind=0), w, 8)
+                changed = np.any(np.abs(lwr_like["qdot"] - ref["qdot"]) > 1e-12, axis=1)
+                assert 0.05 < changed.mean() < 1.0                    # the second clamp really acted on part of the batch
+        finally:
+            e.close()
+    # invalid Powercube limits are refused
+    with pytest.raises(Exception):
+        Engine(chain, precision=64, params=dataclasses.replace(base, bridge_kind=BRIDGE_POWERCUBE, shoulder_vel=(0.0, 0.0)))

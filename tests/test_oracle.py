@@ -238,3 +238,27 @@ def test_operation_count_is_frozen_and_counts_the_oracle(lwr):
         c = opcount.count(ch, m, samples=3)
         assert (c.flops, c.transcendentals) == (flops, trans), ((n, m), c.flops, c.transcendentals)
     assert workloads.algorithmic_flops(7, 64) == workloads.ALGORITHMIC_OPS[(7, 32)][0] + 20 * 32
+
+
+def test_powercube_bridge_restatement_matches_batch(lwr):
+    """Row f4: the statement-for-statement Powercube set_vel of the reference-shaped loop (scripts/bridge:288-305)
+    equals the vectorised oracle, including the doubled leading ratio when the shoulder limit is not hit."""
+    import dataclasses
+    chain, cfg = lwr
+    prm = dataclasses.replace(batch.Params(), speed_scale=0.41, max_vel=0.3, bridge_kind=1, shoulder_vel=(0.05, -0.08))
+    w = workloads.random_batch(chain, 12, 3, seed=23)
+    seen = set()
+    for i in range(12):
+        q, goal, obst = w["q"][:, i], w["goal"][:, i], w["obst"][:, i, :]
+        ref = batch.step(chain, prm, q[None], goal[None], obst[None])
+        g = goal
+        g17 = [g[0], g[1], g[2], g[9], g[3], g[4], g[5], g[10], g[6], g[7], g[8], g[11], 0, 0, 0, 1, g[12]]
+        loop = refshape.ControlLoop(chain, prm, q, g17, obstacles=obst)
+        with redirect_stdout(io.StringIO()):
+            qd = loop.cycle()
+        assert np.allclose(qd, ref["qdot"][0], rtol=1e-9, atol=1e-12)
+        assert np.allclose(loop.last["cmd"], ref["qdot"][0], rtol=1e-9, atol=1e-12)
+        lead = np.max(np.abs(ref["qdot_mix"][0]))
+        first = ref["qdot_mix"][0, 0] * min(1.0, prm.max_vel / lead)
+        seen.add("shoulder" if (first > 0.05 or first < -0.08) else ("double" if lead > prm.max_vel else "none"))
+    assert {"shoulder", "double"} <= seen

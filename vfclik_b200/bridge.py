@@ -9,6 +9,19 @@ batched driver for millions of instances gets both from the fused cycle kernel i
 
 Simulation (``-s``): the reference wires the command to an external ``joint_sim`` process that integrates it
 (``scripts/bridge:136-139``); here ``JointSim`` is the explicit-Euler plant ``q += rate * cmd``.
+
+Back-ends (``construct_arm_bridge``, ``scripts/bridge:102-111``), selected by
+``config.arm_type``; only their simulation / YARP side exists here (the Player, iCub ``remote_controlboard`` and RSI
+device drivers are hardware I/O):
+
+* ``lwr``       offset command ``-q_cmded + q + qdot_lim``; **torso-joint sharing**: when ``config.torso_joints`` is not
+  empty the positions of those joints come from the *other* arm's plant (``config.torso_qin_portname`` connected to
+  ``/<arm_type>/<torso_instance>/joint_sim/qout``, ``scripts/bridge:140-147,174-178``);
+* ``powercube`` ports ``/qin`` ``/qcmd`` under the bridge prefix, leading clamp + shoulder-speed clamp
+  (``config.max_vel_shoulder_pos/neg``, ``scripts/bridge:288-305``, bug-compatible double ratio), command = qdot_lim;
+* ``icub``      ports ``/qin`` ``/qcmd`` ``/torso_cjoints:i`` ``/control_weights:o``: a torso_cjoints bottle of three ints
+  (de)activates torso joints by sending ``['j', w0..w9]`` joint weights to the vector field
+  (``scripts/bridge:437-445,470-506``), command = qdot_lim.
 """
 from __future__ import annotations
 
@@ -18,6 +31,8 @@ from . import ports as yarp
 from .command_mixer import CommandMixer
 from .ports import sendListPort
 from .runtime import ControlRuntime
+
+from .engine import BRIDGE_ICUB, BRIDGE_KINDS, BRIDGE_LWR, BRIDGE_POWERCUBE
 
 MODULE_NAME = "/bridge"
 COMMAND_PORTS = ("/vectorfieldcmd", "/nullcmd", "/jointcmd", "/mechanismcmd", "/xtra1cmd", "/xtra2cmd")
@@ -68,17 +83,52 @@ class BridgeModule:
         y.connect(self.encoders_port, base + "/vectorField", "/qIn")
         y.connect(self.encoders_port, base + "/nullspace", "/qin", necessary=False)
         y.connect(self.encoders_port, base + "/jpctrl", "/in")
-        # LWR_Bridge.open (scripts/bridge:127-150)
-        self.qin_port = y.create_yarp_port(cfg.qin_portname, strict=False)
-        self.qcmded_port = y.create_yarp_port(cfg.qcmded_portname, strict=False)
-        self.qcmd_port = y.create_yarp_port(cfg.qcmd_portname, input_port=False)
-        if sim:
-            y.connect(self.qcmd_port, base + "/joint_sim", "/qvin")
-            y.connect(self.qin_port, base + "/joint_sim", "/qout")
+        arm_type = str(getattr(cfg, "arm_type", "lwr")).lower()
+        if arm_type not in BRIDGE_KINDS:
+            print('warning: do not know class "%s"' % arm_type)            # scripts/bridge:110 (the reference then crashes)
+            raise ValueError("unknown config.arm_type %r" % arm_type)
+        self.kind = BRIDGE_KINDS[arm_type]
+        if runtime.params.bridge_kind != self.kind:
+            shoulder = (float(getattr(cfg, "max_vel_shoulder_pos", 0.0)), float(getattr(cfg, "max_vel_shoulder_neg", 0.0)))
+            runtime.set_params(bridge_kind=self.kind, shoulder_vel=shoulder)
+        self.torso_joints = list(getattr(cfg, "torso_joints", []) or [])
+        self.torso_qin_port = None
+        self.qcmded_port = None
+        if self.kind == BRIDGE_LWR:
+            # LWR_Bridge.open (scripts/bridge:127-155)
+            self.qin_port = y.create_yarp_port(cfg.qin_portname, strict=False)
+            self.qcmded_port = y.create_yarp_port(cfg.qcmded_portname, strict=False)
+            self.qcmd_port = y.create_yarp_port(cfg.qcmd_portname, input_port=False)
+            if sim:
+                y.connect(self.qcmd_port, base + "/joint_sim", "/qvin")
+                y.connect(self.qin_port, base + "/joint_sim", "/qout")
+                if self.torso_joints:
+                    print("Torso is another arm!")
+                    remote = "/" + arm_type + "/" + cfg.torso_instance + "/joint_sim"
+                    self.torso_qin_port = y.create_yarp_port(cfg.torso_qin_portname, strict=False)
+                    y.connect(self.torso_qin_port, remote, "/qout", necessary=False)
+                else:
+                    print("This is the torso!")
+            else:
+                y.connect(self.qcmd_port, base + "/robot", "/cmd")
+                y.connect(self.qcmded_port, base + "/robot", "/cmded")
+                y.connect(self.qin_port, base + "/robot", "/pos")
         else:
-            y.connect(self.qcmd_port, base + "/robot", "/cmd")
-            y.connect(self.qcmded_port, base + "/robot", "/cmded")
-            y.connect(self.qin_port, base + "/robot", "/pos")
+            if not sim:
+                raise NotImplementedError("the %s hardware driver (Player / remote_controlboard) is out of scope; use sim=True"
+                                          % arm_type)
+            # Powercube_Bridge.open / ICUB_Bridge.open, simulation branch (scripts/bridge:261-267,423-429)
+            self.qin_port = y.create_yarp_port("/qin", strict=False)
+            self.qcmd_port = y.create_yarp_port("/qcmd", input_port=False)
+            y.connect(self.qcmd_port, base + "/joint_sim", "/qvin", necessary=False)
+            y.connect(self.qin_port, base + "/joint_sim", "/qout", necessary=False)
+        if self.kind == BRIDGE_ICUB:
+            # scripts/bridge:343-355
+            self.icub_torso_cjoints = list(getattr(cfg, "icub_torso_cjoints", [True, True, True]))
+            self.icub_torso_num_joints = 3
+            self.torso_cjoints_port = y.create_yarp_port("/torso_cjoints:i")
+            self.control_weights_port = y.create_yarp_port("/control_weights:o", input_port=False)
+            y.connect(self.control_weights_port, base + "/vectorField", "/weight", necessary=False)
         self.mixer = CommandMixer(self.cmd_ports, self.weight_port, self.nJoints, GUARD_TIME, list(DEFAULT_WEIGHTS),
                                   engine=runtime.engine)
         self.max_vel = float(cfg.max_vel)
@@ -89,18 +139,58 @@ class BridgeModule:
 
     # LWR_Bridge.read_pos (scripts/bridge:163-180); non-blocking here (single-threaded runtime)
     def read_pos(self):
+        if self.kind == BRIDGE_ICUB:
+            # Added at VVV09 (scripts/bridge:437-445): torso joint (de)activation
+            bin_ = self.torso_cjoints_port.read(False)
+            if bin_:
+                print("Received a torso_joints bottle")
+                self.set_torso_cjoints([bin_.get(i).asInt() for i in range(bin_.size())])
         bottle = self.qin_port.read(False)
         if bottle and bottle.size() == self.nJoints:
             self.last_q = [bottle.get(i).asDouble() for i in range(self.nJoints)]
-        bottle = self.qcmded_port.read(False)
+        bottle = self.qcmded_port.read(False) if self.qcmded_port is not None else None
         if bottle is not None and bottle.size() == self.nJoints:
             self.last_qcmded = [bottle.get(i).asDouble() for i in range(self.nJoints)]
         elif self.last_qcmded == [] or self.sim:
             # no /cmded feedback (always the case in simulation): commanded == measured, so the command is qdot_lim
             self.last_qcmded = self.last_q
+        if self.torso_qin_port is not None:
+            # the torso belongs to the other arm's plant (scripts/bridge:174-178)
+            bottle = self.torso_qin_port.read(False)
+            if bottle:
+                torso_q = [bottle.get(i).asDouble() for i in range(bottle.size())]
+                for joint in self.torso_joints:
+                    if joint < len(torso_q):
+                        self.last_q[joint] = torso_q[joint]
         return self.last_q
 
-    # LWR_Bridge.set_vel (scripts/bridge:182-210): clamp + command forming run in the vfk_set_vel kernel
+    # ICUB_Bridge.set_torso_cjoints (scripts/bridge:470-506)
+    def set_torso_cjoints(self, cjoints):
+        num_weights = 10      # the reference hard-codes the iCub arm+torso size (scripts/bridge:473)
+        weights = [1.0] * num_weights
+        if len(cjoints) == self.icub_torso_num_joints:
+            for i in range(self.icub_torso_num_joints):
+                if cjoints[i] == 1:
+                    self.icub_torso_cjoints[i] = True
+                    weights[i] = 1.0
+                else:
+                    self.icub_torso_cjoints[i] = False
+                    weights[i] = 0.0
+            # tell the Vector Field about the new weights
+            bout = self.control_weights_port.prepare()
+            bout.clear()
+            bout.addString("j")
+            for w in weights:
+                bout.addDouble(w)
+            print("Sending weights: ")
+            print(bout.toString())
+            self.control_weights_port.write(True)
+            return weights
+        print("WARNING: set_torso_cjoints received a vector of controlled joints of a wrong length")
+        return None
+
+    # LWR_Bridge / Powercube_Bridge / ICUB_Bridge .set_vel (scripts/bridge:182-210,288-312,507-530): clamp(s) + command
+    # forming run in the vfk_set_vel kernel, which follows params.bridge_kind
     def set_vel(self, qdot):
         if len(qdot) != self.nJoints or self.last_qcmded == []:
             print('got %d velocities, expected %d. Ignoring input' % (len(qdot), self.nJoints))

@@ -118,6 +118,10 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     c.obst_order = (T)p.obst_order;
     c.ns_mode = p.ns_mode;
     c.direct_control = p.direct_control < 0 ? (all_zero ? 1 : 0) : (p.direct_control ? 1 : 0);
+    if (p.bridge_kind != VFK_BRIDGE_LWR) c.direct_control = 1;          // Powercube / iCub command qdot_lim itself
+    c.shoulder_clamp = p.bridge_kind == VFK_BRIDGE_POWERCUBE;
+    c.shoulder_pos = (T)p.shoulder_vel[0];
+    c.shoulder_neg = (T)p.shoulder_vel[1];
     c.integrate = p.integrate ? 1 : 0;
     c.unit_weights = unit ? 1 : 0;
     c.share_factor = (unit && p.ns_lambda == p.ik_lambda) ? 1 : 0;
@@ -168,6 +172,10 @@ static int check_params(vfk_ctx* h, const vfk_params* p) {
         return fail(h, VFK_ERR_UNSUPPORTED, "VFK_NS_CONTROL needs a 1-D nullspace (n_joints = 7), got %d joints",
                     h->chain.n_joints);
     if (!(p->max_vel >= 0)) return fail(h, VFK_ERR_INVALID, "max_vel must be >= 0");
+    if (p->bridge_kind < VFK_BRIDGE_LWR || p->bridge_kind > VFK_BRIDGE_ICUB)
+        return fail(h, VFK_ERR_INVALID, "bridge_kind must be VFK_BRIDGE_LWR, _POWERCUBE or _ICUB");
+    if (p->bridge_kind == VFK_BRIDGE_POWERCUBE && !(p->shoulder_vel[0] > 0 && p->shoulder_vel[1] < 0))
+        return fail(h, VFK_ERR_INVALID, "Powercube back-end needs shoulder_vel[0] > 0 and shoulder_vel[1] < 0");
     if (!(p->obst_order > 0)) return fail(h, VFK_ERR_INVALID, "obst_order must be > 0");
     return VFK_OK;
 }
@@ -323,12 +331,17 @@ extern "C" int vfk_set_vel(vfk_handle h, const void* qdot, const void* q, const 
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned grid = (unsigned)((n + 255) / 256);
+    const vfk_params& p = h->params;
+    const int shoulder = p.bridge_kind == VFK_BRIDGE_POWERCUBE;
+    if (p.bridge_kind != VFK_BRIDGE_LWR) direct_control = 1;
     if (h->precision == 32)
         vfk_set_vel_kernel<float><<<grid, 256, 0, st>>>((const float*)qdot, (const float*)q, (const float*)q_cmded, (float*)cmd_out,
-                                                       (float*)qdot_lim_out, (float)max_vel, direct_control, n_channels, n);
+                                                       (float*)qdot_lim_out, (float)max_vel, direct_control, shoulder,
+                                                       (float)p.shoulder_vel[0], (float)p.shoulder_vel[1], n_channels, n);
     else
         vfk_set_vel_kernel<double><<<grid, 256, 0, st>>>((const double*)qdot, (const double*)q, (const double*)q_cmded,
-                                                        (double*)cmd_out, (double*)qdot_lim_out, max_vel, direct_control, n_channels, n);
+                                                        (double*)cmd_out, (double*)qdot_lim_out, max_vel, direct_control, shoulder,
+                                                        p.shoulder_vel[0], p.shoulder_vel[1], n_channels, n);
     VFK_CUDA(h, cudaGetLastError());
     return 1;
 }

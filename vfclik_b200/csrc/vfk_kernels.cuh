@@ -62,7 +62,9 @@ struct KConst {
     int32_t xtwist_mask;       // bit j set: tip j's rotation is RotX(alpha) (every DH-specified chain), alpha in tip[j][4], [7]
     int32_t tipident_mask;     // bit j set: tip j's rotation is the identity
     int32_t ns_mode;
-    int32_t direct_control;    // resolved 0/1
+    int32_t direct_control;    // resolved 0/1 (1 for the Powercube / iCub back-ends: they command qdot_lim itself)
+    int32_t shoulder_clamp;    // Powercube_Bridge.set_vel's second clamp on joint 0 (scripts/bridge:295-303)
+    T shoulder_pos, shoulder_neg;
     int32_t integrate;
     int32_t unit_weights;      // w_task and w_joint are all ones
     int32_t share_factor;      // nullspace can reuse the IK Cholesky factor
@@ -785,6 +787,15 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         if (nan) flags |= 4;
         T ratio = T(1);
         if (lead > c.max_vel) { ratio = Prec<T>::div(c.max_vel, lead); flags |= 8; }
+        if (!LEAN && c.shoulder_clamp) {
+            // the reference keeps one `ratio` variable for both clamps: without a shoulder hit the leading ratio is
+            // applied twice (bug-compatible, see include/vfk.h)
+            const T sh = mix[0] * ratio;
+            T r2 = ratio;
+            if (sh > c.shoulder_pos) r2 = Prec<T>::fabs_(Prec<T>::div(c.shoulder_pos, sh));
+            else if (sh < c.shoulder_neg) r2 = Prec<T>::fabs_(Prec<T>::div(c.shoulder_neg, sh));
+            ratio *= r2;
+        }
 
         if (last && active) {
             if (!LEAN && a.qdot_vf) {
@@ -907,13 +918,21 @@ vfk_mix_kernel(const __grid_constant__ MixArgs m, T* __restrict__ out, int32_t* 
 template <typename T>
 __global__ void __launch_bounds__(256)
 vfk_set_vel_kernel(const T* __restrict__ qdot, const T* __restrict__ q, const T* __restrict__ q_cmded, T* __restrict__ cmd,
-                   T* __restrict__ qdot_lim, T max_vel, int direct, int n_channels, int64_t n) {
+                   T* __restrict__ qdot_lim, T max_vel, int direct, int shoulder_clamp, T shoulder_pos, T shoulder_neg,
+                   int n_channels, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const int64_t base = (i >> 5) * (n_channels * 32) + (i & 31);
     T lead = T(0);
     for (int c = 0; c < n_channels; ++c) lead = Prec<T>::fmax_(lead, Prec<T>::fabs_(qdot[base + c * 32]));
-    const T ratio = lead > max_vel ? max_vel / lead : T(1);
+    T ratio = lead > max_vel ? max_vel / lead : T(1);
+    if (shoulder_clamp) {                      // Powercube_Bridge.set_vel (scripts/bridge:295-303), see the cycle kernel
+        const T sh = qdot[base] * ratio;
+        T r2 = ratio;
+        if (sh > shoulder_pos) r2 = Prec<T>::fabs_(shoulder_pos / sh);
+        else if (sh < shoulder_neg) r2 = Prec<T>::fabs_(shoulder_neg / sh);
+        ratio *= r2;
+    }
     for (int c = 0; c < n_channels; ++c) {
         const T v = qdot[base + c * 32] * ratio;
         if (qdot_lim) qdot_lim[base + c * 32] = v;

@@ -33,6 +33,7 @@ constexpr int64_t kCoopMaxInstances = 4096;      // <= 128 tiles: 1024 cooperati
 template <typename T>
 static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
     return c.tool_identity && c.unit_weights && c.share_factor && c.ns_mode == VFK_NS_PROJECTOR && !c.need_jp && !b->ns_in &&
+           !c.shoulder_clamp &&
            !b->jp_ref && !b->q_cmded && !b->ext_cmd[0] && !b->ext_cmd[1] && !b->ext_cmd[2] && !b->qdot_vf && !b->qdot_ns &&
            !b->qdot_jp && !b->cmd && !b->pose && !b->twist && !b->flags && !(b->aux && b->n_aux > 0) && b->qdot && !getenv("VFK_NO_LEAN");
 }

@@ -21,6 +21,10 @@ from . import _lib
 from ._lib import (BuffersC, ParamsC, VfkError, NS_CONTROL, NS_OFF, NS_PROJECTOR)  # noqa: F401
 
 
+BRIDGE_LWR, BRIDGE_POWERCUBE, BRIDGE_ICUB = 0, 1, 2
+BRIDGE_KINDS = {"lwr": BRIDGE_LWR, "powercube": BRIDGE_POWERCUBE, "icub": BRIDGE_ICUB}   # config.arm_type (scripts/bridge:102-111)
+
+
 @dataclasses.dataclass
 class Params:
     """Per-robot constants, mirror of ``vfk_params`` (include/vfk.h)."""
@@ -48,6 +52,8 @@ class Params:
     ns_mode: int = NS_PROJECTOR
     direct_control: int = -1
     integrate: int = 1
+    bridge_kind: int = 0                                   # BRIDGE_LWR / BRIDGE_POWERCUBE / BRIDGE_ICUB
+    shoulder_vel: Sequence[float] = (0.0, 0.0)             # Powercube: config.max_vel_shoulder_pos, max_vel_shoulder_neg
 
     @staticmethod
     def from_config(config, **over) -> "Params":
@@ -60,6 +66,11 @@ class Params:
                 kw[key] = float(getattr(config, attr))
         if hasattr(config, "initial_joint_pos"):
             kw["jp_ref"] = tuple(float(v) for v in config.initial_joint_pos)
+        kind = BRIDGE_KINDS.get(str(getattr(config, "arm_type", "lwr")).lower())
+        if kind is not None:
+            kw["bridge_kind"] = kind
+        if hasattr(config, "max_vel_shoulder_pos") and hasattr(config, "max_vel_shoulder_neg"):
+            kw["shoulder_vel"] = (float(config.max_vel_shoulder_pos), float(config.max_vel_shoulder_neg))
         kw.update(over)
         return Params(**kw)
 
@@ -86,6 +97,8 @@ class Params:
         for k in range(4):
             p.ns_control[k] = float(self.ns_control[k])
         p.ns_mode, p.direct_control, p.integrate = int(self.ns_mode), int(self.direct_control), int(self.integrate)
+        p.bridge_kind = int(self.bridge_kind)
+        p.shoulder_vel[0], p.shoulder_vel[1] = float(self.shoulder_vel[0]), float(self.shoulder_vel[1])
         return p
 
 
