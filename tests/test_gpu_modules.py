@@ -357,3 +357,19 @@ def test_bridge_backends_powercube_icub_and_torso_sharing(lwr, built_lib, fresh_
         assert np.allclose(app.bridge.last_q[2:], cfg.initial_joint_pos[2:])   # the rest: this arm's own joint_sim
     finally:
         app.close()
+
+
+def test_module_programs_run_standalone(built_lib):
+    """`vf -c <config> -n <ns>`, `nullspace ...`, `joint_p_controller ...`, `bridge ... -s` (scripts/vfclik:88-105) each start
+    on their own runtime, poll for --cycles iterations and exit 0."""
+    import os
+    import subprocess
+    import sys
+    from vfclik_b200.config import PACKAGE_CONFIG_DIR, config_filename
+    cfgfile = config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for mod, extra in (("vf", []), ("nullspace", []), ("joint_p_controller", []), ("monitor_distance", []), ("bridge", ["-s"])):
+        r = subprocess.run([sys.executable, "-m", "vfclik_b200." + mod, "-c", cfgfile, "-n", "/9", "--cycles", "3", "--no_sleep"] + extra,
+                           cwd=root, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (mod, r.stdout[-500:], r.stderr[-1500:])
+        assert "iterations: 3" in r.stdout, (mod, r.stdout[-500:])

@@ -137,3 +137,27 @@ def test_stats_reduction_world_size_2_gloo(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0].split()
     assert [float(x) for x in line[1:]] == [10000.0, 2.0, 2e-9, 4.0]
+
+
+def test_module_command_lines_follow_the_launcher_contract(tmp_path, capsys):
+    """scripts/vfclik:88-105 starts every module as `<module> -c <config> -n <namespace>` (bridge adds -s); the parser
+    keeps arcospyu's ConfigFileParser surface: .parser.add_option(...) and .get_all() -> (options, args, config)."""
+    import importlib
+    from vfclik_b200.config import PACKAGE_CONFIG_DIR, config_filename
+    from vfclik_b200.module_cli import ConfigFileParser
+    cfgfile = config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right")
+    cp = ConfigFileParser(["bridge", "-c", cfgfile, "-s", "-n", "/7"])
+    cp.parser.add_option("-s", "--simulation", action="store_true", dest="sim", default=False, help="Simulation")
+    options, args, config = cp.get_all()
+    assert options.namespace == "/7" and options.sim is True and args == [] and config.nJoints == 7
+    assert ConfigFileParser(["vf", "-c", cfgfile]).get_all()[0].namespace == ""
+    with pytest.raises(SystemExit):
+        ConfigFileParser(["vf", "-n", "/0"]).get_all()               # no config file
+    with pytest.raises(FileNotFoundError):
+        ConfigFileParser(["vf", "-c", str(tmp_path / "missing.py")]).get_all()
+    for mod in ("vf", "nullspace", "joint_p_controller", "bridge", "object_feeder", "monitor_distance", "launcher"):
+        assert callable(importlib.import_module("vfclik_b200." + mod).main), mod
+    # a module that needs no GPU runs stand-alone: the feeder publishes config.initial_vf_pose and stops after --cycles
+    from vfclik_b200 import object_feeder
+    assert object_feeder.main(["object_feeder", "-c", cfgfile, "-n", "/7", "--cycles", "2", "--no_sleep"]) == 0
+    assert "iterations: 2" in capsys.readouterr().out

@@ -236,3 +236,20 @@ class BridgeModule:
 
     def close(self):
         self.yarp_ctrl.close()
+
+
+def main(argv=None):
+    """``bridge -c <config> [-s] -n <namespace>`` (``scripts/vfclik:100-105``, ``scripts/bridge:58-66``)."""
+    import sys
+    from .module_cli import run_module
+
+    def build(rt, opt, cfg):
+        mods = [JointSim(cfg, opt.namespace)] if opt.sim else []
+        return mods + [BridgeModule(rt, opt.namespace, sim=opt.sim)]
+    sim_opt = (("-s", "--simulation"), dict(action="store_true", dest="sim", default=False, help="Simulation"))
+    return run_module(sys.argv if argv is None else argv, build, extra_options=[sim_opt])
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

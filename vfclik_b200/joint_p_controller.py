@@ -55,3 +55,15 @@ class JointPControllerModule:
 
     def close(self):
         self.yarp_ctrl.close()
+
+
+def main(argv=None):
+    """``joint_p_controller -c <config> -n <namespace>`` (``scripts/vfclik:92``)."""
+    import sys
+    from .module_cli import run_module
+    return run_module(sys.argv if argv is None else argv, lambda rt, opt, cfg: [JointPControllerModule(rt, opt.namespace)])
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

@@ -110,3 +110,15 @@ class MonitorDistanceModule:
 
     def close(self):
         self.yarp_ctrl.close()
+
+
+def main(argv=None):
+    """``monitor_distance -c <config> -n <namespace>`` (``scripts/vfclik:91``)."""
+    import sys
+    from .module_cli import run_module
+    return run_module(sys.argv if argv is None else argv, lambda rt, opt, cfg: [MonitorDistanceModule(rt, opt.namespace)])
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

@@ -56,3 +56,15 @@ class NullspaceModule:
 
     def close(self):
         self.yarp_ctrl.close()
+
+
+def main(argv=None):
+    """``nullspace -c <config> -n <namespace>`` (``scripts/vfclik:96-98``)."""
+    import sys
+    from .module_cli import run_module
+    return run_module(sys.argv if argv is None else argv, lambda rt, opt, cfg: [NullspaceModule(rt, opt.namespace)])
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

@@ -144,3 +144,16 @@ class ObjectFeederModule:
 
     def close(self):
         self.yarp_ctrl.close()
+
+
+def main(argv=None):
+    """``object_feeder -c <config> -n <namespace>`` (``scripts/vfclik:90``)."""
+    import sys
+    from .module_cli import run_module
+    return run_module(sys.argv if argv is None else argv, lambda rt, opt, cfg: [ObjectFeederModule(cfg, opt.namespace)],
+                      needs_runtime=False)
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

@@ -134,3 +134,15 @@ class VectorFieldModule:
 
     def close(self):
         self.yarp_ctrl.close()
+
+
+def main(argv=None):
+    """``vf -c <config> -n <namespace>`` (``scripts/vfclik:89``)."""
+    import sys
+    from .module_cli import run_module
+    return run_module(sys.argv if argv is None else argv, lambda rt, opt, cfg: [VectorFieldModule(rt, opt.namespace)])
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())
