@@ -557,3 +557,42 @@ def test_powercube_and_icub_bridge_backends(lwr, built_lib, precision):
     # invalid Powercube limits are refused
     with pytest.raises(Exception):
         Engine(chain, precision=64, params=dataclasses.replace(base, bridge_kind=BRIDGE_POWERCUBE, shoulder_vel=(0.0, 0.0)))
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_host_session_direct_host_io(eng, lwr, precision, monkeypatch):
+    """Page-locked caller buffers + a tile-aligned batch: vfk_session_cycle runs ONE kernel that reads q from host memory
+    (TMA bulk copies of the dense rows) and writes qdot back itself.  Results are bit-identical to the device path and to
+    the chunked copy pipeline (VFK_SESSION_DIRECT=0); pageable buffers and ragged batches fall back to the pipeline."""
+    import torch
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(precision)
+    dt, tdt = (np.float32, torch.float32) if precision == 32 else (np.float64, torch.float64)
+    n, M = 70_016, 12                                               # 2188 tiles: not a multiple of the warp count
+    w = workloads.random_batch(chain, n, M, seed=77, dtype=dt)
+    dev = run_gpu(e, w, M, k=3, outputs=("qdot", "flags"))
+    s = e.session(n, M)
+    try:
+        s.set_goal(w["goal"]); s.set_obstacles(w["obst"])
+        q_pin = torch.from_numpy(w["q"]).pin_memory()
+        qd = torch.zeros((7, n), dtype=tdt).pin_memory()
+        qo = torch.zeros((7, n), dtype=tdt).pin_memory()
+        fl = torch.zeros(n, dtype=torch.int32).pin_memory()
+        assert s.cycle(q_in=q_pin.numpy(), k_cycles=3, qdot_out=qd.numpy()) == 1                       # the cycle kernel only
+        assert np.array_equal(qd.numpy().T, dev["qdot"])
+        qd.zero_()
+        assert s.cycle(q_in=q_pin.numpy(), k_cycles=3, qdot_out=qd.numpy(), q_out=qo.numpy(), flags_out=fl.numpy()) == 2
+        assert np.array_equal(qd.numpy().T, dev["qdot"]) and np.array_equal(qo.numpy().T, dev["q"])
+        assert np.array_equal(fl.numpy(), dev["flags"])
+        assert np.array_equal(q_pin.numpy(), w["q"])                                                 # the caller's q is read-only
+        # pageable output -> copy pipeline, same numbers
+        qd_page = np.zeros((7, n), dtype=dt)
+        assert s.cycle(q_in=q_pin.numpy(), k_cycles=3, qdot_out=qd_page) > 1
+        assert np.array_equal(qd_page.T, dev["qdot"])
+        monkeypatch.setenv("VFK_SESSION_DIRECT", "0")
+        qd.zero_()
+        assert s.cycle(q_in=q_pin.numpy(), k_cycles=3, qdot_out=qd.numpy()) > 1
+        assert np.array_equal(qd.numpy().T, dev["qdot"])
+    finally:
+        s.close()

@@ -442,6 +442,9 @@ struct vfk_session_s {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Smallest batch for which vfk_session_cycle reads / writes page-locked caller buffers directly from the kernel.
+constexpr int64_t kDirectMinInstances = 1024;
+
 extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_obst_ext, vfk_session* out) {
     if (!h || !out) return fail(h, VFK_ERR_INVALID, "vfk_session_create: null argument");
     *out = nullptr;
@@ -701,6 +704,58 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
         if (!pinned(q_in)) { memcpy(pin_q, q_in, blk); src_q = pin_q; }
     }
     const bool d_qd = qdot_out && pinned(qdot_out), d_qo = q_out && pinned(q_out), d_fl = flags_out && pinned(flags_out);
+
+    // Direct host I/O (zero-copy): when the caller's q_in / qdot_out are page-locked and the batch is tile-aligned, ONE
+    // kernel launch reads the q tiles straight from host memory through TMA (N x 128 B bulk copies per tile, prefetched one
+    // tile ahead like every other stream of the kernel) and stores qdot straight back with coalesced 128 B writes: no
+    // staging copies, no layout kernels, and the PCIe reads, the arithmetic and the PCIe writes overlap at tile
+    // granularity instead of chunk granularity.  Measured on B200, 1 M instances (scripts/e2e_direct.sh): 0.79 ms per call
+    // against 0.91 ms for the chunked copy pipeline below; hybrids (kernel reads + DMA writes 1.04 ms, DMA reads + kernel
+    // writes 0.83 ms) lose to both-direct.  SM-issued PCIe traffic runs at 51 / 52 GB/s one way whatever the request size
+    // and ~37 GB/s each way when both directions are busy (scripts/pcie_probe.cu), which is where this path sits.
+    // VFK_SESSION_DIRECT=0 selects the copy pipeline.
+    auto mapped = [](const void* p) -> void* {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    };
+    const char* de = getenv("VFK_SESSION_DIRECT");
+    const bool direct_ok = !(de && atoi(de) == 0) && q_in && s->n % 32 == 0 && s->n >= kDirectMinInstances;
+    void* dq = direct_ok ? mapped(q_in) : nullptr;
+    void* dqd = (direct_ok && qdot_out) ? mapped(qdot_out) : nullptr;
+    if (dq && (!qdot_out || dqd) && ((uintptr_t)dq % 16 == 0) && ((uintptr_t)dqd % 16 == 0)) {
+        vfk_buffers b = s->b;
+        b.jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
+        b.ns_in = s->have_ns_in ? s->d_ns_in : nullptr;
+        if (!flags_out) b.flags = nullptr;
+        if (!s->en_vf) b.qdot_vf = nullptr;
+        if (!s->en_ns) b.qdot_ns = nullptr;
+        if (!s->en_jp) b.qdot_jp = nullptr;
+        if (!s->en_cmd) b.cmd = nullptr;
+        if (!s->en_pose) b.pose = nullptr;
+        if (!s->en_twist) b.twist = nullptr;
+        cudaStream_t st = s->pipe[1];
+        h->io.q_src = dq; h->io.q_src_ld = s->n;
+        h->io.qdot = dqd; h->io.qdot_ld = dqd ? s->n : 0;
+        int rc = vfk_step(h, &b, s->n, s->n_obst, k_cycles, st);
+        h->io.q_src = nullptr; h->io.qdot = nullptr; h->io.q_src_ld = h->io.qdot_ld = 0;
+        if (rc < 0) return rc;
+        int launches = rc;
+        char* dst_qo = q_out ? (d_qo ? (char*)q_out : pin_qo) : nullptr;
+        char* dst_fl = flags_out ? (d_fl ? (char*)flags_out : pin_fl) : nullptr;
+        if (dst_qo) {
+            char* stage_qo = (char*)s->stage_out;
+            if ((rc = pack_dispatch(h, stage_qo, b.q, s->N, 1, s->n, true, st, s->n)) < 0) return rc;
+            launches += rc;
+            VFK_CUDA(h, cudaMemcpyAsync(dst_qo, stage_qo, blk, cudaMemcpyDeviceToHost, st));
+        }
+        if (dst_fl) VFK_CUDA(h, cudaMemcpyAsync(dst_fl, s->b.flags, (size_t)s->n * 4, cudaMemcpyDeviceToHost, st));
+        VFK_CUDA(h, cudaStreamSynchronize(st));
+        if (q_out && !d_qo) memcpy(q_out, pin_qo, blk);
+        if (flags_out && !d_fl) memcpy(flags_out, pin_fl, (size_t)s->n * 4);
+        s->launches = launches;
+        return launches;
+    }
     char* dst_qd = qdot_out ? (d_qd ? (char*)qdot_out : pin_qd) : nullptr;
     char* dst_qo = q_out ? (d_qo ? (char*)q_out : pin_qo) : nullptr;
     char* dst_fl = flags_out ? (d_fl ? (char*)flags_out : pin_fl) : nullptr;

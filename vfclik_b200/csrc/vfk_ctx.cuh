@@ -18,6 +18,8 @@ struct vfk_ctx {
     int sm_count;
     int pattern;                // 0: GenericPattern, 1: LwrPattern (structure of the canonical chain)
     uint64_t generation;        // bumped by vfk_set_params: captured CUDA graphs bake the constants in
+    // direct host I/O request of the session (consumed by the next cycle launch; see KArgs::q_src)
+    struct { const void* q_src; int64_t q_src_ld; void* qdot; int64_t qdot_ld; } io;
     vfk::KConst<float> cf;
     vfk::KConst<double> cd;
     std::string err;

@@ -94,6 +94,12 @@ struct KArgs {
     T* pose;
     T* twist;                  // [6] commanded tool twist (velPos, velRot of scripts/vf:346-347)
     int32_t* flags;
+    // Direct host I/O of the host-buffer session (zero-copy): when q_src is set the q tile is read from a DENSE [N][q_src_ld]
+    // array (page-locked host memory mapped into the device address space) instead of the blocked `q`; when qdot_ld is
+    // non-zero `qdot` is such a dense array too.  The integrated q still goes to the blocked `q`.
+    const T* q_src;
+    int64_t q_src_ld;
+    int64_t qdot_ld;
     int64_t n;
     int32_t n_obst;
     int32_t n_chunks;          // ceil(n_obst / kChunk)
@@ -394,7 +400,13 @@ __device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile, int bu
     if (lane == 0) {
         unsigned char* dst = region + (size_t)a.n_stages * WS::kStage + (size_t)buf * WS::kQg;
         mbar_arrive_expect_tx(&bars[kMaxStages + buf], WS::kQg);
-        bulk_g2s(dst, a.q + tile * (N * 32), N * WS::kQgRow, &bars[kMaxStages + buf]);
+        if (a.q_src) {
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                bulk_g2s(dst + j * WS::kQgRow, a.q_src + j * a.q_src_ld + (tile << 5), WS::kQgRow, &bars[kMaxStages + buf]);
+        } else {
+            bulk_g2s(dst, a.q + tile * (N * 32), N * WS::kQgRow, &bars[kMaxStages + buf]);
+        }
         bulk_g2s(dst + N * WS::kQgRow, a.goal + tile * (13 * 32), 13 * WS::kQgRow, &bars[kMaxStages + buf]);
     }
 }
@@ -811,8 +823,10 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 for (int j = 0; j < N; ++j) a.qdot_jp[tN + j * 32] = qd_jp[j];
             }
             if (LEAN || a.qdot) {
+                T* o = a.qdot_ld ? a.qdot + (tile << 5) + slot : a.qdot + tN;
+                const int64_t rs = a.qdot_ld ? a.qdot_ld : 32;
 #pragma unroll
-                for (int j = 0; j < N; ++j) a.qdot[tN + j * 32] = mix[j] * ratio;
+                for (int j = 0; j < N; ++j) o[j * rs] = mix[j] * ratio;
             }
             if (!LEAN && a.cmd) {
 #pragma unroll

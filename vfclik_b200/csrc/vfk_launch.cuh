@@ -62,6 +62,8 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.pose = static_cast<T*>(b->pose);
     a.twist = static_cast<T*>(b->twist);
     a.flags = b->flags;
+    if (h->io.q_src) { a.q_src = static_cast<const T*>(h->io.q_src); a.q_src_ld = h->io.q_src_ld; }
+    if (h->io.qdot) { a.qdot = static_cast<T*>(h->io.qdot); a.qdot_ld = h->io.qdot_ld; }
     a.n = n;
     a.n_obst = n_obst;
     a.k_cycles = k_cycles;
