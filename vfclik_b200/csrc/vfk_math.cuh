@@ -76,11 +76,40 @@ template <> struct Prec<float> {
     static constexpr bool kSeriesAsin = true;
 };
 
+// FP64 reciprocal / reciprocal square root / square root / division without libdevice's special-case branches: the
+// ~2^-20 hardware seed (MUFU.RCP64H / RSQ64H, PTX rcp/rsqrt.approx.ftz.f64) refined by one third-order step (error
+// ~e0^3 < 2^-58) and, for the compound results, one residual correction -- a few ulp at most, straight-line code.  IEEE
+// `/`, sqrt() and rsqrt() each bring a fast path of the same length PLUS a guarded slow-path call, and the kernel has ~40
+// such sites: 63 CALLs, 119 BSSY/BSYNC pairs and ~500 argument moves in the FP64 cycle kernel before this.
+// Domain: rcp / div / sqrt clamp the magnitude into [1e-300, inf) first, so 0 behaves like 1e-300 (1/0 -> 1e300,
+// sqrt(0) -> 0 exactly); rsqrt_pos wants x > 0 and normal -- its call sites carry a 1e-300 bias or guard zero themselves.
+__device__ __forceinline__ double rcp_seed(double x) { double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+__device__ __forceinline__ double rsqrt_seed(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y; }
+__device__ __forceinline__ double rcp_fast(double x) {
+    x = copysign(fabs(x) > 1e-300 ? fabs(x) : 1e-300, x);
+    const double y = rcp_seed(x);
+    const double e = fma(-x, y, 1.0);                 // 1 - x y
+    return fma(y, fma(e, e, e), y);                   // y (1 + e + e^2)
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {          // x > 0 and normal (call sites bias or guard)
+    const double y = rsqrt_seed(x);
+    const double e = fma(-(x * y), y, 1.0);           // 1 - x y^2
+    return fma(y * e, fma(0.375, e, 0.5), y);         // y (1 + e/2 + 3 e^2/8)
+}
+
 template <> struct Prec<double> {
-    static __device__ __forceinline__ double rsqrt_pos(double x) { return rsqrt(x); }      // <= 2 ulp, no IEEE div + sqrt
-    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
-    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
-    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+    static __device__ __forceinline__ double rsqrt_pos(double x) { return rsqrt_fast(x); }
+    static __device__ __forceinline__ double sqrt_(double x) {
+        const double y = rsqrt_fast(x > 1e-300 ? x : 1e-300);
+        const double s = x * y;
+        return fma(fma(-s, s, x), 0.5 * y, s);        // one Newton correction on the product
+    }
+    static __device__ __forceinline__ double rcp(double x) { return rcp_fast(x); }
+    static __device__ __forceinline__ double div(double a, double b) {
+        const double y = rcp_fast(b);
+        const double q = a * y;
+        return fma(fma(-b, q, a), y, q);      // q + (a - b q) y  (b = 0: a - 0 q = a, q + a * 1e300: still huge)
+    }
     // x^y for x >= 0, y > 0.  Decay orders are small integers in practice (20, 5, 3, 2: scripts/object_feeder:274-333):
     // square-and-multiply costs ~2 log2(y) DMULs instead of libdevice pow's ~100 instructions and is exact to a few ulp.
     static __device__ __forceinline__ double pow_pos(double x, double y) {
@@ -97,8 +126,9 @@ template <> struct Prec<double> {
     }
     static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
     static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
-    static __device__ __forceinline__ double fmin_(double a, double b) { return fmin(a, b); }
-    static __device__ __forceinline__ double fmax_(double a, double b) { return fmax(a, b); }
+    // compare-and-select: fmin() / fmax() add NaN-propagation fix-ups (DSETP + 2 SEL + LOP3) the call sites do not need
+    static __device__ __forceinline__ double fmin_(double a, double b) { return a < b ? a : b; }
+    static __device__ __forceinline__ double fmax_(double a, double b) { return a > b ? a : b; }
     static __device__ __forceinline__ double fabs_(double a) { return fabs(a); }
     static __device__ __forceinline__ double big() { return 1e150; }
     static __device__ __forceinline__ double tiny() { return 1e-300; }
