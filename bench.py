@@ -242,7 +242,9 @@ class _StdoutToStderr:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=300,
+                    help="timed launches (default 300 = a ~35 ms burst, like the copy that measured the HBM peak; runs of >= 1000 "
+                         "launches draw enough power for sw_power_cap to lower the SM clock on some boxes, see DESIGN.md)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
@@ -373,7 +375,7 @@ def main():
         io_bytes = N * n_inst * elem
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                "steps": e2e_steps, "ms_per_step": 1e3 * float(e2e_s.item()) / e2e_steps, "gpu_launches": e2e_launches,
-               "api": "vfk_session_cycle (pinned host q in, pinned host qdot out; scene resident; chunk-pipelined copies)"}
+               "api": "vfk_session_cycle (pinned host q in, pinned host qdot out; scene resident; direct host I/O: the cycle kernel reads q from and writes qdot to the host buffers over PCIe)"}
         sess.close()
     else:
         e2e = {"value": None, "unit": UNIT, "note": "not measured for the device-generated config 4 / 5 shards"}
