@@ -161,3 +161,62 @@ def test_module_command_lines_follow_the_launcher_contract(tmp_path, capsys):
     from vfclik_b200 import object_feeder
     assert object_feeder.main(["object_feeder", "-c", cfgfile, "-n", "/7", "--cycles", "2", "--no_sleep"]) == 0
     assert "iterations: 2" in capsys.readouterr().out
+
+
+def test_object_feeder_parses_the_reference_example_bottles(capsys):
+    """The only input fixtures the reference ships are the example bottles of old/README.old:69-78; fed verbatim through the
+    feeder they must come out as the field messages of scripts/object_feeder:229-354 (ids, forces, vfl types, layouts)."""
+    from vfclik_b200 import ports as yarp
+    from vfclik_b200.config import PACKAGE_CONFIG_DIR, config_filename, load_config
+    from vfclik_b200.object_feeder import ObjectFeederModule
+    yarp.Network.reset()
+    cfg = load_config(config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right"))
+    del cfg.initial_vf_pose                                   # no automatic first goal: the examples set it
+    fd = ObjectFeederModule(cfg, "/t")
+    sink = yarp.BufferedPortBottle(); sink.open("/t/sink"); sink.setStrict(True)
+    yarp.Network.connect(fd.paramPort.getName(), "/t/sink")
+    src = yarp.BufferedPortBottle(); src.open("/t/src")
+    yarp.Network.connect("/t/src", fd.objectPort.getName())
+
+    def send(*items):
+        yarp.write_bottle_lists(src, list(items), strict=True)
+        assert fd.update()
+        out = []
+        while True:
+            b = sink.read(False)
+            if b is None:
+                return out
+            row = [b.get(0).asString(), b.get(1).asInt()]
+            if row[0] == "add":
+                pl = b.get(4).asList()
+                row += [b.get(2).asDouble(), b.get(3).asInt(), [pl.get(i).asDouble() for i in range(pl.size())]]
+            out.append(row)
+
+    try:
+        # an obstacle before any goal is stored but not sent (scripts/object_feeder:216-219)
+        obst = [1, 0, 0, 0.0, 0, 1, 0, -0.4, 0, 0, 1, 0.4, 0, 0, 0, 1, 0.05, 20]               # old/README.old:75
+        assert send("set", "ObstacleP", 0, [float(v) for v in obst]) == []
+        assert "waiting for a goal" in capsys.readouterr().out
+        goal = [0, 1, 0, 0, -1, 0, 0, 0.3, 0, 0, 1, 1.1, 0, 0, 0, 1, 0.1]                      # old/README.old:69
+        msgs = send("set", "goal", [float(v) for v in goal])
+        assert msgs[0] == ["add", 1, 1.0, 1, [float(v) for v in goal]]
+        assert msgs[1:3] == [["remove", 2], ["remove", 3]]                                       # no funnel, no near-goal repeller
+        assert msgs[3] == ["add", 5, -10.0, 2, [0.0, -0.4, 0.4, 0.05, 0.001, 20.0]]              # id 4 + (n + 1), xyz, radius, safe, order
+        table = [1, 0, 0, 0, 0, 1, 0, -0.4, 0, 0, 1, 0.3, 0, 0, 0, 1, 0, 0, 1, 0.001, 5]       # old/README.old:78
+        msgs = send("set", "ObstacleH", 1, [float(v) for v in table])
+        assert msgs[-1] == ["add", 6, -50.0, 4, [0.0, -0.4, 0.3, 0.0, 0.0, 1.0, 0.001, 5.0]]
+        gan = [1, 0, 0, 0.4, 0, -1, 0, -0.4, 0, 0, -1, 0.4, 0, 0, 0, 1, 0, -1, 0, 0.1, 0.15, 0.15]   # old/README.old:72-73
+        msgs = send("set", "goalAndNormal", [float(v) for v in gan])
+        assert msgs[0] == ["add", 1, 1.0, 1, [float(v) for v in gan[:16]] + [0.15]]              # frame + slowdown (last value)
+        assert msgs[1] == ["add", 2, 30.0, 5, [0.4, -0.4, 0.4, 0.0, -1.0, 0.0, 0.1, 10.0, 0.15, 2.0]]      # funnel
+        assert msgs[2][:4] == ["add", 3, -10.0, 2] and np.allclose(msgs[2][4], [0.4, -0.45, 0.4, 0.2, 0.001, 5.0])   # near-goal repeller
+        # wrong lengths are reported and ignored; unknown actions too
+        send("set", "goal", [1.0, 2.0, 3.0])
+        send("fly", "goal", [1.0])
+        text = capsys.readouterr().out
+        assert "Wrong number of values, expected 16" in text and "Action not recognized" in text
+        assert send("remove", 0)[0] == ["remove", 5]
+        send("remove", 7)
+        assert "Object doesn't exist" in capsys.readouterr().out
+    finally:
+        fd.close(); sink.close(); src.close(); yarp.Network.reset()

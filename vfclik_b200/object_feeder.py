@@ -112,7 +112,7 @@ class ObjectFeederModule:
         if 0 not in self.objects:
             dprint("Not setting repellers, waiting for a goal. Please set a goal, to apply all the repellers")
             return
-        for objectNum in self.objects:
+        for objectNum in sorted(self.objects):      # Python 2 dicts iterate small int keys in ascending order: goal first
             pl = self.objects[objectNum]
             if objectNum == 0:
                 write_bottle_lists(self.objectOutPort, ["add", objectNum, [float(v) for v in pl[:16]]], strict=True)
