@@ -249,7 +249,7 @@ static int check_layout(vfk_ctx* h, const void* ptr, const char* name, bool requ
     return VFK_OK;
 }
 
-extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, void* stream) {
+static int step_impl(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, void* stream, const vfk_io* io) {
     if (!h || !b) return fail(h, VFK_ERR_INVALID, "vfk_step: null argument");
     if (n < 0) return fail(h, VFK_ERR_INVALID, "n_instances must be >= 0 (got %lld)", (long long)n);
     if (n_obst < 0) return fail(h, VFK_ERR_INVALID, "n_obstacles must be >= 0");
@@ -271,8 +271,13 @@ extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int n_obs
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool small = h->chain.n_joints <= 7;
-    if (h->precision == 32) return small ? vfk_launch_f32_small(h, b, n, n_obst, k_cycles, st) : vfk_launch_f32_large(h, b, n, n_obst, k_cycles, st);
-    return small ? vfk_launch_f64_small(h, b, n, n_obst, k_cycles, st) : vfk_launch_f64_large(h, b, n, n_obst, k_cycles, st);
+    if (h->precision == 32)
+        return small ? vfk_launch_f32_small(h, b, n, n_obst, k_cycles, st, io) : vfk_launch_f32_large(h, b, n, n_obst, k_cycles, st, io);
+    return small ? vfk_launch_f64_small(h, b, n, n_obst, k_cycles, st, io) : vfk_launch_f64_large(h, b, n, n_obst, k_cycles, st, io);
+}
+
+extern "C" int vfk_step(vfk_handle h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, void* stream) {
+    return step_impl(h, b, n, n_obst, k_cycles, stream, nullptr);
 }
 
 extern "C" int vfk_field_eval(vfk_handle h, const void* pose_in, const void* goal, const void* obst, const void* obst_ext,
@@ -735,10 +740,10 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
         if (!s->en_pose) b.pose = nullptr;
         if (!s->en_twist) b.twist = nullptr;
         cudaStream_t st = s->pipe[1];
-        h->io.q_src = dq; h->io.q_src_ld = s->n;
-        h->io.qdot = dqd; h->io.qdot_ld = dqd ? s->n : 0;
-        int rc = vfk_step(h, &b, s->n, s->n_obst, k_cycles, st);
-        h->io.q_src = nullptr; h->io.qdot = nullptr; h->io.q_src_ld = h->io.qdot_ld = 0;
+        vfk_io io;
+        io.q_src = dq; io.q_src_ld = s->n;
+        io.qdot = dqd; io.qdot_ld = dqd ? s->n : 0;
+        int rc = step_impl(h, &b, s->n, s->n_obst, k_cycles, st, &io);
         if (rc < 0) return rc;
         int launches = rc;
         char* dst_qo = q_out ? (d_qo ? (char*)q_out : pin_qo) : nullptr;

@@ -9,6 +9,15 @@
 #include "../../include/vfk.h"
 #include "vfk_kernels.cuh"
 
+// Direct host I/O request of the host-buffer session (see KArgs::q_src): dense [N][ld] arrays in mapped page-locked host
+// memory that the cycle kernel reads q from / writes qdot to instead of the blocked device buffers.
+struct vfk_io {
+    const void* q_src = nullptr;
+    int64_t q_src_ld = 0;
+    void* qdot = nullptr;
+    int64_t qdot_ld = 0;
+};
+
 struct vfk_ctx {
     vfk_chain_desc chain;       // as given
     vfk_chain_desc canon;       // every joint about / along Z
@@ -18,8 +27,6 @@ struct vfk_ctx {
     int sm_count;
     int pattern;                // 0: GenericPattern, 1: LwrPattern (structure of the canonical chain)
     uint64_t generation;        // bumped by vfk_set_params: captured CUDA graphs bake the constants in
-    // direct host I/O request of the session (consumed by the next cycle launch; see KArgs::q_src)
-    struct { const void* q_src; int64_t q_src_ld; void* qdot; int64_t qdot_ld; } io;
     vfk::KConst<float> cf;
     vfk::KConst<double> cd;
     std::string err;
@@ -46,7 +53,7 @@ inline int fail(vfk_ctx* h, int code, const char* fmt, ...) {
 
 
 // Cycle-kernel launchers, one translation unit per (precision, joint-count group) so they compile in parallel.
-int vfk_launch_f32_small(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st);   // N = 6, 7
-int vfk_launch_f32_large(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st);   // N = 10, 17
-int vfk_launch_f64_small(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st);
-int vfk_launch_f64_large(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st);
+int vfk_launch_f32_small(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st, const vfk_io* io);   // N = 6, 7
+int vfk_launch_f32_large(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st, const vfk_io* io);   // N = 10, 17
+int vfk_launch_f64_small(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st, const vfk_io* io);
+int vfk_launch_f64_large(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st, const vfk_io* io);

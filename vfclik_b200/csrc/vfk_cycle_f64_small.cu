@@ -1,11 +1,11 @@
 // Instantiates the fused cycle kernel for double, N in {6, 7} (own translation unit: compiles in parallel).
 #include "vfk_launch.cuh"
 
-int vfk_launch_f64_small(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st) {
+int vfk_launch_f64_small(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st, const vfk_io* io) {
     const KConst<double>& c = h->cd;
     switch (h->chain.n_joints) {
-        case 6: return dispatch_ext<double, 6>(h, c, b, n, n_obst, k_cycles, st);
-        case 7: return dispatch_ext<double, 7>(h, c, b, n, n_obst, k_cycles, st);
+        case 6: return dispatch_ext<double, 6>(h, c, b, n, n_obst, k_cycles, st, io);
+        case 7: return dispatch_ext<double, 7>(h, c, b, n, n_obst, k_cycles, st, io);
     }
     return fail(h, VFK_ERR_UNSUPPORTED, "no kernel for n_joints = %d", h->chain.n_joints);
 }

@@ -43,7 +43,7 @@ static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
 // but 1.6 % slower at K = 100, where the kernel is issue-bound and the tighter register budget costs instructions.
 template <typename T, int N, class PAT, bool EXT, bool LEAN, int G = 1, bool HIOCC = false>
 static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
-                        cudaStream_t st) {
+                        cudaStream_t st, const vfk_io* io) {
     KArgs<T> a;
     memset(&a, 0, sizeof a);
     a.q = static_cast<T*>(b->q);
@@ -65,8 +65,8 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.pose = static_cast<T*>(b->pose);
     a.twist = static_cast<T*>(b->twist);
     a.flags = b->flags;
-    if (h->io.q_src) { a.q_src = static_cast<const T*>(h->io.q_src); a.q_src_ld = h->io.q_src_ld; }
-    if (h->io.qdot) { a.qdot = static_cast<T*>(h->io.qdot); a.qdot_ld = h->io.qdot_ld; }
+    if (io && io->q_src) { a.q_src = static_cast<const T*>(io->q_src); a.q_src_ld = io->q_src_ld; }
+    if (io && io->qdot) { a.qdot = static_cast<T*>(io->qdot); a.qdot_ld = io->qdot_ld; }
     a.n = n;
     a.n_obst = n_obst;
     a.k_cycles = k_cycles;
@@ -80,11 +80,14 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #ifndef VFK_MINB_LEAN
 #define VFK_MINB_LEAN 3
 #endif
+#ifndef VFK_MINB_F64
+#define VFK_MINB_F64 2
+#endif
 #ifndef VFK_MINB_LEAN_K1
 #define VFK_MINB_LEAN_K1 4
 #endif
     constexpr int MINB = (HIOCC ? VFK_MINB_LEAN_K1
-                                : ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? 2 : 1))) * (128 / kBlock);
+                                : ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? VFK_MINB_F64 : 1))) * (128 / kBlock);
     auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB, G>;
     // per (instantiation, device, smem size): opt in to > 48 KB of dynamic shared memory and ask the occupancy once
     static int cached_per_sm[16];
@@ -111,7 +114,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 
 template <typename T, int N, class PAT>
 static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
-                         cudaStream_t st) {
+                         cudaStream_t st, const vfk_io* io) {
     const bool ext = b->obst_ext && n_obst > 0;
     // Small FP64 batches cannot fill the GPU with one thread per instance: switch to the cooperative latency shape.
     // Measured (scripts/latency.py, one robot, 1000 fused cycles): FP64 M = 32: 6.4 vs 7.1 us per cycle, M = 256: 23.6 vs
@@ -119,25 +122,25 @@ static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, i
     // so it is neither selected nor instantiated there.
     if constexpr (sizeof(T) == 8) {
         const bool coop = n <= kCoopMaxInstances && n_obst >= 2 * kChunk && !getenv("VFK_NO_COOP");
-        if (coop) return ext ? launch_cycle<T, N, PAT, true, false, kChunk>(h, c, b, n, n_obst, k_cycles, st)
-                             : launch_cycle<T, N, PAT, false, false, kChunk>(h, c, b, n, n_obst, k_cycles, st);
+        if (coop) return ext ? launch_cycle<T, N, PAT, true, false, kChunk>(h, c, b, n, n_obst, k_cycles, st, io)
+                             : launch_cycle<T, N, PAT, false, false, kChunk>(h, c, b, n, n_obst, k_cycles, st, io);
     }
-    if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st);
+    if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st, io);
     if (is_lean<T>(c, b)) {
         if constexpr (sizeof(T) == 4 && N <= 7) {
-            if (k_cycles == 1) return launch_cycle<T, N, PAT, false, true, 1, true>(h, c, b, n, n_obst, k_cycles, st);
+            if (k_cycles == 1) return launch_cycle<T, N, PAT, false, true, 1, true>(h, c, b, n, n_obst, k_cycles, st, io);
         }
-        return launch_cycle<T, N, PAT, false, true>(h, c, b, n, n_obst, k_cycles, st);
+        return launch_cycle<T, N, PAT, false, true>(h, c, b, n, n_obst, k_cycles, st, io);
     }
-    return launch_cycle<T, N, PAT, false, false>(h, c, b, n, n_obst, k_cycles, st);
+    return launch_cycle<T, N, PAT, false, false>(h, c, b, n, n_obst, k_cycles, st, io);
 }
 
 template <typename T, int N>
 static int dispatch_ext(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
-                        cudaStream_t st) {
+                        cudaStream_t st, const vfk_io* io) {
     if constexpr (N == 7) {
-        if (h->pattern == 1) return dispatch_feat<T, N, LwrPattern>(h, c, b, n, n_obst, k_cycles, st);
+        if (h->pattern == 1) return dispatch_feat<T, N, LwrPattern>(h, c, b, n, n_obst, k_cycles, st, io);
     }
-    return dispatch_feat<T, N, GenericPattern>(h, c, b, n, n_obst, k_cycles, st);
+    return dispatch_feat<T, N, GenericPattern>(h, c, b, n, n_obst, k_cycles, st, io);
 }
 
