@@ -37,6 +37,15 @@ constexpr int kSmallBlock = 128;     // threads per CTA of the small one-element
 constexpr int kChunk = 8;            // obstacles per shared-memory stage
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 512;     // per-warp mbarriers live in the first 512 bytes of dynamic smem
+// FP32 decay order 20 (the reference's typical value, old/README.old:75) by five multiplications instead of MUFU lg2 / ex2:
+// two more instructions per obstacle but two fewer on the quarter-rate XU pipe, which also carries rsqrt and the
+// FP64 <-> FP32 conversions.  Measured on B200 (1 M instances): 109.1 us vs 110.3 us per launch at K = 1, -0.6 % at
+// K = 100; also the more accurate of the two.  -DVFK_NO_F32_POWCHAIN restores the MUFU form.
+#ifdef VFK_NO_F32_POWCHAIN
+constexpr bool kF32PowChain = false;
+#else
+constexpr bool kF32PowChain = true;
+#endif
 
 // Kernel-side constants in the kernel's arithmetic type.  Joints are canonicalised on
 // the host (vfk_api.cu: canonicalise_chain) so that every joint acts about / along its
@@ -551,7 +560,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                             repel<T, ORD>(o, safe_inv, order, pt, acc);
                         }
                     };
-                    if (sizeof(T) == 8 && !EXT && c.order_int == 20) full_chunk(std::integral_constant<int, 20>{});
+                    if ((sizeof(T) == 8 || kF32PowChain) && !EXT && c.order_int == 20) full_chunk(std::integral_constant<int, 20>{});
                     else if (sizeof(T) == 8 && !EXT && c.order_int == 5) full_chunk(std::integral_constant<int, 5>{});
                     else if (sizeof(T) == 8 && !EXT && c.order_int == 2) full_chunk(std::integral_constant<int, 2>{});
                     else full_chunk(std::integral_constant<int, 0>{});
