@@ -107,3 +107,17 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "oracle/" not in text or f.endswith((".cu", ".cuh")) or "oracle/batch.py" in text, f
+
+
+def test_integration_md_ctypes_stub_matches_the_header():
+    """The reference-side stub printed in INTEGRATION.md must describe the same structs as include/vfk.h (via _lib.py)."""
+    import ctypes as C
+    from vfclik_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text[text.index("class ChainDesc(C.Structure):"):text.index("lib.vfk_last_error.restype")]
+    block = "\n".join(l for l in block.splitlines() if not l.startswith("#"))
+    ns = {"C": C}
+    exec(block, ns)
+    assert C.sizeof(ns["ChainDesc"]) == C.sizeof(_lib.ChainDescC)
+    assert C.sizeof(ns["Params"]) == C.sizeof(_lib.ParamsC)
+    assert [f[0] for f in ns["Params"]._fields_] == [f[0] for f in _lib.ParamsC._fields_]
