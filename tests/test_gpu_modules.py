@@ -373,3 +373,34 @@ def test_module_programs_run_standalone(built_lib):
                            cwd=root, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, (mod, r.stdout[-500:], r.stderr[-1500:])
         assert "iterations: 3" in r.stdout, (mod, r.stdout[-500:])
+
+
+def test_joint_controller_position_dependent_limits(lwr, built_lib, fresh_ports, capsys):
+    """Row a12: the joint reference is clamped into config.updateJntLimits(q), which may depend on the posture
+    (scripts/joint_p_controller:79-89)."""
+    import copy
+    from vfclik_b200.joint_p_controller import JointPControllerModule
+    from vfclik_b200.runtime import ControlRuntime
+    _, cfg = lwr
+    c = copy.copy(cfg)
+    c.updateJntLimits = lambda q: [[-0.5 - abs(q[0]), 0.5 + abs(q[0])]] * 7        # widens with |q0|
+    rt = ControlRuntime(c, n_instances=1, precision=64)
+    jp = JointPControllerModule(rt, "/5")
+    try:
+        enc = _out_port(fresh_ports, "/5/test/enc", jp.inPort.getName())
+        ref = _out_port(fresh_ports, "/5/test/ref", jp.refPort.getName())
+        out = fresh_ports.BufferedPortBottle(); out.open("/5/test/out")
+        fresh_ports.Network.connect(jp.outPort.getName(), "/5/test/out")
+        fresh_ports.sendListPort(ref, [1.0, -1.0, 0.2, 0.0, 0.0, 0.0, 0.0])
+        for q0, lim in ((0.0, 0.5), (0.3, 0.8)):
+            q = [q0, 0.1, 0.0, 0.0, 0.0, 0.0, 0.0]
+            fresh_ports.sendListPort(enc, q)
+            assert jp.update()
+            b = out.read(False)
+            got = [b.get(i).asDouble() for i in range(7)]
+            want = cfg.jpctrl_kp * (np.clip([1.0, -1.0, 0.2, 0, 0, 0, 0], -lim, lim) - np.asarray(q))
+            assert np.allclose(got, want, rtol=1e-12, atol=1e-14), (q0, got, want)
+        text = capsys.readouterr().out
+        assert "Limiting high 0" in text and "Limiting low 1" in text
+    finally:
+        jp.close(); rt.close()

@@ -40,10 +40,12 @@ class JointPControllerModule:
         if refbottle and refbottle.size() == self.nJoints:
             self.ref = [refbottle.get(i).asDouble() for i in range(self.nJoints)]
             self.rt.set_jp_ref(self.ref)
+            self._ref_sent = list(self.ref)
         inbottle = self.inPort.read(False)
         if not inbottle or inbottle.size() != self.nJoints:
             return False
         q = [inbottle.get(i).asDouble() for i in range(self.nJoints)]
+        self._apply_position_dependent_limits(q)
         out = self.rt.cycle(np.asarray(q))
         sendListPort(self.outPort, out["qdot_jp"][:, 0])
         self.at_goal = 1 if (int(out["flags"][0]) & FLAG_AT_GOAL) else 0
@@ -52,6 +54,27 @@ class JointPControllerModule:
         b.addInt(self.at_goal)
         self.atGoalPort.write(True)
         return True
+
+    def _apply_position_dependent_limits(self, q):
+        """``check_limits`` (``scripts/joint_p_controller:79-89``) clamps the reference into ``config.updateJntLimits(q)``,
+        which may depend on the current posture (iCub shoulder coupling).  The kernel clamps into the chain's static
+        limits; when the config's hook returns anything tighter for this q, the reference handed to the kernel is
+        clamped here first (a user-supplied Python function cannot run on the device), with the reference's messages."""
+        hook = getattr(self.rt.config, "updateJntLimits", None)
+        if hook is None:
+            return
+        limits = hook(q)
+        ref_out = list(self.ref)
+        for i in range(min(len(limits), self.nJoints)):
+            if self.ref[i] < limits[i][0]:
+                print("Limiting low", i)
+                ref_out[i] = limits[i][0]
+            elif self.ref[i] > limits[i][1]:
+                print("Limiting high", i)
+                ref_out[i] = limits[i][1]
+        if ref_out != getattr(self, "_ref_sent", self.ref):
+            self.rt.set_jp_ref(ref_out)
+        self._ref_sent = ref_out
 
     def close(self):
         self.yarp_ctrl.close()
