@@ -34,7 +34,10 @@ constexpr int kMaxJ = 17;
 #endif
 constexpr int kBlock = VFK_BLOCK;    // threads per CTA of the cycle kernel (warps are independent workers)
 constexpr int kSmallBlock = 128;     // threads per CTA of the small one-element-per-thread kernels
-constexpr int kChunk = 8;            // obstacles per shared-memory stage
+#ifndef VFK_CHUNK
+#define VFK_CHUNK 8
+#endif
+constexpr int kChunk = VFK_CHUNK;            // obstacles per shared-memory stage (4 measured: FP64 config 2 -13 %, -30 % with 3 CTAs/SM; FP32 headline -14 %)
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 512;     // per-warp mbarriers live in the first 512 bytes of dynamic smem
 // FP32 decay order 20 (the reference's typical value, old/README.old:75) by five multiplications instead of MUFU lg2 / ex2:
