@@ -38,7 +38,8 @@ d = json.load(open(tj)) if os.path.exists(tj) else {}
 d[workload] = traffic
 d[workload + "_source"] = "%s_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches" % (tag, len(rd))
 json.dump(d, open(tj, "w"), indent=1)
-dur, _ = col("gpu__time_duration.sum")
+dur, du = col("gpu__time_duration.sum")
+dur = [x * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(du, 1.0) for x in dur]      # microseconds
 print("traffic per launch %.1f MB, duration %s us" % (traffic / 1e6, dur))
 
 
