@@ -596,3 +596,63 @@ def test_host_session_direct_host_io(eng, lwr, precision, monkeypatch):
         assert np.array_equal(qd.numpy().T, dev["qdot"])
     finally:
         s.close()
+
+
+@pytest.mark.parametrize("which", ["config4", "config5"])
+def test_full_size_config4_and_config5_shards(lwr, built_lib, which):
+    """BASELINE configs[3] / [4] at their per-GPU shard size on 8 GPUs (2,097,152 LWR instances x 256 obstacles;
+    524,288 17-DOF instances x 64 obstacles), drawn on the device like bench.py does: finiteness and the clamp bound on
+    the whole shard, the explicit-Euler relation, and the oracle on a random sample of 2048 instances (FP32, 1e-4)."""
+    import torch
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import Engine, Params
+    chain_lwr, cfg = lwr
+    if which == "config4":
+        chain, n, M, params = chain_lwr, 1 << 21, 256, Params.from_config(cfg)
+    else:
+        chain, n, M, params = workloads.dual_arm_torso_chain(), 1 << 19, 64, Params()
+    N = chain.n_joints
+    e = Engine(chain, precision=32, params=params)
+    try:
+        db = workloads.random_batch_device(e, n, M, seed=9)
+        q0 = db.download("q")                                           # dense [N, n]
+        goal = db.download("goal")
+        rng = np.random.default_rng(3)
+        idx = np.sort(rng.choice(n, size=2048, replace=False))
+        ti = torch.from_numpy(idx).to(db.t["obst"].device)
+        obst = db.t["obst"][ti // 32, :, ti % 32, :].permute(1, 0, 2).contiguous().cpu().numpy()     # [M, 2048, 4]
+        assert db.step(1) == 1
+        qd = db.download("qdot")
+        q1 = db.download("q")
+        assert np.all(np.isfinite(qd)) and np.max(np.abs(qd)) <= params.max_vel * (1 + 1e-6)
+        assert np.allclose(q1, q0 + np.float32(params.dt) * qd, rtol=0, atol=5e-7)
+        sub = dict(q=q0[:, idx], goal=goal[:, idx], obst=obst)
+        ref = run_oracle(chain, e.params, sub, M)
+        err = rel_err(qd[:, idx].T.astype(np.float64), ref["qdot"])
+        assert err.max() <= FP32_RTOL, float(err.max())
+        assert qd.shape == (N, n)
+    finally:
+        e.close()
+
+
+def test_fp32_obstacle_almost_at_the_tool_saturates_instead_of_overflowing(eng, lwr):
+    """(radius / d)^20 / d exceeds the FP32 range once d < radius / 75.  The FP32 mode saturates that weight (the field is
+    normalised afterwards, so only the direction matters) and must agree with the FP64 oracle, not return NaN."""
+    from oracle import batch
+    from vfclik_b200 import workloads
+    chain, _ = lwr
+    e = eng(32)
+    n, M = 256, 8
+    w = workloads.random_batch(chain, n, M, seed=61, dtype=np.float32)
+    _, p_tool, _ = batch.fk_jac(chain, w["q"].T.astype(np.float64))              # identity tool: flange = tool position
+    rng = np.random.default_rng(2)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    dist = np.where(np.arange(n) % 2 == 0, 2e-4, 9e-4)[:, None]                  # both far inside radius / 75 = 1.3e-3
+    w["obst"][3, :, 0:3] = (p_tool + dist * u).astype(np.float32)
+    w["obst"][3, :, 3] = 0.1
+    out = run_gpu(e, w, M, outputs=("qdot_vf", "qdot"))
+    assert np.all(np.isfinite(out["qdot"])) and np.all(np.isfinite(out["qdot_vf"]))
+    ref = run_oracle(chain, e.params, w, M)
+    # the FP32 obstacle coordinates quantise d itself (ulp 6e-8 at ~1 m on a 2e-4 m offset): the direction agrees to ~1e-3
+    err = rel_err(out["qdot_vf"].astype(np.float64), ref["qdot_vf"])
+    assert np.quantile(err, 0.95) < 5e-3 and err.max() < 5e-2, (float(np.quantile(err, 0.95)), float(err.max()))

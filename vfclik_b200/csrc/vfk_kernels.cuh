@@ -271,7 +271,11 @@ __device__ __forceinline__ void repel(const Vec4<T>& o, T safe_inv, T order, con
     const T dd = fma(dx, dx, fma(dy, dy, fma(dz, dz, Prec<T>::tiny())));
     const T inv = Prec<T>::rsqrt_pos(dd);                                       // 1/d
     const T ratio = o.w * Prec<T>::fmin_(inv, safe_inv);                        // radius / max(d, safe)
-    const T wgt = pow_fixed<ORDER, T>(ratio, order) * inv;
+    T wgt = pow_fixed<ORDER, T>(ratio, order) * inv;
+    // FP32: (radius / d)^order / d passes 3.4e38 once the tool is within ~radius/75 of an obstacle centre (order 20) --
+    // one instance in a few million at 256 random obstacles.  Saturating the weight keeps the sum finite; such an
+    // obstacle still outweighs everything else by > 1e15, and normCart only keeps the direction.
+    if constexpr (sizeof(T) == 4) wgt = Prec<T>::fmin_(wgt, T(1e30));
     acc[0] = fma(wgt, dx, acc[0]); acc[1] = fma(wgt, dy, acc[1]); acc[2] = fma(wgt, dz, acc[2]);
 }
 
