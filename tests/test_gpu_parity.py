@@ -656,3 +656,59 @@ def test_fp32_obstacle_almost_at_the_tool_saturates_instead_of_overflowing(eng, 
     # the FP32 obstacle coordinates quantise d itself (ulp 6e-8 at ~1 m on a 2e-4 m offset): the direction agrees to ~1e-3
     err = rel_err(out["qdot_vf"].astype(np.float64), ref["qdot_vf"])
     assert np.quantile(err, 0.95) < 5e-3 and err.max() < 5e-2, (float(np.quantile(err, 0.95)), float(err.max()))
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_outputs_stay_inside_their_buffers(eng, lwr, precision):
+    """Guard bands (compute-sanitizer is not available on the pool): every output of the cycle kernel, of the general and
+    the lean instantiation, sits inside a larger tensor filled with a sentinel; after ragged launches (n not a multiple
+    of 32, 13 obstacles, K = 2) the bands are untouched.  Same for the session's page-locked host buffers in the direct
+    host I/O path and in the copy pipeline."""
+    import torch
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch
+    chain, _ = lwr
+    e = eng(precision)
+    dt, tdt = (np.float32, torch.float32) if precision == 32 else (np.float64, torch.float64)
+    SENT = -777.25
+    for n, outputs in ((1000 - 7, ("qdot",)), (1000 - 7, ("qdot_vf", "qdot_ns", "qdot_jp", "qdot", "cmd", "pose", "twist", "flags"))):
+        M = 13
+        w = workloads.random_batch(chain, n, M, seed=91, dtype=dt)
+        db = DeviceBatch(e, n, M, outputs=outputs)
+        db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+        guarded = {}
+        for name in outputs + ("q",):
+            t = db.t[name]
+            pad = 4096 // t.element_size()
+            big = torch.full((t.numel() + 2 * pad,), SENT if t.dtype.is_floating_point else -777, dtype=t.dtype, device=t.device)
+            big[pad:pad + t.numel()] = t.reshape(-1)
+            db.t[name] = big[pad:pad + t.numel()].view(t.shape)
+            guarded[name] = (big, pad, t.numel())
+        assert db.step(2) == 1
+        torch.cuda.synchronize()
+        for name, (big, pad, cnt) in guarded.items():
+            sent = SENT if big.dtype.is_floating_point else -777
+            assert bool((big[:pad] == sent).all()) and bool((big[pad + cnt:] == sent).all()), name
+        ref = run_oracle(chain, e.params, w, M, k=2)
+        assert rel_err(db.download("qdot").T.astype(np.float64), ref["qdot"]).max() <= (FP32_RTOL if precision == 32 else FP64_RTOL)
+    # host side: direct host I/O (n multiple of 32) and the copy pipeline (ragged n), pinned buffers with bands
+    for n in (4096, 4096 - 5):
+        M = 13
+        w = workloads.random_batch(chain, n, M, seed=92, dtype=dt)
+        s = e.session(n, M)
+        try:
+            s.set_goal(w["goal"]); s.set_obstacles(w["obst"])
+            pad = 1024
+            q_big = torch.full((7 * n + 2 * pad,), SENT, dtype=tdt).pin_memory()
+            qd_big = torch.full((7 * n + 2 * pad,), SENT, dtype=tdt).pin_memory()
+            q_big[pad:pad + 7 * n] = torch.from_numpy(np.ascontiguousarray(w["q"])).reshape(-1)
+            q_view = q_big[pad:pad + 7 * n].view(7, n).numpy()
+            qd_view = qd_big[pad:pad + 7 * n].view(7, n).numpy()
+            s.cycle(q_in=q_view, k_cycles=2, qdot_out=qd_view)
+            assert bool((qd_big[:pad] == SENT).all()) and bool((qd_big[pad + 7 * n:] == SENT).all())
+            assert bool((q_big[:pad] == SENT).all()) and bool((q_big[pad + 7 * n:] == SENT).all())
+            assert np.array_equal(q_view, w["q"])
+            ref = run_oracle(chain, e.params, w, M, k=2)
+            assert rel_err(qd_view.T.astype(np.float64), ref["qdot"]).max() <= (FP32_RTOL if precision == 32 else FP64_RTOL)
+        finally:
+            s.close()
