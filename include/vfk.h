@@ -99,7 +99,9 @@ typedef struct vfk_chain_desc {
 /* Per-robot constants (uniform over the batch; kept in constant memory). */
 typedef struct vfk_params {
     double ik_lambda;            /* damping of J^T (J J^T + lambda^2 I)^-1           (getIKV, scripts/vf:461) */
-    double ns_lambda;            /* damping of the projector's pseudo-inverse; 0 = pinv (scripts/nullspace:78) */
+    double ns_lambda;            /* damping of the projector's pseudo-inverse; 0 = pinv (scripts/nullspace:78).  FP32 mode
+                                    needs ik_lambda > 0 and, with the nullspace on, ns_lambda > 0: the undamped normal
+                                    equations lose their pivots to FP32 rounding near singular postures */
     double dt;                   /* config.rate (scripts/bridge:91) */
     double speed_scale;          /* speedScale (scripts/vf:137,197-207) */
     double max_vel;              /* scripts/bridge:69,613-623 */

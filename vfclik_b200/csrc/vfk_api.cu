@@ -167,6 +167,8 @@ static int check_params(vfk_ctx* h, const vfk_params* p) {
     if (!(p->ik_lambda >= 0) || !(p->ns_lambda >= 0)) return fail(h, VFK_ERR_INVALID, "lambda must be >= 0");
     if (p->ik_lambda == 0 && h->precision == 32)
         return fail(h, VFK_ERR_INVALID, "ik_lambda = 0 is outside the FP32 mode's domain (use precision 64)");
+    if (p->ns_lambda == 0 && p->ns_mode != VFK_NS_OFF && h->precision == 32)
+        return fail(h, VFK_ERR_INVALID, "ns_lambda = 0 (undamped pinv) is outside the FP32 mode's domain (use precision 64)");
     if (p->ns_mode < 0 || p->ns_mode > 2) return fail(h, VFK_ERR_INVALID, "ns_mode must be 0, 1 or 2");
     if (p->ns_mode == VFK_NS_CONTROL && h->chain.n_joints != 7)
         return fail(h, VFK_ERR_UNSUPPORTED, "VFK_NS_CONTROL needs a 1-D nullspace (n_joints = 7), got %d joints",
