@@ -220,8 +220,15 @@ int  vfk_unpack(vfk_handle h, const void* blocked, void* dense, int comps, int w
  * pinned staging buffers and a stream.  Host arrays are plain dense SoA of the handle's
  * precision: [comps][n_instances] (obstacles [M][n][4], ext [M][n][2]); the session
  * converts to / from the blocked layout on the GPU.  vfk_session_cycle()
- * copies q host->device (if q_in != NULL), runs k_cycles fused cycles, copies the
- * requested outputs device->host and synchronises. */
+ * takes q from the host (if q_in != NULL), runs k_cycles fused cycles, returns the
+ * requested outputs to the host and synchronises.  How the data moves depends on the
+ * caller's buffers, never on the results (bit-identical either way):
+ *   - q_in (and qdot_out, if wanted) page-locked -- cudaHostAlloc, cudaHostRegister,
+ *     torch pin_memory() -- 16-byte aligned, n_instances a multiple of 32 and >= 1024:
+ *     ONE launch of the cycle kernel reads the q tiles from and writes qdot to the host
+ *     buffers itself over PCIe (no staging copies, no layout kernels);
+ *   - otherwise: a chunked copy pipeline (H2D / pack / cycle / unpack / D2H on three
+ *     streams), pageable buffers going through the session's pinned staging area. */
 int  vfk_session_create(vfk_handle h, int64_t n_instances, int n_obstacles, int with_obst_ext, vfk_session* out);
 int  vfk_session_set_goal(vfk_session s, const void* goal_host);            /* [13][n] */
 int  vfk_session_set_obstacles(vfk_session s, const void* obst_host,         /* [M][n][4] */
