@@ -5,8 +5,10 @@ instances.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU
 baseline legs may import this package; the product (``vfclik_b200``) never does.
 
 PARITY STATUS: **partially pinned.**  The parts of the path whose source is in the
-reference and runs in a py3 container -- ``CommandMixer.read`` (src/command_mixer.py:46-82)
-and the ``scripts/nullspace`` functions (:67-131) -- are pinned by golden vectors
+reference and runs in a py3 container -- ``CommandMixer.read`` (src/command_mixer.py:46-82),
+the ``scripts/nullspace`` functions (:67-131), the bridge back-ends' ``set_vel``
+(scripts/bridge:182-210,288-312,507-530), ``joint_p_controller.check_limits`` (:79-89) and
+``vf.get_weight_matrix`` (scripts/vf:164-179) -- are pinned by golden vectors
 generated from the real reference code (``oracle/gen_golden.py`` ->
 ``tests/golden/``).  Everything behind the un-vendored, un-pinned PyKDL / arcospyu.Lafik /
 vfl boundary is **parity unpinned**: the reference ships no test, fixture or golden
@@ -323,6 +325,28 @@ def ns_check_limits(prm: Params, chain, q: np.ndarray, qdot: np.ndarray):
     return np.where(bad[:, None], 0.0, qdot), bad
 
 
+def bridge_set_vel(prm: Params, mix: np.ndarray, q: np.ndarray, qc: np.ndarray, direct: bool):
+    """``set_vel`` of the three bridge back-ends on a batch: returns (qdot_lim, cmd, leading-clamp-active).
+
+    LWR (``scripts/bridge:182-210``): ratio = max_vel / max|qdot| when exceeded; cmd = qdot_lim (direct) or
+    ``-q_cmded + q + qdot_lim``.  Powercube (``:288-312``): the same clamp, then the shoulder-speed clamp of joint 0 --
+    one ``ratio`` variable serves both, so when the shoulder limit is not hit the leading ratio is applied a second
+    time (kept: bug-compatible); cmd = qdot_lim.  iCub (``:507-530``): leading clamp, cmd = qdot_lim.
+    Pinned by golden vectors produced by executing those reference methods (``oracle/gen_golden.py:gen_bridge``)."""
+    lead = np.max(np.abs(mix), axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ratio = np.where(lead > prm.max_vel, prm.max_vel / lead, 1.0)
+    qd = mix * ratio[:, None]
+    if prm.bridge_kind == 1:
+        sh = qd[:, 0]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            r2 = np.where(sh > prm.shoulder_vel[0], np.abs(prm.shoulder_vel[0] / sh),
+                          np.where(sh < prm.shoulder_vel[1], np.abs(prm.shoulder_vel[1] / sh), ratio))
+        qd = qd * r2[:, None]
+    cmd = qd if (direct or prm.bridge_kind != 0) else (-qc + q + qd)
+    return qd, cmd, lead > prm.max_vel
+
+
 # --------------------------------------------------------------------------- full cycle
 
 def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastvec=None,
@@ -393,23 +417,10 @@ def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastve
             nan |= np.any(np.isnan(c), axis=1)
             mix = mix + c * wp
         flags |= np.where(nan, FLAG_NAN, 0).astype(np.int32)
-        # 9. velocity clamp (scripts/bridge:188-196)
-        lead = np.max(np.abs(mix), axis=1)
-        with np.errstate(invalid="ignore", divide="ignore"):
-            ratio = np.where(lead > prm.max_vel, prm.max_vel / lead, 1.0)
-        flags |= np.where(lead > prm.max_vel, FLAG_CLAMPED, 0).astype(np.int32)
-        qd = mix * ratio[:, None]
-        if prm.bridge_kind == 1:
-            # Powercube_Bridge.set_vel (scripts/bridge:288-305).  One `ratio` variable serves both clamps, so when the
-            # shoulder limit is not hit the leading ratio is applied a second time (kept: bug-compatible).
-            sh = qd[:, 0]
-            with np.errstate(invalid="ignore", divide="ignore"):
-                r2 = np.where(sh > prm.shoulder_vel[0], np.abs(prm.shoulder_vel[0] / sh),
-                              np.where(sh < prm.shoulder_vel[1], np.abs(prm.shoulder_vel[1] / sh), ratio))
-            qd = qd * r2[:, None]
+        # 9. velocity clamp + command forming (scripts/bridge:188-203, 288-305, 507-530)
         qc = q if q_cmded is None else np.asarray(q_cmded, dtype=np.float64)
-        # scripts/bridge:198-203 (LWR offset form); the Powercube and iCub back-ends command qdot_lim itself (:304-312,:517-530)
-        cmd = qd if (direct or prm.bridge_kind != 0) else (-qc + q + qd)
+        qd, cmd, clamped = bridge_set_vel(prm, mix, q, qc, direct)
+        flags |= np.where(clamped, FLAG_CLAMPED, 0).astype(np.int32)
         out = dict(qdot_vf=qd_vf, qdot_ns=qd_ns, qdot_jp=qd_jp, qdot_mix=mix, qdot=qd, cmd=cmd,
                    pose=np.concatenate([Rt.reshape(I, 9), pt], axis=1), flags=flags, twist=out_twist)
         # 10. plant: explicit Euler (joint_sim is external to the reference)

@@ -4,7 +4,7 @@ Run in the build container, where ``/root/reference`` exists:
 
     python -m oracle.gen_golden
 
-Two pieces of the reference's hot path run under python 3:
+These pieces of the reference's hot path run under python 3:
 
 * ``src/command_mixer.py::CommandMixer`` -- imported with ``yarp`` and
   ``arcospyu.config_parser`` stubbed (they are only used for ports / CLI parsing);
@@ -13,6 +13,10 @@ Two pieces of the reference's hot path run under python 3
   (it opens YARP ports at import time and numpy 2 removed ``numpy.mat``), so the
   ``FunctionDef`` nodes are extracted with ``ast`` and executed with
   ``mat = numpy.asmatrix`` and the module globals ``nJoints, sig, lastvec``.
+
+* the three bridge back-ends' ``set_vel`` and ``ICUB_Bridge.set_torso_cjoints`` (``scripts/bridge``),
+  ``joint_p_controller.check_limits`` and ``vf.get_weight_matrix`` -- those files hold python-2 ``print`` statements
+  elsewhere, so the wanted ``def`` is cut out by indentation and executed on its own with stand-in ports.
 
 Nothing is copied from the reference: its code is executed where it lies and only the
 inputs and outputs are stored.  The vectors pin ``oracle/refshape.py``'s restatements
@@ -195,6 +199,124 @@ def gen_nullspace(rng):
                 ns_limited=limited, ns_hit=hit, ns_rank=np.asarray(rank), ns_Jrand=Jr, ns_Brand=Br)
 
 
+def load_reference_function(relpath: str, name: str, cls: str = None):
+    """Source text of one function (or method of ``cls``) of a reference script, dedented, ready for ``exec``.
+
+    ``scripts/vf`` and ``scripts/bridge`` contain python-2 ``print`` statements elsewhere in the file, so they cannot be
+    parsed as a whole; the wanted ``def`` itself is python-3 clean and is cut out by indentation."""
+    import textwrap
+    lines = open(os.path.join(REF, relpath)).read().splitlines()
+    start = 0
+    if cls is not None:
+        start = next(i for i, l in enumerate(lines) if l.startswith("class %s(" % cls) or l.startswith("class %s:" % cls)) + 1
+    indent = "    " if cls is not None else ""
+    head = indent + "def %s(" % name
+    i0 = next(i for i in range(start, len(lines)) if lines[i].startswith(head))
+    i1 = i0 + 1
+    while i1 < len(lines) and (lines[i1].strip() == "" or lines[i1].startswith(indent + " ")):
+        i1 += 1
+    return textwrap.dedent("\n".join(lines[i0:i1])) + "\n"
+
+
+class CapturePort:
+    """Output port stand-in: ``prepare()`` returns a bottle that records ``addDouble`` / ``addString``."""
+
+    def __init__(self):
+        self.items = []
+
+    def prepare(self):
+        return self
+
+    def clear(self):
+        self.items = []
+
+    def addDouble(self, v):
+        self.items.append(float(v))
+
+    def addString(self, v):
+        self.items.append(str(v))
+
+    def toString(self):
+        return " ".join(str(v) for v in self.items)
+
+    def write(self, *a):
+        pass
+
+
+def gen_bridge(rng):
+    """The three back-ends' ``set_vel`` (scripts/bridge:182-210, 288-312, 507-530), ``ICUB_Bridge.set_torso_cjoints``
+    (:470-506), ``joint_p_controller.check_limits`` (:79-89) and ``vf.get_weight_matrix`` (:164-179), executed as they
+    stand in the reference on random inputs."""
+    N = 7
+    cases = 64
+    qdot = rng.normal(scale=0.7, size=(cases, N))
+    qdot[::5] *= 0.05                                              # some below every limit
+    q = rng.normal(size=(cases, N))
+    qc = q + rng.normal(scale=0.02, size=(cases, N))
+    cfg = types.SimpleNamespace(max_vel=0.6, max_vel_shoulder_pos=0.15, max_vel_shoulder_neg=-0.1)
+    out = {"br_qdot": qdot, "br_q": q, "br_qcmded": qc,
+           "br_cfg": np.array([cfg.max_vel, cfg.max_vel_shoulder_pos, cfg.max_vel_shoulder_neg])}
+    sink = io.StringIO()
+    # LWR: both command forms
+    for direct in (0, 1):
+        glb = {"direct_control": bool(direct), "max_vel": cfg.max_vel}
+        exec(load_reference_function("scripts/bridge", "set_vel", cls="LWR_Bridge"), glb)
+        rows = []
+        for k in range(cases):
+            me = types.SimpleNamespace(nJoints=N, last_q=list(q[k]), last_qcmded=list(qc[k]), qcmd_port=CapturePort())
+            with redirect_stdout(sink):
+                glb["set_vel"](me, list(qdot[k]))
+            rows.append(me.qcmd_port.items)
+        out["br_lwr_cmd_direct%d" % direct] = np.asarray(rows)
+    # Powercube and iCub, simulation branch
+    for cls, key in (("Powercube_Bridge", "br_powercube_cmd"), ("ICUB_Bridge", "br_icub_cmd")):
+        glb = {"config": cfg}
+        exec(load_reference_function("scripts/bridge", "set_vel", cls=cls), glb)
+        rows = []
+        for k in range(cases):
+            me = types.SimpleNamespace(sim=True, qcmd_port=CapturePort())
+            with redirect_stdout(sink):
+                glb["set_vel"](me, list(qdot[k]))
+            rows.append(me.qcmd_port.items)
+        out[key] = np.asarray(rows)
+    # iCub torso (de)activation -> joint weights message
+    glb = {}
+    exec(load_reference_function("scripts/bridge", "set_torso_cjoints", cls="ICUB_Bridge"), glb)
+    msgs = []
+    for cj in ([1, 0, 1], [0, 0, 0], [1, 1, 1]):
+        me = types.SimpleNamespace(sim=True, icub_torso_num_joints=3, icub_torso_cjoints=[True] * 3,
+                                   control_weights_port=CapturePort())
+        with redirect_stdout(sink):
+            glb["set_torso_cjoints"](me, cj)
+        assert me.control_weights_port.items[0] == "j"
+        msgs.append(me.control_weights_port.items[1:])
+    out["br_icub_weights"] = np.asarray(msgs)
+    # joint_p_controller.check_limits with posture-dependent limits
+    lim_of = lambda cur: [[-0.5 - abs(cur[0]), 0.4 + abs(cur[1])]] * N
+    glb = {"config": types.SimpleNamespace(updateJntLimits=lim_of)}
+    exec(load_reference_function("scripts/joint_p_controller", "check_limits"), glb)
+    ref = rng.normal(scale=1.0, size=(cases, N))
+    with redirect_stdout(sink):
+        out["jp_ref_clamped"] = np.asarray([glb["check_limits"](list(ref[k]), list(q[k])) for k in range(cases)])
+    out["jp_ref"] = ref
+    # vf.get_weight_matrix: good and wrong sizes
+    glb = {"zeros": np.zeros, "dprint": lambda *a: None}
+    exec(load_reference_function("scripts/vf", "get_weight_matrix"), glb)
+
+    class WB(FakeBottle):
+        def get(self, i):
+            v = FakeValue(self.vals[i])
+            v.asString = lambda: str(self.vals[i])
+            return v
+    wt = rng.uniform(0.1, 2.0, size=6)
+    wj = rng.uniform(0.1, 2.0, size=N)
+    out["vf_wt"], out["vf_wj"] = wt, wj
+    out["vf_wt_matrix"] = glb["get_weight_matrix"](WB(["t"] + list(wt)), 6)
+    out["vf_wj_matrix"] = glb["get_weight_matrix"](WB(["j"] + list(wj)), N)
+    assert glb["get_weight_matrix"](WB(["j"] + list(wj[:5])), N) is None          # wrong size: ignored
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
@@ -203,6 +325,7 @@ def main():
     data = {}
     data.update(gen_mixer(rng))
     data.update(gen_nullspace(rng))
+    data.update(gen_bridge(rng))
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

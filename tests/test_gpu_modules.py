@@ -404,3 +404,26 @@ def test_joint_controller_position_dependent_limits(lwr, built_lib, fresh_ports,
         assert "Limiting high 0" in text and "Limiting low 1" in text
     finally:
         jp.close(); rt.close()
+
+
+def test_set_vel_kernel_against_reference_golden_vectors(lwr, golden, built_lib):
+    """vfk_set_vel for the LWR (both command forms), Powercube and iCub back-ends against vectors produced by executing the
+    reference's own set_vel methods (scripts/bridge:182-210, 288-312, 507-530; oracle/gen_golden.py:gen_bridge)."""
+    import dataclasses
+    from vfclik_b200.engine import BRIDGE_ICUB, BRIDGE_LWR, BRIDGE_POWERCUBE, DeviceBatch, Engine, Params
+    chain, cfg = lwr
+    g = golden
+    qd, q, qc = g["br_qdot"].T.copy(), g["br_q"].T.copy(), g["br_qcmded"].T.copy()          # [7, cases]
+    max_vel, sh_pos, sh_neg = [float(v) for v in g["br_cfg"]]
+    n = qd.shape[1]
+    for kind, direct, key in ((BRIDGE_LWR, False, "br_lwr_cmd_direct0"), (BRIDGE_LWR, True, "br_lwr_cmd_direct1"),
+                              (BRIDGE_POWERCUBE, False, "br_powercube_cmd"), (BRIDGE_ICUB, False, "br_icub_cmd")):
+        prm = dataclasses.replace(Params.from_config(cfg), bridge_kind=kind, shoulder_vel=(sh_pos, sh_neg), max_vel=max_vel)
+        e = Engine(chain, precision=64, params=prm)
+        try:
+            db = DeviceBatch(e, n, 0, outputs=("cmd", "qdot"))
+            e.set_vel(db.to_blocked(qd), db.to_blocked(q), db.t["cmd"], max_vel, direct, 7, n, q_cmded=db.to_blocked(qc),
+                      qdot_lim_out=db.t["qdot"])
+            assert np.allclose(db.download("cmd").T, g[key], rtol=1e-14, atol=1e-15), key
+        finally:
+            e.close()

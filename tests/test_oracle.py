@@ -214,6 +214,7 @@ def test_golden_is_reproducible_from_reference(golden):
     rng = np.random.default_rng(20261018)
     data = gen_golden.gen_mixer(rng)
     data.update(gen_golden.gen_nullspace(rng))
+    data.update(gen_golden.gen_bridge(rng))
     for k, v in data.items():
         assert np.allclose(np.asarray(v, dtype=np.float64), np.asarray(golden[k], dtype=np.float64), equal_nan=True,
                            atol=1e-12), k
@@ -262,3 +263,48 @@ def test_powercube_bridge_restatement_matches_batch(lwr):
         first = ref["qdot_mix"][0, 0] * min(1.0, prm.max_vel / lead)
         seen.add("shoulder" if (first > 0.05 or first < -0.08) else ("double" if lead > prm.max_vel else "none"))
     assert {"shoulder", "double"} <= seen
+
+
+def test_golden_bridge_backends_joint_limits_and_weight_matrix(golden, capsys):
+    """Vectors produced by executing the reference's own `set_vel` of the three bridge back-ends, `set_torso_cjoints`,
+    `joint_p_controller.check_limits` and `vf.get_weight_matrix` (oracle/gen_golden.py:gen_bridge) against the oracle's
+    restatement and the host modules' parsers."""
+    import dataclasses
+    import types
+    g = golden
+    qdot, q, qc = g["br_qdot"], g["br_q"], g["br_qcmded"]
+    max_vel, sh_pos, sh_neg = [float(v) for v in g["br_cfg"]]
+    base = dataclasses.replace(batch.Params(), max_vel=max_vel, shoulder_vel=(sh_pos, sh_neg))
+    for direct in (0, 1):
+        _, cmd, _ = batch.bridge_set_vel(base, qdot, q, qc, bool(direct))
+        assert np.allclose(cmd, g["br_lwr_cmd_direct%d" % direct], rtol=1e-14, atol=1e-15)
+    for kind, key in ((1, "br_powercube_cmd"), (2, "br_icub_cmd")):
+        qd, cmd, _ = batch.bridge_set_vel(dataclasses.replace(base, bridge_kind=kind), qdot, q, qc, False)
+        assert np.allclose(cmd, g[key], rtol=1e-14, atol=1e-15) and np.array_equal(cmd, qd)
+    # the vectors exercise every branch: no clamp, leading clamp only (applied twice by the Powercube code), shoulder clamp
+    lead = np.max(np.abs(qdot), axis=1)
+    first = qdot[:, 0] * np.minimum(1.0, max_vel / lead)
+    assert np.any(lead <= max_vel) and np.any((lead > max_vel) & (first <= sh_pos) & (first >= sh_neg))
+    assert np.any(first > sh_pos) and np.any(first < sh_neg)
+    # joint_p_controller.check_limits through the module's own clamp (posture-dependent limits)
+    from vfclik_b200.joint_p_controller import JointPControllerModule
+    sent = []
+    jp = object.__new__(JointPControllerModule)
+    jp.nJoints = 7
+    jp.rt = types.SimpleNamespace(config=types.SimpleNamespace(updateJntLimits=lambda cur: [[-0.5 - abs(cur[0]), 0.4 + abs(cur[1])]] * 7),
+                                  set_jp_ref=lambda r: sent.append(list(r)))
+    for k in range(g["jp_ref"].shape[0]):
+        jp.ref = list(g["jp_ref"][k])
+        jp._ref_sent = None
+        jp._apply_position_dependent_limits(list(q[k]))
+        assert np.array_equal(jp._ref_sent, g["jp_ref_clamped"][k])
+    capsys.readouterr()
+    # vf.get_weight_matrix: diagonal of the reference's matrix; wrong sizes ignored
+    from vfclik_b200 import ports as yarp
+    from vfclik_b200.vf import get_weight_matrix
+    for tag, w, mat, n in (("t", g["vf_wt"], g["vf_wt_matrix"], 6), ("j", g["vf_wj"], g["vf_wj_matrix"], 7)):
+        b = yarp.Bottle.from_list([tag] + [float(v) for v in w])
+        got = get_weight_matrix(b, n)
+        assert np.array_equal(np.diag(got), mat)
+        assert get_weight_matrix(yarp.Bottle.from_list([tag] + [float(v) for v in w[:3]]), n) is None
+    assert "Wrong size" in capsys.readouterr().out
