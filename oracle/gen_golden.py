@@ -317,6 +317,96 @@ def gen_bridge(rng):
     return out
 
 
+def load_reference_loop_body(relpath: str, head: str, end_marker: str) -> str:
+    """Body of a top-level ``while`` loop of a reference script (from the line after ``head`` to the line before
+    ``end_marker``), dedented -- the module programs keep their logic inline in that loop."""
+    import textwrap
+    lines = open(os.path.join(REF, relpath)).read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if l.startswith(head)) + 1
+    i1 = next(i for i in range(i0, len(lines)) if lines[i].startswith(end_marker))
+    return textwrap.dedent("\n".join(lines[i0:i1])) + "\n"
+
+
+class Py2IntKeyDict(dict):
+    """The reference runs under python 2, whose dicts iterate small non-negative int keys in ascending order;
+    python 3 keeps insertion order.  Used for the feeder's ``objects`` so the emission order is the reference's."""
+
+    def __iter__(self):
+        return iter(sorted(dict.keys(self)))
+
+
+FEEDER_SCRIPT = [
+    ["set", "ObstacleP", 0, [1, 0, 0, 0.0, 0, 1, 0, -0.4, 0, 0, 1, 0.4, 0, 0, 0, 1, 0.05, 20]],          # old/README.old:75 (before any goal)
+    ["set", "goal", [0, 1, 0, 0, -1, 0, 0, 0.3, 0, 0, 1, 1.1, 0, 0, 0, 1, 0.1]],                         # old/README.old:69
+    ["set", "ObstacleH", 1, [1, 0, 0, 0, 0, 1, 0, -0.4, 0, 0, 1, 0.3, 0, 0, 0, 1, 0, 0, 1, 0.001, 5]],   # old/README.old:78
+    ["set", "goalAndNormal", [1, 0, 0, 0.4, 0, -1, 0, -0.4, 0, 0, -1, 0.4, 0, 0, 0, 1, 0, -1, 0, 0.1, 0.15, 0.15]],   # :72-73
+    ["set", "goal", [1, 0, 0, 0.5, 0, 1, 0, 0.1, 0, 0, 1, 0.9, 0, 0, 0, 1]],                             # 16 values: default slowdown
+    ["set", "goal", [1.0, 2.0, 3.0]],                                                                   # wrong length
+    ["set", "ObstacleP", 2, [1, 0, 0, 0.2, 0, 1, 0, 0.1, 0, 0, 1, 0.7, 0, 0, 0, 1, 0.08, 7]],
+    ["remove", 0],
+    ["remove", 5],                                                                                       # does not exist
+    ["fly", "goal", [1.0]],                                                                              # unknown action
+    ["set", "goalAndNormal", [1, 0, 0, 0.4, 0, -1, 0, -0.4, 0, 0, -1, 0.4, 0, 0, 0, 1, 0, 0, 2, 0.1, 0.15]],   # 21 values
+]
+
+
+def gen_feeder(rng=None):
+    """``scripts/object_feeder``'s loop body (:93-359) executed message by message on the scripted sequence above, with
+    this repo's in-process bottles / ports standing in for YARP and ``vfl.vfl.length`` taken as the Euclidean norm.
+    Returns the messages it wrote to ``/param`` and ``/objectOut`` as one JSON string per input message."""
+    import json
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vfclik_b200 import ports as yarp
+    body = load_reference_loop_body("scripts/object_feeder", "while not stop:", "paramPort.close()")
+    code = compile("def _iteration():\n    global init_pose\n    while True:\n" +
+                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
+                   "<reference scripts/object_feeder loop>", "exec")
+
+    class Out:
+        def __init__(self):
+            self.sent = []
+            self.b = None
+
+        def prepare(self):
+            self.b = yarp.Bottle()
+            return self.b
+
+        def writeStrict(self):
+            self.sent.append(self.b.to_list())
+
+        write = writeStrict
+
+    class In:
+        def __init__(self):
+            self.q = []
+
+        def read(self, wait=False):
+            if not self.q:
+                raise EndOfScript()           # the loop came back for another message (`continue`): iteration over
+            return self.q.pop(0)
+
+    class EndOfScript(Exception):
+        pass
+
+    param, objout, objf, obj = Out(), Out(), Out(), In()
+    glb = dict(yarp=types.SimpleNamespace(Bottle=yarp.Bottle, Time_delay=lambda t: None), yarp_ctrl=types.SimpleNamespace(update=lambda: None),
+               objectPort=obj, object_f_port=objf, paramPort=param, objectOutPort=objout, objects=Py2IntKeyDict(),
+               init_pose=False, config=types.SimpleNamespace(), dprint=lambda *a: None, array=np.array,
+               length=lambda v: float(np.linalg.norm(v)), recur=None, stop=False)
+    exec(code, glb)
+    rows = []
+    for msg in FEEDER_SCRIPT:
+        obj.q.append(yarp.Bottle.from_list(msg))
+        param.sent, objout.sent = [], []
+        with redirect_stdout(io.StringIO()):
+            try:
+                glb["_iteration"]()
+            except EndOfScript:
+                pass
+        rows.append(json.dumps({"param": param.sent, "objectOut": objout.sent}))
+    return {"feeder_script": np.array([json.dumps(m) for m in FEEDER_SCRIPT]), "feeder_out": np.array(rows)}
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
@@ -326,6 +416,7 @@ def main():
     data.update(gen_mixer(rng))
     data.update(gen_nullspace(rng))
     data.update(gen_bridge(rng))
+    data.update(gen_feeder())
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

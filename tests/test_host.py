@@ -220,3 +220,43 @@ def test_object_feeder_parses_the_reference_example_bottles(capsys):
         assert "Object doesn't exist" in capsys.readouterr().out
     finally:
         fd.close(); sink.close(); src.close(); yarp.Network.reset()
+
+
+def test_object_feeder_matches_the_reference_loop_message_for_message(golden, capsys):
+    """tests/golden holds what scripts/object_feeder's own loop body (:93-359), executed by oracle/gen_golden.py:gen_feeder,
+    wrote to /param and /objectOut for a scripted message sequence (the README examples, default slowdown, wrong lengths,
+    removals, an unknown action).  The host module must write exactly the same messages in the same order."""
+    import json
+    from vfclik_b200 import ports as yarp
+    from vfclik_b200.config import PACKAGE_CONFIG_DIR, config_filename, load_config
+    from vfclik_b200.object_feeder import ObjectFeederModule
+    yarp.Network.reset()
+    cfg = load_config(config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right"))
+    del cfg.initial_vf_pose
+    fd = ObjectFeederModule(cfg, "/g")
+    sinks = {}
+    for name, port in (("param", fd.paramPort), ("objectOut", fd.objectOutPort)):
+        p = yarp.BufferedPortBottle(); p.open("/g/sink_" + name); p.setStrict(True)
+        yarp.Network.connect(port.getName(), "/g/sink_" + name)
+        sinks[name] = p
+    src = yarp.BufferedPortBottle(); src.open("/g/src")
+    yarp.Network.connect("/g/src", fd.objectPort.getName())
+    try:
+        for msg, want in zip(golden["feeder_script"], golden["feeder_out"]):
+            yarp.write_bottle_lists(src, json.loads(str(msg)), strict=True)
+            assert fd.update()
+            got = {}
+            for name, p in sinks.items():
+                got[name] = []
+                while True:
+                    b = p.read(False)
+                    if b is None:
+                        break
+                    got[name].append(b.to_list())
+            assert got == json.loads(str(want)), str(msg)
+    finally:
+        fd.close(); src.close()
+        for p in sinks.values():
+            p.close()
+        yarp.Network.reset()
+    capsys.readouterr()
