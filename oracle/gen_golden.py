@@ -407,6 +407,69 @@ def gen_feeder(rng=None):
     return {"feeder_script": np.array([json.dumps(m) for m in FEEDER_SCRIPT]), "feeder_out": np.array(rows)}
 
 
+def gen_jp(rng):
+    """``scripts/joint_p_controller``'s loop body (:96-146) with the reference's own ``check_limits`` (:79-89), one
+    iteration per scripted step: an optional new reference on ``/ref``, joint positions on ``/in``; records ``/out`` and
+    ``/at_goal``.  Two limit hooks: the LWR's static limits and posture-dependent ones (the clamped reference persists
+    between cycles -- the loop overwrites ``ref`` -- which only shows with the latter).  ``map`` is given its python-2
+    meaning (a list), which the loop relies on for its side effects."""
+    import builtins
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vfclik_b200 import ports as yarp
+    N, steps, kp, delta = 7, 18, 1.5, 0.087
+    deg = np.pi / 180.0
+    static = [[-170 * deg, 170 * deg], [-120 * deg, 120 * deg]] * 3 + [[-170 * deg, 170 * deg]]
+    hooks = {"static": lambda cur: static, "dynamic": lambda cur: [[-0.5 - abs(cur[0]), 0.4 + abs(cur[1])]] * N}
+    q = rng.uniform(-1.0, 1.0, size=(steps, N))
+    q[12:] = q[11] + rng.normal(scale=0.01, size=(steps - 12, N))          # nearly at rest near the last reference
+    refs = {0: rng.uniform(-3.5, 3.5, size=N), 5: rng.uniform(-0.3, 0.3, size=N), 11: q[11] + 0.05}
+    body = load_reference_loop_body("scripts/joint_p_controller", "while not stop:", "inPort.close()")
+    code = compile("def _iteration():\n    global ref, waitRef, refbottle\n    while True:\n" +
+                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
+                   "<reference scripts/joint_p_controller loop>", "exec")
+
+    class In:
+        def __init__(self):
+            self.q = []
+
+        def read(self, wait=False):
+            return self.q.pop(0) if self.q else None
+
+    class Out:
+        def __init__(self):
+            self.sent, self.b = [], None
+
+        def prepare(self):
+            self.b = yarp.Bottle()
+            return self.b
+
+        def write(self, *a):
+            self.sent.append(self.b.to_list())
+
+    out = {"jp_q": q, "jp_ref_steps": np.array(sorted(refs)), "jp_ref_msgs": np.array([refs[k] for k in sorted(refs)]),
+           "jp_static_limits": np.array(static)}
+    for name, hook in hooks.items():
+        refp, inp, outp, goalp = In(), In(), Out(), Out()
+        cfg = types.SimpleNamespace(nJoints=N, initial_joint_pos=[0.0, -1.2, 0.7, 1.4, 0.35, -1.4, 0.0], updateJntLimits=hook)
+        glb = dict(yarp=types.SimpleNamespace(Bottle=yarp.Bottle, Value=yarp.Value, Time=types.SimpleNamespace(delay=lambda t: None)),
+                   yarp_ctrl=types.SimpleNamespace(update=lambda: None), refPort=refp, inPort=inp, outPort=outp, atGoalPort=goalp,
+                   config=cfg, kp=kp, delta=delta, array=np.array, stop=False,
+                   map=lambda f, *a: list(builtins.map(f, *a)), ref=cfg.initial_joint_pos, waitRef=False, refbottle=yarp.Bottle())
+        with redirect_stdout(io.StringIO()):
+            exec(load_reference_function("scripts/joint_p_controller", "check_limits"), glb)
+            exec(code, glb)
+            for k in range(steps):
+                if k in refs:
+                    refp.q.append(yarp.Bottle.from_list([float(v) for v in refs[k]]))
+                inp.q.append(yarp.Bottle.from_list([float(v) for v in q[k]]))
+                glb["_iteration"]()
+        assert len(outp.sent) == steps and len(goalp.sent) == steps
+        out["jp_out_" + name] = np.asarray(outp.sent)
+        out["jp_at_goal_" + name] = np.asarray([g[0] for g in goalp.sent])
+    out["jp_kp_delta"] = np.array([kp, delta])
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
@@ -417,6 +480,7 @@ def main():
     data.update(gen_nullspace(rng))
     data.update(gen_bridge(rng))
     data.update(gen_feeder())
+    data.update(gen_jp(rng))
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

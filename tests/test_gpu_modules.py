@@ -392,14 +392,17 @@ def test_joint_controller_position_dependent_limits(lwr, built_lib, fresh_ports,
         out = fresh_ports.BufferedPortBottle(); out.open("/5/test/out")
         fresh_ports.Network.connect(jp.outPort.getName(), "/5/test/out")
         fresh_ports.sendListPort(ref, [1.0, -1.0, 0.2, 0.0, 0.0, 0.0, 0.0])
-        for q0, lim in ((0.0, 0.5), (0.3, 0.8)):
+        ref_now = np.array([1.0, -1.0, 0.2, 0, 0, 0, 0])
+        for q0, lim in ((0.3, 0.8), (0.0, 0.5), (0.3, 0.8)):
             q = [q0, 0.1, 0.0, 0.0, 0.0, 0.0, 0.0]
             fresh_ports.sendListPort(enc, q)
             assert jp.update()
             b = out.read(False)
             got = [b.get(i).asDouble() for i in range(7)]
-            want = cfg.jpctrl_kp * (np.clip([1.0, -1.0, 0.2, 0, 0, 0, 0], -lim, lim) - np.asarray(q))
+            ref_now = np.clip(ref_now, -lim, lim)        # the clamp persists (scripts/joint_p_controller:121): 0.8 -> 0.5 -> stays 0.5
+            want = cfg.jpctrl_kp * (ref_now - np.asarray(q))
             assert np.allclose(got, want, rtol=1e-12, atol=1e-14), (q0, got, want)
+        assert np.allclose(ref_now[:3], [0.5, -0.5, 0.2])
         text = capsys.readouterr().out
         assert "Limiting high 0" in text and "Limiting low 1" in text
     finally:
@@ -427,3 +430,44 @@ def test_set_vel_kernel_against_reference_golden_vectors(lwr, golden, built_lib)
             assert np.allclose(db.download("cmd").T, g[key], rtol=1e-14, atol=1e-15), key
         finally:
             e.close()
+
+
+def test_joint_controller_module_matches_the_reference_loop(lwr, golden, built_lib, fresh_ports, capsys):
+    """/jpctrl/out and /jpctrl/at_goal against what the reference's own loop body (scripts/joint_p_controller:96-146, with
+    its check_limits) produced for a scripted sequence of /ref and /in messages -- static LWR limits and posture-dependent
+    limits, where the persisting clamp and the signed at-goal compare both show."""
+    import copy
+    from vfclik_b200.joint_p_controller import JointPControllerModule
+    from vfclik_b200.runtime import ControlRuntime
+    _, cfg = lwr
+    g = golden
+    steps = {int(k): g["jp_ref_msgs"][i] for i, k in enumerate(g["jp_ref_steps"])}
+    kp, delta = [float(v) for v in g["jp_kp_delta"]]
+    hooks = {"static": lambda cur: [list(r) for r in g["jp_static_limits"]],
+             "dynamic": lambda cur: [[-0.5 - abs(cur[0]), 0.4 + abs(cur[1])]] * 7}
+    for name, hook in hooks.items():
+        fresh_ports.Network.reset()
+        c = copy.copy(cfg)
+        c.updateJntLimits, c.jpctrl_kp = hook, kp
+        rt = ControlRuntime(c, n_instances=1, precision=64)
+        jp = JointPControllerModule(rt, "/6")
+        try:
+            enc = _out_port(fresh_ports, "/6/test/enc", jp.inPort.getName())
+            ref = _out_port(fresh_ports, "/6/test/ref", jp.refPort.getName())
+            out = fresh_ports.BufferedPortBottle(); out.open("/6/test/out")
+            goal = fresh_ports.BufferedPortBottle(); goal.open("/6/test/goal")
+            fresh_ports.Network.connect(jp.outPort.getName(), "/6/test/out")
+            fresh_ports.Network.connect(jp.atGoalPort.getName(), "/6/test/goal")
+            for k in range(g["jp_q"].shape[0]):
+                if k in steps:
+                    fresh_ports.sendListPort(ref, [float(v) for v in steps[k]])
+                fresh_ports.sendListPort(enc, [float(v) for v in g["jp_q"][k]])
+                assert jp.update()
+                b, a = out.read(False), goal.read(False)
+                got = [b.get(i).asDouble() for i in range(7)]
+                assert np.allclose(got, g["jp_out_" + name][k], rtol=1e-12, atol=1e-14), (name, k)
+                assert a.get(0).asInt() == int(g["jp_at_goal_" + name][k]), (name, k)
+        finally:
+            jp.close(); rt.close()
+    capsys.readouterr()
+    assert g["jp_at_goal_static"].max() == 1 and g["jp_at_goal_static"].min() == 0

@@ -216,6 +216,7 @@ def test_golden_is_reproducible_from_reference(golden):
     data.update(gen_golden.gen_nullspace(rng))
     data.update(gen_golden.gen_bridge(rng))
     data.update(gen_golden.gen_feeder())
+    data.update(gen_golden.gen_jp(rng))
     for k, v in data.items():
         if np.asarray(v).dtype.kind in "US":
             assert [str(x) for x in v] == [str(x) for x in golden[k]], k
@@ -312,3 +313,27 @@ def test_golden_bridge_backends_joint_limits_and_weight_matrix(golden, capsys):
         assert np.array_equal(np.diag(got), mat)
         assert get_weight_matrix(yarp.Bottle.from_list([tag] + [float(v) for v in w[:3]]), n) is None
     assert "Wrong size" in capsys.readouterr().out
+
+
+def test_golden_joint_p_controller_loop(golden, lwr):
+    """The reference-shaped loop's joint-controller stage against the reference's own loop (scripts/joint_p_controller:96-146)
+    run on a scripted sequence with the LWR's static limits: clamp, P law and the signed at-goal compare."""
+    chain, cfg = lwr
+    g = golden
+    kp, delta = [float(v) for v in g["jp_kp_delta"]]
+    assert np.allclose(g["jp_static_limits"], np.stack([chain.q_lo, chain.q_hi], axis=1))
+    prm = batch.Params(jp_kp=kp, jp_delta=delta, jp_ref=tuple(cfg.initial_joint_pos))
+    steps = {int(k): g["jp_ref_msgs"][i] for i, k in enumerate(g["jp_ref_steps"])}
+    loop = refshape.ControlLoop(chain, prm, g["jp_q"][0], cfg.initial_vf_pose[2])
+    for k in range(g["jp_q"].shape[0]):
+        if k in steps:
+            loop.ref = [float(v) for v in steps[k]]
+        loop.q = [float(v) for v in g["jp_q"][k]]
+        with redirect_stdout(io.StringIO()):
+            loop.cycle()
+        assert np.allclose(loop.last["qdot_jp"], g["jp_out_static"][k], rtol=1e-13, atol=1e-15), k
+        assert bool(loop.last["flags"] & batch.FLAG_AT_GOAL) == bool(g["jp_at_goal_static"][k]), k
+        # the vectorised oracle on the same step (any goal: the joint controller does not look at it)
+        goal = np.array([[1, 0, 0, 0, 1, 0, 0, 0, 1, 0.5, 0.0, 0.8, 0.05]], dtype=np.float64)
+        ref_b = batch.step(chain, prm, g["jp_q"][k][None], goal, None, jp_ref=np.asarray(steps[max(s for s in steps if s <= k)])[None])
+        assert np.allclose(ref_b["qdot_jp"][0], g["jp_out_static"][k], rtol=1e-13, atol=1e-15), k

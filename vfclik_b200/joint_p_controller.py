@@ -75,6 +75,7 @@ class JointPControllerModule:
         if ref_out != getattr(self, "_ref_sent", self.ref):
             self.rt.set_jp_ref(ref_out)
         self._ref_sent = ref_out
+        self.ref = ref_out            # the reference's loop overwrites `ref` with the clamped value (:121): the clamp persists
 
     def close(self):
         self.yarp_ctrl.close()
