@@ -324,7 +324,8 @@ def load_reference_loop_body(relpath: str, head: str, end_marker: str) -> str:
     lines = open(os.path.join(REF, relpath)).read().splitlines()
     i0 = next(i for i, l in enumerate(lines) if l.startswith(head)) + 1
     i1 = next(i for i in range(i0, len(lines)) if lines[i].startswith(end_marker))
-    return textwrap.dedent("\n".join(lines[i0:i1])) + "\n"
+    body = [l for l in lines[i0:i1] if not l.lstrip().startswith("#")]      # column-0 comments would defeat the dedent
+    return textwrap.dedent("\n".join(body)) + "\n"
 
 
 class Py2IntKeyDict(dict):
@@ -470,6 +471,126 @@ def gen_jp(rng):
     return out
 
 
+def gen_vf(rng):
+    """``scripts/vf``'s loop body (:193-505) executed cycle by cycle.  PyKDL, arcospyu.Lafik and vfl are un-vendored, so the
+    oracle's stand-ins (``oracle/refshape.py``) take their names: what this pins is everything the reference's own loop does
+    around them -- field bookkeeping and composition order, weight and tool handling, the speed-scale rule, the pose /
+    tracking-error / vector_out / goal_out ports and their cadence, the tool twist shift and the call into the IK.
+    The plant is closed around it (q += rate * qdot) so the tracking-error block sees a moving arm."""
+    import builtins
+    import json
+    from math import acos, sqrt
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vfclik_b200 import ports as yarp
+    from . import refshape
+    from .batch import Params
+    cfgfile = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vfclik_b200", "config_data", "lwr",
+                           "config-lwr-right.py")
+    from vfclik_b200.config import chain_from_config, load_config
+    cfg = load_config(cfgfile)
+    chain = chain_from_config(cfg)
+    prm = Params(ik_lambda=cfg.ik_lambda, speed_scale=cfg.speedScale)
+    body = load_reference_loop_body("scripts/vf", "while not stop:", "qdotOutPort.close()")
+    state = ["speedScale", "start_attractor", "first_arm_data", "first_arm_frame", "oldtoolFrame", "totalVF", "totalSF", "vftemp",
+             "vfparams", "counter_test", "reporting_port_counter", "frame_list", "cmd_buffer", "vectorFields", "first_cycle"]
+    code = compile("def _iteration():\n    global " + ", ".join(s for s in state if s != "speedScale") + "\n    while True:\n" +
+                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
+                   "<reference scripts/vf loop>", "exec")
+
+    class In:
+        def __init__(self):
+            self.q = []
+
+        def read(self, wait=False):
+            return self.q.pop(0) if self.q else None
+
+    class Out:
+        def __init__(self):
+            self.sent, self.b = [], None
+
+        def prepare(self):
+            self.b = yarp.Bottle()
+            return self.b
+
+        def write(self, *a):
+            self.sent.append(self.b.to_list())
+
+        writeStrict = write
+
+    ins = {k: In() for k in ("maxvel_port", "paramPort", "weightPort", "qInPort", "toolPort", "pose_in_port")}
+    outs = {k: Out() for k in ("qdotOutPort", "posePort", "pose_no_tool_Port", "tracking_error_port", "vector_port", "goal_port")}
+
+    def sendListPort(port, l):
+        b = port.prepare()
+        for v in l:
+            b.addDouble(v)
+        port.write()
+
+    def readListPort(port, blocking=False):
+        b = port.read(blocking)
+        return None if b is None else [b.get(i).asDouble() for i in range(b.size())]
+
+    vfDB = refshape.vfl_library()
+    refshape._PointAttractor.rot_slowdown = prm.rot_slowdown
+    vft = vfDB[0]()
+    vft.setParams([])
+    glb = dict(yarp=types.SimpleNamespace(Value=yarp.Value, Value_makeString=yarp.Value_makeString, Bottle=yarp.Bottle,
+                                          Time=types.SimpleNamespace(delay=lambda t: None)),
+               yarp_ctrl=types.SimpleNamespace(update=lambda: None), config=cfg, numJntsArm=cfg.nJoints, config_max_vel=0.41,
+               speedScale=cfg.speedScale, vfDB=vfDB, VectorField=refshape.VectorField, ScalarField=refshape.ScalarField,
+               lafik=refshape.Lafik(chain, prm), PyKDL=types.SimpleNamespace(diff=refshape.kdl_diff, Twist=refshape.Twist,
+                                                                           Vector=lambda x, y, z: np.array([x, y, z])),
+               listToKdlFrame=refshape.listToKdlFrame, kdlFrameToList=refshape.kdlFrameToList, sendListPort=sendListPort,
+               readListPort=readListPort, sqrt=sqrt, acos=acos, dot=np.dot, array=np.array, dprint=lambda *a: None,
+               map=lambda f, *a: list(builtins.map(f, *a)), stop=False,
+               vectorFields=Py2IntKeyDict(), vfparams=[], vftemp=vft, totalVF=refshape.VectorField(vft.getVector),
+               totalSF=refshape.ScalarField(vft.getScalar), oldtoolFrame=[1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1],
+               frame_list=[], cmd_buffer=[], cmd_buffer_size=4, frame_list_size=5, check_delay=4, first_cycle=True,
+               start_attractor=False, first_arm_data=True, first_arm_frame=None, reporting_port_counter=0, counter_test=0)
+    glb.update(ins)
+    glb.update(outs)
+    with redirect_stdout(io.StringIO()):
+        exec(load_reference_function("scripts/vf", "get_weight_matrix"), dict(zeros=np.zeros, dprint=lambda *a: None), glb)
+    glb["zeros"] = np.zeros
+    exec(load_reference_function("scripts/vf", "get_weight_matrix"), glb)
+    exec(code, glb)
+
+    goal = [float(v) for v in cfg.initial_vf_pose[2]]
+    script = {
+        1: {"paramPort": ["add", 1, 1.0, 1, goal]},
+        2: {"paramPort": ["add", 5, -10.0, 2, [0.55, 0.10, 1.05, 0.06, 0.001, 20.0]]},
+        3: {"paramPort": ["add", 6, -10.0, 2, [0.30, 0.25, 1.20, 0.05, 0.001, 20.0]]},
+        6: {"weightPort": ["t", 1.0, 1.0, 1.0, 0.5, 0.5, 0.5]},
+        8: {"toolPort": [1.0, 0.0, 0.0, 0.02, 0.0, 1.0, 0.0, -0.01, 0.0, 0.0, 1.0, 0.12, 0.0, 0.0, 0.0, 1.0]},
+        10: {"maxvel_port": [0.3]},
+        12: {"maxvel_port": [0.9]},                                        # out of range: ignored
+        14: {"paramPort": ["add", 9, -10.0, 7, [0.0, 0.0, 0.0]]},           # unknown field type: ignored
+        16: {"weightPort": ["j", 1.0, 1.0, 0.7, 1.0, 1.0, 0.4]},            # wrong length: ignored
+        18: {"paramPort": ["remove", 6]},
+        20: {"weightPort": ["j", 1.0, 1.0, 0.7, 1.0, 1.0, 0.4, 1.0]},
+        24: {"pose_in_port": [1.0, 0.0, 0.0, 0.5, 0.0, 1.0, 0.0, 0.2, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0]},
+        30: {"paramPort": ["add", 2, 30.0, 5, [goal[3], goal[7], goal[11], 0.0, 0.0, -1.0, 0.3, 10.0, 0.15, 2.0]]},
+    }
+    steps = 48
+    q = [float(v) for v in cfg.initial_joint_pos]
+    rows, qs = [], []
+    for k in range(steps):
+        for port, msg in script.get(k, {}).items():
+            ins[port].q.append(yarp.Bottle.from_list(msg))
+        ins["qInPort"].q.append(yarp.Bottle.from_list(q))
+        for o in outs.values():
+            o.sent = []
+        with redirect_stdout(io.StringIO()):
+            glb["_iteration"]()
+        rows.append(json.dumps({name: o.sent for name, o in outs.items()}))
+        qs.append(list(q))
+        if outs["qdotOutPort"].sent:
+            qd = outs["qdotOutPort"].sent[-1]
+            q = [q[i] + float(cfg.rate) * 25.0 * qd[i] for i in range(len(q))]      # exaggerated step: visible motion in 48 cycles
+    return {"vf_script": np.array([json.dumps({str(k): v for k, v in script.items()})]), "vf_q": np.asarray(qs),
+            "vf_out": np.array(rows)}
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
@@ -481,6 +602,7 @@ def main():
     data.update(gen_bridge(rng))
     data.update(gen_feeder())
     data.update(gen_jp(rng))
+    data.update(gen_vf(rng))
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

@@ -471,3 +471,52 @@ def test_joint_controller_module_matches_the_reference_loop(lwr, golden, built_l
             jp.close(); rt.close()
     capsys.readouterr()
     assert g["jp_at_goal_static"].max() == 1 and g["jp_at_goal_static"].min() == 0
+
+
+def test_vf_module_matches_the_reference_loop_cycle_by_cycle(lwr, golden, built_lib, fresh_ports, capsys):
+    """Every port of the vf module against what the reference's own loop body (scripts/vf:193-505; PyKDL / Lafik / vfl replaced
+    by the oracle's stand-ins, oracle/gen_golden.py:gen_vf) published for a scripted run: field add / remove / unknown type,
+    task and joint weights (one with a wrong length), a tool frame, speed-scale changes (one out of range), a pose query, the
+    message swallowed by `start_attractor`, tracking errors from the 6th frame, vector_out / goal_out every 21st cycle."""
+    import json
+    from vfclik_b200.runtime import ControlRuntime
+    from vfclik_b200.vf import VectorFieldModule
+    _, cfg = lwr
+    g = golden
+    script = {int(k): v for k, v in json.loads(str(g["vf_script"][0])).items()}
+    rt = ControlRuntime(cfg, n_instances=1, precision=64)
+    vf = VectorFieldModule(rt, "/8")
+    names = {"qdotOutPort": vf.qdotOutPort, "posePort": vf.posePort, "pose_no_tool_Port": vf.pose_no_tool_Port,
+             "tracking_error_port": vf.tracking_error_port, "vector_port": vf.vector_port, "goal_port": vf.goal_port}
+    ins = {"maxvel_port": vf.maxvel_port, "paramPort": vf.paramPort, "weightPort": vf.weightPort, "qInPort": vf.qInPort,
+           "toolPort": vf.toolPort, "pose_in_port": vf.pose_in_port}
+    try:
+        sinks = {}
+        for name, port in names.items():
+            p = fresh_ports.BufferedPortBottle(); p.open("/8/sink/" + name); p.setStrict(True)
+            fresh_ports.Network.connect(port.getName(), "/8/sink/" + name)
+            sinks[name] = p
+        feeds = {name: _out_port(fresh_ports, "/8/feed/" + name, port.getName()) for name, port in ins.items()}
+        for k in range(g["vf_q"].shape[0]):
+            for port, msg in script.get(k, {}).items():
+                fresh_ports.write_bottle_lists(feeds[port], msg, strict=True)
+            fresh_ports.sendListPort(feeds["qInPort"], [float(v) for v in g["vf_q"][k]])
+            vf.update()
+            want = json.loads(str(g["vf_out"][k]))
+            for name, p in sinks.items():
+                got = []
+                while True:
+                    b = p.read(False)
+                    if b is None:
+                        break
+                    got.append(b.to_list())
+                assert len(got) == len(want[name]), (k, name, len(got), len(want[name]))
+                for a, w in zip(got, want[name]):
+                    if name == "tracking_error_port":
+                        assert np.allclose(a[:7], w[:7], rtol=1e-6, atol=1e-9), (k, name, a, w)
+                        assert int(a[7]) == int(w[7]), (k, name)
+                    else:
+                        assert np.allclose(a, w, rtol=1e-8, atol=1e-11), (k, name, a, w)
+    finally:
+        vf.close(); rt.close()
+    capsys.readouterr()

@@ -74,9 +74,8 @@ class MonitorDistanceModule:
         self._seen_cycle = self.rt.cycles
         e, m = self.rt.engine, self._device_state()
         b = _session_device_view(self.rt)
-        e.monitor(int(b.pose), int(b.twist), int(b.goal), m["f"], m["i"], self.rt.I, track_out=m["track"],
-                  dist_out=m["dist"], tracking_state_out=m["state"])
-        dist, state, track = self._unblock(m["dist"]), self._unblock(m["state"]), self._unblock(m["track"])
+        shared = self.rt.monitor()                    # one vfk_monitor launch per cycle, shared with vf's /track_error
+        dist, state, track = shared["dist"], shared["state"], shared["track"]
         out = self.distOutPort.prepare()
         out.clear()
         entries = []

@@ -60,6 +60,9 @@ class ControlRuntime:
         self._q_cached = None
         self._out = None
         self.cycles = 0
+        self._mon = None
+        self._mon_out = None
+        self._mon_cycle = -1
 
     # ------------------------------------------------------------------ parameters
     @property
@@ -226,6 +229,39 @@ class ControlRuntime:
         used = int(np.any(self.aux[:, 0, :] != 0, axis=1).sum())
         self.session.set_aux(self.aux[:used] if used else None)
         self._scene_dirty = False
+
+    # ------------------------------------------------------------------ monitoring
+    def monitor(self, advance: bool = False) -> dict:
+        """Tracking diagnostics (``scripts/vf:349-428``) and goal distance / majority state
+        (``scripts/monitor_distance:76-84,148-219``) of the last cycle, from ONE ``vfk_monitor`` launch per cycle: the vf
+        module publishes ``track`` on ``/track_error``, the distance monitor reads all three.  ``seen`` counts the frames
+        the history holds (the reference publishes tracking errors from the 6th frame on)."""
+        import torch
+        # advance=True (the vf module, once per iteration with joint data -- the reference appends a frame every iteration,
+        # moving or not) always evaluates; otherwise the result of the current cycle is reused
+        if not advance and getattr(self, "_mon_cycle", -1) == self.cycles and self._mon_out is not None:
+            return self._mon_out
+        e = self.engine
+        if getattr(self, "_mon", None) is None:
+            self._mon = dict(f=e.alloc(32, self.I), i=e.alloc(6, self.I, dtype=torch.int32), track=e.alloc(8, self.I),
+                             dist=e.alloc(2, self.I), state=e.alloc(2, self.I, dtype=torch.int32))
+            self._mon_seen = 0
+        m = self._mon
+        b = _session_device_view(self)
+        e.monitor(int(b.pose), int(b.twist), int(b.goal), m["f"], m["i"], self.I, track_out=m["track"], dist_out=m["dist"],
+                  tracking_state_out=m["state"])
+        self._mon_seen += 1
+
+        def unblock(t):
+            comps = t.shape[1]
+            if t.dtype == torch.int32:
+                return t.cpu().numpy().transpose(1, 0, 2).reshape(comps, -1)[:, :self.I]
+            d = torch.empty((comps, self.I), dtype=t.dtype, device=t.device)
+            e.unpack(t, d, comps, 1, self.I)
+            return d.cpu().numpy()
+        self._mon_out = dict(track=unblock(m["track"]), dist=unblock(m["dist"]), state=unblock(m["state"]), seen=self._mon_seen)
+        self._mon_cycle = self.cycles
+        return self._mon_out
 
     def close(self):
         self.session.close()

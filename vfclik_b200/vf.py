@@ -60,6 +60,8 @@ class VectorFieldModule:
         self.oldtoolFrame = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]       # scripts/vf:154
         self.reporting_port_counter = 0
         self.last_qdot = None
+        self.first_arm_data = True        # scripts/vf:183-184,335-338
+        self.start_attractor = False
 
     # -- one loop iteration ------------------------------------------------------------------
     def update(self):
@@ -71,6 +73,12 @@ class VectorFieldModule:
 
         # field parameters (scripts/vf:210-293); strict port: drain everything that is queued
         parambottle = self.paramPort.read(False)
+        if self.start_attractor:
+            # scripts/vf:212-225: the iteration after the first joint data takes the "start_attractor" action instead of
+            # the message it has just read from /param -- that message is consumed and lost (kept: bug-compatible; the
+            # feeder re-sends every object with its next message)
+            self.start_attractor = False
+            parambottle = self.paramPort.read(False)
         while parambottle is not None:
             if parambottle.size() >= 1:
                 action = parambottle.get(0).toString()
@@ -114,8 +122,24 @@ class VectorFieldModule:
                 self.oldtoolFrame = toolFrame
                 rt.set_tool(toolFrame)
             out = rt.cycle(np.asarray(q))
-            sendListPort(self.posePort, pose12_to_list16(out["pose"][:, 0]))
+            if self.first_arm_data:
+                self.first_arm_data = False
+                self.start_attractor = True
+            pose16 = pose12_to_list16(out["pose"][:, 0])
+            sendListPort(self.posePort, pose16)
+            # flange frame = tool frame * tool^-1 (scripts/vf:329-342 publishes both)
+            T = np.asarray(pose16).reshape(4, 4) @ np.linalg.inv(np.asarray(self.oldtoolFrame, dtype=np.float64).reshape(4, 4))
+            sendListPort(self.pose_no_tool_Port, T.reshape(16).tolist())
             self.last_qdot = out["qdot_vf"][:, 0]
+            mon = rt.monitor(advance=True)                                # scripts/vf:349-428, from the 6th frame on
+            if mon["seen"] > 5:
+                t = mon["track"][:, 0]
+                b = self.tracking_error_port.prepare()
+                b.clear()
+                for v in t[:7]:
+                    b.addDouble(float(v))
+                b.addInt(int(t[7]))
+                self.tracking_error_port.write()
             self.reporting_port_counter += 1
             if self.reporting_port_counter > 20:                      # scripts/vf:432-453
                 self.reporting_port_counter = 0
