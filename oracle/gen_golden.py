@@ -591,6 +591,103 @@ def gen_vf(rng):
             "vf_out": np.array(rows)}
 
 
+def gen_bridge_loop(rng):
+    """``scripts/bridge``'s main loop body (:600-634) with the reference's own ``LWR_Bridge.read_pos`` / ``set_vel``
+    (:163-210), ``ut_writebottle`` / ``ut_bottle2list`` (:540-549) and the real ``CommandMixer``: one iteration per scripted
+    step.  Inputs: plant positions, /cmded feedback, the three controller command ports, mixer weights (incl. all-zero =
+    direct control) and max_vel messages (one out of range); records ``/encoders``, the robot command and
+    ``/current_weights``."""
+    import json
+    import time as _time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vfclik_b200 import ports as yarp
+    N, steps = 7, 24
+    CommandMixer = load_real_command_mixer()
+    import textwrap
+    lines = open(os.path.join(REF, "scripts", "bridge")).read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if l.startswith("    while (not stop):")) + 1
+    i1 = next(i for i in range(i0, len(lines)) if lines[i].startswith("    encoders_port.close()"))
+    body = textwrap.dedent("\n".join(l for l in lines[i0:i1] if not l.lstrip().startswith("#")))
+    code = compile("def _iteration():\n    global direct_control, max_vel\n    while True:\n" +
+                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
+                   "<reference scripts/bridge loop>", "exec")
+
+    class In:
+        def __init__(self):
+            self.q = []
+
+        def read(self, wait=False):
+            return self.q.pop(0) if self.q else None
+
+    class Out:
+        def __init__(self):
+            self.sent, self.b = [], None
+
+        def prepare(self):
+            self.b = yarp.Bottle()
+            return self.b
+
+        def write(self, *a):
+            self.sent.append(self.b.to_list())
+
+    cmd_ports = [In() for _ in range(6)]
+    weight_port, maxvel_port, qin, qcmded = In(), In(), In(), In()
+    encoders, qcmd, cur_w = Out(), Out(), Out()
+    cfg = types.SimpleNamespace(nJoints=N, max_vel=0.5, torso_joints=[])
+    glb = dict(config=cfg, config_max_vel=cfg.max_vel, max_vel=cfg.max_vel, direct_control=False, rate=0.0, time=_time, stop=False,
+               yarp_ctrl=types.SimpleNamespace(update=lambda: None), encoders_port=encoders, current_weight_port=cur_w,
+               maxvel_port=maxvel_port)
+    for name in ("ut_bottle2list", "ut_writebottle"):
+        exec(load_reference_function("scripts/bridge", name), glb)
+    ns = {}
+    for name in ("read_pos", "set_vel"):
+        exec(load_reference_function("scripts/bridge", name, cls="LWR_Bridge"), glb, ns)
+    bridge = types.SimpleNamespace(nJoints=N, last_q=N * [0.0], last_qcmded=[], torso_joints=[], qin_port=qin, qcmded_port=qcmded,
+                                   qcmd_port=qcmd)
+    bridge.read_pos = lambda: ns["read_pos"](bridge)
+    bridge.set_vel = lambda qdot: ns["set_vel"](bridge, qdot)
+    glb["bridge"] = bridge
+    glb["mixer"] = CommandMixer(cmd_ports, weight_port, N, 2.0, [1.0, 1.0, 0.0, 0.0, 0.0, 0.0])
+    exec(code, glb)
+
+    q = rng.uniform(-1, 1, size=N)
+    script, rows = [], []
+    for k in range(steps):
+        q = q + rng.normal(scale=0.01, size=N)
+        ev = {"q": q.tolist(), "cmd": {}}
+        if k > 0:
+            ev["cmded"] = (q + rng.normal(scale=0.003, size=N)).tolist()
+        for p, scale in ((0, 0.6), (1, 0.05), (2, 0.3)):
+            if k % (p + 1) == 0:
+                ev["cmd"][str(p)] = rng.normal(scale=scale, size=N).tolist()
+        if k == 6:
+            ev["weights"] = [0.0, 0.0, 1.0]
+        if k == 12:
+            ev["weights"] = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+        if k == 17:
+            ev["weights"] = [1.0, 0.5, 0.0, 0.0, 0.0, 0.0]
+        if k == 9:
+            ev["max_vel"] = 0.2
+        if k == 15:
+            ev["max_vel"] = 3.0                                  # out of range: ignored
+        script.append(ev)
+        qin.q.append(yarp.Bottle.from_list(ev["q"]))
+        if "cmded" in ev:
+            qcmded.q.append(yarp.Bottle.from_list(ev["cmded"]))
+        for p, v in ev["cmd"].items():
+            cmd_ports[int(p)].q.append(yarp.Bottle.from_list(v))
+        if "weights" in ev:
+            weight_port.q.append(yarp.Bottle.from_list(ev["weights"]))
+        if "max_vel" in ev:
+            maxvel_port.q.append(yarp.Bottle.from_list([ev["max_vel"]]))
+        encoders.sent, qcmd.sent, cur_w.sent = [], [], []
+        with redirect_stdout(io.StringIO()):
+            glb["_iteration"]()
+        rows.append(json.dumps({"encoders": encoders.sent, "qcmd": qcmd.sent, "current_weights": cur_w.sent}))
+    return {"bl_script": np.array([json.dumps(e) for e in script]), "bl_out": np.array(rows),
+            "bl_cfg": np.array([cfg.max_vel])}
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
@@ -603,6 +700,7 @@ def main():
     data.update(gen_feeder())
     data.update(gen_jp(rng))
     data.update(gen_vf(rng))
+    data.update(gen_bridge_loop(rng))
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

@@ -520,3 +520,69 @@ def test_vf_module_matches_the_reference_loop_cycle_by_cycle(lwr, golden, built_
     finally:
         vf.close(); rt.close()
     capsys.readouterr()
+
+
+def test_bridge_module_matches_the_reference_main_loop(lwr, golden, built_lib, fresh_ports, capsys, monkeypatch):
+    """/bridge/encoders, the robot command and /bridge/current_weights against what the reference's own main loop body
+    (scripts/bridge:600-634, with its read_pos / set_vel and the real CommandMixer; oracle/gen_golden.py:gen_bridge_loop)
+    produced for a scripted run: /cmded feedback, three command ports at different rates, weight changes down to all-zero
+    (direct control, one iteration late like the reference), max_vel changes (one refused)."""
+    import copy
+    import json
+    from vfclik_b200.bridge import BridgeModule
+    from vfclik_b200.runtime import ControlRuntime
+    import types
+    from vfclik_b200 import command_mixer
+    _, cfg = lwr
+    g = golden
+    # the guard time is wall-clock (src/command_mixer.py:64-66): the first CUDA calls of a fresh process take longer than its
+    # 2 s, which would zero the slower ports after the first iteration -- run the mixer on a scripted clock instead
+    ticks = iter(range(10 ** 9))
+    monkeypatch.setattr(command_mixer, "time", types.SimpleNamespace(time=lambda: 0.001 * next(ticks)))
+    c = copy.copy(cfg)
+    c.max_vel = float(g["bl_cfg"][0])
+    rt = ControlRuntime(c, n_instances=1, precision=64)
+    base = "/4" + c.robotarm_portbasename
+    robot = {name: fresh_ports.BufferedPortBottle() for name in ("pos", "cmded", "cmd")}
+    for name, p in robot.items():
+        p.open(base + "/robot/" + name)
+    robot["cmd"].setStrict(True)
+    br = BridgeModule(rt, "/4", sim=False)
+    try:
+        sinks = {}
+        for name, port in (("encoders", br.encoders_port), ("current_weights", br.current_weight_port)):
+            p = fresh_ports.BufferedPortBottle(); p.open("/4/sink/" + name); p.setStrict(True)
+            fresh_ports.Network.connect(port.getName(), "/4/sink/" + name)
+            sinks[name] = p
+        sinks["qcmd"] = robot["cmd"]
+        feeds = [_out_port(fresh_ports, "/4/feed/cmd%d" % i, br.cmd_ports[i].getName()) for i in range(3)]
+        wfeed = _out_port(fresh_ports, "/4/feed/w", br.weight_port.getName())
+        mfeed = _out_port(fresh_ports, "/4/feed/mv", br.maxvel_port.getName())
+        for k in range(g["bl_script"].shape[0]):
+            ev = json.loads(str(g["bl_script"][k]))
+            fresh_ports.sendListPort(robot["pos"], ev["q"])
+            if "cmded" in ev:
+                fresh_ports.sendListPort(robot["cmded"], ev["cmded"])
+            for p, v in ev["cmd"].items():
+                fresh_ports.sendListPort(feeds[int(p)], v)
+            if "weights" in ev:
+                fresh_ports.sendListPort(wfeed, ev["weights"])
+            if "max_vel" in ev:
+                fresh_ports.sendListPort(mfeed, [ev["max_vel"]])
+            br.update()
+            br.finish()
+            want = json.loads(str(g["bl_out"][k]))
+            for name, p in sinks.items():
+                got = []
+                while True:
+                    b = p.read(False)
+                    if b is None:
+                        break
+                    got.append(b.to_list())
+                assert len(got) == len(want[name]) == 1, (k, name, len(got))
+                assert np.allclose(got[0], want[name][0], rtol=1e-12, atol=1e-14), (k, name, got[0], want[name][0])
+    finally:
+        br.close(); rt.close()
+        for p in robot.values():
+            p.close()
+    capsys.readouterr()
