@@ -688,6 +688,96 @@ def gen_bridge_loop(rng):
             "bl_cfg": np.array([cfg.max_vel])}
 
 
+def gen_dmonitor(rng):
+    """``scripts/monitor_distance``'s loop body (:107-221) with its own ``orientLength`` (:76-84); PyKDL ``Frame`` / ``diff``
+    and ``vfl.length`` replaced by the oracle's stand-ins.  One iteration per scripted step: objects, the tool pose and the
+    vf module's tracking errors in; ``/distOut`` and the ``/tracking_state`` change messages out (20-sample majority,
+    including the reference sending the *xyz* state under the ``rot`` tag)."""
+    import builtins
+    import json
+    from math import pi, sqrt
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vfclik_b200 import ports as yarp
+    from . import refshape
+    body = load_reference_loop_body("scripts/monitor_distance", "while not stop:", "track_error_in_port.close()")
+    state = ["track_error_xyz", "track_error_rot", "tracking_buffer", "last_tracking_xyz_state", "last_tracking_rot_state",
+             "tracking_xyz_state", "tracking_rot_state", "objects"]
+    code = compile("def _iteration():\n    global " + ", ".join(state) + "\n    while True:\n" +
+                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
+                   "<reference scripts/monitor_distance loop>", "exec")
+
+    class In:
+        def __init__(self):
+            self.q = []
+
+        def read(self, wait=False):
+            return self.q.pop(0) if self.q else None
+
+    class Out:
+        def __init__(self):
+            self.sent, self.b = [], None
+
+        def prepare(self):
+            self.b = yarp.Bottle()
+            return self.b
+
+        def write(self, *a):
+            self.sent.append(self.b.to_list())
+
+        writeStrict = write
+
+    objs, terr, pose = In(), In(), In()
+    dist, tstate = Out(), Out()
+    glb = dict(yarp=types.SimpleNamespace(Value=yarp.Value, Time=types.SimpleNamespace(delay=lambda t: None), Time_delay=lambda t: None),
+               yarp_ctrl=types.SimpleNamespace(update=lambda: None), objectsInPort=objs, track_error_in_port=terr, currentPosIn=pose,
+               distOutPort=dist, tracking_state_port=tstate, objects=Py2IntKeyDict(), array=np.array,
+               length=lambda v: float(np.linalg.norm(v)), Frame=refshape.KdlFrame, diff=refshape.kdl_diff, sqrt=sqrt, pi=pi,
+               map=lambda f, *a: list(builtins.map(f, *a)), zip=lambda *a: list(builtins.zip(*a)), stop=False,
+               track_error_xyz=0.0, track_error_rot=0.0, distanceXYZ_th=0.02, track_error_xyz_th=0.1, distanceOrient_th=1.0,
+               track_error_rot_th=0.1, tracking_buffer=[], tracking_buffer_size=20, last_tracking_xyz_state="on goal",
+               last_tracking_rot_state="on goal", tracking_xyz_state="on goal", tracking_rot_state="on goal")
+    exec(load_reference_function("scripts/monitor_distance", "orientLength"), glb)
+    exec(code, glb)
+
+    def frame16(R, p):
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = p
+        return T.reshape(16).tolist()
+
+    def rot(axis, ang):
+        a = np.asarray(axis, dtype=float); a /= np.linalg.norm(a)
+        K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+
+    Rg, pg = rot([0.2, 1.0, 0.3], 0.7), np.array([0.5, 0.1, 0.9])
+    steps = 70
+    script, rows = [], []
+    for k in range(steps):
+        ev = {}
+        if k == 0:
+            ev["objects"] = [["add", 0, frame16(Rg, pg)], ["add", 3, frame16(np.eye(3), [0.2, -0.3, 0.6])]]
+        if k == 40:
+            ev["objects"] = [["remove", 3]]
+        s_ = max(0.0, 1.0 - k / 50.0)                                   # approach: the distance shrinks to zero at step 50
+        R = Rg @ rot([1.0, 0.2, -0.4], 0.9 * s_)
+        p = pg + np.array([0.3, -0.2, 0.25]) * s_
+        ev["pose"] = frame16(R, p)
+        # tracking errors: fine, then a stretch where the arm does not follow (both), then fine again
+        bad = 12 <= k < 36
+        ev["track_error"] = [0.5 if bad else 0.02, 0.4 if bad else 0.03, 0.1, 0.1, 0.1, 0.1, 0.0, 1]
+        script.append(ev)
+        for m in ev.get("objects", []):
+            objs.q.append(yarp.Bottle.from_list(m))
+        terr.q.append(yarp.Bottle.from_list(ev["track_error"]))
+        pose.q.append(yarp.Bottle.from_list(ev["pose"]))
+        n_iter = max(1, len(ev.get("objects", [])))                     # the loop reads one /objectsIn message per iteration
+        dist.sent, tstate.sent = [], []
+        with redirect_stdout(io.StringIO()):
+            for _ in range(n_iter):
+                glb["_iteration"]()
+        rows.append(json.dumps({"distOut": dist.sent, "tracking_state": tstate.sent}))
+    return {"dm_script": np.array([json.dumps(e) for e in script]), "dm_out": np.array(rows)}
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
@@ -701,6 +791,7 @@ def main():
     data.update(gen_jp(rng))
     data.update(gen_vf(rng))
     data.update(gen_bridge_loop(rng))
+    data.update(gen_dmonitor(rng))
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

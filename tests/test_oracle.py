@@ -219,6 +219,7 @@ def test_golden_is_reproducible_from_reference(golden):
     data.update(gen_golden.gen_jp(rng))
     data.update(gen_golden.gen_vf(rng))
     data.update(gen_golden.gen_bridge_loop(rng))
+    data.update(gen_golden.gen_dmonitor(rng))
     for k, v in data.items():
         if np.asarray(v).dtype.kind in "US":
             assert [str(x) for x in v] == [str(x) for x in golden[k]], k
@@ -339,3 +340,53 @@ def test_golden_joint_p_controller_loop(golden, lwr):
         goal = np.array([[1, 0, 0, 0, 1, 0, 0, 0, 1, 0.5, 0.0, 0.8, 0.05]], dtype=np.float64)
         ref_b = batch.step(chain, prm, g["jp_q"][k][None], goal, None, jp_ref=np.asarray(steps[max(s for s in steps if s <= k)])[None])
         assert np.allclose(ref_b["qdot_jp"][0], g["jp_out_static"][k], rtol=1e-13, atol=1e-15), k
+
+
+def test_golden_distance_monitor_loop(golden):
+    """oracle/monitor.py (the restatement the vfk_monitor kernel is tested against) versus what the reference's own
+    monitor_distance loop body (scripts/monitor_distance:107-221, with its orientLength) wrote for a scripted approach:
+    distances to every object each cycle, and the 20-sample majority state messages -- including the reference sending the
+    xyz state under the "rot" tag."""
+    import json
+    from oracle import monitor
+    from oracle.refshape import listToKdlFrame
+    g = golden
+    dm = monitor.DistanceMonitor()
+    objects = {}
+    last_x = last_r = "on goal"
+    n_msgs = 0
+    for k in range(g["dm_script"].shape[0]):
+        ev = json.loads(str(g["dm_script"][k]))
+        want = json.loads(str(g["dm_out"][k]))
+        def apply(m):
+            if m[0] == "add":
+                objects[m[1]] = m[2]
+            else:
+                objects.pop(m[1], None)
+        pending = list(ev.get("objects", []))
+        if pending:                        # the loop takes ONE /objectsIn message per iteration; the pose is consumed by the first
+            apply(pending.pop(0))
+        frame = listToKdlFrame(ev["pose"])
+        msgs = []
+        rows = []
+        for oid in sorted(objects):
+            goal = listToKdlFrame(objects[oid])
+            if oid == 0:
+                dx, do, mx, mr = dm.update(frame, goal, ev["track_error"])
+                if mx is not None and mx != last_x:
+                    last_x = mx
+                    msgs.append(["xyz", mx])
+                if mr is not None and mr != last_r:
+                    last_r = mr
+                    msgs.append(["rot", mx])                  # sic: scripts/monitor_distance:215 sends the xyz state
+            else:
+                d = frame.p - goal.p
+                dx, do = float(np.sqrt(d @ d)), monitor.orientLength(goal, frame)
+            rows.append([float(oid), dx, do])
+        assert len(want["distOut"]) == 1
+        assert np.allclose(rows, want["distOut"][0], rtol=1e-12, atol=1e-12), k
+        assert msgs == want["tracking_state"], (k, msgs, want["tracking_state"])
+        n_msgs += len(msgs)
+        for m in pending:
+            apply(m)
+    assert n_msgs >= 6

@@ -103,7 +103,8 @@ class MonitorDistanceModule:
             yarp.write_bottle_lists(self.tracking_state_port, ["xyz", STATES[sx]], strict=True)
         if sr >= 0 and STATES[sr] != self.last_tracking_rot_state:
             self.last_tracking_rot_state = STATES[sr]
-            yarp.write_bottle_lists(self.tracking_state_port, ["rot", STATES[sr]], strict=True)
+            # the reference writes tracking_xyz_state under the "rot" tag (scripts/monitor_distance:215): kept, bug-compatible
+            yarp.write_bottle_lists(self.tracking_state_port, ["rot", STATES[sx] if sx >= 0 else STATES[sr]], strict=True)
         self.last = dict(dist=entries, track_error=track[:, 0].tolist(), xyz_state=sx, rot_state=sr)
         return True
 
