@@ -778,6 +778,69 @@ def gen_dmonitor(rng):
     return {"dm_script": np.array([json.dumps(e) for e in script]), "dm_out": np.array(rows)}
 
 
+def gen_nullspace_loop(rng):
+    """``scripts/nullspace``'s main loop body (:159-187) with the reference's own functions (:67-131) and the oracle's Lafik
+    stand-in as ``rob``: joint positions and four-float control bottles in, ``/qdotout`` (gain applied) out."""
+    import json
+    import textwrap
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vfclik_b200 import ports as yarp
+    from . import refshape
+    from .batch import Params
+    chain, _ = lwr_chain()
+    glb = load_real_nullspace(chain.n_joints)
+    lines = open(os.path.join(REF, "scripts", "nullspace")).read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if l.startswith("    while not stop:")) + 1
+    i1 = next(i for i in range(i0, len(lines)) if lines[i].startswith("    qin_port.close()"))
+    body = textwrap.dedent("\n".join(l for l in lines[i0:i1] if not l.lstrip().startswith("#")))
+    code = compile("def _iteration():\n    global control\n    while True:\n" +
+                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
+                   "<reference scripts/nullspace loop>", "exec")
+
+    class In:
+        def __init__(self):
+            self.q = []
+
+        def read(self, wait=False):
+            return self.q.pop(0) if self.q else None
+
+    class Out:
+        def __init__(self):
+            self.sent, self.b = [], None
+
+        def prepare(self):
+            self.b = yarp.Bottle()
+            return self.b
+
+        def write(self, *a):
+            self.sent.append(self.b.to_list())
+
+    qin, ctl, out = In(), In(), Out()
+    glb.update(yarp=types.SimpleNamespace(Time_delay=lambda t: None), yarp_ctrl=types.SimpleNamespace(update=lambda: None),
+               qin_port=qin, control_port=ctl, qdotout_port=out, rob=refshape.Lafik(chain, Params()), P=np.asmatrix(np.eye(6)),
+               control=[0] * 4, gain=0.5, stop=False)
+    exec(code, glb)
+    steps = 16
+    q = rng.uniform(0.5 * chain.q_lo, 0.5 * chain.q_hi)
+    script, rows = [], []
+    for k in range(steps):
+        q = q + rng.normal(scale=0.02, size=chain.n_joints)
+        ev = {"q": q.tolist()}
+        if k == 2:
+            ev["control"] = [0.4, 0.0, 0.0, 0.0]
+        if k == 8:
+            ev["control"] = [-0.8, 0.1, 0.0, 0.0]
+        script.append(ev)
+        qin.q.append(yarp.Bottle.from_list(ev["q"]))
+        if "control" in ev:
+            ctl.q.append(yarp.Bottle.from_list(ev["control"]))
+        out.sent = []
+        with redirect_stdout(io.StringIO()):
+            glb["_iteration"]()
+        rows.append(out.sent[0])
+    return {"nl_script": np.array([json.dumps(e) for e in script]), "nl_qdotout": np.asarray(rows)}
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
@@ -792,6 +855,7 @@ def main():
     data.update(gen_vf(rng))
     data.update(gen_bridge_loop(rng))
     data.update(gen_dmonitor(rng))
+    data.update(gen_nullspace_loop(rng))
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

@@ -586,3 +586,40 @@ def test_bridge_module_matches_the_reference_main_loop(lwr, golden, built_lib, f
         for p in robot.values():
             p.close()
     capsys.readouterr()
+
+
+def test_nullspace_module_matches_the_reference_main_loop(lwr, golden, built_lib, fresh_ports, capsys):
+    """/nullspace/qdotout against the reference's own main loop body (scripts/nullspace:159-187) running its own
+    restrict / nullspace / move_in_nullspace / check_limits on the oracle's Lafik stand-in: the four-float control interface,
+    sticky control bottles, gain 0.5.  LAPACK's first-cycle sign of the nullspace vector is arbitrary (ORACLE_CHOICES), the
+    reference then keeps it by continuity, so the records agree up to ONE global sign."""
+    import json
+    from vfclik_b200.nullspace import NullspaceModule
+    from vfclik_b200.runtime import NS_CONTROL, ControlRuntime
+    _, cfg = lwr
+    g = golden
+    rt = ControlRuntime(cfg, n_instances=1, precision=64)
+    rt.set_params(ns_mode=NS_CONTROL, ns_lambda=0.0)
+    ns = NullspaceModule(rt, "/7")
+    try:
+        qfeed = _out_port(fresh_ports, "/7/feed/q", ns.qin_port.getName())
+        cfeed = _out_port(fresh_ports, "/7/feed/c", ns.control_port.getName())
+        sink = fresh_ports.BufferedPortBottle(); sink.open("/7/sink"); sink.setStrict(True)
+        fresh_ports.Network.connect(ns.qdotout_port.getName(), "/7/sink")
+        sign = None
+        for k in range(g["nl_script"].shape[0]):
+            ev = json.loads(str(g["nl_script"][k]))
+            if "control" in ev:
+                fresh_ports.sendListPort(cfeed, ev["control"])
+            fresh_ports.sendListPort(qfeed, ev["q"])
+            assert ns.update()
+            b = sink.read(False)
+            got = np.asarray([b.get(i).asDouble() for i in range(7)])
+            want = g["nl_qdotout"][k]
+            if sign is None and np.max(np.abs(want)) > 0:
+                sign = 1.0 if np.dot(got, want) > 0 else -1.0
+            assert np.allclose(got * (sign or 1.0), want, rtol=1e-7, atol=1e-10), (k, got, want)
+        assert sign is not None
+    finally:
+        ns.close(); rt.close()
+    capsys.readouterr()
