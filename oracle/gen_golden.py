@@ -841,6 +841,98 @@ def gen_nullspace_loop(rng):
     return {"nl_script": np.array([json.dumps(e) for e in script]), "nl_qdotout": np.asarray(rows)}
 
 
+HANDLER_SINKS = ["/ofeeder/object", "/robot/stiffness", "/vectorField/tool", "/bridge/weight", "/bridge/weights",
+                 "/vectorField/weight", "/jpctrl/ref", "/joint_sim/qin", "/bridge/torso_cjoints:i"]
+
+
+def handler_calls(mod, prefix, sinks, drain):
+    """The scripted client calls (shared by the generator and the test): every sender of the four handler classes."""
+    rec = []
+
+    def note(label):
+        rec.append([label, drain()])
+    arm = mod.HandleArmNew(namespace="/0", module_name="/handle_arm", arm_namespace="/0", robot="/lwr", arm="/right", sim=True)
+    frame = [0.0, 1.0, 0.0, 0.5, -1.0, 0.0, 0.0, 0.1, 0.0, 0.0, 1.0, 0.9, 0.0, 0.0, 0.0, 1.0]
+    arm.set_sim_arm_q([0.1, -0.2, 0.3, 0.4, -0.5, 0.6, 0.7]); note("new.set_sim_arm_q")
+    arm.go_cart(frame); note("new.go_cart")
+    arm.go_joint([0.0, -1.2, 0.7, 1.4, 0.35, -1.4, 0.0]); note("new.go_joint")
+    arm.set_controller_mixer(cart=True, joint=True, null=False); note("new.set_controller_mixer")
+    arm.set_cartesian_control(); note("new.set_cartesian_control")
+    arm.set_joint_control(); note("new.set_joint_control")
+    arm.set_wik_joint_weights([1.0, 1.0, 0.5, 1.0, 1.0, 0.25, 1.0]); note("new.set_wik_joint_weights")
+    arm.set_wik_cart_weights([1.0, 1.0, 1.0, 0.5, 0.5, 0.5]); note("new.set_wik_cart_weights")
+    arm.set_tool([1.0, 0.0, 0.0, 0.02, 0.0, 1.0, 0.0, -0.01, 0.0, 0.0, 1.0, 0.12, 0.0, 0.0, 0.0, 1.0]); note("new.set_tool")
+    old = mod.HandleArm(prefix, namespace="", handlername="/HandlerArm")
+    old.set_stiffness([200.0] * 7); note("arm.set_stiffness")
+    old.sendFrame(); note("arm.sendFrame")
+    old.gotoPos([0.4, -0.1, 1.0]); note("arm.gotoPos")
+    old.setOrient([0.0, -1.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0]); note("arm.setOrient")
+    old.gotoPose([0.3, 0.2, 0.8], [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]); note("arm.gotoPose")
+    br = mod.HandleBridge(prefix, handlername="HandlerArmBridge", torso=True)
+    br.joint_controller(); note("bridge.joint_controller")
+    br.cartesian_controller(); note("bridge.cartesian_controller")
+    br.torso_joints([1, 0, 1]); note("bridge.torso_joints")
+    br.set_weights("task", [1.0, 1.0, 1.0, 0.2, 0.2, 0.2]); note("bridge.set_weights task")
+    br.set_VFW("joint", [1.0] * 6 + [0.5]); note("bridge.set_VFW joint")
+    jc = mod.HandleJController(prefix, handlername="HandlerArmJoint")
+    res = jc.set_ref_js([0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7]); note("jctrl.set_ref_js")
+    rec.append(["jctrl.set_ref_js result", [bool(res[0]), [float(v) for v in res[1]]]])
+    return rec
+
+
+def gen_handlers(rng=None):
+    """``src/handlers.py`` (the client API) executed with this repo's in-process ports as ``yarp``: every sender of
+    ``HandleArmNew``, ``HandleArm``, ``HandleBridge`` and ``HandleJController`` is called once and the messages arriving at the
+    arm-side port names it connects to are recorded.  The file's python-2 ``print`` statements are rewritten in memory
+    (``print x`` -> ``print(x)``); nothing else is touched and nothing is stored."""
+    import json
+    import re
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vfclik_b200 import ports as yarp
+    from . import refshape
+    src = open(os.path.join(REF, "src", "handlers.py")).read()
+    src = re.sub(r"^(\s*)print (.+)$", r"\1print(\2)", src, flags=re.M)
+    for line in ("import yarp\n", "from arcospyu.yarp_tools.yarp_comm_helpers import yarp_connect_blocking, \\\n    new_port\n",
+                 "from arcospyu.kdl_helpers.kdl_helpers import frame_to_list\n"):
+        assert line in src, line
+        src = src.replace(line, "")
+    yarp.Network.reset()
+    prefix = "/0/lwr/right"
+    sinks = {}
+    for name in HANDLER_SINKS:
+        p = yarp.BufferedPortBottle(); p.open(prefix + name); p.setStrict(True)
+        sinks[name] = p
+    for name in ("/vectorField/pose", "/dmonitor/distOut", "/bridge/encoders"):       # sources the handlers subscribe to
+        p = yarp.BufferedPortBottle(); p.open(prefix + name)
+        sinks["src:" + name] = p
+
+    def new_port(name, direction, remote, timeout=None):
+        p = yarp.BufferedPortBottle(); p.open(name)
+        if direction == "out":
+            yarp.Network.connect(name, remote)
+        else:
+            yarp.Network.connect(remote, name)
+        return p
+
+    def drain():
+        got = {}
+        for name in HANDLER_SINKS:
+            while True:
+                b = sinks[name].read(False)
+                if b is None:
+                    break
+                got.setdefault(name, []).append(b.to_list())
+        return got
+    mod = types.ModuleType("ref_handlers")
+    mod.__dict__.update(yarp=yarp, yarp_connect_blocking=lambda a, b, timeout=None: yarp.Network.connect(a, b), new_port=new_port,
+                        frame_to_list=refshape.kdlFrameToList)
+    with redirect_stdout(io.StringIO()):
+        exec(compile(src, "<reference src/handlers.py>", "exec"), mod.__dict__)
+        rec = handler_calls(mod, prefix, sinks, drain)
+    yarp.Network.reset()
+    return {"handlers_record": np.array([json.dumps(rec)])}
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not found at %s: golden vectors can only be regenerated in the build container" % REF)
@@ -856,6 +948,7 @@ def main():
     data.update(gen_bridge_loop(rng))
     data.update(gen_dmonitor(rng))
     data.update(gen_nullspace_loop(rng))
+    data.update(gen_handlers())
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})
