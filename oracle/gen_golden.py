@@ -106,6 +106,40 @@ class FakePort:
         return self.q.pop(0) if self.q else None
 
 
+class ScriptIn:
+    """Input port stand-in for the executed loops: messages queued by the script, ``None`` when there is nothing."""
+
+    def __init__(self):
+        self.q = []
+
+    def read(self, wait=False):
+        return self.q.pop(0) if self.q else None
+
+
+class ScriptOut:
+    """Output port stand-in: every written bottle is kept as a plain (nested) list."""
+
+    def __init__(self):
+        self.sent, self.b = [], None
+
+    def prepare(self):
+        from vfclik_b200 import ports as yarp
+        self.b = yarp.Bottle()
+        return self.b
+
+    def write(self, *a):
+        self.sent.append(self.b.to_list())
+
+    writeStrict = write
+
+
+def compile_iteration(body: str, global_names, label: str):
+    """One pass through a reference loop body as a function: ``while True: <body>; break`` keeps its ``continue`` legal."""
+    head = "def _iteration():\n" + ("    global " + ", ".join(global_names) + "\n" if global_names else "")
+    return compile(head + "    while True:\n" + "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
+                   label, "exec")
+
+
 # ------------------------------------------------------------------------- generators
 
 def gen_mixer(rng):
@@ -359,37 +393,18 @@ def gen_feeder(rng=None):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from vfclik_b200 import ports as yarp
     body = load_reference_loop_body("scripts/object_feeder", "while not stop:", "paramPort.close()")
-    code = compile("def _iteration():\n    global init_pose\n    while True:\n" +
-                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
-                   "<reference scripts/object_feeder loop>", "exec")
+    code = compile_iteration(body, ['init_pose'], "<reference scripts/object_feeder loop>")
 
-    class Out:
-        def __init__(self):
-            self.sent = []
-            self.b = None
+    class EndOfScript(Exception):
+        pass
 
-        def prepare(self):
-            self.b = yarp.Bottle()
-            return self.b
-
-        def writeStrict(self):
-            self.sent.append(self.b.to_list())
-
-        write = writeStrict
-
-    class In:
-        def __init__(self):
-            self.q = []
-
+    class FeederIn(ScriptIn):
         def read(self, wait=False):
             if not self.q:
                 raise EndOfScript()           # the loop came back for another message (`continue`): iteration over
             return self.q.pop(0)
 
-    class EndOfScript(Exception):
-        pass
-
-    param, objout, objf, obj = Out(), Out(), Out(), In()
+    param, objout, objf, obj = ScriptOut(), ScriptOut(), ScriptOut(), FeederIn()
     glb = dict(yarp=types.SimpleNamespace(Bottle=yarp.Bottle, Time_delay=lambda t: None), yarp_ctrl=types.SimpleNamespace(update=lambda: None),
                objectPort=obj, object_f_port=objf, paramPort=param, objectOutPort=objout, objects=Py2IntKeyDict(),
                init_pose=False, config=types.SimpleNamespace(), dprint=lambda *a: None, array=np.array,
@@ -425,32 +440,12 @@ def gen_jp(rng):
     q[12:] = q[11] + rng.normal(scale=0.01, size=(steps - 12, N))          # nearly at rest near the last reference
     refs = {0: rng.uniform(-3.5, 3.5, size=N), 5: rng.uniform(-0.3, 0.3, size=N), 11: q[11] + 0.05}
     body = load_reference_loop_body("scripts/joint_p_controller", "while not stop:", "inPort.close()")
-    code = compile("def _iteration():\n    global ref, waitRef, refbottle\n    while True:\n" +
-                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
-                   "<reference scripts/joint_p_controller loop>", "exec")
-
-    class In:
-        def __init__(self):
-            self.q = []
-
-        def read(self, wait=False):
-            return self.q.pop(0) if self.q else None
-
-    class Out:
-        def __init__(self):
-            self.sent, self.b = [], None
-
-        def prepare(self):
-            self.b = yarp.Bottle()
-            return self.b
-
-        def write(self, *a):
-            self.sent.append(self.b.to_list())
+    code = compile_iteration(body, ['ref', 'waitRef', 'refbottle'], "<reference scripts/joint_p_controller loop>")
 
     out = {"jp_q": q, "jp_ref_steps": np.array(sorted(refs)), "jp_ref_msgs": np.array([refs[k] for k in sorted(refs)]),
            "jp_static_limits": np.array(static)}
     for name, hook in hooks.items():
-        refp, inp, outp, goalp = In(), In(), Out(), Out()
+        refp, inp, outp, goalp = ScriptIn(), ScriptIn(), ScriptOut(), ScriptOut()
         cfg = types.SimpleNamespace(nJoints=N, initial_joint_pos=[0.0, -1.2, 0.7, 1.4, 0.35, -1.4, 0.0], updateJntLimits=hook)
         glb = dict(yarp=types.SimpleNamespace(Bottle=yarp.Bottle, Value=yarp.Value, Time=types.SimpleNamespace(delay=lambda t: None)),
                    yarp_ctrl=types.SimpleNamespace(update=lambda: None), refPort=refp, inPort=inp, outPort=outp, atGoalPort=goalp,
@@ -493,32 +488,10 @@ def gen_vf(rng):
     body = load_reference_loop_body("scripts/vf", "while not stop:", "qdotOutPort.close()")
     state = ["speedScale", "start_attractor", "first_arm_data", "first_arm_frame", "oldtoolFrame", "totalVF", "totalSF", "vftemp",
              "vfparams", "counter_test", "reporting_port_counter", "frame_list", "cmd_buffer", "vectorFields", "first_cycle"]
-    code = compile("def _iteration():\n    global " + ", ".join(s for s in state if s != "speedScale") + "\n    while True:\n" +
-                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
-                   "<reference scripts/vf loop>", "exec")
+    code = compile_iteration(body, [s for s in state if s != "speedScale"], "<reference scripts/vf loop>")
 
-    class In:
-        def __init__(self):
-            self.q = []
-
-        def read(self, wait=False):
-            return self.q.pop(0) if self.q else None
-
-    class Out:
-        def __init__(self):
-            self.sent, self.b = [], None
-
-        def prepare(self):
-            self.b = yarp.Bottle()
-            return self.b
-
-        def write(self, *a):
-            self.sent.append(self.b.to_list())
-
-        writeStrict = write
-
-    ins = {k: In() for k in ("maxvel_port", "paramPort", "weightPort", "qInPort", "toolPort", "pose_in_port")}
-    outs = {k: Out() for k in ("qdotOutPort", "posePort", "pose_no_tool_Port", "tracking_error_port", "vector_port", "goal_port")}
+    ins = {k: ScriptIn() for k in ("maxvel_port", "paramPort", "weightPort", "qInPort", "toolPort", "pose_in_port")}
+    outs = {k: ScriptOut() for k in ("qdotOutPort", "posePort", "pose_no_tool_Port", "tracking_error_port", "vector_port", "goal_port")}
 
     def sendListPort(port, l):
         b = port.prepare()
@@ -608,31 +581,11 @@ def gen_bridge_loop(rng):
     i0 = next(i for i, l in enumerate(lines) if l.startswith("    while (not stop):")) + 1
     i1 = next(i for i in range(i0, len(lines)) if lines[i].startswith("    encoders_port.close()"))
     body = textwrap.dedent("\n".join(l for l in lines[i0:i1] if not l.lstrip().startswith("#")))
-    code = compile("def _iteration():\n    global direct_control, max_vel\n    while True:\n" +
-                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
-                   "<reference scripts/bridge loop>", "exec")
+    code = compile_iteration(body, ['direct_control', 'max_vel'], "<reference scripts/bridge loop>")
 
-    class In:
-        def __init__(self):
-            self.q = []
-
-        def read(self, wait=False):
-            return self.q.pop(0) if self.q else None
-
-    class Out:
-        def __init__(self):
-            self.sent, self.b = [], None
-
-        def prepare(self):
-            self.b = yarp.Bottle()
-            return self.b
-
-        def write(self, *a):
-            self.sent.append(self.b.to_list())
-
-    cmd_ports = [In() for _ in range(6)]
-    weight_port, maxvel_port, qin, qcmded = In(), In(), In(), In()
-    encoders, qcmd, cur_w = Out(), Out(), Out()
+    cmd_ports = [ScriptIn() for _ in range(6)]
+    weight_port, maxvel_port, qin, qcmded = ScriptIn(), ScriptIn(), ScriptIn(), ScriptIn()
+    encoders, qcmd, cur_w = ScriptOut(), ScriptOut(), ScriptOut()
     cfg = types.SimpleNamespace(nJoints=N, max_vel=0.5, torso_joints=[])
     glb = dict(config=cfg, config_max_vel=cfg.max_vel, max_vel=cfg.max_vel, direct_control=False, rate=0.0, time=_time, stop=False,
                yarp_ctrl=types.SimpleNamespace(update=lambda: None), encoders_port=encoders, current_weight_port=cur_w,
@@ -702,32 +655,10 @@ def gen_dmonitor(rng):
     body = load_reference_loop_body("scripts/monitor_distance", "while not stop:", "track_error_in_port.close()")
     state = ["track_error_xyz", "track_error_rot", "tracking_buffer", "last_tracking_xyz_state", "last_tracking_rot_state",
              "tracking_xyz_state", "tracking_rot_state", "objects"]
-    code = compile("def _iteration():\n    global " + ", ".join(state) + "\n    while True:\n" +
-                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
-                   "<reference scripts/monitor_distance loop>", "exec")
+    code = compile_iteration(body, state, "<reference scripts/monitor_distance loop>")
 
-    class In:
-        def __init__(self):
-            self.q = []
-
-        def read(self, wait=False):
-            return self.q.pop(0) if self.q else None
-
-    class Out:
-        def __init__(self):
-            self.sent, self.b = [], None
-
-        def prepare(self):
-            self.b = yarp.Bottle()
-            return self.b
-
-        def write(self, *a):
-            self.sent.append(self.b.to_list())
-
-        writeStrict = write
-
-    objs, terr, pose = In(), In(), In()
-    dist, tstate = Out(), Out()
+    objs, terr, pose = ScriptIn(), ScriptIn(), ScriptIn()
+    dist, tstate = ScriptOut(), ScriptOut()
     glb = dict(yarp=types.SimpleNamespace(Value=yarp.Value, Time=types.SimpleNamespace(delay=lambda t: None), Time_delay=lambda t: None),
                yarp_ctrl=types.SimpleNamespace(update=lambda: None), objectsInPort=objs, track_error_in_port=terr, currentPosIn=pose,
                distOutPort=dist, tracking_state_port=tstate, objects=Py2IntKeyDict(), array=np.array,
@@ -793,29 +724,9 @@ def gen_nullspace_loop(rng):
     i0 = next(i for i, l in enumerate(lines) if l.startswith("    while not stop:")) + 1
     i1 = next(i for i in range(i0, len(lines)) if lines[i].startswith("    qin_port.close()"))
     body = textwrap.dedent("\n".join(l for l in lines[i0:i1] if not l.lstrip().startswith("#")))
-    code = compile("def _iteration():\n    global control\n    while True:\n" +
-                   "".join("        " + l + "\n" for l in body.splitlines()) + "        break\n",
-                   "<reference scripts/nullspace loop>", "exec")
+    code = compile_iteration(body, ['control'], "<reference scripts/nullspace loop>")
 
-    class In:
-        def __init__(self):
-            self.q = []
-
-        def read(self, wait=False):
-            return self.q.pop(0) if self.q else None
-
-    class Out:
-        def __init__(self):
-            self.sent, self.b = [], None
-
-        def prepare(self):
-            self.b = yarp.Bottle()
-            return self.b
-
-        def write(self, *a):
-            self.sent.append(self.b.to_list())
-
-    qin, ctl, out = In(), In(), Out()
+    qin, ctl, out = ScriptIn(), ScriptIn(), ScriptOut()
     glb.update(yarp=types.SimpleNamespace(Time_delay=lambda t: None), yarp_ctrl=types.SimpleNamespace(update=lambda: None),
                qin_port=qin, control_port=ctl, qdotout_port=out, rob=refshape.Lafik(chain, Params()), P=np.asmatrix(np.eye(6)),
                control=[0] * 4, gain=0.5, stop=False)
