@@ -32,7 +32,7 @@ constexpr int kMaxJ = 17;
 #ifndef VFK_BLOCK
 #define VFK_BLOCK 128
 #endif
-constexpr int kBlock = VFK_BLOCK;    // threads per CTA of the cycle kernel (warps are independent workers)
+constexpr int kBlock = VFK_BLOCK;    // threads per CTA of the cycle kernel (warps are independent workers; 64 measured 0.3 % slower, must divide 128)
 constexpr int kSmallBlock = 128;     // threads per CTA of the small one-element-per-thread kernels
 #ifndef VFK_CHUNK
 #define VFK_CHUNK 8
