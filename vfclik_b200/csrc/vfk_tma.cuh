@@ -1,9 +1,9 @@
 // vfk_tma.cuh -- mbarrier + 1-D bulk async copy (TMA, cp.async.bulk) wrappers for sm_100a.
 //
-// The obstacle list of a CTA's 128 instances is a set of contiguous global rows
-// (one row per obstacle: 128 x {x,y,z,radius}); each row is moved global -> shared by
-// one cp.async.bulk (SASS: UBLKCP) that signals an mbarrier with the byte count, so
-// the whole tile is in flight while the threads run forward kinematics.
+// In the tile-blocked layout everything a warp needs for a tile of 32 instances is a few contiguous
+// bursts (q rows, goal rows, chunks of 8 obstacles x 32 {x,y,z,radius} vectors); each burst is moved
+// global -> shared by ONE cp.async.bulk (SASS: UBLKCP) issued by one lane, signalling a per-warp
+// mbarrier with the byte count, so the next tile is in flight while the warp computes this one.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
