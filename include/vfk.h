@@ -73,7 +73,9 @@ enum { VFK_FLAG_AT_GOAL = 1,     /* scripts/joint_p_controller:135-146 (signed c
 
 enum { VFK_NS_OFF = 0,           /* --no_nullspace (scripts/vfclik:73-79) */
        VFK_NS_PROJECTOR = 1,     /* qdot_ns = gain * check((I - J^+ J) qdot0) */
-       VFK_NS_CONTROL = 2 };     /* reference 4-float control interface, 1-D nullspace (N = 7) */
+       VFK_NS_CONTROL = 2 };     /* the reference's 4-float control interface (scripts/nullspace:110-117): qdot_ns =
+                                    gain * check(sum_{i < min(4, k)} control_i u_i), u_i an orthonormal basis of null(J),
+                                    k = N - 6 vectors, each kept sign-continuous from cycle to cycle.  Any N; ns_lambda unused. */
 
 /* Robot back-end whose set_vel() the clamp / command step restates:
  *   LWR       leading-joint clamp; cmd = qdot_lim (direct) or -q_cmded + q + qdot_lim      (scripts/bridge:182-210)
@@ -99,9 +101,10 @@ typedef struct vfk_chain_desc {
 /* Per-robot constants (uniform over the batch; kept in constant memory). */
 typedef struct vfk_params {
     double ik_lambda;            /* damping of J^T (J J^T + lambda^2 I)^-1           (getIKV, scripts/vf:461) */
-    double ns_lambda;            /* damping of the projector's pseudo-inverse; 0 = pinv (scripts/nullspace:78).  FP32 mode
-                                    needs ik_lambda > 0 and, with the nullspace on, ns_lambda > 0: the undamped normal
-                                    equations lose their pivots to FP32 rounding near singular postures */
+    double ns_lambda;            /* damping of the projector's pseudo-inverse (VFK_NS_PROJECTOR); 0 = the reference's pinv
+                                    (scripts/nullspace:78), computed through a Householder basis of null(J) (error cond(J)*eps,
+                                    valid in both precisions).  FP32 mode needs ik_lambda > 0: the undamped normal equations
+                                    of the velocity IK lose their pivots to FP32 rounding near singular postures */
     double dt;                   /* config.rate (scripts/bridge:91) */
     double speed_scale;          /* speedScale (scripts/vf:137,197-207) */
     double max_vel;              /* scripts/bridge:69,613-623 */
@@ -144,7 +147,9 @@ typedef struct vfk_buffers {
     const void* jp_ref;          /* [N]  joint reference (/jpctrl/ref) or NULL -> params.jp_ref   */
     const void* ns_in;           /* PROJECTOR: qdot0 [N] or NULL -> limit-avoidance gradient;
                                     CONTROL:   control [4] or NULL -> params.ns_control             */
-    void*       ns_lastvec;      /* CONTROL: [N] in/out sign-continuity state (scripts/nullspace:91-107) */
+    void*       ns_lastvec;      /* CONTROL: [min(4, N-6) * N] in/out: the basis vectors of the previous cycle, vector i at
+                                    components i*N .. i*N+N-1 -- the sign-continuity state `lastvec` of scripts/nullspace:91-107
+                                    (start zeroed).  Not needed when N <= 6 (empty nullspace). */
     const void* q_cmded;         /* [N]  last commanded q (scripts/bridge:169-172) or NULL -> q     */
     const void* ext_cmd[3];      /* mixer ports 3..5, [N] each, or NULL -> 0                        */
     void*       qdot_vf;         /* out [N]  /vectorField/qdotOut                                  */

@@ -36,9 +36,10 @@ ORACLE_CHOICES = [
     ("funnel attractor (vfl type 5)", "a = axis/|axis|, r = p - goal, s = r.a, r_perp = r - s a, theta = atan2(|r_perp|, s); V = -r_perp/|r_perp| * wa * wd with wa = 1 if theta <= cut_angle else (cut_angle/theta)^order_a and wd = 1 if |r| <= cut_dist else (cut_dist/|r|)^order_d"),
     ("normCart", "divides the translational part of the summed field by its Euclidean norm (zero stays zero); rotational part untouched"),
     ("velocity IK", "north_star closed form qdot = Wj Jw^T (Jw Jw^T + lambda^2 I)^-1 Wt t, Jw = Wt J Wj; lambda explicit"),
-    ("nullspace projector", "B = I - J^T (J J^T + ns_lambda^2 I)^-1 J; ns_lambda = 0 is the reference's pinv form (scripts/nullspace:75-79)"),
+    ("nullspace projector", "ns_lambda > 0: B = I - J^T (J J^T + ns_lambda^2 I)^-1 J (north_star's damped form); ns_lambda = 0: the reference's own B = I - pinv(J) J with numpy's SVD pinv (scripts/nullspace:75-79)"),
     ("limit-avoidance qdot0", "qdot0_i = -k (q_i - mid_i) / (hi_i - lo_i)^2"),
-    ("nullspace basis for the 4-float control interface", "1-D nullspaces only: u = B e_j / |B e_j|, j = argmax diag(B), with sign continuity against lastvec; first-cycle sign = sign that makes the largest-magnitude component positive (the reference's is LAPACK-dependent). Equals the reference's singular vector when ns_lambda = 0; with ns_lambda > 0 it is the damped approximation"),
+    ("nullspace basis for the 4-float control interface", "the reference takes the sigma >= 1e-8 left singular vectors of B^T (scripts/nullspace:95-107): ANY orthonormal basis of null(J), k = N - rank(J) vectors -- for k = 1 unique up to sign, for k > 1 whatever rotation of the k-fold singular value 1 LAPACK's gesdd happens to return (not a property of the reference's algorithm). The oracle fixes it as columns 6..N-1 of the Q of a Householder QR of J^T with LAPACK's dgeqr2/dlarfg sign convention (== numpy.linalg.qr(J.T, 'complete')); each vector then follows the reference's sign-continuity rule against lastvec, the first cycle keeping the raw sign as the reference does (sig starts at +1). Pinned against the executed reference by the projector sum_i u_i u_i^T (unique) and, for k = 1, by the vector itself up to the first-cycle sign. J is assumed to have full row rank (k = N - 6); at an exactly rank-deficient posture the reference finds one more vector"),
+    ("velocity IK vs KDL", "Lafik.getIKV wraps a KDL velocity solver whose source is not in the reference. [recollection, unverifiable here] KDL's ChainIkSolverVel_wdls applies lambda only to singular values below eps and is a plain weighted pseudo-inverse elsewhere, which would differ from north_star's uniformly damped form by O(lambda^2/sigma^2) away from singularities. Params.ik_mode = 1 evaluates that truncated form (SVD; FP64 oracle only) so a future Lafik comparison is one flag away; the product implements ik_mode 0, north_star's closed form"),
     ("plant", "explicit Euler q += dt * qdot_lim (the reference's integrator is the external joint_sim)"),
     ("synchronous cycle", "vf, nullspace and joint_p_controller all see the same q in one cycle (the reference's processes run asynchronously on latest values)"),
 ]
@@ -80,6 +81,8 @@ class Params:
     integrate: int = 1
     bridge_kind: int = 0               # 0 LWR_Bridge, 1 Powercube_Bridge, 2 ICUB_Bridge (scripts/bridge:102-111)
     shoulder_vel: tuple = (0.0, 0.0)   # Powercube: config.max_vel_shoulder_pos (> 0), max_vel_shoulder_neg (< 0)
+    ik_mode: int = 0                   # 0: north_star's uniformly damped closed form; 1: KDL-wdls-style (see ORACLE_CHOICES; oracle only)
+    ik_eps: float = 1e-5               # ik_mode 1: singular values below this are damped, the rest inverted plainly
 
 
 # --------------------------------------------------------------------------- FK / J
@@ -273,6 +276,14 @@ def ikv_dls(prm: Params, J: np.ndarray, tw: np.ndarray, N: int) -> np.ndarray:
     wt = np.asarray(prm.w_task, dtype=np.float64)
     wj = np.ones(N) if prm.w_joint is None else np.asarray(prm.w_joint, dtype=np.float64)[:N]
     Jw = wt[None, :, None] * J * wj[None, None, :]
+    if getattr(prm, "ik_mode", 0) == 1:
+        # [recollection of KDL's ChainIkSolverVel_wdls] qdot = Wj V diag(f(sigma)) U^T Wt t with f = 1/sigma above eps and
+        # sigma/(sigma^2 + lambda^2) below it
+        U, sg, Vt = np.linalg.svd(Jw, full_matrices=False)
+        with np.errstate(divide="ignore"):
+            f = np.where(sg < prm.ik_eps, sg / (sg * sg + prm.ik_lambda ** 2), 1.0 / sg)
+        y = np.einsum("ikr,ik->ir", U, wt[None, :] * tw) * f
+        return wj[None, :] * np.einsum("irn,ir->in", Vt, y)
     A = Jw @ np.transpose(Jw, (0, 2, 1)) + (prm.ik_lambda ** 2) * np.eye(6)[None]
     y = np.linalg.solve(A, (wt[None, :] * tw)[..., None])[..., 0]
     return wj[None, :] * np.einsum("ikn,ik->in", Jw, y)
@@ -281,9 +292,12 @@ def ikv_dls(prm: Params, J: np.ndarray, tw: np.ndarray, N: int) -> np.ndarray:
 def ns_project(prm: Params, J: np.ndarray, x: np.ndarray) -> np.ndarray:
     """``B x`` with ``B = I - pinv(PJ) PJ``, ``P = I6`` (a8, ``scripts/nullspace:75-79,136``).
 
-    ``pinv`` is taken as ``J^T (J J^T + ns_lambda^2 I)^-1`` (ns_lambda = 0: the
-    reference's Moore-Penrose form for full-row-rank J).
+    ``ns_lambda = 0``: the reference's own form, ``pinv`` being numpy's SVD pseudo-inverse.
+    ``ns_lambda > 0``: north_star's damped form ``J^T (J J^T + ns_lambda^2 I)^-1``.
     """
+    if prm.ns_lambda == 0:
+        Jp = np.linalg.pinv(J)                                   # [I, N, 6]
+        return x - np.einsum("ink,ik->in", Jp, np.einsum("ikn,in->ik", J, x))
     A = J @ np.transpose(J, (0, 2, 1)) + (prm.ns_lambda ** 2) * np.eye(6)[None]
     Jx = np.einsum("ikn,in->ik", J, x)
     y = np.linalg.solve(A, Jx[..., None])[..., 0]
@@ -296,26 +310,76 @@ def ns_limit_gradient(prm: Params, chain, q: np.ndarray) -> np.ndarray:
     return -prm.ns_limit_gain * (q - mid[None, :]) / (rng * rng)[None, :]
 
 
-def ns_basis_1d(prm: Params, J: np.ndarray, lastvec: np.ndarray) -> np.ndarray:
-    """Unit nullspace vector with sign continuity (a9, ``scripts/nullspace:91-107``), 1-D case.
+def ns_ctrl_vectors(n_joints: int) -> int:
+    """Basis vectors the four-float control interface can address: ``min(nJoints, len(control), k)`` with ``k = N - 6``
+    (``scripts/nullspace:113``)."""
+    return max(0, min(4, n_joints - 6))
 
-    The reference takes the sigma >= 1e-8 left singular vectors of ``B^T`` and flips each to
-    stay close to ``lastvec``.  For a 1-D nullspace ``B = u u^T``; here ``u`` is the
-    normalised column of ``B`` with the largest diagonal entry.  Sign: continuity with
-    ``lastvec`` when it is non-zero (``|u - last| <= |u + last|``), otherwise the
-    largest-magnitude component is made positive (ORACLE_CHOICE; LAPACK's is arbitrary).
-    """
+
+def ns_basis(J: np.ndarray, n_vec: Optional[int] = None) -> np.ndarray:
+    """Orthonormal vectors of null(J): columns ``6 .. 6 + n_vec - 1`` of the Q of a Householder QR of ``J^T`` [I, N, 6].
+
+    Restates LAPACK's published ``dgeqr2`` / ``dlarfg`` (column by column: ``beta = -sign(alpha) |x|``,
+    ``tau = (beta - alpha) / beta``, ``v = x / (alpha - beta)`` with ``v_0 = 1``, ``H = I - tau v v^T``), vectorised over the
+    instance axis; ``tests/test_oracle.py`` checks it against ``numpy.linalg.qr(J.T, 'complete')`` and, through the
+    projector ``sum_i u_i u_i^T``, against the executed ``scripts/nullspace:91-107`` (see ORACLE_CHOICES).
+    Returns [I, n_vec, N] (default: all ``N - 6``)."""
     I, _, N = J.shape
-    B = np.stack([ns_project(prm, J, np.broadcast_to(np.eye(N)[j], (I, N))) for j in range(N)], axis=2)  # [I,N,N] columns
-    jstar = np.argmax(np.einsum("ijj->ij", B), axis=1)
-    u = B[np.arange(I), :, jstar]
-    u = u / np.linalg.norm(u, axis=1, keepdims=True)
-    has_last = np.any(lastvec != 0.0, axis=1)
-    dotl = np.einsum("in,in->i", u, lastvec)
-    kmax = np.argmax(np.abs(u), axis=1)
-    sgn_first = np.sign(u[np.arange(I), kmax])
-    sgn = np.where(has_last, np.where(dotl < 0.0, -1.0, 1.0), np.where(sgn_first < 0, -1.0, 1.0))
-    return u * sgn[:, None]
+    k = max(0, N - 6)
+    n_vec = k if n_vec is None else min(n_vec, k)
+    a = np.transpose(J, (0, 2, 1)).copy()                        # [I, N, 6]
+    tau = np.zeros((I, 6))
+    for j in range(min(6, N)):
+        alpha = a[:, j, j].copy()
+        xn2 = np.einsum("ir,ir->i", a[:, j + 1:, j], a[:, j + 1:, j])
+        live = xn2 > 0.0
+        beta = -np.copysign(np.sqrt(alpha * alpha + xn2), alpha)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            t = np.where(live, (beta - alpha) / beta, 0.0)
+            sc = np.where(live, 1.0 / (alpha - beta), 1.0)
+        tau[:, j] = t
+        a[:, j + 1:, j] *= sc[:, None]
+        a[:, j, j] = np.where(live, beta, alpha)
+        v = a[:, j + 1:, j]
+        for c in range(j + 1, 6):
+            w = (a[:, j, c] + np.einsum("ir,ir->i", v, a[:, j + 1:, c])) * t
+            a[:, j, c] -= w
+            a[:, j + 1:, c] -= v * w[:, None]
+    out = np.zeros((I, n_vec, N))
+    for i in range(n_vec):
+        w = np.zeros((I, N))
+        w[:, 6 + i] = 1.0
+        for j in range(min(6, N) - 1, -1, -1):
+            v = a[:, j + 1:, j]
+            d = (w[:, j] + np.einsum("ir,ir->i", v, w[:, j + 1:])) * tau[:, j]
+            w[:, j] -= d
+            w[:, j + 1:] -= v * d[:, None]
+        out[:, i, :] = w
+    return out
+
+
+def ns_control_motion(J: np.ndarray, lastvec: np.ndarray, control: np.ndarray):
+    """``move_in_nullspace`` (a9, a10; ``scripts/nullspace:91-117``) on a batch.
+
+    ``lastvec`` [I, kk * N] is the reference's ``lastvec`` state (vector i at ``[i * N, (i + 1) * N)``, zeros at the start),
+    ``control`` [I, 4].  Each basis vector is flipped when ``|s u - last| > |s u + last|``, i.e. when it points away from
+    the previous cycle's vector; then ``qdot = sum_{i < kk} control_i u_i``.  Returns (qdot [I, N], new lastvec)."""
+    I, _, N = J.shape
+    kk = ns_ctrl_vectors(N)
+    if kk == 0:
+        return np.zeros((I, N)), lastvec
+    u = ns_basis(J, kk)                                           # [I, kk, N]
+    last = lastvec.reshape(I, kk, N)
+    dotl = np.einsum("ikn,ikn->ik", u, last)
+    u = np.where((dotl < 0.0)[:, :, None], -u, u)
+    qd = np.einsum("ik,ikn->in", control[:, :kk], u)
+    return qd, u.reshape(I, kk * N)
+
+
+def ns_basis_1d(prm: Params, J: np.ndarray, lastvec: np.ndarray) -> np.ndarray:
+    """The single nullspace vector of a 6 x 7 Jacobian with the reference's sign continuity (kept for the 7-joint tests)."""
+    assert J.shape[2] == 7
+    return ns_control_motion(J, lastvec, np.ones((J.shape[0], 4)))[1]
 
 
 def ns_check_limits(prm: Params, chain, q: np.ndarray, qdot: np.ndarray):
@@ -390,12 +454,10 @@ def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastve
                 raw = ns_project(prm, J, x)
             else:
                 if lastvec is None:
-                    lastvec = np.zeros((I, N))
-                u = ns_basis_1d(prm, J, lastvec)
-                lastvec = u
+                    lastvec = np.zeros((I, max(1, ns_ctrl_vectors(N)) * N))
                 ctrl = (np.broadcast_to(np.asarray(prm.ns_control, dtype=np.float64), (I, 4))
                         if ns_in is None else np.asarray(ns_in, dtype=np.float64))
-                raw = u * ctrl[:, 0:1]                 # min(N, len(control), k=1) terms (scripts/nullspace:113-116)
+                raw, lastvec = ns_control_motion(J, lastvec, ctrl)     # min(N, len(control), k) terms (scripts/nullspace:113-116)
             raw, bad = ns_check_limits(prm, chain, q, raw)
             flags |= np.where(bad, FLAG_NS_LIMIT, 0).astype(np.int32)
             qd_ns = raw * prm.ns_gain                  # scripts/nullspace:183

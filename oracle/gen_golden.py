@@ -233,6 +233,42 @@ def gen_nullspace(rng):
                 ns_limited=limited, ns_hit=hit, ns_rank=np.asarray(rank), ns_Jrand=Jr, ns_Brand=Br)
 
 
+def gen_nullspace_wide(rng=None):
+    """The same reference functions with ``nJoints = 10`` (the reference's iCub shape, ``scripts/bridge:344-345``: a 4-D
+    nullspace) and 8 (2-D) along short joint trajectories of a torso + arm chain: projector, the ``k = N - 6`` basis vectors
+    ``nullspace()`` returns with their sign-continuity state, and ``move_in_nullspace`` on four control floats.  For
+    ``k > 1`` LAPACK's choice of basis inside the degenerate singular subspace is arbitrary, so what the record pins is the
+    projector ``sum_i u_i u_i^T``, the span, ``k`` and the norm of the motion (own seed: the older keys stay as they are)."""
+    from oracle import batch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT_DIR)))
+    from vfclik_b200 import workloads
+    rng = np.random.default_rng(20261019)
+    out = {}
+    for n in (10, 8):
+        chain = workloads.torso_arm_chain(n)
+        steps = 8
+        q = np.zeros((steps, n))
+        q[0] = rng.uniform(0.4 * chain.q_lo, 0.4 * chain.q_hi)
+        for s in range(1, steps):
+            q[s] = q[s - 1] + rng.normal(scale=0.03, size=n)
+        _, _, J = batch.fk_jac(chain, q)
+        glb = load_real_nullspace(n)
+        P = np.asmatrix(np.eye(6))
+        control = [0.7, -0.2, 0.1, 0.4]
+        B = np.zeros((steps, n, n))
+        basis = np.zeros((steps, n - 6, n))
+        qd = np.zeros((steps, n))
+        for s in range(steps):
+            Jm = np.asmatrix(J[s])
+            B[s] = np.asarray(glb["restrict"](P, Jm))
+            qd[s] = glb["move_in_nullspace"](P, Jm, control)
+            basis[s] = np.asarray(glb["lastvec"])[:, :n - 6].T
+        tag = "ns%d_" % n
+        out.update({tag + "q": q, tag + "J": J, tag + "B": B, tag + "basis": basis, tag + "qdot": qd,
+                    tag + "control": np.asarray(control)})
+    return out
+
+
 def load_reference_function(relpath: str, name: str, cls: str = None):
     """Source text of one function (or method of ``cls``) of a reference script, dedented, ready for ``exec``.
 
@@ -860,6 +896,7 @@ def main():
     data.update(gen_dmonitor(rng))
     data.update(gen_nullspace_loop(rng))
     data.update(gen_handlers())
+    data.update(gen_nullspace_wide())
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

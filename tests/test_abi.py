@@ -71,8 +71,8 @@ def test_argument_errors_are_codes_not_exceptions(built_lib, lwr):
     cd = _lib.chain_to_c(chain)
     assert lib.vfk_create(C.byref(h), C.byref(cd), 16, 0) == _lib.VFK_ERR_INVALID
     assert b"precision" in lib.vfk_last_error(None)
-    cd.n_joints = 5
-    assert lib.vfk_create(C.byref(h), C.byref(cd), 32, 0) == _lib.VFK_ERR_UNSUPPORTED
+    cd.n_joints = 0
+    assert lib.vfk_create(C.byref(h), C.byref(cd), 32, 0) == _lib.VFK_ERR_INVALID
     cd.n_joints = 99
     assert lib.vfk_create(C.byref(h), C.byref(cd), 32, 0) == _lib.VFK_ERR_INVALID
     assert lib.vfk_step(None, None, 1, 32, 0, 4, 1, None) == _lib.VFK_ERR_INVALID

@@ -618,7 +618,7 @@ def test_nullspace_module_matches_the_reference_main_loop(lwr, golden, built_lib
             want = g["nl_qdotout"][k]
             if sign is None and np.max(np.abs(want)) > 0:
                 sign = 1.0 if np.dot(got, want) > 0 else -1.0
-            assert np.allclose(got * (sign or 1.0), want, rtol=1e-7, atol=1e-10), (k, got, want)
+            assert np.allclose(got * (sign or 1.0), want, rtol=1e-9, atol=1e-12), (k, got, want)
         assert sign is not None
     finally:
         ns.close(); rt.close()

@@ -207,6 +207,79 @@ def test_golden_nullspace(golden, lwr):
         assert np.allclose(Bb, golden["ns_Brand"][k], atol=1e-9)
 
 
+@pytest.mark.parametrize("n", [10, 8])
+def test_golden_nullspace_wide(golden, n):
+    """k = N - 6 > 1 (the reference's iCub shape, 10 joints -> 4 vectors; 8 joints -> 2): the oracle's basis against the
+    executed ``scripts/nullspace`` functions.  The basis of a degenerate singular subspace is LAPACK's free choice, so the
+    comparison is through what IS determined: the projector ``sum u u^T``, the span, the number of vectors, orthonormality,
+    sign continuity, and the length of the motion for the same four control floats."""
+    tag = "ns%d_" % n
+    J, B, Uref, qd_ref = golden[tag + "J"], golden[tag + "B"], golden[tag + "basis"], golden[tag + "qdot"]
+    control = golden[tag + "control"]
+    steps, k = J.shape[0], n - 6
+    assert Uref.shape == (steps, k, n) and batch.ns_ctrl_vectors(n) == min(4, k)
+    chain = workloads.torso_arm_chain(n)
+    assert np.allclose(batch.fk_jac(chain, golden[tag + "q"])[2], J, atol=1e-14)
+    prm0 = batch.Params(ns_lambda=0.0)
+    U = batch.ns_basis(J)                                                   # [steps, k, n]
+    for s in range(steps):
+        # the executed reference: projector and its own basis agree, and the basis is orthonormal
+        assert np.allclose(Uref[s].T @ Uref[s], B[s], atol=1e-10)
+        Q = np.linalg.qr(J[s].T, mode="complete")[0]
+        assert np.allclose(U[s], Q[:, 6:].T, atol=1e-12)                    # LAPACK's own Householder QR
+        assert np.allclose(U[s] @ U[s].T, np.eye(k), atol=1e-12)
+        assert np.allclose(U[s].T @ U[s], B[s], atol=1e-9)                  # same projector
+        assert np.allclose(U[s] @ B[s], U[s], atol=1e-9)                    # same span
+        assert np.linalg.matrix_rank(np.vstack([U[s], Uref[s]]), tol=1e-8) == k
+        Bb = np.stack([batch.ns_project(prm0, J[s:s + 1], np.eye(n)[j:j + 1])[0] for j in range(n)], axis=1)
+        assert np.allclose(Bb, B[s], atol=1e-10)
+    # control motion: sum of min(4, k) orthonormal vectors -> |qdot| = |control[:kk]|, inside null(J); sign-continuous
+    kk = min(4, k)
+    last = np.zeros((1, kk * n))
+    prev = None
+    for s in range(steps):
+        qd, last = batch.ns_control_motion(J[s:s + 1], last, control[None, :])
+        assert np.allclose(np.linalg.norm(qd), np.linalg.norm(control[:kk]), rtol=1e-12)
+        assert np.allclose(np.linalg.norm(qd_ref[s]), np.linalg.norm(control[:kk]), rtol=1e-10)
+        assert np.allclose(J[s] @ qd[0], 0, atol=1e-12) and np.allclose(J[s] @ qd_ref[s], 0, atol=1e-10)
+        assert np.allclose(B[s] @ qd[0], qd[0], atol=1e-9)
+        u = last.reshape(kk, n)
+        if prev is not None:
+            assert np.all(np.einsum("kn,kn->k", u, prev) >= 0.0)
+        prev = u
+
+
+def test_ns_basis_small_and_padded_chains():
+    """N <= 6: empty nullspace, zero motion.  Zero Jacobian columns (how the kernel pads a short chain into a larger
+    instantiation) leave the leading vectors of the basis untouched."""
+    rng = np.random.default_rng(12)
+    for n in (3, 6):
+        J = rng.normal(size=(5, 6, n))
+        assert batch.ns_basis(J).shape == (5, 0, n)
+        qd, _ = batch.ns_control_motion(J, np.zeros((5, n)), np.ones((5, 4)))
+        assert np.all(qd == 0)
+    J = rng.normal(size=(5, 6, 8))
+    Jp = np.concatenate([J, np.zeros((5, 6, 2))], axis=2)
+    assert np.allclose(batch.ns_basis(Jp, 2)[:, :, :8], batch.ns_basis(J), atol=1e-14)
+    assert np.all(batch.ns_basis(Jp, 2)[:, :, 8:] == 0)
+
+
+def test_ik_mode_kdl_wdls_form(lwr):
+    """ORACLE_CHOICES 'velocity IK vs KDL': away from singularities the truncated form is the plain weighted pseudo-inverse
+    and differs from north_star's uniformly damped form by O(lambda^2 / sigma^2); with lambda = 0 the two coincide."""
+    chain, _ = lwr
+    rng = np.random.default_rng(13)
+    q = rng.uniform(0.5 * chain.q_lo, 0.5 * chain.q_hi, size=(64, 7))
+    _, _, J = batch.fk_jac(chain, q)
+    tw = rng.normal(size=(64, 6))
+    a = batch.ikv_dls(batch.Params(ik_lambda=0.0), J, tw, 7)
+    b = batch.ikv_dls(batch.Params(ik_lambda=0.1, ik_mode=1), J, tw, 7)
+    assert np.allclose(a, b, rtol=1e-7, atol=1e-9)
+    assert np.allclose(np.einsum("ikn,in->ik", J, b), tw, atol=1e-8)          # exact task-space tracking
+    c = batch.ikv_dls(batch.Params(ik_lambda=0.1), J, tw, 7)
+    assert not np.allclose(c, b, rtol=1e-3)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference only exists in the build container")
 def test_golden_is_reproducible_from_reference(golden):
     """Regenerating from the real reference gives the committed vectors (guards a stale fixture)."""
@@ -222,6 +295,7 @@ def test_golden_is_reproducible_from_reference(golden):
     data.update(gen_golden.gen_dmonitor(rng))
     data.update(gen_golden.gen_nullspace_loop(rng))
     data.update(gen_golden.gen_handlers())
+    data.update(gen_golden.gen_nullspace_wide())
     for k, v in data.items():
         if np.asarray(v).dtype.kind in "US":
             assert [str(x) for x in v] == [str(x) for x in golden[k]], k

@@ -124,7 +124,10 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     c.shoulder_neg = (T)p.shoulder_vel[1];
     c.integrate = p.integrate ? 1 : 0;
     c.unit_weights = unit ? 1 : 0;
-    c.share_factor = (unit && p.ns_lambda == p.ik_lambda) ? 1 : 0;
+    // the reference's nullspace (control interface) and the undamped projector go through the Householder basis of
+    // null(J) (vfk_nullspace.cuh): no normal equations, so no cond(J)^2 and no pivot to lose at ns_lambda = 0
+    c.ns_qr = (p.ns_mode == VFK_NS_CONTROL || (p.ns_mode == VFK_NS_PROJECTOR && p.ns_lambda == 0.0)) ? 1 : 0;
+    c.share_factor = (unit && p.ns_lambda == p.ik_lambda && !c.ns_qr) ? 1 : 0;
     c.need_jp = p.mixer_w[2] != 0.0 ? 1 : 0;
     c.asin_series = (p.rot_slowdown > 0 && p.rot_slowdown <= 0.3) ? 1 : 0;
     c.order_int = (p.obst_order == std::floor(p.obst_order) && p.obst_order >= 1 && p.obst_order <= 64) ? (int)p.obst_order : 0;
@@ -161,18 +164,14 @@ extern "C" void vfk_default_params(vfk_params* p, int n_joints) {
     (void)n_joints;
 }
 
-static bool n_supported(int n) { return n == 6 || n == 7 || n == 10 || n == 17; }
+// Instantiated joint counts; any other chain length runs padded in the next larger one (generic pattern).
+static int kernel_joints(int n) { return n <= 6 ? 6 : n <= 7 ? 7 : n <= 10 ? 10 : 17; }
 
 static int check_params(vfk_ctx* h, const vfk_params* p) {
     if (!(p->ik_lambda >= 0) || !(p->ns_lambda >= 0)) return fail(h, VFK_ERR_INVALID, "lambda must be >= 0");
     if (p->ik_lambda == 0 && h->precision == 32)
         return fail(h, VFK_ERR_INVALID, "ik_lambda = 0 is outside the FP32 mode's domain (use precision 64)");
-    if (p->ns_lambda == 0 && p->ns_mode != VFK_NS_OFF && h->precision == 32)
-        return fail(h, VFK_ERR_INVALID, "ns_lambda = 0 (undamped pinv) is outside the FP32 mode's domain (use precision 64)");
     if (p->ns_mode < 0 || p->ns_mode > 2) return fail(h, VFK_ERR_INVALID, "ns_mode must be 0, 1 or 2");
-    if (p->ns_mode == VFK_NS_CONTROL && h->chain.n_joints != 7)
-        return fail(h, VFK_ERR_UNSUPPORTED, "VFK_NS_CONTROL needs a 1-D nullspace (n_joints = 7), got %d joints",
-                    h->chain.n_joints);
     if (!(p->max_vel >= 0)) return fail(h, VFK_ERR_INVALID, "max_vel must be >= 0");
     if (p->bridge_kind < VFK_BRIDGE_LWR || p->bridge_kind > VFK_BRIDGE_ICUB)
         return fail(h, VFK_ERR_INVALID, "bridge_kind must be VFK_BRIDGE_LWR, _POWERCUBE or _ICUB");
@@ -188,8 +187,6 @@ extern "C" int vfk_create(vfk_handle* out, const vfk_chain_desc* chain, int prec
     if (precision != 32 && precision != 64) return fail(nullptr, VFK_ERR_INVALID, "precision must be 32 or 64");
     const int n = chain->n_joints;
     if (n < 1 || n > VFK_MAX_JOINTS) return fail(nullptr, VFK_ERR_INVALID, "n_joints %d out of range", n);
-    if (!n_supported(n))
-        return fail(nullptr, VFK_ERR_UNSUPPORTED, "no kernel compiled for n_joints = %d (have 6, 7, 10, 17)", n);
     for (int j = 0; j < n; ++j) {
         if (chain->joint_type[j] < VFK_JOINT_ROTX || chain->joint_type[j] > VFK_JOINT_TRANSZ)
             return fail(nullptr, VFK_ERR_INVALID, "joint %d: type %d (fold fixed segments on the host)", j, chain->joint_type[j]);
@@ -210,6 +207,7 @@ extern "C" int vfk_create(vfk_handle* out, const vfk_chain_desc* chain, int prec
     h->chain = *chain;
     canonicalise_chain(h->chain, h->canon);
     h->pattern = chain_matches<LwrPattern>(h->canon, 7) ? 1 : 0;
+    h->n_kernel = kernel_joints(n);
     h->precision = precision;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
@@ -261,7 +259,7 @@ static int step_impl(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, in
     if ((rc = check_layout(h, b->q, "q", true)) || (rc = check_layout(h, b->goal, "goal", true)) ||
         (rc = check_layout(h, b->obst, "obst", n_obst > 0)) || (rc = check_layout(h, b->obst_ext, "obst_ext", false)) || (rc = check_layout(h, b->aux, "aux", false)) ||
         (rc = check_layout(h, b->jp_ref, "jp_ref", false)) || (rc = check_layout(h, b->ns_in, "ns_in", false)) ||
-        (rc = check_layout(h, b->ns_lastvec, "ns_lastvec", h->params.ns_mode == VFK_NS_CONTROL)) ||
+        (rc = check_layout(h, b->ns_lastvec, "ns_lastvec", h->params.ns_mode == VFK_NS_CONTROL && ns_ctrl_vectors(h->chain.n_joints) > 0)) ||
         (rc = check_layout(h, b->q_cmded, "q_cmded", false)) || (rc = check_layout(h, b->qdot_vf, "qdot_vf", false)) ||
         (rc = check_layout(h, b->qdot_ns, "qdot_ns", false)) || (rc = check_layout(h, b->qdot_jp, "qdot_jp", false)) ||
         (rc = check_layout(h, b->qdot, "qdot", false)) || (rc = check_layout(h, b->cmd, "cmd", false)) ||
@@ -272,7 +270,7 @@ static int step_impl(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, in
     if (n == 0) return 0;
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool small = h->chain.n_joints <= 7;
+    const bool small = h->n_kernel <= 7;
     if (h->precision == 32)
         return small ? vfk_launch_f32_small(h, b, n, n_obst, k_cycles, st, io) : vfk_launch_f32_large(h, b, n, n_obst, k_cycles, st, io);
     return small ? vfk_launch_f64_small(h, b, n, n_obst, k_cycles, st, io) : vfk_launch_f64_large(h, b, n, n_obst, k_cycles, st, io);
@@ -472,9 +470,11 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     const size_t row = align_up((size_t)s->tiles * 32 * s->es, 128);     // one component over all tiles
     const size_t obst_rows = (size_t)n_obst * (4 + (s->has_ext ? 2 : 0));
     // blocked: q N, goal 13, obst, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, twist 6, flags 1
-    const size_t rows = (size_t)N * 9 + 13 + obst_rows + 12 + 6 + 1;
+    const int lv_rows = (ns_ctrl_vectors(N) > 0 ? ns_ctrl_vectors(N) : 1) * N;   // sign-continuity state: [min(4, N - 6)][N]
+    const size_t rows = (size_t)N * 8 + lv_rows + 13 + obst_rows + 12 + 6 + 1;
     const size_t stage_in_rows = obst_rows > (size_t)(N > 13 ? N : 13) ? obst_rows : (size_t)(N > 13 ? N : 13);
-    const size_t stage_out_rows = (size_t)(N > 12 ? N : 12) + (size_t)N;      // qdot (or a read()) + q_out
+    const size_t first_out = (size_t)(lv_rows > 12 ? lv_rows : 12);
+    const size_t stage_out_rows = first_out + (size_t)N;                          // qdot (or a read()) + q_out
     s->dev_bytes = (rows + stage_in_rows + stage_out_rows) * row;
     cudaError_t e = cudaMalloc((void**)&s->dev, s->dev_bytes);
     if (e != cudaSuccess) { delete s; return fail(h, VFK_ERR_CUDA, "cudaMalloc(%zu): %s", s->dev_bytes, cudaGetErrorString(e)); }
@@ -487,7 +487,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->b.obst_ext = (n_obst && s->has_ext) ? take((size_t)n_obst * 2) : nullptr;
     s->d_jp_ref = take(N);
     s->d_ns_in = take(N);
-    s->b.ns_lastvec = take(N);
+    s->b.ns_lastvec = take(lv_rows);
     s->b.qdot_vf = take(N);
     s->b.qdot_ns = take(N);
     s->b.qdot_jp = take(N);
@@ -609,7 +609,7 @@ static vfk_buffers offset_view(const vfk_buffers& b, int64_t tile0, int N, int M
     };
     o.q = off(b.q, N); o.goal = off(b.goal, 13); o.obst = off(b.obst, (size_t)M * 4); o.obst_ext = off(b.obst_ext, (size_t)M * 2);
     o.aux = off(b.aux, (size_t)b.n_aux * 12);
-    o.jp_ref = off(b.jp_ref, N); o.ns_lastvec = off(b.ns_lastvec, N); o.q_cmded = off(b.q_cmded, N);
+    o.jp_ref = off(b.jp_ref, N); o.ns_lastvec = off(b.ns_lastvec, (size_t)(ns_ctrl_vectors(N) > 0 ? ns_ctrl_vectors(N) : 1) * N); o.q_cmded = off(b.q_cmded, N);
     for (int e = 0; e < 3; ++e) o.ext_cmd[e] = off(b.ext_cmd[e], N);
     o.qdot_vf = off(b.qdot_vf, N); o.qdot_ns = off(b.qdot_ns, N); o.qdot_jp = off(b.qdot_jp, N); o.qdot = off(b.qdot, N);
     o.cmd = off(b.cmd, N); o.pose = off(b.pose, 12); o.twist = off(b.twist, 6);
@@ -640,7 +640,8 @@ static int enqueue_cycle(vfk_session_s* s, const char* src_q, int k_cycles, char
     const int64_t tiles_per_chunk = (s->tiles + n_chunks - 1) / n_chunks;
     char* stage_q = (char*)s->stage_in;                         // dense [N][n]
     char* stage_qd = (char*)s->stage_out;                       // dense [N][n]
-    char* stage_qo = (char*)s->stage_out + (size_t)(N > 12 ? N : 12) * (align_up((size_t)s->tiles * 32 * es, 128));
+    const size_t lv_rows = (size_t)(ns_ctrl_vectors(N) > 0 ? ns_ctrl_vectors(N) : 1) * N;
+    char* stage_qo = (char*)s->stage_out + (lv_rows > 12 ? lv_rows : 12) * (align_up((size_t)s->tiles * 32 * es, 128));
     const size_t pitch = (size_t)s->n * es;
     int launches = 0, rc;
     for (int c = 0; c < n_chunks; ++c) {
@@ -856,7 +857,7 @@ extern "C" int vfk_session_read(vfk_session s, const char* what, void* out) {
     else if (!strcmp(what, "qdot")) src = s->b.qdot;
     else if (!strcmp(what, "cmd")) src = s->b.cmd;
     else if (!strcmp(what, "q")) src = s->b.q;
-    else if (!strcmp(what, "lastvec")) src = s->b.ns_lastvec;
+    else if (!strcmp(what, "lastvec")) { src = s->b.ns_lastvec; rows = (ns_ctrl_vectors(s->N) > 0 ? ns_ctrl_vectors(s->N) : 1) * s->N; }
     else if (!strcmp(what, "pose")) { src = s->b.pose; rows = 12; }
     else if (!strcmp(what, "twist")) { src = s->b.twist; rows = 6; }
     else return fail(s->h, VFK_ERR_INVALID, "vfk_session_read: unknown field '%s'", what);

@@ -25,6 +25,7 @@
 #include <stdint.h>
 #include "vfk_math.cuh"
 #include "vfk_tma.cuh"
+#include "vfk_nullspace.cuh"
 
 namespace vfk {
 
@@ -84,6 +85,7 @@ struct KConst {
     int32_t need_jp;           // joint P controller observable (weight != 0 or an output wants it)
     int32_t asin_series;       // rot_slowdown <= 0.3 rad: small-angle series replaces atan2 in FP32
     int32_t order_int;         // obst_order when it is a small integer, else 0
+    int32_t ns_qr;             // nullspace through the Householder basis of null(J): control mode, or the projector with ns_lambda = 0
 };
 
 template <typename T>
@@ -120,6 +122,7 @@ struct KArgs {
     int32_t n_stages;          // shared-memory stages (<= kMaxStages); >= n_chunks means resident
     int32_t k_cycles;
     int32_t n_aux;
+    int32_t n_comp;            // joint components per instance in memory (<= N: generic chains of fewer joints run padded, see nc below)
 };
 
 // ------------------------------------------------------------------------------ chain patterns
@@ -159,7 +162,7 @@ struct LwrPattern {
 // in T.  Outputs: R, and the tool-less flange position as hi + lo parts in T (lo = 0 when T is already wide).
 template <typename T, int N, class PAT>
 __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N], typename WideOf<T>::type (&R)[9],
-                                            typename WideOf<T>::type (&p)[3], T (&Jl)[N][3], T (&Ja)[N][3]) {
+                                            typename WideOf<T>::type (&p)[3], T (&Jl)[N][3], T (&Ja)[N][3], int nc) {
     using W = typename WideOf<T>::type;
     if constexpr (PAT::base_identity) {
 #pragma unroll
@@ -172,6 +175,11 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
     for (int k = 0; k < 3; ++k) p[k] = c.base[9 + k];
     static_for<0, N>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
+        if (PAT::generic && j >= nc) {                                  // padding joint of a shorter chain: no motion, zero column
+            Ja[j][0] = Ja[j][1] = Ja[j][2] = T(0);
+            Jl[j][0] = Jl[j][1] = Jl[j][2] = T(0);
+            return;
+        }
         Ja[j][0] = (T)R[2]; Ja[j][1] = (T)R[5]; Ja[j][2] = (T)R[8];
         Jl[j][0] = (T)p[0]; Jl[j][1] = (T)p[1]; Jl[j][2] = (T)p[2];      // holds p_j until p_e is known
         const W qj = (W)q[j];
@@ -411,17 +419,17 @@ __device__ __forceinline__ void issue_obst(const KArgs<T>& a, int64_t tile, int 
 // q tile (N rows) + goal tile (13 rows): two bulk copies into q/goal buffer `buf`.
 template <typename T, int N, bool EXT>
 __device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile, int buf, unsigned char* region, uint64_t* bars,
-                                         int lane) {
+                                         int lane, int nc) {
     using WS = WarpStage<T, N, EXT>;
     if (lane == 0) {
         unsigned char* dst = region + (size_t)a.n_stages * WS::kStage + (size_t)buf * WS::kQg;
-        mbar_arrive_expect_tx(&bars[kMaxStages + buf], WS::kQg);
+        mbar_arrive_expect_tx(&bars[kMaxStages + buf], (uint32_t)(nc + 13) * WS::kQgRow);
         if (a.q_src) {
 #pragma unroll
             for (int j = 0; j < N; ++j)
-                bulk_g2s(dst + j * WS::kQgRow, a.q_src + j * a.q_src_ld + (tile << 5), WS::kQgRow, &bars[kMaxStages + buf]);
+                if (j < nc) bulk_g2s(dst + j * WS::kQgRow, a.q_src + j * a.q_src_ld + (tile << 5), WS::kQgRow, &bars[kMaxStages + buf]);
         } else {
-            bulk_g2s(dst, a.q + tile * (N * 32), N * WS::kQgRow, &bars[kMaxStages + buf]);
+            bulk_g2s(dst, a.q + tile * (nc * 32), (uint32_t)nc * WS::kQgRow, &bars[kMaxStages + buf]);
         }
         bulk_g2s(dst + N * WS::kQgRow, a.goal + tile * (13 * 32), 13 * WS::kQgRow, &bars[kMaxStages + buf]);
     }
@@ -454,6 +462,9 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     int64_t unit = (int64_t)blockIdx.x * (kBlock / 32) + warp;
     if (unit >= n_units) return;
     const int ol = lane & (G - 1);                              // obstacle lane within the group
+    // Joint components in memory.  Chains with a joint count that has no instantiation of its own run in the next larger
+    // generic one: joints >= nc are padding (zero Jacobian column, no motion, nothing loaded or stored for them).
+    const int nc = PAT::generic ? a.n_comp : N;
 
     // Ring bookkeeping.  A "use" is one consumption of one chunk; a tile has U uses and the ring S slots.
     // resident: S = n_chunks, every chunk is loaded once per tile and reused by all K cycles (U = n_chunks);
@@ -469,7 +480,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         mbar_fence_init();
     }
     __syncwarp();
-    issue_qg<T, N, EXT>(a, unit / kSub, 0, region, bars, lane);
+    issue_qg<T, N, EXT>(a, unit / kSub, 0, region, bars, lane, nc);
     int64_t p_unit = unit;
     int p_u = 0, p_chunk = 0;
     for (int u = 0; u < S; ++u) {
@@ -484,24 +495,18 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         const int64_t tile = unit / kSub;
         const int slot = G == 1 ? lane : (int)(unit % kSub) * (32 / G) + (lane / G);     // instance within the tile
         const bool active = (tile << 5) + slot < a.n && ol == 0;     // padding / helper lanes compute, never store
-        const int64_t tN = tile * (N * 32) + slot;              // this instance's slot in an N-component blocked array
+        const int64_t tN = tile * (nc * 32) + slot;             // this instance's slot in a blocked array of nc joint components
         __syncwarp();
-        if (unit + stride < n_units) issue_qg<T, N, EXT>(a, (unit + stride) / kSub, (it + 1) & 1, region, bars, lane);
+        if (unit + stride < n_units) issue_qg<T, N, EXT>(a, (unit + stride) / kSub, (it + 1) & 1, region, bars, lane, nc);
         mbar_wait(&bars[kMaxStages + (it & 1)], (uint32_t)(it >> 1) & 1u);
         const T* qg = reinterpret_cast<const T*>(region + (size_t)a.n_stages * WS::kStage + (size_t)(it & 1) * WS::kQg) + slot;
 
     T q[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) q[j] = qg[j * 32];
+    for (int j = 0; j < N; ++j) q[j] = j < nc ? qg[j * 32] : T(0);
     T g[13];
 #pragma unroll
     for (int k = 0; k < 13; ++k) g[k] = qg[(N + k) * 32];
-
-    T lastv[N];
-    if (!LEAN && c.ns_mode == 2) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) lastv[j] = a.ns_lastvec[tN + j * 32];
-    }
 
     for (int cyc = 0; cyc < a.k_cycles; ++cyc) {
         const bool last = (cyc == a.k_cycles - 1);
@@ -514,7 +519,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         Pos<T> pt;
         {
             W Rw[9], pw[3];
-            fk_jacobian<T, N, PAT>(c, q, Rw, pw, Jl, Ja);
+            fk_jacobian<T, N, PAT>(c, q, Rw, pw, Jl, Ja, nc);
             if (LEAN || c.tool_identity) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Rt[k] = (T)Rw[k];
@@ -624,7 +629,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         if (ns_proj) {
             if (!LEAN && a.ns_in) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) x[j] = __ldg(a.ns_in + tN + j * 32);
+                for (int j = 0; j < N; ++j) x[j] = j < nc ? __ldg(a.ns_in + tN + j * 32) : T(0);
             } else {
 #pragma unroll
                 for (int j = 0; j < N; ++j) x[j] = c.ns_q0_scale[j] * (q[j] - c.ns_mid[j]);
@@ -678,84 +683,86 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 #pragma unroll
         for (int j = 0; j < N; ++j) qd_ns[j] = T(0);
         if (ns_on) {
-            if (!share) {                                   // own damping or weighted IK: factor J J^T + ns_lambda^2 I
+            T raw[N];
+            const bool qr = !LEAN && c.ns_qr;
+            if (!qr) {
+                // damped projector through the normal equations: raw = x - J^T (J J^T + l^2 I)^-1 (J x)
+                if (!share) {                               // own damping or weighted IK: factor J J^T + ns_lambda^2 I
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    Jx[r] = WN(0);
+                    for (int r = 0; r < 6; ++r) {
+                        Jx[r] = WN(0);
 #pragma unroll
-                    for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ns_lambda2 : WN(0);
-                }
-                static_for<0, N>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    const WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
-                    if (ns_proj) {
+                        for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ns_lambda2 : WN(0);
+                    }
+                    static_for<0, N>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        const WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
 #pragma unroll
                         for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (WN)x[j], Jx[r]);
+#pragma unroll
+                        for (int r = 0; r < 6; ++r)
+#pragma unroll
+                            for (int s = 0; s <= r; ++s) A[tri(r, s)] = fma(col[r], col[s], A[tri(r, s)]);
+                    });
+                    chol6<WN>(A, invd);
+                }
+                chol6_fwd<WN>(A, invd, Jx);
+                chol6_bwd<WN>(A, invd, Jx);
+                T yt[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) yt[r] = (T)Jx[r];
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    T acc = x[j];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) acc = fma(-(r < 3 ? Jl[j][r] : Ja[j][r - 3]), yt[r], acc);
+                    raw[j] = acc;
+                }
+            } else {
+                // the reference's own form (scripts/nullspace:75-117): orthonormal basis u_i of null(J) -- Householder QR of
+                // J^T, error cond(J) * eps, no damping (vfk_nullspace.cuh) -- then either the projector
+                // (I - pinv(J) J) x = sum_i u_i (u_i . x), or the control interface sum_{i < min(4, k)} control_i u_i with
+                // every u_i's sign kept continuous against the previous cycle's vector (ns_lastvec, [min(4, k)][N]).
+#pragma unroll
+                for (int j = 0; j < N; ++j) raw[j] = T(0);
+                if constexpr (!LEAN && ns_null_vectors(N) > 0) {
+                    double At[N * 6], tau[6], wv[N];
+#pragma unroll
+                    for (int j = 0; j < N; ++j)
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) At[j * 6 + r] = (double)(r < 3 ? Jl[j][r] : Ja[j][r - 3]);
+                    ns_qr_factor(At, nc, tau);
+                    if (ns_proj) {
+#pragma unroll
+                        for (int j = 0; j < N; ++j) wv[j] = (double)x[j];
+                        ns_qr_project(At, tau, nc, wv);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) raw[j] = j < nc ? (T)wv[j] : T(0);
+                    } else {
+                        const int kk = ns_ctrl_vectors(nc);                      // rows of ns_lastvec
+                        double rawd[N];
+#pragma unroll
+                        for (int j = 0; j < N; ++j) rawd[j] = 0.0;
+#pragma unroll 1
+                        for (int i = 0; i < kk; ++i) {
+                            ns_qr_column(At, tau, nc, 6 + i, wv);
+                            T* lv = a.ns_lastvec + tile * (kk * nc * 32) + i * (nc * 32) + slot;
+                            double dotl = 0.0;
+#pragma unroll
+                            for (int j = 0; j < N; ++j) if (j < nc) dotl = fma(wv[j], (double)lv[j * 32], dotl);
+                            const double sgn = dotl < 0.0 ? -1.0 : 1.0;      // |s u - last| > |s u + last|  <=>  s u . last < 0
+                            const double ci = a.ns_in ? (double)__ldg(a.ns_in + tile * (4 * 32) + i * 32 + slot) : (double)c.ns_control[i];
+                            if (active) {
+#pragma unroll
+                                for (int j = 0; j < N; ++j) if (j < nc) lv[j * 32] = (T)(sgn * wv[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < N; ++j) if (j < nc) rawd[j] = fma(sgn * ci, wv[j], rawd[j]);
+                        }
+                        if (G > 1) __syncwarp();             // a group's lanes re-read what its lane 0 stored
+#pragma unroll
+                        for (int j = 0; j < N; ++j) raw[j] = (T)rawd[j];
                     }
-#pragma unroll
-                    for (int r = 0; r < 6; ++r)
-#pragma unroll
-                        for (int s = 0; s <= r; ++s) A[tri(r, s)] = fma(col[r], col[s], A[tri(r, s)]);
-                });
-                chol6<WN>(A, invd);
-            }
-            if (!ns_proj) {
-                // 1-D nullspace: pick the column of B = I - J^T A^-1 J with the largest
-                // diagonal entry B_jj = 1 - |L^-1 J[:,j]|^2 (first maximum wins).
-                int jstar = 0;
-                WN best = WN(-1);
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
-                    chol6_fwd<WN>(A, invd, col);
-                    WN s2 = WN(0);
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) s2 = fma(col[r], col[r], s2);
-                    const WN bjj = WN(1) - s2;
-                    if (bjj > best) { best = bjj; jstar = j; }
-                }
-#pragma unroll
-                for (int r = 0; r < 6; ++r) Jx[r] = WN(0);
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    x[j] = (j == jstar) ? T(1) : T(0);
-                    if (j == jstar) {
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) Jx[r] = (WN)(r < 3 ? Jl[j][r] : Ja[j][r - 3]);
-                    }
-                }
-            }
-            // raw = x - J^T A^-1 (J x)
-            chol6_fwd<WN>(A, invd, Jx);
-            chol6_bwd<WN>(A, invd, Jx);
-            T yt[6];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) yt[r] = (T)Jx[r];
-            T raw[N];
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                T acc = x[j];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) acc = fma(-(r < 3 ? Jl[j][r] : Ja[j][r - 3]), yt[r], acc);
-                raw[j] = acc;
-            }
-            if (!ns_proj) {
-                T nn = T(0), dotl = T(0), l2 = T(0), amax = T(-1), vmax = T(0);
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    nn = fma(raw[j], raw[j], nn);
-                    dotl = fma(raw[j], lastv[j], dotl);
-                    l2 = fma(lastv[j], lastv[j], l2);
-                    if (Prec<T>::fabs_(raw[j]) > amax) { amax = Prec<T>::fabs_(raw[j]); vmax = raw[j]; }
-                }
-                T sc = Prec<T>::rsqrt_pos(nn);
-                const bool neg = (l2 > T(0)) ? (dotl < T(0)) : (vmax < T(0));
-                if (neg) sc = -sc;
-                T c0 = a.ns_in ? __ldg(a.ns_in + tile * (4 * 32) + slot) : c.ns_control[0];
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    lastv[j] = raw[j] * sc;
-                    raw[j] = lastv[j] * c0;
                 }
             }
             // all-or-nothing lookahead limit check, then gain
@@ -778,7 +785,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             bool all_reached = true;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                T ref = a.jp_ref ? __ldg(a.jp_ref + tN + j * 32) : c.jp_ref[j];
+                T ref = (a.jp_ref && j < nc) ? __ldg(a.jp_ref + tN + j * 32) : c.jp_ref[j];
                 ref = ref < c.q_lo[j] ? c.q_lo[j] : (ref > c.q_hi[j] ? c.q_hi[j] : ref);
                 const T err = ref - q[j];
                 qd_jp[j] = err * c.jp_kp;
@@ -804,7 +811,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             if (!LEAN && a.ext_cmd[e]) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const T x = __ldg(a.ext_cmd[e] + tN + j * 32);
+                    const T x = j < nc ? __ldg(a.ext_cmd[e] + tN + j * 32) : T(0);
                     nan = nan || (x != x);
                     mix[j] = fma(x, c.mixer_w[3 + e], mix[j]);
                 }
@@ -828,25 +835,26 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         if (last && active) {
             if (!LEAN && a.qdot_vf) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) a.qdot_vf[tN + j * 32] = qd_vf[j];
+                for (int j = 0; j < N; ++j) if (j < nc) a.qdot_vf[tN + j * 32] = qd_vf[j];
             }
             if (!LEAN && a.qdot_ns) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) a.qdot_ns[tN + j * 32] = qd_ns[j];
+                for (int j = 0; j < N; ++j) if (j < nc) a.qdot_ns[tN + j * 32] = qd_ns[j];
             }
             if (!LEAN && a.qdot_jp) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) a.qdot_jp[tN + j * 32] = qd_jp[j];
+                for (int j = 0; j < N; ++j) if (j < nc) a.qdot_jp[tN + j * 32] = qd_jp[j];
             }
             if (LEAN || a.qdot) {
                 T* o = a.qdot_ld ? a.qdot + (tile << 5) + slot : a.qdot + tN;
                 const int64_t rs = a.qdot_ld ? a.qdot_ld : 32;
 #pragma unroll
-                for (int j = 0; j < N; ++j) o[j * rs] = mix[j] * ratio;
+                for (int j = 0; j < N; ++j) if (j < nc) o[j * rs] = mix[j] * ratio;
             }
             if (!LEAN && a.cmd) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
+                    if (j >= nc) continue;
                     const T qd = mix[j] * ratio;
                     const T qc = a.q_cmded ? __ldg(a.q_cmded + tN + j * 32) : q[j];
                     a.cmd[tN + j * 32] = c.direct_control ? qd : (-qc + q[j] + qd);
@@ -869,11 +877,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     if (active) {
         if (c.integrate) {
 #pragma unroll
-            for (int j = 0; j < N; ++j) a.q[tN + j * 32] = q[j];
-        }
-        if (!LEAN && c.ns_mode == 2) {
-#pragma unroll
-            for (int j = 0; j < N; ++j) a.ns_lastvec[tN + j * 32] = lastv[j];
+            for (int j = 0; j < N; ++j) if (j < nc) a.q[tN + j * 32] = q[j];
         }
     }
     }   // tile loop

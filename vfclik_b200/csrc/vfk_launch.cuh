@@ -68,6 +68,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     if (io && io->q_src) { a.q_src = static_cast<const T*>(io->q_src); a.q_src_ld = io->q_src_ld; }
     if (io && io->qdot) { a.qdot = static_cast<T*>(io->qdot); a.qdot_ld = io->qdot_ld; }
     a.n = n;
+    a.n_comp = h->chain.n_joints;
     a.n_obst = n_obst;
     a.k_cycles = k_cycles;
     size_t smem = 0;

@@ -102,6 +102,12 @@ class Params:
         return p
 
 
+def ns_ctrl_vectors(n_joints: int) -> int:
+    """Basis vectors the reference's four-float nullspace control interface addresses: ``min(4, N - 6)``
+    (``scripts/nullspace:113``); ``ns_lastvec`` holds that many vectors of N components per instance."""
+    return max(0, min(4, int(n_joints) - 6))
+
+
 def round_up(n: int, m: int = 32) -> int:
     return (int(n) + m - 1) // m * m
 
@@ -363,7 +369,7 @@ class Session:
             self.e._check(self.e._lib.vfk_session_enable(self._s, w.encode(), int(on)))
 
     def read(self, what: str) -> np.ndarray:
-        rows = {"pose": 12, "twist": 6}.get(what, self.e.n_joints)
+        rows = {"pose": 12, "twist": 6, "lastvec": max(1, ns_ctrl_vectors(self.e.n_joints)) * self.e.n_joints}.get(what, self.e.n_joints)
         out = np.empty((rows, self.n), dtype=self.e.np_dtype)
         self.e._check(self.e._lib.vfk_session_read(self._s, what.encode(), _lib.np_ptr(out)))
         return out
@@ -397,6 +403,8 @@ class DeviceBatch:
     def _comps(self, name):
         if name == "ns_in":
             return 4 if self.e.params.ns_mode == NS_CONTROL else self.e.n_joints
+        if name == "ns_lastvec":
+            return max(1, ns_ctrl_vectors(self.e.n_joints)) * self.e.n_joints
         return self._ROWS.get(name, self.e.n_joints)
 
     def _ensure(self, name):

@@ -7,8 +7,8 @@ sticky, ``:169-173``), ``/qdotout`` -> ``/bridge/nullcmd``.  The arithmetic -- J
 (``:62,183``) -- runs inside the fused CUDA kernel; this class only moves bottles.
 
 Two modes (``vfk_params.ns_mode``): ``NS_CONTROL`` is the reference's 4-float control interface
-(7-DOF chains, undamped pinv: ``ns_lambda = 0``); ``NS_PROJECTOR`` is north_star's joint-limit
-avoidance ``(I - J^+ J) qdot0``.
+(any joint count: the four floats mix ``min(4, nJoints - 6)`` sign-continuous basis vectors of null(J), undamped like the
+reference); ``NS_PROJECTOR`` is north_star's joint-limit avoidance ``(I - J^+ J) qdot0``.
 """
 from __future__ import annotations
 

@@ -132,7 +132,13 @@ def config1(chain: ChainDesc, config, seed: int = 0):
     return dict(q=q, goal=goal, obst=obst)
 
 
-def dual_arm_torso_chain() -> ChainDesc:
+def torso_arm_chain(n_joints: int = 10) -> ChainDesc:
+    """The first ``n_joints`` joints of :func:`dual_arm_torso_chain`; the default 10 = 3-DOF torso + one 7-joint arm, the
+    shape of the reference's iCub configuration (``scripts/bridge:344-345``: arm 7 + torso 3 -> a 4-D nullspace)."""
+    return dual_arm_torso_chain(n_joints)
+
+
+def dual_arm_torso_chain(n_joints: int = 17) -> ChainDesc:
     """BASELINE config 5: 3-DOF torso + 14 arm joints treated as one 17-joint serial chain
     (6x17 Jacobian).  Synthetic geometry: a yaw-pitch-roll torso followed by two LWR-like
     7-joint segments; only the shape (N = 17) matters for the benchmark."""
@@ -157,4 +163,4 @@ def dual_arm_torso_chain() -> ChainDesc:
     limits = [[-60 * deg, 60 * deg], [-30 * deg, 60 * deg], [-30 * deg, 30 * deg]] + \
              ([[-170 * deg, 170 * deg], [-120 * deg, 120 * deg]] * 3 + [[-170 * deg, 170 * deg]]) * 2
     from .config import chain_from_segments
-    return chain_from_segments(segs, limits)
+    return chain_from_segments(segs[:n_joints], limits[:n_joints])
