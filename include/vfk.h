@@ -23,12 +23,20 @@
  * (one warp).  A per-instance array with C components stores element (component c,
  * instance i) at
  *         base[ ((i / 32) * C + c) * 32 + i % 32 ]
- * and the obstacle list stores obstacle m of instance i as one {x, y, z, radius}
- * vector at
- *         base[ (((i / 32) * M + m) * 32 + i % 32) * 4 + k ],  k = 0..3
- * (obst_ext likewise with 2 scalars {safe distance, decay order}).  A warp's access to
- * one component is one contiguous 128/256-byte line, and everything a warp needs for
- * a tile -- q, goal, each chunk of 8 obstacles -- is one contiguous burst moved
+ * The obstacle list {x, y, z, radius} is stored in PAIRS (obstacles 2p and 2p+1 of an
+ * instance; an odd count M is padded with one zero-radius slot, Mp = M rounded up to
+ * even), so that each lane's 16-byte vector holds the same component(s) of both
+ * obstacles of a pair -- the operand form of sm_100's packed FP32 instructions, and a
+ * conflict-free shared-memory access in both precisions.  With t = i / 32, l = i % 32,
+ * p = m / 2, s = m % 2 and component c = 0..3 (x, y, z, radius), in scalars:
+ *   precision 32:  base[ (((t * Mp/2 + p) * 2 + c/2) * 32 + l) * 4 + (c%2) * 2 + s ]
+ *                  (two planes per pair: {x0, x1, y0, y1} and {z0, z1, r0, r1})
+ *   precision 64:  base[ (((t * Mp/2 + p) * 4 + c) * 32 + l) * 2 + s ]
+ *                  (four planes per pair: {x0, x1}, {y0, y1}, {z0, z1}, {r0, r1})
+ * i.e. Mp * 32 * 4 scalars per tile either way.  obst_ext stores {safe distance, decay
+ * order} of obstacle m of instance i at base[ ((t * M + m) * 32 + l) * 2 + k ].  A warp's
+ * access to one component is one contiguous 128/256-byte line, and everything a warp
+ * needs for a tile -- q, goal, each chunk of 8 obstacles -- is one contiguous burst moved
  * global -> shared by a single cp.async.bulk (TMA) copy.  Arrays cover
  * ceil(n_instances / 32) whole tiles (the padding lanes of the last tile must be
  * allocated; they are read, never written).  Base pointers must be 128-byte aligned.
@@ -137,7 +145,8 @@ typedef struct vfk_params {
 typedef struct vfk_buffers {
     void*       q;               /* [N]  in; out when params.integrate                            */
     const void* goal;            /* [13] attractor (vfl type 1) per instance                       */
-    const void* obst;            /* M obstacles x {x, y, z, radius}: decay repellers (vfl type 2); radius 0 = empty slot */
+    const void* obst;            /* M obstacles x {x, y, z, radius}, pair-interleaved (see above): decay repellers (vfl type 2);
+                                    radius 0 = empty slot (the padding slot of an odd M must be zero) */
     const void* obst_ext;        /* M obstacles x {safe distance, decay order} (wire-faithful,
                                     scripts/object_feeder:326-333) or NULL -> params.obst_safe / obst_order */
     const void* aux;             /* [n_aux * 12] auxiliary field records {type, force, p0..p9} or NULL:
@@ -216,7 +225,8 @@ int  vfk_monitor(vfk_handle h, const void* pose, const void* twist, const void* 
                  void* track_out, void* dist_out, int32_t* tracking_state_out, int64_t n_instances, void* stream);
 
 /* Layout conversion on the device: dense SoA [comps][n] (width scalars per element: 1 for
- * per-instance components, 4 for obstacles [M][n][4], 2 for obst_ext [M][n][2]) <-> tile-blocked. */
+ * per-instance components, 2 for obst_ext [M][n][2]) <-> tile-blocked; width 4 = the obstacle list:
+ * dense [M][n][4] <-> the pair-interleaved blocked array (Mp rows per tile, padding slot zeroed). */
 int  vfk_pack(vfk_handle h, const void* dense, void* blocked, int comps, int width, int64_t n_instances, void* stream);
 int  vfk_unpack(vfk_handle h, const void* blocked, void* dense, int comps, int width, int64_t n_instances, void* stream);
 

@@ -5,7 +5,7 @@ TAG=${1:-t}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -q -x --durations=8 > $OUT/${TAG}_pytest.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q --durations=8 > $OUT/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
 tail -25 $OUT/${TAG}_pytest.log
 timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1

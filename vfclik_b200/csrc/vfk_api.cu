@@ -383,6 +383,18 @@ static cudaError_t run_pack(const void* dense, int64_t dense_ld, void* blocked, 
     return cudaGetLastError();
 }
 
+// obstacles (width 4): dense [M][ld] {x, y, z, radius} <-> the pair-interleaved blocked array (vfk.h, ObstPairs)
+template <typename T>
+static cudaError_t run_pack_obst(const void* dense, int64_t dense_ld, void* blocked, int M, int64_t n, bool unpack, cudaStream_t st) {
+    const int64_t tiles = (n + 31) / 32;
+    const unsigned grid = (unsigned)((tiles * ((M + 1) / 2) * 32 + 255) / 256);
+    if (unpack)
+        vfk_unpack_obst_kernel<T><<<grid, 256, 0, st>>>((const Vec4<T>*)blocked, (Vec4<T>*)const_cast<void*>(dense), dense_ld, M, n, tiles);
+    else
+        vfk_pack_obst_kernel<T><<<grid, 256, 0, st>>>((const Vec4<T>*)dense, dense_ld, (Vec4<T>*)blocked, M, n, tiles);
+    return cudaGetLastError();
+}
+
 // width = scalars per element: 1 (per-instance components), 2 (obstacle ext) or 4 (obstacles);
 // dense_ld = row pitch of the dense array in elements (>= n; lets a column range of a larger array be converted)
 static int pack_dispatch(vfk_ctx* h, const void* dense, void* blocked, int C, int width, int64_t n, bool unpack,
@@ -395,7 +407,7 @@ static int pack_dispatch(vfk_ctx* h, const void* dense, void* blocked, int C, in
     const bool f = h->precision == 32;
     if (width == 1) e = f ? run_pack<float>(dense, dense_ld, blocked, C, n, unpack, st) : run_pack<double>(dense, dense_ld, blocked, C, n, unpack, st);
     else if (width == 2) e = f ? run_pack<Vec2<float>>(dense, dense_ld, blocked, C, n, unpack, st) : run_pack<Vec2<double>>(dense, dense_ld, blocked, C, n, unpack, st);
-    else if (width == 4) e = f ? run_pack<Vec4<float>>(dense, dense_ld, blocked, C, n, unpack, st) : run_pack<Vec4<double>>(dense, dense_ld, blocked, C, n, unpack, st);
+    else if (width == 4) e = f ? run_pack_obst<float>(dense, dense_ld, blocked, C, n, unpack, st) : run_pack_obst<double>(dense, dense_ld, blocked, C, n, unpack, st);
     else return fail(h, VFK_ERR_INVALID, "vfk_pack/unpack: width must be 1, 2 or 4");
     if (e != cudaSuccess) return fail(h, VFK_ERR_CUDA, "layout kernel: %s", cudaGetErrorString(e));
     return 1;
@@ -468,7 +480,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->es = h->precision == 32 ? 4 : 8;
     const int N = s->N;
     const size_t row = align_up((size_t)s->tiles * 32 * s->es, 128);     // one component over all tiles
-    const size_t obst_rows = (size_t)n_obst * (4 + (s->has_ext ? 2 : 0));
+    const size_t obst_rows = (size_t)((n_obst + 1) & ~1) * 4 + (size_t)n_obst * (s->has_ext ? 2 : 0);
     // blocked: q N, goal 13, obst, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, twist 6, flags 1
     const int lv_rows = (ns_ctrl_vectors(N) > 0 ? ns_ctrl_vectors(N) : 1) * N;   // sign-continuity state: [min(4, N - 6)][N]
     const size_t rows = (size_t)N * 8 + lv_rows + 13 + obst_rows + 12 + 6 + 1;
@@ -483,7 +495,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     auto take = [&](size_t nrows) { char* r = p; p += nrows * row; return (void*)r; };
     s->b.q = take(N);
     s->b.goal = take(13);
-    s->b.obst = n_obst ? take((size_t)n_obst * 4) : nullptr;
+    s->b.obst = n_obst ? take((size_t)((n_obst + 1) & ~1) * 4) : nullptr;     // whole pairs
     s->b.obst_ext = (n_obst && s->has_ext) ? take((size_t)n_obst * 2) : nullptr;
     s->d_jp_ref = take(N);
     s->d_ns_in = take(N);
@@ -607,7 +619,7 @@ static vfk_buffers offset_view(const vfk_buffers& b, int64_t tile0, int N, int M
     auto off = [&](const void* p, size_t comps) -> void* {
         return p ? (void*)((char*)const_cast<void*>(p) + (size_t)tile0 * comps * 32 * es) : nullptr;
     };
-    o.q = off(b.q, N); o.goal = off(b.goal, 13); o.obst = off(b.obst, (size_t)M * 4); o.obst_ext = off(b.obst_ext, (size_t)M * 2);
+    o.q = off(b.q, N); o.goal = off(b.goal, 13); o.obst = off(b.obst, (size_t)((M + 1) & ~1) * 4); o.obst_ext = off(b.obst_ext, (size_t)M * 2);
     o.aux = off(b.aux, (size_t)b.n_aux * 12);
     o.jp_ref = off(b.jp_ref, N); o.ns_lastvec = off(b.ns_lastvec, (size_t)(ns_ctrl_vectors(N) > 0 ? ns_ctrl_vectors(N) : 1) * N); o.q_cmded = off(b.q_cmded, N);
     for (int e = 0; e < 3; ++e) o.ext_cmd[e] = off(b.ext_cmd[e], N);

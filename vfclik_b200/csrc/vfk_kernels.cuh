@@ -92,7 +92,7 @@ template <typename T>
 struct KArgs {
     T* q;
     const T* goal;
-    const Vec4<T>* obst;       // blocked [tile][M][32]
+    const Vec4<T>* obst;       // pair-interleaved blocked [tile][Mp / 2][planes][32 x 16 B], Mp = M rounded up to even (ObstPairs)
     const Vec2<T>* obst_ext;   // blocked [tile][M][32] {safe, order} or null
     const T* aux;              // blocked [n_aux * 12] auxiliary field records or null
     const T* jp_ref;
@@ -116,6 +116,7 @@ struct KArgs {
     int64_t qdot_ld;
     int64_t n;
     int32_t n_obst;
+    int32_t n_obst_p;          // n_obst rounded up to even: rows of 32 Vec4<T> per tile in `obst`
     int32_t n_chunks;          // ceil(n_obst / kChunk)
     int32_t n_full;            // n_obst / kChunk (chunks with all kChunk obstacles)
     int32_t n_rem;             // n_obst % kChunk
@@ -269,6 +270,45 @@ struct Pos {
     }
 };
 
+// ------------------------------------------------------------------------------ obstacle storage
+// Obstacles are stored in PAIRS so that one 16-byte vector per lane holds the same component(s) of two obstacles:
+//   FP32: pair p of a tile = 2 planes of 32 lanes x float4:  {x0, x1, y0, y1}, {z0, z1, r0, r1}
+//   FP64: pair p of a tile = 4 planes of 32 lanes x double2: {x0, x1}, {y0, y1}, {z0, z1}, {r0, r1}
+// (obstacle 2p in slot 0, obstacle 2p + 1 in slot 1; an odd obstacle count is padded with a zero-radius slot).  A pair takes
+// the bytes of two {x, y, z, radius} vectors per lane, so a chunk of kChunk obstacles is still one contiguous burst.  What
+// it buys: every shared-memory read is a conflict-free 16-byte access in both precisions (a lane-strided 32-byte FP64 vector
+// was a 2-way bank conflict), and in FP32 the two obstacles of a pair sit in adjacent registers exactly as sm_100's packed
+// FP32 instructions (fma / mul / add .f32x2 -> SASS FFMA2 / FMUL2 / FADD2) want their operands: the repulsor of TWO
+// obstacles issues as ~25 instructions instead of 2 x 22.
+template <typename T> struct ObstPairs;
+template <> struct ObstPairs<float> {
+    static constexpr int kPlanes = 2;
+    // obstacle `s` (0 / 1) of the pair whose first plane starts at `pair` (lane 0), for `lane`
+    static __device__ __forceinline__ Vec4<float> load(const Vec4<float>* pair, int lane, int s) {
+        const float* f = reinterpret_cast<const float*>(pair) + lane * 4 + s;
+        Vec4<float> o;
+        o.x = f[0]; o.y = f[2]; o.z = f[128]; o.w = f[130];
+        return o;
+    }
+    static __device__ __forceinline__ void store(Vec4<float>* pair, int lane, int s, const Vec4<float>& o) {
+        float* f = reinterpret_cast<float*>(pair) + lane * 4 + s;
+        f[0] = o.x; f[2] = o.y; f[128] = o.z; f[130] = o.w;
+    }
+};
+template <> struct ObstPairs<double> {
+    static constexpr int kPlanes = 4;
+    static __device__ __forceinline__ Vec4<double> load(const Vec4<double>* pair, int lane, int s) {
+        const double* f = reinterpret_cast<const double*>(pair) + lane * 2 + s;
+        Vec4<double> o;
+        o.x = f[0]; o.y = f[64]; o.z = f[128]; o.w = f[192];
+        return o;
+    }
+    static __device__ __forceinline__ void store(Vec4<double>* pair, int lane, int s, const Vec4<double>& o) {
+        double* f = reinterpret_cast<double*>(pair) + lane * 2 + s;
+        f[0] = o.x; f[64] = o.y; f[128] = o.z; f[192] = o.w;
+    }
+};
+
 // ------------------------------------------------------------------------------ field pieces
 // One decay repeller (vfl type 2): acc += (o - p)/d * (radius / max(d, safe))^order.
 // d^2 carries a 1e-30 (1e-300 in FP64) bias so that d = 0 gives a finite 1/d and a zero contribution
@@ -285,6 +325,40 @@ __device__ __forceinline__ void repel(const Vec4<T>& o, T safe_inv, T order, con
     // obstacle still outweighs everything else by > 1e15, and normCart only keeps the direction.
     if constexpr (sizeof(T) == 4) wgt = Prec<T>::fmin_(wgt, T(1e30));
     acc[0] = fma(wgt, dx, acc[0]); acc[1] = fma(wgt, dy, acc[1]); acc[2] = fma(wgt, dz, acc[2]);
+}
+
+// The same for the two obstacles of a pair at once in FP32, on sm_100's packed instructions.  A = {x0, x1, y0, y1},
+// B = {z0, z1, r0, r1} as they come out of shared memory; np = the tool position as negated, lane-duplicated hi / lo pairs;
+// acc = {sum over slot-0 obstacles, sum over slot-1 obstacles} per axis (added together after the loop).  Every packed
+// instruction is the IEEE operation on each half, so one obstacle's contribution is bit-identical to repel<float>().
+struct NegPos2 {
+    float2 hi[3], lo[3];
+    __device__ __forceinline__ void set(const Pos<float>& p) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { hi[k] = make_float2(-p.hi[k], -p.hi[k]); lo[k] = make_float2(-p.lo[k], -p.lo[k]); }
+    }
+};
+
+template <int ORDER>
+__device__ __forceinline__ void repel2(const float4& A, const float4& B, float safe_inv, float order, const NegPos2& np,
+                                       float2 (&acc)[3]) {
+    const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(A.x, A.y), np.hi[0]), np.lo[0]);
+    const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(A.z, A.w), np.hi[1]), np.lo[1]);
+    const float2 dz = __fadd2_rn(__fadd2_rn(make_float2(B.x, B.y), np.hi[2]), np.lo[2]);
+    const float2 tiny = make_float2(1e-30f, 1e-30f);
+    const float2 dd = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, tiny)));
+    const float2 inv = make_float2(Prec<float>::rsqrt_pos(dd.x), Prec<float>::rsqrt_pos(dd.y));
+    const float2 ratio = __fmul2_rn(make_float2(B.z, B.w), make_float2(fminf(inv.x, safe_inv), fminf(inv.y, safe_inv)));
+    float2 pw;
+    if constexpr (ORDER == 20) {
+        const float2 x2 = __fmul2_rn(ratio, ratio), x4 = __fmul2_rn(x2, x2), x5 = __fmul2_rn(x4, ratio), x10 = __fmul2_rn(x5, x5);
+        pw = __fmul2_rn(x10, x10);
+    } else {
+        pw = make_float2(Prec<float>::pow_pos(ratio.x, order), Prec<float>::pow_pos(ratio.y, order));
+    }
+    float2 wgt = __fmul2_rn(pw, inv);
+    wgt = make_float2(fminf(wgt.x, 1e30f), fminf(wgt.y, 1e30f));          // see repel(): saturate instead of overflowing
+    acc[0] = __ffma2_rn(wgt, dx, acc[0]); acc[1] = __ffma2_rn(wgt, dy, acc[1]); acc[2] = __ffma2_rn(wgt, dz, acc[2]);
 }
 
 // Goal attractor (vfl type 1) at tool frame (Rt, pt): unit direction to the goal, unit rotation
@@ -409,9 +483,10 @@ __device__ __forceinline__ void issue_obst(const KArgs<T>& a, int64_t tile, int 
     if (lane == 0) {
         const int m0 = chunk * kChunk;
         const uint32_t cnt = (uint32_t)min(kChunk, a.n_obst - m0);
+        const uint32_t cntp = (cnt + 1u) & ~1u;                           // whole pairs (the odd one out carries a zero-radius slot)
         unsigned char* dst = region + (size_t)stage * WS::kStage;
-        mbar_arrive_expect_tx(&bars[stage], cnt * (WS::kRow + WS::kRowExt));
-        bulk_g2s(dst, a.obst + (tile * a.n_obst + m0) * 32, cnt * WS::kRow, &bars[stage]);
+        mbar_arrive_expect_tx(&bars[stage], cntp * WS::kRow + cnt * WS::kRowExt);
+        bulk_g2s(dst, a.obst + (tile * a.n_obst_p + m0) * 32, cntp * WS::kRow, &bars[stage]);
         if (EXT) bulk_g2s(dst + kChunk * WS::kRow, a.obst_ext + (tile * a.n_obst + m0) * 32, cnt * WS::kRowExt, &bars[stage]);
     }
 }
@@ -546,43 +621,54 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         {
             T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)};
             attract<T>(c, g, Rt, pt, V, S0, w);
+            [[maybe_unused]] NegPos2 np2;                               // FP32 packed repulsor: duplicated tool position, paired sums
+            [[maybe_unused]] float2 acc2[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            if constexpr (sizeof(T) == 4 && !EXT && G == 1) np2.set(pt);
             for (int ch = 0; ch < a.n_chunks; ++ch) {
                 const int stage = resident ? ch : c_stage;
                 mbar_wait(&bars[stage], resident ? (uint32_t)(it & 1) : c_phase);
                 const unsigned char* sb = region + (size_t)stage * WS::kStage;
-                const Vec4<T>* so = reinterpret_cast<const Vec4<T>*>(sb) + slot;
+                const Vec4<T>* sp = reinterpret_cast<const Vec4<T>*>(sb);                      // pair p starts at sp + p * 64
                 const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * WS::kRow) + slot;
+                const int n_here = ch < a.n_full ? kChunk : a.n_rem;                           // obstacles in this chunk
+                // one obstacle by its index in the chunk: scalar form (FP64, per-obstacle {safe, order}, cooperative shape)
+                auto one = [&](int m, auto order_c) {
+                    constexpr int ORD = decltype(order_c)::value;
+                    const Vec4<T> o = ObstPairs<T>::load(sp + (m >> 1) * 64, slot, m & 1);
+                    T safe_inv = c.obst_safe_inv, order = c.obst_order;
+                    if (EXT) { const Vec2<T> e = se[m * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
+                    repel<T, ORD>(o, safe_inv, order, pt, acc);
+                };
                 if constexpr (G > 1) {
                     // cooperative shape: lane ol of the group takes obstacle ol of this chunk
-                    if (ol < (ch < a.n_full ? kChunk : a.n_rem)) {
-                        const Vec4<T> o = so[ol * 32];
-                        T safe_inv = c.obst_safe_inv, order = c.obst_order;
-                        if (EXT) { const Vec2<T> e = se[ol * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
-                        repel<T>(o, safe_inv, order, pt, acc);
+                    if (ol < n_here) one(ol, std::integral_constant<int, 0>{});
+                } else if constexpr (sizeof(T) == 4 && !EXT) {
+                    // FP32: two obstacles per step on the packed FP32 pipe; a zero-radius padding slot contributes exactly 0
+                    const float4* pl = reinterpret_cast<const float4*>(sb) + slot;
+                    if (ch < a.n_full) {
+                        auto full_chunk = [&](auto order_c) {
+#pragma unroll
+                            for (int p = 0; p < kChunk / 2; ++p)
+                                repel2<decltype(order_c)::value>(pl[p * 64], pl[p * 64 + 32], c.obst_safe_inv, c.obst_order, np2, acc2);
+                        };
+                        if (kF32PowChain && c.order_int == 20) full_chunk(std::integral_constant<int, 20>{});
+                        else full_chunk(std::integral_constant<int, 0>{});
+                    } else {
+                        for (int p = 0; p < (a.n_rem + 1) >> 1; ++p)
+                            repel2<0>(pl[p * 64], pl[p * 64 + 32], c.obst_safe_inv, c.obst_order, np2, acc2);
                     }
                 } else if (ch < a.n_full) {
                     // FP64 with a uniform small-integer decay order: fixed multiplication chain instead of pow()
                     auto full_chunk = [&](auto order_c) {
-                        constexpr int ORD = decltype(order_c)::value;
 #pragma unroll
-                        for (int m = 0; m < kChunk; ++m) {
-                            const Vec4<T> o = so[m * 32];
-                            T safe_inv = c.obst_safe_inv, order = c.obst_order;
-                            if (EXT) { const Vec2<T> e = se[m * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
-                            repel<T, ORD>(o, safe_inv, order, pt, acc);
-                        }
+                        for (int m = 0; m < kChunk; ++m) one(m, order_c);
                     };
-                    if ((sizeof(T) == 8 || kF32PowChain) && !EXT && c.order_int == 20) full_chunk(std::integral_constant<int, 20>{});
+                    if (sizeof(T) == 8 && !EXT && c.order_int == 20) full_chunk(std::integral_constant<int, 20>{});
                     else if (sizeof(T) == 8 && !EXT && c.order_int == 5) full_chunk(std::integral_constant<int, 5>{});
                     else if (sizeof(T) == 8 && !EXT && c.order_int == 2) full_chunk(std::integral_constant<int, 2>{});
                     else full_chunk(std::integral_constant<int, 0>{});
                 } else {
-                    for (int m = 0; m < a.n_rem; ++m) {
-                        const Vec4<T> o = so[m * 32];
-                        T safe_inv = c.obst_safe_inv, order = c.obst_order;
-                        if (EXT) { const Vec2<T> e = se[m * 32]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
-                        repel<T>(o, safe_inv, order, pt, acc);
-                    }
+                    for (int m = 0; m < a.n_rem; ++m) one(m, std::integral_constant<int, 0>{});
                 }
                 // this slot is free again: request the chunk that will occupy it S uses from now
                 if (!resident || last) {
@@ -592,6 +678,10 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                     if (++p_u == U) { p_u = 0; p_unit += stride; }
                 }
                 if (!resident && ++c_stage == S) { c_stage = 0; c_phase ^= 1u; }
+            }
+            if constexpr (sizeof(T) == 4 && !EXT && G == 1) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[k] = acc2[k].x + acc2[k].y;
             }
             if constexpr (G > 1) {                          // combine the group's partial repulsor sums
 #pragma unroll
@@ -645,18 +735,12 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         static_for<0, N>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
-            if (ns_proj && share) {
-#pragma unroll
-                for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (WN)x[j], Jx[r]);
-            }
+            if (ns_proj && share) axpy6(Jx, col, (WN)x[j]);
             if (!unitw) {
 #pragma unroll
                 for (int r = 0; r < 6; ++r) col[r] *= (WN)c.w_task[r] * (WN)c.w_joint[j];
             }
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int s = 0; s <= r; ++s) A[tri(r, s)] = fma(col[r], col[s], A[tri(r, s)]);
+            syr6(A, col);
         });
         chol6<WN>(A, invd);
         T qd_vf[N];
@@ -671,9 +755,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             for (int r = 0; r < 6; ++r) yt[r] = unitw ? (T)y[r] : (T)(y[r] * (WN)c.w_task[r]);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                T acc = T(0);
-#pragma unroll
-                for (int r = 0; r < 6; ++r) acc = fma(r < 3 ? Jl[j][r] : Ja[j][r - 3], yt[r], acc);
+                const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
+                const T acc = dot6(cj, yt, T(0), false);
                 qd_vf[j] = unitw ? acc : acc * c.w_joint[j] * c.w_joint[j];
             }
         }
@@ -697,12 +780,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                     static_for<0, N>([&](auto jc) {
                         constexpr int j = decltype(jc)::value;
                         const WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) Jx[r] = fma(col[r], (WN)x[j], Jx[r]);
-#pragma unroll
-                        for (int r = 0; r < 6; ++r)
-#pragma unroll
-                            for (int s = 0; s <= r; ++s) A[tri(r, s)] = fma(col[r], col[s], A[tri(r, s)]);
+                        axpy6(Jx, col, (WN)x[j]);
+                        syr6(A, col);
                     });
                     chol6<WN>(A, invd);
                 }
@@ -713,10 +792,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 for (int r = 0; r < 6; ++r) yt[r] = (T)Jx[r];
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    T acc = x[j];
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) acc = fma(-(r < 3 ? Jl[j][r] : Ja[j][r - 3]), yt[r], acc);
-                    raw[j] = acc;
+                    const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
+                    raw[j] = dot6(cj, yt, x[j], true);
                 }
             } else {
                 // the reference's own form (scripts/nullspace:75-117): orthonormal basis u_i of null(J) -- Householder QR of
@@ -904,8 +981,9 @@ vfk_field_kernel(const __grid_constant__ KConst<T> c, const T* __restrict__ pose
     for (int k = 0; k < 13; ++k) g[k] = goal[(tile * 13 + k) * 32 + lane];
     T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)}, v[3];
     attract<T>(c, g, Rt, pt, V, S0, w);
+    const int n_obst_p = (n_obst + 1) & ~1;
     for (int m = 0; m < n_obst; ++m) {
-        const Vec4<T> o = obst[(tile * n_obst + m) * 32 + lane];
+        const Vec4<T> o = ObstPairs<T>::load(obst + (tile * n_obst_p + (m & ~1)) * 32, lane, m & 1);
         T safe_inv = c.obst_safe_inv, order = c.obst_order;
         if (obst_ext) { const Vec2<T> e = obst_ext[(tile * n_obst + m) * 32 + lane]; safe_inv = Prec<T>::rcp(e.x); order = e.y; }
         repel<T>(o, safe_inv, order, pt, acc);
@@ -1155,6 +1233,47 @@ vfk_unpack_kernel(const V* __restrict__ blocked, V* __restrict__ dense, int64_t 
     const int cidx = (int)(tc - tile * C);
     const int64_t i = (tile << 5) + lane;
     if (i < n) dense[(int64_t)cidx * dense_ld + i] = blocked[e];
+}
+
+// Obstacles: dense [M][dense_ld >= n] of {x, y, z, radius}  <->  the pair-interleaved blocked array (ObstPairs), one thread
+// per (tile, pair, lane).  Packing zero-fills the padding lanes of the last tile and the padding slot of an odd M.
+template <typename T>
+__global__ void __launch_bounds__(256)
+vfk_pack_obst_kernel(const Vec4<T>* __restrict__ dense, int64_t dense_ld, Vec4<T>* __restrict__ blocked, int M, int64_t n, int64_t n_tiles) {
+    const int M2 = (M + 1) >> 1;
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n_tiles * M2 * 32) return;
+    const int lane = (int)(e & 31);
+    const int64_t tp = e >> 5;
+    const int64_t tile = tp / M2;
+    const int p = (int)(tp - tile * M2);
+    const int64_t i = (tile << 5) + lane;
+    Vec4<T> zero;
+    memset(&zero, 0, sizeof zero);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int m = 2 * p + s;
+        ObstPairs<T>::store(blocked + (tile * M2 + p) * 64, lane, s, (i < n && m < M) ? dense[(int64_t)m * dense_ld + i] : zero);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+vfk_unpack_obst_kernel(const Vec4<T>* __restrict__ blocked, Vec4<T>* __restrict__ dense, int64_t dense_ld, int M, int64_t n, int64_t n_tiles) {
+    const int M2 = (M + 1) >> 1;
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n_tiles * M2 * 32) return;
+    const int lane = (int)(e & 31);
+    const int64_t tp = e >> 5;
+    const int64_t tile = tp / M2;
+    const int p = (int)(tp - tile * M2);
+    const int64_t i = (tile << 5) + lane;
+    if (i >= n) return;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int m = 2 * p + s;
+        if (m < M) dense[(int64_t)m * dense_ld + i] = ObstPairs<T>::load(blocked + (tile * M2 + p) * 64, lane, s);
+    }
 }
 
 }  // namespace vfk

@@ -70,6 +70,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.n = n;
     a.n_comp = h->chain.n_joints;
     a.n_obst = n_obst;
+    a.n_obst_p = (n_obst + 1) & ~1;
     a.k_cycles = k_cycles;
     size_t smem = 0;
     plan_stages<T, N, EXT>(n_obst, k_cycles, &a.n_chunks, &a.n_stages, &smem);

@@ -252,9 +252,13 @@ class Engine:
 
     def alloc(self, comps: int, n_instances: int, width: int = 1, dtype=None):
         """Zeroed blocked device tensor ``[tiles, comps, 32(, width)]`` for ``n_instances`` instances
-        (torch's caching allocator returns >= 512-byte aligned blocks)."""
+        (torch's caching allocator returns >= 512-byte aligned blocks).  ``width == 4`` is the obstacle array: rows
+        ``2p, 2p + 1`` of a tile hold the pair-interleaved planes of obstacles ``2p, 2p + 1`` (include/vfk.h), not two
+        plain ``{x, y, z, radius}`` rows -- use ``pack`` / ``unpack`` (or ``obstacles_of``) to convert."""
         import torch
         tiles = round_up(n_instances, 32) // 32
+        if width == 4:
+            comps = round_up(comps, 2)          # obstacles are stored in pairs (include/vfk.h): an odd count gets a zero slot
         shape = (tiles, comps, 32) if width == 1 else (tiles, comps, 32, width)
         t = torch.zeros(shape, dtype=dtype or self.torch_dtype, device="cuda:%d" % self.device)
         assert t.data_ptr() % 128 == 0
@@ -447,8 +451,9 @@ class DeviceBatch:
         a = np.asarray(arr)
         if width == 1:
             a = a.reshape(-1, self.n)
-        if a.shape[0] != t.shape[1]:
-            raise ValueError("%s: %d components given, buffer has %d" % (name, a.shape[0], t.shape[1]))
+        have = self.m if name in ("obst", "obst_ext") else t.shape[1]
+        if a.shape[0] != have:
+            raise ValueError("%s: %d components given, buffer has %d" % (name, a.shape[0], have))
         return self.to_blocked(a, out=t, width=width)
 
     def download(self, name: str) -> np.ndarray:
@@ -458,12 +463,27 @@ class DeviceBatch:
         if t.dtype == torch.int32:                                   # int32 arrays: un-block on the host
             a = t.cpu().numpy()                                      # [tiles, comps, 32]
             return np.ascontiguousarray(a.transpose(1, 0, 2).reshape(a.shape[1], -1)[:, :self.n])
-        comps = t.shape[1]
+        comps = self.m if name in ("obst", "obst_ext") else t.shape[1]
         width = t.shape[3] if t.dim() == 4 else 1
         shape = (comps, self.n) if width == 1 else (comps, self.n, width)
         dense = torch.empty(shape, dtype=t.dtype, device=t.device)
         self.e.unpack(t, dense, comps, width, self.n)
         return dense.cpu().numpy()
+
+    def obstacles_of(self, idx) -> np.ndarray:
+        """``{x, y, z, radius}`` of every obstacle of the instances ``idx`` -> numpy ``[M, len(idx), 4]``, gathered from
+        the pair-interleaved blocked array on the device (for sampling batches too large to convert as a whole)."""
+        import torch
+        t = self.t["obst"]
+        ti = torch.as_tensor(np.asarray(idx), device=t.device)
+        tiles, mp, k = t.shape[0], t.shape[1], int(ti.numel())
+        if self.e.precision == 32:       # pair = planes {x0, x1, y0, y1}, {z0, z1, r0, r1} of 32 lanes x float4
+            pr = t.reshape(tiles, mp // 2, 2, 32, 2, 2)[ti // 32, :, :, ti % 32]       # [k, pair, plane, component-in-plane, slot]
+            o = pr.permute(1, 4, 0, 2, 3).reshape(mp, k, 4)                            # obstacle 2 * pair + slot
+        else:                            # pair = planes {x0, x1}, {y0, y1}, {z0, z1}, {r0, r1} of 32 lanes x double2
+            pr = t.reshape(tiles, mp // 2, 4, 32, 2)[ti // 32, :, :, ti % 32]          # [k, pair, component, slot]
+            o = pr.permute(1, 3, 0, 2).reshape(mp, k, 4)
+        return o[:self.m].contiguous().cpu().numpy()
 
     @property
     def bufs(self) -> Dict[str, object]:

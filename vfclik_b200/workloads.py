@@ -98,7 +98,7 @@ def random_batch_device(engine, n_instances: int, n_obstacles: int, seed: int, s
     db = DeviceBatch(engine, I, M, outputs=("qdot",))
     engine.pack(q.contiguous(), db.t["q"], N, 1, I)
     engine.pack(goal.contiguous(), db.t["goal"], 13, 1, I)
-    step = max(1, min(M, (1 << 26) // max(I, 1)))            # obstacles per slice: bound the dense temporary
+    step = max(2, min(M, (1 << 26) // max(I, 1)) & ~1)       # obstacles per slice (whole pairs): bound the dense temporary
     tiles = db.t["obst"].shape[0]
     for m0 in range(0, M, step):
         m1 = min(M, m0 + step)
@@ -107,7 +107,7 @@ def random_batch_device(engine, n_instances: int, n_obstacles: int, seed: int, s
         o[:, :, 3] = 0.03 + 0.07 * torch.rand((m1 - m0, I), generator=g, dtype=dt, device=dev)
         blk = engine.alloc(m1 - m0, I, width=4)
         engine.pack(o, blk, m1 - m0, 4, I)
-        db.t["obst"][:, m0:m1] = blk
+        db.t["obst"][:, m0:m0 + blk.shape[1]] = blk             # pair rows 2p, 2p + 1 <-> obstacles 2p, 2p + 1 (m0 is even)
         del o, blk
     torch.cuda.synchronize(engine.device)
     return db
