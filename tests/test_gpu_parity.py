@@ -235,6 +235,38 @@ def test_control_nullspace_against_the_executed_reference_n10(built_lib, golden)
         e.close()
 
 
+@pytest.mark.parametrize("precision,n_joints,m,k,n", [(32, 17, 64, 1, 4096), (32, 17, 9, 3, 1000), (32, 10, 32, 2, 2080),
+                                                        (64, 7, 32, 1, 4096), (64, 7, 3, 4, 37), (64, 17, 20, 2, 1500),
+                                                        (64, 10, 8, 1, 999), (32, 14, 33, 2, 777)])
+def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k, n):
+    """Two lanes per instance (vfk_split.cuh: long chains and FP64, the lean call shape): against the oracle at the mode's
+    tolerance, and against the one-thread-per-instance kernel on the same inputs."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import Engine, Params
+    chain = lwr[0] if n_joints == 7 else workloads.torso_arm_chain(n_joints)
+    tol, dt = (FP64_RTOL, np.float64) if precision == 64 else (FP32_RTOL, np.float32)
+    e = Engine(chain, precision=precision, params=Params.from_config(lwr[1]) if n_joints == 7 else Params())
+    try:
+        w = workloads.random_batch(chain, n, m, seed=40 + n_joints + m, dtype=dt)
+        monkeypatch.delenv("VFK_NO_SPLIT", raising=False)
+        out = run_gpu(e, w, m, k=k, outputs=("qdot",))
+        monkeypatch.setenv("VFK_NO_SPLIT", "1")
+        solo = run_gpu(e, w, m, k=k, outputs=("qdot",))
+        monkeypatch.delenv("VFK_NO_SPLIT", raising=False)
+        ref = run_oracle(chain, e.params, w, m, k=k)
+        # FP32 over several cycles: an instance within rounding of the all-or-nothing limit check or the clamp may take the
+        # other branch in an earlier cycle; bound the bulk there, everything otherwise
+        worst = (lambda e_: np.quantile(e_, 0.995)) if (precision == 32 and k > 1) else np.max
+        assert worst(rel_err(out["qdot"].astype(np.float64), ref["qdot"])) <= tol
+        assert worst(rel_err(solo["qdot"].astype(np.float64), ref["qdot"])) <= tol
+        qtol = 1e-11 if precision == 64 else 2e-5
+        assert worst(np.abs(out["q"] - ref["q"]).max(axis=1)) <= qtol and worst(np.abs(out["q"] - solo["q"]).max(axis=1)) <= qtol
+        assert np.all(np.isfinite(out["qdot"]))
+        assert not np.array_equal(out["qdot"], solo["qdot"]) or n_joints < 7        # two different kernels really ran
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("n_joints", [1, 3, 5, 8, 9, 12, 14, 16])
 def test_any_joint_count(built_lib, n_joints):
     """Chains whose joint count has no instantiation of its own run padded in the next larger generic one

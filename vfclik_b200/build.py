@@ -13,7 +13,7 @@ OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")
 # one translation unit per (precision, joint-count group) of the cycle kernel + the ABI: compiled in parallel
 UNITS = ["vfk_api", "vfk_cycle_f32_small", "vfk_cycle_f32_large", "vfk_cycle_f64_small", "vfk_cycle_f64_large"]
 SOURCES = [os.path.join(CSRC, u + ".cu") for u in UNITS]
-HEADERS = [os.path.join(CSRC, f) for f in ("vfk_kernels.cuh", "vfk_math.cuh", "vfk_tma.cuh", "vfk_nullspace.cuh", "vfk_ctx.cuh", "vfk_launch.cuh")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("vfk_kernels.cuh", "vfk_math.cuh", "vfk_tma.cuh", "vfk_nullspace.cuh", "vfk_split.cuh", "vfk_ctx.cuh", "vfk_launch.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "vfk.h")]
 DEPS = SOURCES + HEADERS
 

@@ -73,7 +73,7 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     const int n = ch.n_joints;
     using W = typename KConst<T>::W;
     for (int k = 0; k < 12; ++k) c.base[k] = (W)ch.base[k];
-    bool unit = true;
+    bool unit = true, all_xt = true;
     for (int j = 0; j < n; ++j) {
         for (int k = 0; k < 12; ++k) c.tip[j][k] = (W)ch.tip[j][k];
         c.q_lo[j] = (T)ch.q_lo[j];
@@ -90,7 +90,9 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
         const bool xtwist = r[0] == 1.0 && r[1] == 0.0 && r[2] == 0.0 && r[3] == 0.0 && r[6] == 0.0 && r[4] == r[8] && r[5] == -r[7];
         if (xtwist && r[4] == 1.0 && r[7] == 0.0) c.tipident_mask |= (1 << j);
         else if (xtwist) c.xtwist_mask |= (1 << j);
+        if (!xtwist) all_xt = false;
     }
+    c.all_xtwist = all_xt ? 1 : 0;
     bool all_zero = true;
     for (int k = 0; k < 6; ++k) {
         c.w_task[k] = (T)p.w_task[k];

@@ -85,6 +85,7 @@ struct KConst {
     int32_t need_jp;           // joint P controller observable (weight != 0 or an output wants it)
     int32_t asin_series;       // rot_slowdown <= 0.3 rad: small-angle series replaces atan2 in FP32
     int32_t order_int;         // obst_order when it is a small integer, else 0
+    int32_t all_xtwist;        // every tip rotation is the identity or RotX(alpha): the lane-split kernel's uniform fast path
     int32_t ns_qr;             // nullspace through the Householder basis of null(J): control mode, or the projector with ns_lambda = 0
 };
 

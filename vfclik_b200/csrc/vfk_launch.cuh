@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "vfk_ctx.cuh"
+#include "vfk_split.cuh"
 
 using namespace vfk;
 
@@ -26,6 +27,10 @@ static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, 
     *n_stages = stages;
     *smem_bytes = kSmemHeader + (size_t)(kBlock / 32) * WS::warp_bytes(stages);
 }
+
+// Lanes per instance of the split shape for (precision, joints, pattern); 0 = the one-thread-per-instance kernel only.
+template <typename T, int N, class PAT>
+constexpr int kSplitLanes = (N >= 10 || (sizeof(T) == 8 && N == 7)) ? 2 : 0;
 
 constexpr int64_t kCoopMaxInstances = 4096;      // <= 128 tiles: 1024 cooperative warps instead of 128 solo ones
 
@@ -114,6 +119,109 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     return 1;
 }
 
+// ------------------------------------------------------------------------------ lane-split shape (vfk_split.cuh)
+typedef CUresult (*vfk_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static vfk_encode_tiled_fn encode_tiled_entry() {
+    static vfk_encode_tiled_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<vfk_encode_tiled_fn>(p);
+    }();
+    return fn;
+}
+
+// [tiles][rows][inner] array of T, box {box_inner, box_rows, 1}: the 32 / L lanes a warp takes of `box_rows` rows of one tile
+template <typename T>
+static int encode_map3(vfk_ctx* h, CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t tiles, uint32_t box_inner,
+                       uint32_t box_rows) {
+    vfk_encode_tiled_fn enc = encode_tiled_entry();
+    if (!enc) return fail(h, VFK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[3] = {inner, rows, tiles};
+    const cuuint64_t gstr[2] = {inner * sizeof(T), inner * rows * sizeof(T)};
+    const cuuint32_t box[3] = {box_inner, box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(m, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base),
+                           gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, VFK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VFK_OK;
+}
+
+// May this call run in the lane-split shape?  (lean call on blocked device buffers; the chain pattern does not matter)
+template <typename T>
+static bool split_ok(const KConst<T>& c, const vfk_buffers* b, const vfk_io* io) {
+    return is_lean<T>(c, b) && !(io && (io->q_src || io->qdot)) && !getenv("VFK_NO_SPLIT");
+}
+
+template <typename T, int N, int L>
+static int launch_split(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles, cudaStream_t st) {
+    using SH = SplitShape<T, N, L>;
+    KArgs<T> a;
+    memset(&a, 0, sizeof a);
+    a.q = static_cast<T*>(b->q);
+    a.qdot = static_cast<T*>(b->qdot);
+    a.n = n;
+    a.n_comp = h->chain.n_joints;
+    a.n_obst = n_obst;
+    a.n_obst_p = (n_obst + 1) & ~1;
+    a.k_cycles = k_cycles;
+    a.n_chunks = (n_obst + kChunk - 1) / kChunk;
+    a.n_full = n_obst / kChunk;
+    a.n_rem = n_obst % kChunk;
+    int stages = 2;
+    if (const char* e = getenv("VFK_STAGES")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxStages) stages = v;
+    }
+    if (a.n_chunks < stages) stages = a.n_chunks;
+    a.n_stages = stages;
+    const size_t smem = kSmemHeader + SH::kTab + (size_t)(kBlock / 32) * SH::warp_bytes(stages);
+    const uint64_t tiles = (uint64_t)((n + 31) / 32);
+    SplitMaps maps;
+    memset(&maps, 0, sizeof maps);
+    int rc;
+    if ((rc = encode_map3<T>(h, &maps.q, b->q, 32, (uint64_t)a.n_comp, tiles, SH::SUB, (uint32_t)a.n_comp)) != VFK_OK) return rc;
+    if ((rc = encode_map3<T>(h, &maps.goal, b->goal, 32, 13, tiles, SH::SUB, 13)) != VFK_OK) return rc;
+    if (n_obst > 0) {
+        const uint64_t rows = (uint64_t)a.n_obst_p / 2 * ObstPairs<T>::kPlanes;                   // plane rows of 32 lanes x 16 bytes per tile
+        if ((rc = encode_map3<T>(h, &maps.obst, b->obst, 32 * 16 / sizeof(T), rows, tiles, SH::kRowBytes / sizeof(T), SH::kRowsPerChunk)) != VFK_OK)
+            return rc;
+    }
+#ifndef VFK_MINB_SPLIT_F32
+#define VFK_MINB_SPLIT_F32 4
+#endif
+#ifndef VFK_MINB_SPLIT_F64
+#define VFK_MINB_SPLIT_F64 3
+#endif
+    constexpr int MINB = (sizeof(T) == 4 ? VFK_MINB_SPLIT_F32 : VFK_MINB_SPLIT_F64) * (128 / kBlock);
+    auto kern = vfk_split_kernel<T, N, L, MINB>;
+    static int cached_per_sm[16];
+    static size_t cached_smem[16];
+    int per_sm = 0;
+    const int dslot = h->device & 15;
+    if (cached_per_sm[dslot] > 0 && cached_smem[dslot] == smem) {
+        per_sm = cached_per_sm[dslot];
+    } else {
+        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+        VFK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+        if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "split kernel does not fit an SM with %zu bytes of shared memory", smem);
+        cached_per_sm[dslot] = per_sm;
+        cached_smem[dslot] = smem;
+    }
+    const int64_t units = (n + 31) / 32 * L;
+    const int64_t want = (units + kBlock / 32 - 1) / (kBlock / 32);
+    const int64_t cap = (int64_t)h->sm_count * per_sm;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    kern<<<grid, kBlock, smem, st>>>(c, a, maps);
+    VFK_CUDA(h, cudaGetLastError());
+    return 1;
+}
+
 template <typename T, int N, class PAT>
 static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, int64_t n, int n_obst, int k_cycles,
                          cudaStream_t st, const vfk_io* io) {
@@ -128,6 +236,10 @@ static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, i
                              : launch_cycle<T, N, PAT, false, false, kChunk>(h, c, b, n, n_obst, k_cycles, st, io);
     }
     if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st, io);
+    // Long chains and FP64: two lanes per instance (vfk_split.cuh).  Measured on B200: see DESIGN.md section 4.1.
+    if constexpr (kSplitLanes<T, N, PAT> > 0) {
+        if (n_obst > 0 && split_ok<T>(c, b, io)) return launch_split<T, N, kSplitLanes<T, N, PAT>>(h, c, b, n, n_obst, k_cycles, st);
+    }
     if (is_lean<T>(c, b)) {
         if constexpr (sizeof(T) == 4 && N <= 7) {
             if (k_cycles == 1) return launch_cycle<T, N, PAT, false, true, 1, true>(h, c, b, n, n_obst, k_cycles, st, io);
