@@ -185,7 +185,8 @@ int  vfk_create(vfk_handle* out, const vfk_chain_desc* chain, int precision, int
 int  vfk_set_params(vfk_handle h, const vfk_params* p);
 int  vfk_get_params(vfk_handle h, vfk_params* out);
 /* Which compile-time chain pattern the handle's kernels use: 0 = generic (any chain),
- * 1 = LWR-style 7R structure (tip rotations are +-90 degree twists, sparse offsets). */
+ * 1 = LWR-style 7R structure (tip rotations are +-90 degree twists, sparse offsets),
+ * 2 = Denavit-Hartenberg form (10 or 17 revolute joints, every tip rotation RotX(alpha)). */
 int  vfk_chain_pattern(vfk_handle h);
 void vfk_destroy(vfk_handle h);
 const char* vfk_last_error(vfk_handle h);   /* h may be NULL: last error of vfk_create */

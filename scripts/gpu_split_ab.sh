@@ -4,7 +4,7 @@ set -u
 TAG=${1:-ab}
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "lane_split or any_joint or 17_dof" > $OUT/${TAG}_pytest.log 2>&1
+timeout 600 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
 tail -15 $OUT/${TAG}_pytest.log
 for W in config5 config2; do

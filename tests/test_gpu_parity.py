@@ -236,14 +236,14 @@ def test_control_nullspace_against_the_executed_reference_n10(built_lib, golden)
 
 
 @pytest.mark.parametrize("precision,n_joints,m,k,n", [(32, 17, 64, 1, 4096), (32, 17, 9, 3, 1000), (32, 10, 32, 2, 2080),
-                                                        (64, 7, 32, 1, 4096), (64, 7, 3, 4, 37), (64, 17, 20, 2, 1500),
-                                                        (64, 10, 8, 1, 999), (32, 14, 33, 2, 777)])
+                                                        (64, 7, 32, 1, 4128), (64, 7, 3, 4, 37), (64, 17, 20, 2, 4100),
+                                                        (64, 10, 8, 1, 999)])
 def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k, n):
     """Two lanes per instance (vfk_split.cuh: long chains and FP64, the lean call shape): against the oracle at the mode's
     tolerance, and against the one-thread-per-instance kernel on the same inputs."""
     from vfclik_b200 import workloads
     from vfclik_b200.engine import Engine, Params
-    chain = lwr[0] if n_joints == 7 else workloads.torso_arm_chain(n_joints)
+    chain = lwr[0] if n_joints == 7 else workloads.dual_arm_torso_chain(n_joints)       # DH form: what the split kernel takes
     tol, dt = (FP64_RTOL, np.float64) if precision == 64 else (FP32_RTOL, np.float32)
     e = Engine(chain, precision=precision, params=Params.from_config(lwr[1]) if n_joints == 7 else Params())
     try:
@@ -262,7 +262,7 @@ def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k
         qtol = 1e-11 if precision == 64 else 2e-5
         assert worst(np.abs(out["q"] - ref["q"]).max(axis=1)) <= qtol and worst(np.abs(out["q"] - solo["q"]).max(axis=1)) <= qtol
         assert np.all(np.isfinite(out["qdot"]))
-        assert not np.array_equal(out["qdot"], solo["qdot"]) or n_joints < 7        # two different kernels really ran
+        assert not np.array_equal(out["qdot"], solo["qdot"])                       # two different kernels really ran
     finally:
         e.close()
 
@@ -354,13 +354,16 @@ def test_edge_cases(eng, lwr):
     assert np.max(np.abs(out["qdot_vf"][0])) < 1e-6
 
 
-def test_17_dof_chain(eng, built_lib):
-    """BASELINE config 5 shape: 3-DOF torso + 14 arm joints as one serial chain (6x17 Jacobian), mixed joint axes."""
+@pytest.mark.parametrize("dh", [True, False])
+def test_17_dof_chain(eng, built_lib, dh):
+    """BASELINE config 5 shape: 3-DOF torso + 14 arm joints as one serial chain (6x17 Jacobian): in DH form (the kernels'
+    DhPattern) and with a mixed-axis torso (RotX joint -> general tip -> GenericPattern)."""
     from vfclik_b200 import workloads
     from vfclik_b200.engine import Engine
-    chain = workloads.dual_arm_torso_chain()
+    chain = workloads.dual_arm_torso_chain(dh=dh)
     for precision, tol, dt in ((64, FP64_RTOL, np.float64), (32, FP32_RTOL, np.float32)):
         e = Engine(chain, precision=precision)
+        assert e.chain_pattern == ("dh" if dh else "generic")
         try:
             w = workloads.random_batch(chain, 1500, 8, seed=7, dtype=dt)
             out = run_gpu(e, w, 8, outputs=("qdot_vf", "qdot_ns", "qdot", "pose"))
@@ -739,6 +742,45 @@ def test_host_session_direct_host_io(eng, lwr, precision, monkeypatch):
         assert np.array_equal(qd.numpy().T, dev["qdot"])
     finally:
         s.close()
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_direct_host_io_keeps_the_sessions_device_state_current(lwr, built_lib, precision):
+    """integrate = 0 (ControlRuntime's default: the plant is elsewhere) through the direct path: the kernel reads q from the
+    caller's buffer, so the session's own q / qdot must still follow -- q_out, read("q"), read("qdot") and a later cycle
+    WITHOUT q_in all see the state of the last call, exactly as through the copy pipeline."""
+    import torch
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import Engine, Params
+    chain, cfg = lwr
+    dt, tdt = (np.float32, torch.float32) if precision == 32 else (np.float64, torch.float64)
+    n, M = 4096, 5
+    e = Engine(chain, precision=precision, params=Params.from_config(cfg, integrate=0))
+    try:
+        wa = workloads.random_batch(chain, n, M, seed=91, dtype=dt)
+        wb = workloads.random_batch(chain, n, M, seed=92, dtype=dt)
+        results = {}
+        for mode in ("direct", "pipeline"):
+            s = e.session(n, M)
+            s.set_goal(wa["goal"]); s.set_obstacles(wa["obst"]); s.set_q(wa["q"])
+            if mode == "direct":
+                q_in = torch.from_numpy(wb["q"]).pin_memory().numpy()
+                qd = torch.zeros((7, n), dtype=tdt).pin_memory().numpy()
+                qo = torch.zeros((7, n), dtype=tdt).pin_memory().numpy()
+                assert s.cycle(q_in=q_in, qdot_out=qd, q_out=qo) == 2            # cycle kernel + the un-blocking of q_out
+            else:
+                q_in, qd, qo = wb["q"].copy(), np.zeros((7, n), dtype=dt), np.zeros((7, n), dtype=dt)
+                assert s.cycle(q_in=q_in, qdot_out=qd, q_out=qo) > 2
+            assert np.array_equal(qo, wb["q"])                                   # integrate = 0: q_out is the q that came in
+            assert np.array_equal(s.read("q"), wb["q"]) and np.array_equal(s.read("qdot"), qd)
+            again = np.zeros((7, n), dtype=dt)
+            s.cycle(qdot_out=again)                                              # no q_in: continues from the session's q
+            assert np.array_equal(again, qd)
+            results[mode] = qd.copy()
+            s.close()
+        assert np.array_equal(results["direct"], results["pipeline"])
+    finally:
+        e.close()
 
 
 @pytest.mark.parametrize("which", ["config4", "config5"])

@@ -208,8 +208,14 @@ extern "C" int vfk_create(vfk_handle* out, const vfk_chain_desc* chain, int prec
     if (!h) return fail(nullptr, VFK_ERR_INVALID, "out of host memory");
     h->chain = *chain;
     canonicalise_chain(h->chain, h->canon);
-    h->pattern = chain_matches<LwrPattern>(h->canon, 7) ? 1 : 0;
     h->n_kernel = kernel_joints(n);
+    h->dh_chain = 1;
+    for (int j = 0; j < n; ++j) {
+        const double* r = h->canon.tip[j];
+        const bool xtwist = r[0] == 1.0 && r[1] == 0.0 && r[2] == 0.0 && r[3] == 0.0 && r[6] == 0.0 && r[4] == r[8] && r[5] == -r[7];
+        if (!xtwist || h->canon.joint_type[j] != VFK_JOINT_ROTZ) h->dh_chain = 0;
+    }
+    h->pattern = chain_matches<LwrPattern>(h->canon, 7) ? 1 : ((h->dh_chain && n == h->n_kernel && n >= 10) ? 2 : 0);
     h->precision = precision;
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
@@ -434,6 +440,7 @@ constexpr int kMaxSessionChunks = 32;
 
 struct vfk_session_s {
     vfk_ctx* h;
+    int device;                      // copied from the handle: destroy must not touch a handle that may be gone
     int64_t n, tiles;
     int n_obst, has_ext, N, n_aux;
     size_t es;                       // element size
@@ -460,6 +467,7 @@ struct vfk_session_s {
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static void session_release(vfk_session_s* s);
 
 // Smallest batch for which vfk_session_cycle reads / writes page-locked caller buffers directly from the kernel.
 constexpr int64_t kDirectMinInstances = 1024;
@@ -474,6 +482,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     if (!s) return fail(h, VFK_ERR_INVALID, "out of host memory");
     memset(&s->b, 0, sizeof s->b);
     s->h = h;
+    s->device = h->device;
     s->n = n;
     s->tiles = (n + 31) / 32;
     s->n_obst = n_obst;
@@ -491,7 +500,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     const size_t stage_out_rows = first_out + (size_t)N;                          // qdot (or a read()) + q_out
     s->dev_bytes = (rows + stage_in_rows + stage_out_rows) * row;
     cudaError_t e = cudaMalloc((void**)&s->dev, s->dev_bytes);
-    if (e != cudaSuccess) { delete s; return fail(h, VFK_ERR_CUDA, "cudaMalloc(%zu): %s", s->dev_bytes, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { s->dev = nullptr; session_release(s); return fail(h, VFK_ERR_CUDA, "cudaMalloc(%zu): %s", s->dev_bytes, cudaGetErrorString(e)); }
     e = cudaMemset(s->dev, 0, s->dev_bytes);
     char* p = s->dev;
     auto take = [&](size_t nrows) { char* r = p; p += nrows * row; return (void*)r; };
@@ -532,8 +541,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&s->ev_join[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&s->pin, s->pin_bytes);
     if (e != cudaSuccess) {
-        cudaFree(s->dev);
-        delete s;
+        session_release(s);
         return fail(h, VFK_ERR_CUDA, "session allocation: %s", cudaGetErrorString(e));
     }
     *out = s;
@@ -578,8 +586,12 @@ extern "C" int vfk_session_set_aux(vfk_session s, const void* aux, int n_aux) {
     if (!aux || n_aux == 0) { s->b.n_aux = 0; return VFK_OK; }
     const size_t row = align_up((size_t)s->tiles * 32 * s->es, 128);
     if (n_aux > s->n_aux) {                                   // grow the dedicated buffers (blocked + dense staging)
-        if (s->aux_dev) VFK_CUDA(h, cudaFree(s->aux_dev));
+        s->b.aux = nullptr;                                   // nothing may point at the old block once it is gone
+        s->b.n_aux = 0;
+        s->n_aux = 0;
+        char* old = s->aux_dev;
         s->aux_dev = nullptr;
+        if (old) VFK_CUDA(h, cudaFree(old));
         VFK_CUDA(h, cudaMalloc((void**)&s->aux_dev, 2 * (size_t)n_aux * 12 * row));
         s->n_aux = n_aux;
     }
@@ -892,17 +904,27 @@ extern "C" int vfk_session_buffers(vfk_session s, vfk_buffers* out) {
     return VFK_OK;
 }
 
-extern "C" void vfk_session_destroy(vfk_session s) {
-    if (!s) return;
-    cudaSetDevice(s->h->device);
-    cudaStreamSynchronize(s->stream);
-    cudaFreeHost(s->pin);
-    cudaFree(s->dev);
+// Releases whatever a (possibly half-built) session owns; every member starts null (value-initialised struct).
+static void session_release(vfk_session_s* s) {
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int k = 0; k < 3; ++k) if (s->pipe[k]) cudaStreamSynchronize(s->pipe[k]);
+    if (s->pin) cudaFreeHost(s->pin);
+    if (s->dev) cudaFree(s->dev);
     if (s->aux_dev) cudaFree(s->aux_dev);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-    cudaStreamDestroy(s->stream);
-    for (int k = 0; k < 3; ++k) cudaStreamDestroy(s->pipe[k]);
-    for (int k = 0; k < kMaxSessionChunks; ++k) { cudaEventDestroy(s->ev_up[k]); cudaEventDestroy(s->ev_done[k]); }
-    cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join[0]); cudaEventDestroy(s->ev_join[1]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    for (int k = 0; k < 3; ++k) if (s->pipe[k]) cudaStreamDestroy(s->pipe[k]);
+    for (int k = 0; k < kMaxSessionChunks; ++k) {
+        if (s->ev_up[k]) cudaEventDestroy(s->ev_up[k]);
+        if (s->ev_done[k]) cudaEventDestroy(s->ev_done[k]);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    for (int k = 0; k < 2; ++k) if (s->ev_join[k]) cudaEventDestroy(s->ev_join[k]);
+    cudaGetLastError();
     delete s;
+}
+
+extern "C" void vfk_session_destroy(vfk_session s) {
+    if (s) session_release(s);
 }

@@ -25,7 +25,8 @@ struct vfk_ctx {
     int precision;
     int device;
     int sm_count;
-    int pattern;                // 0: GenericPattern, 1: LwrPattern (structure of the canonical chain)
+    int pattern;                // 0: GenericPattern, 1: LwrPattern, 2: DhPattern (structure of the canonical chain)
+    int dh_chain;               // all joints revolute, all tip rotations RotX(alpha): what DhPattern and the lane-split kernel take
     int n_kernel;               // joint count of the instantiation that runs this chain: the smallest of 6, 7, 10, 17 that is
                                 // >= n_joints (shorter chains run padded: KArgs::n_comp)
     uint64_t generation;        // bumped by vfk_set_params: captured CUDA graphs bake the constants in

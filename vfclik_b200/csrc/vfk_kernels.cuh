@@ -115,6 +115,7 @@ struct KArgs {
     const T* q_src;
     int64_t q_src_ld;
     int64_t qdot_ld;
+    T* qdot_dev;               // direct host I/O: the blocked device mirror of qdot (kept current for vfk_session_read), or null
     int64_t n;
     int32_t n_obst;
     int32_t n_obst_p;          // n_obst rounded up to even: rows of 32 Vec4<T> per tile in `obst`
@@ -135,6 +136,7 @@ struct KArgs {
 // GenericPattern makes no assumption (full 3x3 products, runtime prismatic mask).
 struct GenericPattern {
     static constexpr bool generic = true;
+    static constexpr bool dh = false;
     static constexpr bool base_identity = false;
     __host__ __device__ static constexpr int perm(int, int) { return 0; }
     __host__ __device__ static constexpr int sign(int, int) { return 1; }
@@ -146,6 +148,7 @@ struct GenericPattern {
 // new column k of (R * R_tip) = sign(j,k) * old column perm(j,k).
 struct LwrPattern {
     static constexpr bool generic = false;
+    static constexpr bool dh = false;
     static constexpr bool base_identity = true;
     __host__ __device__ static constexpr int kind(int j) {       // +1: RotX(+90), -1: RotX(-90), 0: identity
         return (j == 0 || j == 3 || j == 4) ? 1 : (j == 6 ? 0 : -1);
@@ -155,6 +158,19 @@ struct LwrPattern {
         return kind(j) == 0 ? 1 : (k == 0 ? 1 : (k == 1 ? (kind(j) > 0 ? 1 : -1) : (kind(j) > 0 ? -1 : 1)));
     }
     __host__ __device__ static constexpr bool pnz(int j, int k) { return ((j == 1 || j == 3) && k == 1) || (j == 6 && k == 2); }
+};
+
+// Any chain given in Denavit-Hartenberg form: every joint revolute (about its local Z after the host's canonicalisation), every
+// tip rotation RotX(alpha) -- alpha = 0, i.e. the identity, included -- and any tip translation.  Values come from KConst; what
+// the pattern removes is every per-joint run-time decision of GenericPattern (prismatic?, identity / X-twist / general tip?,
+// padding joint?) together with the register copies their join points cost: the tip product is 12 operations in place.
+struct DhPattern {
+    static constexpr bool generic = false;
+    static constexpr bool dh = true;
+    static constexpr bool base_identity = false;
+    __host__ __device__ static constexpr int perm(int, int) { return 0; }
+    __host__ __device__ static constexpr int sign(int, int) { return 1; }
+    __host__ __device__ static constexpr bool pnz(int, int) { return true; }
 };
 
 // ------------------------------------------------------------------------------ FK + J
@@ -205,6 +221,16 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
                 for (int r = 0; r < 3; ++r) p[r] = fma(R[3 * r + k], tp[9 + k], p[r]);
             }
         });
+        if constexpr (PAT::dh) {
+            const W ca = tp[4], sa = tp[7];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const W a = R[3 * r + 1], b = R[3 * r + 2];
+                R[3 * r + 1] = fma(ca, a, sa * b);
+                R[3 * r + 2] = fma(ca, b, -sa * a);
+            }
+            return;
+        }
         W Rn[9];
         if constexpr (PAT::generic) {
             // warp-uniform choice on the robot's constants: identity tip (nothing), X-twist tip (12 ops), general (27)
@@ -540,7 +566,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     const int ol = lane & (G - 1);                              // obstacle lane within the group
     // Joint components in memory.  Chains with a joint count that has no instantiation of its own run in the next larger
     // generic one: joints >= nc are padding (zero Jacobian column, no motion, nothing loaded or stored for them).
-    const int nc = PAT::generic ? a.n_comp : N;
+    const int nc = (PAT::generic && !LEAN) ? a.n_comp : N;        // the lean instantiations only take chains of exactly N joints
 
     // Ring bookkeeping.  A "use" is one consumption of one chunk; a tile has U uses and the ring S slots.
     // resident: S = n_chunks, every chunk is loaded once per tile and reused by all K cycles (U = n_chunks);
@@ -743,7 +769,13 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             }
             syr6(A, col);
         });
-        chol6<WN>(A, invd);
+        // FP64 accepts ik_lambda = 0 (the reference's undamped pinv): at a singular posture a pivot of J J^T is zero or, by
+        // rounding, negative.  Flooring it relative to the trace keeps the factor finite (the step is then clamped like any
+        // other); FP32 requires lambda > 0, whose pivots are >= lambda^2.
+        [[maybe_unused]] WN pivot_floor = WN(0);
+        if constexpr (sizeof(WN) == 8)
+            pivot_floor = WN(1e-28) * (A[tri(0, 0)] + A[tri(1, 1)] + A[tri(2, 2)] + A[tri(3, 3)] + A[tri(4, 4)] + A[tri(5, 5)]) + WN(1e-300);
+        chol6<WN>(A, invd, pivot_floor);
         T qd_vf[N];
         {
             WN y[6];
@@ -784,7 +816,9 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                         axpy6(Jx, col, (WN)x[j]);
                         syr6(A, col);
                     });
-                    chol6<WN>(A, invd);
+                    if constexpr (sizeof(WN) == 8)
+                        pivot_floor = WN(1e-28) * (A[tri(0, 0)] + A[tri(1, 1)] + A[tri(2, 2)] + A[tri(3, 3)] + A[tri(4, 4)] + A[tri(5, 5)]) + WN(1e-300);
+                    chol6<WN>(A, invd, pivot_floor);
                 }
                 chol6_fwd<WN>(A, invd, Jx);
                 chol6_bwd<WN>(A, invd, Jx);
@@ -897,6 +931,18 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         T lead = T(0);
 #pragma unroll
         for (int j = 0; j < N; ++j) lead = Prec<T>::fmax_(lead, Prec<T>::fabs_(mix[j]));
+        if constexpr (!LEAN || sizeof(T) == 8) {
+            // never integrate a non-finite step (a NaN in q or in an input port, an overflow): command zero and say so
+            T z = T(0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) z = fma(mix[j], T(0), z);
+            if (z != T(0)) {
+                nan = true;
+                lead = T(0);
+#pragma unroll
+                for (int j = 0; j < N; ++j) mix[j] = T(0);
+            }
+        }
         if (nan) flags |= 4;
         T ratio = T(1);
         if (lead > c.max_vel) { ratio = Prec<T>::div(c.max_vel, lead); flags |= 8; }
@@ -928,6 +974,10 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 const int64_t rs = a.qdot_ld ? a.qdot_ld : 32;
 #pragma unroll
                 for (int j = 0; j < N; ++j) if (j < nc) o[j * rs] = mix[j] * ratio;
+                if (a.qdot_ld && a.qdot_dev) {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) if (j < nc) a.qdot_dev[tN + j * 32] = mix[j] * ratio;
+                }
             }
             if (!LEAN && a.cmd) {
 #pragma unroll
@@ -953,7 +1003,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         }
     }
     if (active) {
-        if (c.integrate) {
+        if (c.integrate || a.q_src) {                  // direct host I/O: the session's device copy of q follows the caller's
 #pragma unroll
             for (int j = 0; j < N; ++j) if (j < nc) a.q[tN + j * 32] = q[j];
         }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "vfk_ctx.cuh"
 #include "vfk_split.cuh"
@@ -31,6 +32,27 @@ static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, 
 // Lanes per instance of the split shape for (precision, joints, pattern); 0 = the one-thread-per-instance kernel only.
 template <typename T, int N, class PAT>
 constexpr int kSplitLanes = (N >= 10 || (sizeof(T) == 8 && N == 7)) ? 2 : 0;
+
+// Launch plan of one kernel instantiation: resident CTAs per SM for a given dynamic shared-memory size, per device.  One
+// instance per instantiation (function-local static at the call site); a handful of (device, smem) entries behind a mutex, so
+// concurrent host threads and sessions with different obstacle counts neither race nor evict one another.
+struct PlanCache {
+    std::mutex mu;
+    struct Entry { int device; size_t smem; int per_sm; } e[16];
+    int used = 0;
+    template <typename K>
+    cudaError_t get(K kern, int device, size_t smem, int* per_sm) {
+        std::lock_guard<std::mutex> lock(mu);
+        for (int i = 0; i < used; ++i)
+            if (e[i].device == device && e[i].smem == smem) { *per_sm = e[i].per_sm; return cudaSuccess; }
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10);
+        if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, kBlock, smem);
+        if (err != cudaSuccess) return err;
+        const int slot = used < 16 ? used++ : 15;
+        e[slot] = Entry{device, smem, *per_sm};
+        return cudaSuccess;
+    }
+};
 
 constexpr int64_t kCoopMaxInstances = 4096;      // <= 128 tiles: 1024 cooperative warps instead of 128 solo ones
 
@@ -71,7 +93,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.twist = static_cast<T*>(b->twist);
     a.flags = b->flags;
     if (io && io->q_src) { a.q_src = static_cast<const T*>(io->q_src); a.q_src_ld = io->q_src_ld; }
-    if (io && io->qdot) { a.qdot = static_cast<T*>(io->qdot); a.qdot_ld = io->qdot_ld; }
+    if (io && io->qdot) { a.qdot = static_cast<T*>(io->qdot); a.qdot_ld = io->qdot_ld; a.qdot_dev = static_cast<T*>(b->qdot); }
     a.n = n;
     a.n_comp = h->chain.n_joints;
     a.n_obst = n_obst;
@@ -97,19 +119,10 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
                                 : ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? VFK_MINB_F64 : 1))) * (128 / kBlock);
     auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB, G>;
     // per (instantiation, device, smem size): opt in to > 48 KB of dynamic shared memory and ask the occupancy once
-    static int cached_per_sm[16];
-    static size_t cached_smem[16];
+    static PlanCache plans;
     int per_sm = 0;
-    const int dslot = h->device & 15;
-    if (cached_per_sm[dslot] > 0 && cached_smem[dslot] == smem) {
-        per_sm = cached_per_sm[dslot];
-    } else {
-        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-        VFK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
-        if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "kernel does not fit an SM with %zu bytes of shared memory", smem);
-        cached_per_sm[dslot] = per_sm;
-        cached_smem[dslot] = smem;
-    }
+    VFK_CUDA(h, plans.get(kern, h->device, smem, &per_sm));
+    if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "kernel does not fit an SM with %zu bytes of shared memory", smem);
     const int64_t units = (n + 31) / 32 * G;                 // G = 8: a tile is spread over 8 warps (4 instances each)
     const int64_t want = (units + kBlock / 32 - 1) / (kBlock / 32);
     const int64_t cap = (int64_t)h->sm_count * per_sm;
@@ -154,8 +167,8 @@ static int encode_map3(vfk_ctx* h, CUtensorMap* m, const void* base, uint64_t in
 
 // May this call run in the lane-split shape?  (lean call on blocked device buffers; the chain pattern does not matter)
 template <typename T>
-static bool split_ok(const KConst<T>& c, const vfk_buffers* b, const vfk_io* io) {
-    return is_lean<T>(c, b) && !(io && (io->q_src || io->qdot)) && !getenv("VFK_NO_SPLIT");
+static bool split_ok(vfk_ctx* h, int n_kernel, const KConst<T>& c, const vfk_buffers* b, const vfk_io* io) {
+    return h->dh_chain && h->chain.n_joints == n_kernel && is_lean<T>(c, b) && !(io && (io->q_src || io->qdot)) && !getenv("VFK_NO_SPLIT");
 }
 
 template <typename T, int N, int L>
@@ -200,19 +213,10 @@ static int launch_split(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #endif
     constexpr int MINB = (sizeof(T) == 4 ? VFK_MINB_SPLIT_F32 : VFK_MINB_SPLIT_F64) * (128 / kBlock);
     auto kern = vfk_split_kernel<T, N, L, MINB>;
-    static int cached_per_sm[16];
-    static size_t cached_smem[16];
+    static PlanCache plans;
     int per_sm = 0;
-    const int dslot = h->device & 15;
-    if (cached_per_sm[dslot] > 0 && cached_smem[dslot] == smem) {
-        per_sm = cached_per_sm[dslot];
-    } else {
-        VFK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-        VFK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
-        if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "split kernel does not fit an SM with %zu bytes of shared memory", smem);
-        cached_per_sm[dslot] = per_sm;
-        cached_smem[dslot] = smem;
-    }
+    VFK_CUDA(h, plans.get(kern, h->device, smem, &per_sm));
+    if (per_sm < 1) return fail(h, VFK_ERR_CUDA, "split kernel does not fit an SM with %zu bytes of shared memory", smem);
     const int64_t units = (n + 31) / 32 * L;
     const int64_t want = (units + kBlock / 32 - 1) / (kBlock / 32);
     const int64_t cap = (int64_t)h->sm_count * per_sm;
@@ -238,9 +242,9 @@ static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, i
     if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st, io);
     // Long chains and FP64: two lanes per instance (vfk_split.cuh).  Measured on B200: see DESIGN.md section 4.1.
     if constexpr (kSplitLanes<T, N, PAT> > 0) {
-        if (n_obst > 0 && split_ok<T>(c, b, io)) return launch_split<T, N, kSplitLanes<T, N, PAT>>(h, c, b, n, n_obst, k_cycles, st);
+        if (n_obst > 0 && split_ok<T>(h, N, c, b, io)) return launch_split<T, N, kSplitLanes<T, N, PAT>>(h, c, b, n, n_obst, k_cycles, st);
     }
-    if (is_lean<T>(c, b)) {
+    if (is_lean<T>(c, b) && h->chain.n_joints == N) {
         if constexpr (sizeof(T) == 4 && N <= 7) {
             if (k_cycles == 1) return launch_cycle<T, N, PAT, false, true, 1, true>(h, c, b, n, n_obst, k_cycles, st, io);
         }
@@ -254,6 +258,9 @@ static int dispatch_ext(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
                         cudaStream_t st, const vfk_io* io) {
     if constexpr (N == 7) {
         if (h->pattern == 1) return dispatch_feat<T, N, LwrPattern>(h, c, b, n, n_obst, k_cycles, st, io);
+    }
+    if constexpr (N >= 10) {
+        if (h->pattern == 2) return dispatch_feat<T, N, DhPattern>(h, c, b, n, n_obst, k_cycles, st, io);
     }
     return dispatch_feat<T, N, GenericPattern>(h, c, b, n, n_obst, k_cycles, st, io);
 }

@@ -2,10 +2,12 @@
 //
 // Everything here works on values held in registers by ONE thread for ONE instance
 // (fully unrolled, compile-time indexed).  Precision-specific primitives live in
-// Prec<float> / Prec<double>: the FP32 path uses the MUFU approximations
-// (rsqrt / lg2 / ex2) whose error budget is stated in DESIGN.md (1e-4 relative on
-// qdot); the FP64 path uses correctly rounded sqrt / div and libdevice pow / atan2 /
-// sincos (1e-9 relative on qdot).
+// Prec<float> / Prec<double>: the FP32 path uses single MUFU approximations (rsqrt / rcp /
+// sqrt / lg2 / ex2) whose error budget is stated in DESIGN.md (1e-4 relative on qdot); the
+// FP64 path builds reciprocal, rsqrt, sqrt and division from the hardware seed plus one
+// third-order step (branch-free, a few ulp), decay orders from multiplication chains and
+// sin / cos from its own reduction + polynomials -- only atan2 and non-integer pow are
+// libdevice (1e-9 relative on qdot).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -292,8 +294,9 @@ __device__ __forceinline__ float dot6(const float (&c)[6], const float (&y)[6], 
 
 // In-place Cholesky A = L L^T of a packed SPD 6x6.  On return a[] holds L's strict
 // lower part and inv_d[j] = 1 / L[j][j] (the diagonal is only ever needed inverted).
+// `floor` (double only): pivots are not allowed below it -- see the call site; the float instantiation ignores it.
 template <typename T>
-__device__ __forceinline__ void chol6(T (&a)[21], T (&inv_d)[6]) {
+__device__ __forceinline__ void chol6(T (&a)[21], T (&inv_d)[6], T floor = T(0)) {
     static_for<0, 6>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         T s = a[tri(j, j)];
@@ -301,6 +304,7 @@ __device__ __forceinline__ void chol6(T (&a)[21], T (&inv_d)[6]) {
             constexpr int k = decltype(kc)::value;
             s = fma(-a[tri(j, k)], a[tri(j, k)], s);
         });
+        if constexpr (sizeof(T) == 8) s = s > floor ? s : floor;
         const T id = Prec<T>::rsqrt_pos(s);
         inv_d[j] = id;
         static_for<j + 1, 6>([&](auto ic) {

@@ -38,11 +38,12 @@ struct alignas(64) SplitMaps {
 
 constexpr int kSplitTabJoints = kMaxJ + 3;       // L * NL can exceed N by up to L - 1 padding joints
 
+// Per-joint constants of a DH chain: tip = {cos alpha, sin alpha, tx, ty, tz} (RotX(alpha) and the translation), limits and
+// the limit-avoidance gradient's scale / centre.  Padding joints (index >= N): identity tip, zeros.
 template <typename T>
 struct SplitTab {
-    typename WideOf<T>::type tip[kSplitTabJoints][12];
-    T q_lo[kSplitTabJoints], q_hi[kSplitTabJoints], ns_scale[kSplitTabJoints], ns_mid[kSplitTabJoints];
-    int32_t prismatic[kSplitTabJoints];
+    typename WideOf<T>::type tip[kSplitTabJoints][6];
+    T lim[kSplitTabJoints][4];                   // q_lo, q_hi, ns_scale, ns_mid
 };
 
 __host__ __device__ constexpr uint32_t round128(uint32_t x) { return (x + 127u) & ~127u; }
@@ -95,23 +96,30 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     const int h = lane / SUB;                                    // which part of the chain this lane owns
     const int sl = lane % SUB;                                   // instance within the warp
     const int j0 = h * NL;                                       // first joint of this lane
-    const int nc = a.n_comp;
+    constexpr int nc = N;                                        // chains of exactly N joints only (the host checks)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * SH::kBars;
     SplitTab<T>* tab = reinterpret_cast<SplitTab<T>*>(smem + kSmemHeader);
     unsigned char* region = smem + kSmemHeader + SH::kTab + (size_t)warp * SH::warp_bytes(a.n_stages);
 
-    // per-joint robot constants -> shared memory (joints >= nc: identity tip, zero everything: padding)
+    // per-joint robot constants -> shared memory
     for (int j = threadIdx.x; j < L * NL; j += kBlock) {
-        const bool real = j < nc;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) tab->tip[j][k] = real ? c.tip[j][k] : ((k == 0 || k == 4 || k == 8) ? W(1) : W(0));
-        tab->q_lo[j] = real ? c.q_lo[j] : T(0);
-        tab->q_hi[j] = real ? c.q_hi[j] : T(0);
-        tab->ns_scale[j] = real ? c.ns_q0_scale[j] : T(0);
-        tab->ns_mid[j] = real ? c.ns_mid[j] : T(0);
-        tab->prismatic[j] = real ? ((c.prismatic_mask >> j) & 1) : 0;
+        const bool real = j < N;
+        tab->tip[j][0] = real ? c.tip[j][4] : W(1);
+        tab->tip[j][1] = real ? c.tip[j][7] : W(0);
+        tab->tip[j][2] = real ? c.tip[j][9] : W(0);
+        tab->tip[j][3] = real ? c.tip[j][10] : W(0);
+        tab->tip[j][4] = real ? c.tip[j][11] : W(0);
+        tab->tip[j][5] = W(0);
+        tab->lim[j][0] = real ? c.q_lo[j] : T(0);
+        tab->lim[j][1] = real ? c.q_hi[j] : T(0);
+        tab->lim[j][2] = real ? c.ns_q0_scale[j] : T(0);
+        tab->lim[j][3] = real ? c.ns_mid[j] : T(0);
     }
     __syncthreads();
+    const typename WideOf<T>::type (*tipb)[6] = tab->tip + j0;   // this lane's joints: compile-time offsets from here on
+    const T (*limb)[4] = tab->lim + j0;
+    // joint k of this lane exists unless it is one of the last lane's padding slots (N is not a multiple of L)
+    auto real_joint = [&](int k) { return k < N - (L - 1) * NL || h != L - 1; };
 
     const int64_t n_tiles = (a.n + 31) >> 5;
     const int64_t n_units = n_tiles * L;                         // a unit = the 32 / L instances one warp takes at a time
@@ -171,7 +179,7 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 
         T q[NL];
 #pragma unroll
-        for (int k = 0; k < NL; ++k) q[k] = (j0 + k < nc) ? qs[(j0 + k) * SUB] : T(0);
+        for (int k = 0; k < NL; ++k) q[k] = real_joint(k) ? qs[(j0 + k) * SUB] : T(0);
         T g[13];
 #pragma unroll
         for (int k = 0; k < 13; ++k) g[k] = gs[k * SUB];
@@ -191,84 +199,80 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 for (int k = 0; k < 3; ++k) p[k] = (h == 0) ? c.base[9 + k] : W(0);
                 static_for<0, NL>([&](auto kc) {
                     constexpr int k = decltype(kc)::value;
-                    const int j = j0 + k;
                     Ja[k][0] = (T)R[2]; Ja[k][1] = (T)R[5]; Ja[k][2] = (T)R[8];
                     Jl[k][0] = (T)p[0]; Jl[k][1] = (T)p[1]; Jl[k][2] = (T)p[2];
-                    const W* tp = tab->tip[j];
-                    const bool prism = tab->prismatic[j] != 0;
-                    const W qj = (W)q[k];
-                    const W qrot = prism ? W(0) : qj, qtr = prism ? qj : W(0);
+                    const W* tp = tipb[k];
                     W s, co;
-                    sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(qrot, &s, &co);
+                    sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>((W)q[k], &s, &co);
+                    const W ca = tp[0], sa = tp[1], t0 = tp[2], t1 = tp[3], t2 = tp[4];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        const W x = R[3 * r + 0], y = R[3 * r + 1];
-                        R[3 * r + 0] = fma(co, x, s * y);
-                        R[3 * r + 1] = fma(co, y, -s * x);
-                        p[r] = fma(R[3 * r + 2], qtr, p[r]);
-                    }
-                    const W t0 = tp[9], t1 = tp[10], t2 = tp[11];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) p[r] = fma(R[3 * r + 0], t0, fma(R[3 * r + 1], t1, fma(R[3 * r + 2], t2, p[r])));
-                    if (c.all_xtwist) {                          // every tip rotation is RotX(alpha) (alpha = 0 included)
-                        const W ca = tp[4], sa = tp[7];
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) {
-                            const W y = R[3 * r + 1], z = R[3 * r + 2];
-                            R[3 * r + 1] = fma(ca, y, sa * z);
-                            R[3 * r + 2] = fma(ca, z, -sa * y);
-                        }
-                    } else {
-                        W Rn[9];
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int cc = 0; cc < 3; ++cc)
-                                Rn[3 * r + cc] = fma(R[3 * r + 0], tp[cc], fma(R[3 * r + 1], tp[3 + cc], R[3 * r + 2] * tp[6 + cc]));
-#pragma unroll
-                        for (int k2 = 0; k2 < 9; ++k2) R[k2] = Rn[k2];
+                        const W x0 = R[3 * r + 0], y0 = R[3 * r + 1], z0 = R[3 * r + 2];
+                        const W x = fma(co, x0, s * y0), y = fma(co, y0, -s * x0);            // RotZ(q)
+                        p[r] = fma(x, t0, fma(y, t1, fma(z0, t2, p[r])));                     // tip translation
+                        R[3 * r + 0] = x;
+                        R[3 * r + 1] = fma(ca, y, sa * z0);                                   // tip rotation RotX(alpha)
+                        R[3 * r + 2] = fma(ca, z0, -sa * y);
                     }
                 });
 
-                // inclusive scan of the partial frames over the L lanes of the instance: P_h = X_0 X_1 ... X_h
-                W Rx[9], px[3];
-#pragma unroll
-                for (int d = 1; d < L; d <<= 1) {
+                // Combine the partial frames.  Every lane needs the frame its part starts from (lane 0: none -- it began at the
+                // base) and all need the flange frame.
+                T Rs[9], ps[3];
+                W pe[3];
+                if constexpr (L == 2) {
+                    // one exchange: lane 0 holds X0 and receives X1, lane 1 the other way round; flange = X0 X1 on both
                     W Ry[9], py[3];
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) Ry[k] = __shfl_up_sync(0xffffffffu, R[k], d * SUB);
+                    for (int k = 0; k < 9; ++k) Ry[k] = __shfl_xor_sync(0xffffffffu, R[k], SUB);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) py[k] = __shfl_up_sync(0xffffffffu, p[k], d * SUB);
-                    frame_mul<W>(Ry, py, R, p, Rx, px);
-                    const bool take = h >= d;
+                    for (int k = 0; k < 3; ++k) py[k] = __shfl_xor_sync(0xffffffffu, p[k], SUB);
+                    W Ra[9], pa[3], Rb[9], pb[3], Re[9];
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) R[k] = take ? Rx[k] : R[k];
+                    for (int k = 0; k < 9; ++k) { Ra[k] = h ? Ry[k] : R[k]; Rb[k] = h ? R[k] : Ry[k]; }
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) p[k] = take ? px[k] : p[k];
+                    for (int k = 0; k < 3; ++k) { pa[k] = h ? py[k] : p[k]; pb[k] = h ? p[k] : py[k]; }
+                    frame_mul<W>(Ra, pa, Rb, pb, Re, pe);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) { Rt[k] = (T)Re[k]; Rs[k] = h ? (T)Ry[k] : ((k % 4 == 0) ? T(1) : T(0)); }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) ps[k] = h ? (T)py[k] : T(0);
+                } else {
+                    // inclusive scan P_h = X_0 ... X_h, then the exclusive prefix one lane up and the total from the last lane
+                    W Rx[9], px[3];
+#pragma unroll
+                    for (int d = 1; d < L; d <<= 1) {
+                        W Ry[9], py[3];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) Ry[k] = __shfl_up_sync(0xffffffffu, R[k], d * SUB);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) py[k] = __shfl_up_sync(0xffffffffu, p[k], d * SUB);
+                        frame_mul<W>(Ry, py, R, p, Rx, px);
+                        const bool take = h >= d;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) R[k] = take ? Rx[k] : R[k];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) p[k] = take ? px[k] : p[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const W v = __shfl_up_sync(0xffffffffu, R[k], SUB);
+                        Rs[k] = (h == 0) ? ((k % 4 == 0) ? T(1) : T(0)) : (T)v;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const W v = __shfl_up_sync(0xffffffffu, p[k], SUB);
+                        ps[k] = (h == 0) ? T(0) : (T)v;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Rt[k] = (T)__shfl_sync(0xffffffffu, R[k], (L - 1) * SUB + sl);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) pe[k] = __shfl_sync(0xffffffffu, p[k], (L - 1) * SUB + sl);
                 }
-                // the frame this lane's part starts from (lane 0: identity -- its part already began at the base) ...
-                T Rs[9], ps[3];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const W v = __shfl_up_sync(0xffffffffu, R[k], SUB);
-                    Rs[k] = (h == 0) ? ((k % 4 == 0) ? T(1) : T(0)) : (T)v;
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const W v = __shfl_up_sync(0xffffffffu, p[k], SUB);
-                    ps[k] = (h == 0) ? T(0) : (T)v;
-                }
-                // ... and the flange frame, from the last lane of the instance
-                W pe[3];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) Rt[k] = (T)__shfl_sync(0xffffffffu, R[k], (L - 1) * SUB + sl);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) pe[k] = __shfl_sync(0xffffffffu, p[k], (L - 1) * SUB + sl);
                 pt.set(pe);
-                // joint axes and origins to the base frame, then the Jacobian columns [z x (p_e - p_j); z] / [z; 0]
+                // joint axes and origins to the base frame, then the Jacobian columns [z x (p_e - p_j); z]
                 static_for<0, NL>([&](auto kc) {
                     constexpr int k = decltype(kc)::value;
-                    const int j = j0 + k;
                     const T zx = Ja[k][0], zy = Ja[k][1], zz = Ja[k][2], ox = Jl[k][0], oy = Jl[k][1], oz = Jl[k][2];
                     T z[3], o[3];
 #pragma unroll
@@ -277,15 +281,13 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                         o[r] = fma(Rs[3 * r + 0], ox, fma(Rs[3 * r + 1], oy, fma(Rs[3 * r + 2], oz, ps[r])));
                     }
                     const T ex = (pt.hi[0] - o[0]) + pt.lo[0], ey = (pt.hi[1] - o[1]) + pt.lo[1], ez = (pt.hi[2] - o[2]) + pt.lo[2];   // p_e - o
-                    const bool prism = tab->prismatic[j] != 0;
-                    const bool real = j < nc;
-                    const T lx = z[1] * ez - z[2] * ey, ly = z[2] * ex - z[0] * ez, lz = z[0] * ey - z[1] * ex;
-                    Jl[k][0] = real ? (prism ? z[0] : lx) : T(0);
-                    Jl[k][1] = real ? (prism ? z[1] : ly) : T(0);
-                    Jl[k][2] = real ? (prism ? z[2] : lz) : T(0);
-                    Ja[k][0] = (real && !prism) ? z[0] : T(0);
-                    Ja[k][1] = (real && !prism) ? z[1] : T(0);
-                    Ja[k][2] = (real && !prism) ? z[2] : T(0);
+                    if constexpr (k >= N - (L - 1) * NL) {           // a padding slot on the last lane: zero column
+                        const bool real = h != L - 1;
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) z[r] = real ? z[r] : T(0);
+                    }
+                    Jl[k][0] = z[1] * ez - z[2] * ey; Jl[k][1] = z[2] * ex - z[0] * ez; Jl[k][2] = z[0] * ey - z[1] * ex;
+                    Ja[k][0] = z[0]; Ja[k][1] = z[1]; Ja[k][2] = z[2];
                 });
             }
 
@@ -306,25 +308,31 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                     if constexpr (sizeof(T) == 4) {
                         // stage = [pair][plane][SUB lanes] of float4; the pairs of the chunk are dealt round-robin to the lanes
                         const float4* pl = reinterpret_cast<const float4*>(sb) + sl;
-                        auto deal = [&](auto order_c) {
+                        auto deal = [&](auto order_c, auto full_c) {
 #pragma unroll
                             for (int i = 0; i < (kChunk / 2 + L - 1) / L; ++i) {
                                 const int pr = i * L + h;
-                                if (pr < n_pairs)
+                                if (decltype(full_c)::value || pr < n_pairs)
                                     repel2<decltype(order_c)::value>(pl[(2 * pr) * SUB], pl[(2 * pr + 1) * SUB], c.obst_safe_inv, c.obst_order, np2, acc2);
                             }
                         };
-                        if (kF32PowChain && c.order_int == 20) deal(std::integral_constant<int, 20>{});
-                        else deal(std::integral_constant<int, 0>{});
+                        static_assert((kChunk / 2) % L == 0, "a full chunk deals the same number of pairs to every lane");
+                        if (ch < a.n_full) {
+                            if (kF32PowChain && c.order_int == 20) deal(std::integral_constant<int, 20>{}, std::true_type{});
+                            else deal(std::integral_constant<int, 0>{}, std::true_type{});
+                        } else {
+                            deal(std::integral_constant<int, 0>{}, std::false_type{});
+                        }
                     } else {
                         // stage = [pair][4 planes][SUB lanes] of double2 {slot 0, slot 1}
                         const double2* pl = reinterpret_cast<const double2*>(sb) + sl;
                         auto deal = [&](auto order_c) {
                             constexpr int ORD = decltype(order_c)::value;
+                            const bool full = ch < a.n_full;
 #pragma unroll
                             for (int i = 0; i < (kChunk / 2 + L - 1) / L; ++i) {
                                 const int pr = i * L + h;
-                                if (pr < n_pairs) {
+                                if (full || pr < n_pairs) {
                                     const double2 X = pl[(4 * pr) * SUB], Y = pl[(4 * pr + 1) * SUB], Z = pl[(4 * pr + 2) * SUB], Rr = pl[(4 * pr + 3) * SUB];
                                     Vec4<T> o0, o1;
                                     o0.x = X.x; o0.y = Y.x; o0.z = Z.x; o0.w = Rr.x;
@@ -365,7 +373,7 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             // 5. damped least squares: this lane's columns into J J^T and J x, summed over the instance's lanes
             T x[NL];
 #pragma unroll
-            for (int k = 0; k < NL; ++k) x[k] = tab->ns_scale[j0 + k] * (q[k] - tab->ns_mid[j0 + k]);
+            for (int k = 0; k < NL; ++k) x[k] = limb[k][2] * (q[k] - limb[k][3]);
             WN A[21], invd[6], Jx[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
@@ -388,7 +396,10 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             }
 #pragma unroll
             for (int r = 0; r < 6; ++r) A[tri(r, r)] += c.ik_lambda2;
-            chol6<WN>(A, invd);
+            [[maybe_unused]] WN pivot_floor = WN(0);                  // see vfk_cycle_kernel: FP64 accepts ik_lambda = 0
+            if constexpr (sizeof(WN) == 8)
+                pivot_floor = WN(1e-28) * (A[tri(0, 0)] + A[tri(1, 1)] + A[tri(2, 2)] + A[tri(3, 3)] + A[tri(4, 4)] + A[tri(5, 5)]) + WN(1e-300);
+            chol6<WN>(A, invd, pivot_floor);
             T yv[6], yn[6];
             {
                 WN y[6];
@@ -410,7 +421,7 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 const T cj[6] = {Jl[k][0], Jl[k][1], Jl[k][2], Ja[k][0], Ja[k][1], Ja[k][2]};
                 const T raw = dot6(cj, yn, x[k], true);
                 const T d = fma(c.ns_lookahead, raw, q[k]);
-                bad = bad || (d < tab->q_lo[j0 + k]) || (d > tab->q_hi[j0 + k]);
+                bad = bad || (d < limb[k][0]) || (d > limb[k][1]);
                 x[k] = raw;                                              // x is not needed any more
                 mix[k] = dot6(cj, yv, T(0), false) * c.mixer_w[0];
             }
@@ -431,11 +442,24 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             for (int off = SUB; off < 32; off <<= 1) lead = Prec<T>::fmax_(lead, __shfl_xor_sync(0xffffffffu, lead, off));
             T ratio = T(1);
             if (lead > c.max_vel) ratio = Prec<T>::div(c.max_vel, lead);
+            if constexpr (sizeof(T) == 8) {                          // never integrate a non-finite step
+                T z = T(0);
+#pragma unroll
+                for (int k = 0; k < NL; ++k) z = fma(mix[k], T(0), z);
+                int nf = (z != T(0)) ? 1 : 0;                        // NaN or inf anywhere in this lane's part
+#pragma unroll
+                for (int off = SUB; off < 32; off <<= 1) nf |= __shfl_xor_sync(0xffffffffu, nf, off);
+                if (nf) {
+                    ratio = T(0);
+#pragma unroll
+                    for (int k = 0; k < NL; ++k) mix[k] = T(0);
+                }
+            }
 
             if (last && active) {
 #pragma unroll
                 for (int k = 0; k < NL; ++k)
-                    if (j0 + k < nc) a.qdot[tN + (j0 + k) * 32] = mix[k] * ratio;
+                    if (real_joint(k)) a.qdot[tN + (j0 + k) * 32] = mix[k] * ratio;
             }
             // 10. plant
             if (c.integrate) {
@@ -446,7 +470,7 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         if (active && c.integrate) {
 #pragma unroll
             for (int k = 0; k < NL; ++k)
-                if (j0 + k < nc) a.q[tN + (j0 + k) * 32] = q[k];
+                if (real_joint(k)) a.q[tN + (j0 + k) * 32] = q[k];
         }
     }
 }

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import weakref
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -144,13 +145,16 @@ class Engine:
         if rc != 0:
             raise VfkError(rc, self._lib.vfk_last_error(None).decode())
         self.launches = 0                       # kernels launched through this engine
-        self.chain_pattern = {0: "generic", 1: "lwr"}.get(self._lib.vfk_chain_pattern(self._h), "?")
+        self._sessions = weakref.WeakSet()      # live host-buffer sessions: closed before the handle goes
+        self.chain_pattern = {0: "generic", 1: "lwr", 2: "dh"}.get(self._lib.vfk_chain_pattern(self._h), "?")
         self.params = params if params is not None else Params()
         self.set_params(self.params)
 
     # -- lifecycle
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
+            for s in list(getattr(self, "_sessions", ())):
+                s.close()
             self._lib.vfk_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -278,6 +282,7 @@ class Session:
         self.n, self.m, self.ext = int(n_instances), int(n_obstacles), bool(obst_ext)
         self._s = C.c_void_p()
         engine._check(engine._lib.vfk_session_create(engine._h, self.n, self.m, int(self.ext), C.byref(self._s)))
+        engine._sessions.add(self)
 
     def close(self):
         if getattr(self, "_s", None) is not None and self._s:

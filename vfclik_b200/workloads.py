@@ -21,7 +21,7 @@ def quat_to_rot_rows(quat: np.ndarray) -> np.ndarray:
 # oracle's cycle on a counting scalar type (the `opcount` module of the test oracle; add / sub / mul / div / sqrt = 1 FLOP, FMA = 2; sin, cos,
 # atan2, pow counted apart; constant folding and structural 0 / 1 entries free).  Frozen here; tests/test_oracle.py
 # re-derives them.  The K-fused roofline (FP32 pipe) in bench.py is computed from these.
-ALGORITHMIC_OPS = {(7, 3): (1064, 18), (7, 32): (1644, 47), (7, 256): (6124, 271), (17, 64): (3443, 99)}
+ALGORITHMIC_OPS = {(7, 3): (1064, 18), (7, 32): (1644, 47), (7, 256): (6124, 271), (17, 64): (3449, 99)}
 
 
 def algorithmic_flops(n_joints: int, n_obst: int) -> int:
@@ -133,21 +133,28 @@ def config1(chain: ChainDesc, config, seed: int = 0):
 
 
 def torso_arm_chain(n_joints: int = 10) -> ChainDesc:
-    """The first ``n_joints`` joints of :func:`dual_arm_torso_chain`; the default 10 = 3-DOF torso + one 7-joint arm, the
-    shape of the reference's iCub configuration (``scripts/bridge:344-345``: arm 7 + torso 3 -> a 4-D nullspace)."""
-    return dual_arm_torso_chain(n_joints)
+    """The first ``n_joints`` joints of the mixed-axis :func:`dual_arm_torso_chain`; the default 10 = 3-DOF torso + one
+    7-joint arm, the shape of the reference's iCub configuration (``scripts/bridge:344-345``: arm 7 + torso 3 -> a 4-D
+    nullspace)."""
+    return dual_arm_torso_chain(n_joints, dh=False)
 
 
-def dual_arm_torso_chain(n_joints: int = 17) -> ChainDesc:
+def dual_arm_torso_chain(n_joints: int = 17, dh: bool = True) -> ChainDesc:
     """BASELINE config 5: 3-DOF torso + 14 arm joints treated as one 17-joint serial chain
-    (6x17 Jacobian).  Synthetic geometry: a yaw-pitch-roll torso followed by two LWR-like
-    7-joint segments; only the shape (N = 17) matters for the benchmark."""
+    (6x17 Jacobian).  Synthetic geometry: a 3-axis torso followed by two LWR-like 7-joint
+    segments; only the shape (N = 17) matters for the benchmark.
+
+    ``dh=True`` (default): the whole chain in Denavit-Hartenberg form -- revolute Z joints, X-twist tips -- the way humanoid
+    models are published (e.g. iCub's iKin tables); such chains take the kernels' ``DhPattern``.  ``dh=False``: the torso's
+    third joint is a KDL ``RotX`` joint (yaw-pitch-roll), which the host canonicalises into a general tip rotation and the
+    kernels run through ``GenericPattern``."""
     from . import kdl
     from math import pi
     segs = [
         kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame(kdl.Rotation.RotX(pi / 2), kdl.Vector(0, 0, 0.20))),
         kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame(kdl.Rotation.RotX(-pi / 2), kdl.Vector(0, 0, 0.0))),
-        kdl.Segment(kdl.Joint(kdl.Joint.RotX), kdl.Frame(kdl.Rotation.Identity(), kdl.Vector(0, 0, 0.25))),
+        (kdl.Segment(kdl.Joint(kdl.Joint.RotZ), kdl.Frame(kdl.Rotation.RotX(pi / 2), kdl.Vector(0.05, 0, 0.25))) if dh else
+         kdl.Segment(kdl.Joint(kdl.Joint.RotX), kdl.Frame(kdl.Rotation.Identity(), kdl.Vector(0, 0, 0.25)))),
     ]
     for _ in range(2):
         segs += [
