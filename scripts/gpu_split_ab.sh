@@ -9,7 +9,7 @@ echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
 tail -15 $OUT/${TAG}_pytest.log
 for W in config5 config2; do
   for NS in 0 1; do
-    if [ $NS = 1 ]; then export VFK_NO_SPLIT=1; else unset VFK_NO_SPLIT; fi
+    if [ $NS = 1 ]; then unset VFK_SPLIT; else export VFK_SPLIT=1; fi
     timeout 300 python bench.py --workload $W --steps 100 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_${W}_nosplit${NS}.json 2> $OUT/${TAG}_${W}_nosplit${NS}.err
     echo "$W nosplit=$NS exit $?"
     python - <<PY
@@ -21,4 +21,4 @@ except Exception as e: print("parse failed", e)
 PY
   done
 done
-unset VFK_NO_SPLIT
+unset VFK_SPLIT

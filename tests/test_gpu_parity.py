@@ -239,8 +239,8 @@ def test_control_nullspace_against_the_executed_reference_n10(built_lib, golden)
                                                         (64, 7, 32, 1, 4128), (64, 7, 3, 4, 37), (64, 17, 20, 2, 4100),
                                                         (64, 10, 8, 1, 999)])
 def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k, n):
-    """Two lanes per instance (vfk_split.cuh: long chains and FP64, the lean call shape): against the oracle at the mode's
-    tolerance, and against the one-thread-per-instance kernel on the same inputs."""
+    """Two lanes per instance (vfk_split.cuh: long chains and FP64, the lean call shape; opt-in with VFK_SPLIT=1 because it
+    measured slower): against the oracle at the mode's tolerance, and against the one-thread-per-instance kernel."""
     from vfclik_b200 import workloads
     from vfclik_b200.engine import Engine, Params
     chain = lwr[0] if n_joints == 7 else workloads.dual_arm_torso_chain(n_joints)       # DH form: what the split kernel takes
@@ -248,11 +248,10 @@ def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k
     e = Engine(chain, precision=precision, params=Params.from_config(lwr[1]) if n_joints == 7 else Params())
     try:
         w = workloads.random_batch(chain, n, m, seed=40 + n_joints + m, dtype=dt)
-        monkeypatch.delenv("VFK_NO_SPLIT", raising=False)
+        monkeypatch.setenv("VFK_SPLIT", "1")
         out = run_gpu(e, w, m, k=k, outputs=("qdot",))
-        monkeypatch.setenv("VFK_NO_SPLIT", "1")
+        monkeypatch.delenv("VFK_SPLIT")
         solo = run_gpu(e, w, m, k=k, outputs=("qdot",))
-        monkeypatch.delenv("VFK_NO_SPLIT", raising=False)
         ref = run_oracle(chain, e.params, w, m, k=k)
         # FP32 over several cycles: an instance within rounding of the all-or-nothing limit check or the clamp may take the
         # other branch in an earlier cycle; bound the bulk there, everything otherwise

@@ -165,10 +165,14 @@ static int encode_map3(vfk_ctx* h, CUtensorMap* m, const void* base, uint64_t in
     return VFK_OK;
 }
 
-// May this call run in the lane-split shape?  (lean call on blocked device buffers; the chain pattern does not matter)
+// May this call run in the lane-split shape?  Lean call on blocked device buffers, DH-form chain of exactly the instantiated
+// length -- and VFK_SPLIT=1 in the environment: measured on B200 the shape LOSES to the one-thread-per-instance kernel on both
+// workloads it was built for (config 5: 184 vs 154 us per launch; FP64 config 2: 29.6 vs 23.4 us), so it
+// is kept as a tested opt-in, not a default.
 template <typename T>
 static bool split_ok(vfk_ctx* h, int n_kernel, const KConst<T>& c, const vfk_buffers* b, const vfk_io* io) {
-    return h->dh_chain && h->chain.n_joints == n_kernel && is_lean<T>(c, b) && !(io && (io->q_src || io->qdot)) && !getenv("VFK_NO_SPLIT");
+    const char* e = getenv("VFK_SPLIT");
+    return e && atoi(e) != 0 && h->dh_chain && h->chain.n_joints == n_kernel && is_lean<T>(c, b) && !(io && (io->q_src || io->qdot));
 }
 
 template <typename T, int N, int L>
@@ -240,7 +244,7 @@ static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, i
                              : launch_cycle<T, N, PAT, false, false, kChunk>(h, c, b, n, n_obst, k_cycles, st, io);
     }
     if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st, io);
-    // Long chains and FP64: two lanes per instance (vfk_split.cuh).  Measured on B200: see DESIGN.md section 4.1.
+    // Long chains and FP64: two lanes per instance (vfk_split.cuh), opt-in.
     if constexpr (kSplitLanes<T, N, PAT> > 0) {
         if (n_obst > 0 && split_ok<T>(h, N, c, b, io)) return launch_split<T, N, kSplitLanes<T, N, PAT>>(h, c, b, n, n_obst, k_cycles, st);
     }
