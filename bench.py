@@ -267,6 +267,9 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    from vfclik_b200.distributed import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)          # before any page-locked allocation: staging memory lands next to the GPU
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -389,9 +392,52 @@ def main():
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e_value = world * n_inst * args.kcycles * e2e_steps / float(e2e_s.item())
         io_bytes = N * n_inst * elem
+        e2e_ms = 1e3 * float(e2e_s.item()) / e2e_steps
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
-               "steps": e2e_steps, "ms_per_step": 1e3 * float(e2e_s.item()) / e2e_steps, "gpu_launches": e2e_launches,
-               "api": "vfk_session_cycle (pinned host q in, pinned host qdot out; scene resident; direct host I/O: the cycle kernel reads q from and writes qdot to the host buffers over PCIe)"}
+               "steps": e2e_steps, "ms_per_step": e2e_ms, "gpu_launches": e2e_launches,
+               "api": "vfk_session_cycle (pinned host q in, pinned host qdot out; scene resident; direct host I/O: the cycle kernel reads q from and writes qdot to the host buffers over PCIe)",
+               "numa": numa}
+        # The ceiling of this box for this I/O pattern, measured now with every rank doing it at once: the same two buffers
+        # moved by the two DMA engines (H2D and D2H concurrently, no kernel), max over ranks.
+        d_in = torch.empty((N, n_inst), dtype=t_dt, device="cuda")
+        d_out = torch.empty((N, n_inst), dtype=t_dt, device="cuda")
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def dma_pair():
+            with torch.cuda.stream(s_up):
+                d_in.copy_(q_host, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                qd_host.copy_(d_out, non_blocking=True)
+            s_up.synchronize(); s_dn.synchronize()
+        for _ in range(3):
+            dma_pair()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            dma_pair()
+        barrier()
+        dma_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dma_s, op=dist.ReduceOp.MAX)
+        floor_ms = 1e3 * float(dma_s.item()) / e2e_steps
+        e2e["roofline"] = {"bound": "pcie", "floor_ms_per_step": floor_ms, "peak_gbs_each_way": io_bytes / (floor_ms * 1e-3) / 1e9,
+                           "achieved_gbs_each_way": io_bytes / (e2e_ms * 1e-3) / 1e9, "frac": floor_ms / e2e_ms,
+                           "how": "H2D + D2H of the same %d-byte buffers on the two DMA engines concurrently, all %d ranks at once, "
+                                  "max over ranks, same run" % (io_bytes, world)}
+        # simulated plant (the reference's bridge -s): 100 control cycles per call, one q in and one command out per call
+        k_sim = 100
+        sess.cycle(q_in=q_np, k_cycles=k_sim, qdot_out=qd_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_launches += sess.cycle(q_in=q_np, k_cycles=k_sim, qdot_out=qd_np)
+        barrier()
+        sim_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(sim_s, op=dist.ReduceOp.MAX)
+        e2e["k100"] = {"kcycles": k_sim, "value": world * n_inst * k_sim * 3 / float(sim_s.item()), "unit": UNIT,
+                       "ms_per_step": 1e3 * float(sim_s.item()) / 3}
+        del d_in, d_out
         sess.close()
     else:
         e2e = {"value": None, "unit": UNIT, "note": "not measured for the device-generated config 4 / 5 shards"}
@@ -468,6 +514,8 @@ def main():
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
+            if all_cpus is not None:
+                os.sched_setaffinity(0, all_cpus)        # the CPU arm uses every core of the box, not only the GPU's NUMA node
             arm = CpuArm(n_obst)
             arm.step(20)                       # warm the pool (imports)
             c, t = arm.step(args.cpu_cycles * 4)

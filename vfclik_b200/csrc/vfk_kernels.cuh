@@ -606,9 +606,15 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     T q[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) q[j] = j < nc ? qg[j * 32] : T(0);
+    // Long chains (N >= 10) live at the register limit: the lean instantiation re-reads the goal from the staging buffer when
+    // the attractor needs it, never materialises the nullspace input or the per-controller velocity vectors, and takes the
+    // all-or-nothing limit check as a pass of its own (two cheap dot products per joint recomputed instead of 3 N live values).
+    constexpr bool kSlim = LEAN && N >= 10;
     T g[13];
+    if constexpr (!kSlim) {
 #pragma unroll
-    for (int k = 0; k < 13; ++k) g[k] = qg[(N + k) * 32];
+        for (int k = 0; k < 13; ++k) g[k] = qg[(N + k) * 32];
+    }
 
     for (int cyc = 0; cyc < a.k_cycles; ++cyc) {
         const bool last = (cyc == a.k_cycles - 1);
@@ -647,6 +653,10 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         T tw[6];
         {
             T V[3], S0, w[3], acc[3] = {T(0), T(0), T(0)};
+            if constexpr (kSlim) {
+#pragma unroll
+                for (int k = 0; k < 13; ++k) g[k] = qg[(N + k) * 32];
+            }
             attract<T>(c, g, Rt, pt, V, S0, w);
             [[maybe_unused]] NegPos2 np2;                               // FP32 packed repulsor: duplicated tool position, paired sums
             [[maybe_unused]] float2 acc2[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -743,7 +753,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         const bool ns_proj = LEAN || c.ns_mode == 1;
         const bool share = LEAN || c.share_factor;
         T x[N];                                             // nullspace input (projector mode): known before the factorisation
-        if (ns_proj) {
+        auto x_slim = [&](int j) { return c.ns_q0_scale[j] * (q[j] - c.ns_mid[j]); };
+        if (ns_proj && !kSlim) {
             if (!LEAN && a.ns_in) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) x[j] = j < nc ? __ldg(a.ns_in + tN + j * 32) : T(0);
@@ -762,7 +773,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         static_for<0, N>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
-            if (ns_proj && share) axpy6(Jx, col, (WN)x[j]);
+            if (ns_proj && share) axpy6(Jx, col, kSlim ? (WN)x_slim(j) : (WN)x[j]);
             if (!unitw) {
 #pragma unroll
                 for (int r = 0; r < 6; ++r) col[r] *= (WN)c.w_task[r] * (WN)c.w_joint[j];
@@ -776,158 +787,185 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         if constexpr (sizeof(WN) == 8)
             pivot_floor = WN(1e-28) * (A[tri(0, 0)] + A[tri(1, 1)] + A[tri(2, 2)] + A[tri(3, 3)] + A[tri(4, 4)] + A[tri(5, 5)]) + WN(1e-300);
         chol6<WN>(A, invd, pivot_floor);
-        T qd_vf[N];
-        {
-            WN y[6];
+        T mix[N];
+        [[maybe_unused]] T qd_vf[N], qd_ns[N], qd_jp[N];
+        bool nan = false;
+        if constexpr (kSlim) {
+            T yv[6], yn[6];
+            {
+                WN y[6];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) y[r] = unitw ? (WN)tw[r] : (WN)tw[r] * (WN)c.w_task[r];
-            chol6_fwd<WN>(A, invd, y);
-            chol6_bwd<WN>(A, invd, y);
-            T yt[6];
+                for (int r = 0; r < 6; ++r) y[r] = (WN)tw[r];
+                chol6_fwd<WN>(A, invd, y);
+                chol6_bwd<WN>(A, invd, y);
+                chol6_fwd<WN>(A, invd, Jx);
+                chol6_bwd<WN>(A, invd, Jx);
 #pragma unroll
-            for (int r = 0; r < 6; ++r) yt[r] = unitw ? (T)y[r] : (T)(y[r] * (WN)c.w_task[r]);
+                for (int r = 0; r < 6; ++r) { yv[r] = (T)y[r]; yn[r] = (T)Jx[r]; }
+            }
+            bool bad = false;                               // pass 1: the lookahead check over ALL joints decides for all
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
-                const T acc = dot6(cj, yt, T(0), false);
-                qd_vf[j] = unitw ? acc : acc * c.w_joint[j] * c.w_joint[j];
-            }
-        }
-
-        // 6. nullspace
-        T qd_ns[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) qd_ns[j] = T(0);
-        if (ns_on) {
-            T raw[N];
-            const bool qr = !LEAN && c.ns_qr;
-            if (!qr) {
-                // damped projector through the normal equations: raw = x - J^T (J J^T + l^2 I)^-1 (J x)
-                if (!share) {                               // own damping or weighted IK: factor J J^T + ns_lambda^2 I
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) {
-                        Jx[r] = WN(0);
-#pragma unroll
-                        for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ns_lambda2 : WN(0);
-                    }
-                    static_for<0, N>([&](auto jc) {
-                        constexpr int j = decltype(jc)::value;
-                        const WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
-                        axpy6(Jx, col, (WN)x[j]);
-                        syr6(A, col);
-                    });
-                    if constexpr (sizeof(WN) == 8)
-                        pivot_floor = WN(1e-28) * (A[tri(0, 0)] + A[tri(1, 1)] + A[tri(2, 2)] + A[tri(3, 3)] + A[tri(4, 4)] + A[tri(5, 5)]) + WN(1e-300);
-                    chol6<WN>(A, invd, pivot_floor);
-                }
-                chol6_fwd<WN>(A, invd, Jx);
-                chol6_bwd<WN>(A, invd, Jx);
-                T yt[6];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) yt[r] = (T)Jx[r];
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
-                    raw[j] = dot6(cj, yt, x[j], true);
-                }
-            } else {
-                // the reference's own form (scripts/nullspace:75-117): orthonormal basis u_i of null(J) -- Householder QR of
-                // J^T, error cond(J) * eps, no damping (vfk_nullspace.cuh) -- then either the projector
-                // (I - pinv(J) J) x = sum_i u_i (u_i . x), or the control interface sum_{i < min(4, k)} control_i u_i with
-                // every u_i's sign kept continuous against the previous cycle's vector (ns_lastvec, [min(4, k)][N]).
-#pragma unroll
-                for (int j = 0; j < N; ++j) raw[j] = T(0);
-                if constexpr (!LEAN && ns_null_vectors(N) > 0) {
-                    double At[N * 6], tau[6], wv[N];
-#pragma unroll
-                    for (int j = 0; j < N; ++j)
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) At[j * 6 + r] = (double)(r < 3 ? Jl[j][r] : Ja[j][r - 3]);
-                    ns_qr_factor(At, nc, tau);
-                    if (ns_proj) {
-#pragma unroll
-                        for (int j = 0; j < N; ++j) wv[j] = (double)x[j];
-                        ns_qr_project(At, tau, nc, wv);
-#pragma unroll
-                        for (int j = 0; j < N; ++j) raw[j] = j < nc ? (T)wv[j] : T(0);
-                    } else {
-                        const int kk = ns_ctrl_vectors(nc);                      // rows of ns_lastvec
-                        double rawd[N];
-#pragma unroll
-                        for (int j = 0; j < N; ++j) rawd[j] = 0.0;
-#pragma unroll 1
-                        for (int i = 0; i < kk; ++i) {
-                            ns_qr_column(At, tau, nc, 6 + i, wv);
-                            T* lv = a.ns_lastvec + tile * (kk * nc * 32) + i * (nc * 32) + slot;
-                            double dotl = 0.0;
-#pragma unroll
-                            for (int j = 0; j < N; ++j) if (j < nc) dotl = fma(wv[j], (double)lv[j * 32], dotl);
-                            const double sgn = dotl < 0.0 ? -1.0 : 1.0;      // |s u - last| > |s u + last|  <=>  s u . last < 0
-                            const double ci = a.ns_in ? (double)__ldg(a.ns_in + tile * (4 * 32) + i * 32 + slot) : (double)c.ns_control[i];
-                            if (active) {
-#pragma unroll
-                                for (int j = 0; j < N; ++j) if (j < nc) lv[j * 32] = (T)(sgn * wv[j]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < N; ++j) if (j < nc) rawd[j] = fma(sgn * ci, wv[j], rawd[j]);
-                        }
-                        if (G > 1) __syncwarp();             // a group's lanes re-read what its lane 0 stored
-#pragma unroll
-                        for (int j = 0; j < N; ++j) raw[j] = (T)rawd[j];
-                    }
-                }
-            }
-            // all-or-nothing lookahead limit check, then gain
-            bool bad = false;
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const T d = fma(c.ns_lookahead, raw[j], q[j]);
+                const T d = fma(c.ns_lookahead, dot6(cj, yn, x_slim(j), true), q[j]);
                 bad = bad || (d < c.q_lo[j]) || (d > c.q_hi[j]);
             }
             if (bad) flags |= 2;
+            const T w1 = bad ? T(0) : c.ns_gain * c.mixer_w[1];
 #pragma unroll
-            for (int j = 0; j < N; ++j) qd_ns[j] = bad ? T(0) : raw[j] * c.ns_gain;
-        }
-
-        // 7. joint P controller (skipped when nothing can observe it)
-        T qd_jp[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) qd_jp[j] = T(0);
-        if (!LEAN && (c.need_jp || a.qdot_jp || a.flags)) {
-            bool all_reached = true;
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                T ref = (a.jp_ref && j < nc) ? __ldg(a.jp_ref + tN + j * 32) : c.jp_ref[j];
-                ref = ref < c.q_lo[j] ? c.q_lo[j] : (ref > c.q_hi[j] ? c.q_hi[j] : ref);
-                const T err = ref - q[j];
-                qd_jp[j] = err * c.jp_kp;
-                all_reached = all_reached && (err < c.jp_delta);
+            for (int j = 0; j < N; ++j) {                   // pass 2: both controllers' velocities straight into the mixer sum
+                const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
+                mix[j] = fma(dot6(cj, yn, x_slim(j), true), w1, dot6(cj, yv, T(0), false) * c.mixer_w[0]);
             }
-            if (all_reached) flags |= 1;
-        }
-
-        // 8-9. mixer, clamp
-        T mix[N];
-        bool nan = false;
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            T m = T(0);
-            m = fma(qd_vf[j], c.mixer_w[0], m);
-            m = fma(qd_ns[j], c.mixer_w[1], m);
-            m = fma(qd_jp[j], c.mixer_w[2], m);
-            if (!LEAN) nan = nan || (qd_vf[j] != qd_vf[j]) || (qd_ns[j] != qd_ns[j]) || (qd_jp[j] != qd_jp[j]);
-            mix[j] = m;
-        }
-#pragma unroll
-        for (int e = 0; e < 3; ++e)
-            if (!LEAN && a.ext_cmd[e]) {
-#pragma unroll
+        } else {
+            {
+                WN y[6];
+    #pragma unroll
+                for (int r = 0; r < 6; ++r) y[r] = unitw ? (WN)tw[r] : (WN)tw[r] * (WN)c.w_task[r];
+                chol6_fwd<WN>(A, invd, y);
+                chol6_bwd<WN>(A, invd, y);
+                T yt[6];
+    #pragma unroll
+                for (int r = 0; r < 6; ++r) yt[r] = unitw ? (T)y[r] : (T)(y[r] * (WN)c.w_task[r]);
+    #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const T x = j < nc ? __ldg(a.ext_cmd[e] + tN + j * 32) : T(0);
-                    nan = nan || (x != x);
-                    mix[j] = fma(x, c.mixer_w[3 + e], mix[j]);
+                    const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
+                    const T acc = dot6(cj, yt, T(0), false);
+                    qd_vf[j] = unitw ? acc : acc * c.w_joint[j] * c.w_joint[j];
                 }
             }
+
+            // 6. nullspace
+    #pragma unroll
+            for (int j = 0; j < N; ++j) qd_ns[j] = T(0);
+            if (ns_on) {
+                T raw[N];
+                const bool qr = !LEAN && c.ns_qr;
+                if (!qr) {
+                    // damped projector through the normal equations: raw = x - J^T (J J^T + l^2 I)^-1 (J x)
+                    if (!share) {                               // own damping or weighted IK: factor J J^T + ns_lambda^2 I
+    #pragma unroll
+                        for (int r = 0; r < 6; ++r) {
+                            Jx[r] = WN(0);
+    #pragma unroll
+                            for (int s = 0; s <= r; ++s) A[tri(r, s)] = (r == s) ? c.ns_lambda2 : WN(0);
+                        }
+                        static_for<0, N>([&](auto jc) {
+                            constexpr int j = decltype(jc)::value;
+                            const WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
+                            axpy6(Jx, col, (WN)x[j]);
+                            syr6(A, col);
+                        });
+                        if constexpr (sizeof(WN) == 8)
+                            pivot_floor = WN(1e-28) * (A[tri(0, 0)] + A[tri(1, 1)] + A[tri(2, 2)] + A[tri(3, 3)] + A[tri(4, 4)] + A[tri(5, 5)]) + WN(1e-300);
+                        chol6<WN>(A, invd, pivot_floor);
+                    }
+                    chol6_fwd<WN>(A, invd, Jx);
+                    chol6_bwd<WN>(A, invd, Jx);
+                    T yt[6];
+    #pragma unroll
+                    for (int r = 0; r < 6; ++r) yt[r] = (T)Jx[r];
+    #pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
+                        raw[j] = dot6(cj, yt, x[j], true);
+                    }
+                } else {
+                    // the reference's own form (scripts/nullspace:75-117): orthonormal basis u_i of null(J) -- Householder QR of
+                    // J^T, error cond(J) * eps, no damping (vfk_nullspace.cuh) -- then either the projector
+                    // (I - pinv(J) J) x = sum_i u_i (u_i . x), or the control interface sum_{i < min(4, k)} control_i u_i with
+                    // every u_i's sign kept continuous against the previous cycle's vector (ns_lastvec, [min(4, k)][N]).
+    #pragma unroll
+                    for (int j = 0; j < N; ++j) raw[j] = T(0);
+                    if constexpr (!LEAN && ns_null_vectors(N) > 0) {
+                        double At[N * 6], tau[6], wv[N];
+    #pragma unroll
+                        for (int j = 0; j < N; ++j)
+    #pragma unroll
+                            for (int r = 0; r < 6; ++r) At[j * 6 + r] = (double)(r < 3 ? Jl[j][r] : Ja[j][r - 3]);
+                        ns_qr_factor(At, nc, tau);
+                        if (ns_proj) {
+    #pragma unroll
+                            for (int j = 0; j < N; ++j) wv[j] = (double)x[j];
+                            ns_qr_project(At, tau, nc, wv);
+    #pragma unroll
+                            for (int j = 0; j < N; ++j) raw[j] = j < nc ? (T)wv[j] : T(0);
+                        } else {
+                            const int kk = ns_ctrl_vectors(nc);                      // rows of ns_lastvec
+                            double rawd[N];
+    #pragma unroll
+                            for (int j = 0; j < N; ++j) rawd[j] = 0.0;
+    #pragma unroll 1
+                            for (int i = 0; i < kk; ++i) {
+                                ns_qr_column(At, tau, nc, 6 + i, wv);
+                                T* lv = a.ns_lastvec + tile * (kk * nc * 32) + i * (nc * 32) + slot;
+                                double dotl = 0.0;
+    #pragma unroll
+                                for (int j = 0; j < N; ++j) if (j < nc) dotl = fma(wv[j], (double)lv[j * 32], dotl);
+                                const double sgn = dotl < 0.0 ? -1.0 : 1.0;      // |s u - last| > |s u + last|  <=>  s u . last < 0
+                                const double ci = a.ns_in ? (double)__ldg(a.ns_in + tile * (4 * 32) + i * 32 + slot) : (double)c.ns_control[i];
+                                if (active) {
+    #pragma unroll
+                                    for (int j = 0; j < N; ++j) if (j < nc) lv[j * 32] = (T)(sgn * wv[j]);
+                                }
+    #pragma unroll
+                                for (int j = 0; j < N; ++j) if (j < nc) rawd[j] = fma(sgn * ci, wv[j], rawd[j]);
+                            }
+                            if (G > 1) __syncwarp();             // a group's lanes re-read what its lane 0 stored
+    #pragma unroll
+                            for (int j = 0; j < N; ++j) raw[j] = (T)rawd[j];
+                        }
+                    }
+                }
+                // all-or-nothing lookahead limit check, then gain
+                bool bad = false;
+    #pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const T d = fma(c.ns_lookahead, raw[j], q[j]);
+                    bad = bad || (d < c.q_lo[j]) || (d > c.q_hi[j]);
+                }
+                if (bad) flags |= 2;
+    #pragma unroll
+                for (int j = 0; j < N; ++j) qd_ns[j] = bad ? T(0) : raw[j] * c.ns_gain;
+            }
+
+            // 7. joint P controller (skipped when nothing can observe it)
+    #pragma unroll
+            for (int j = 0; j < N; ++j) qd_jp[j] = T(0);
+            if (!LEAN && (c.need_jp || a.qdot_jp || a.flags)) {
+                bool all_reached = true;
+    #pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    T ref = (a.jp_ref && j < nc) ? __ldg(a.jp_ref + tN + j * 32) : c.jp_ref[j];
+                    ref = ref < c.q_lo[j] ? c.q_lo[j] : (ref > c.q_hi[j] ? c.q_hi[j] : ref);
+                    const T err = ref - q[j];
+                    qd_jp[j] = err * c.jp_kp;
+                    all_reached = all_reached && (err < c.jp_delta);
+                }
+                if (all_reached) flags |= 1;
+            }
+
+            // 8-9. mixer, clamp
+    #pragma unroll
+            for (int j = 0; j < N; ++j) {
+                T m = T(0);
+                m = fma(qd_vf[j], c.mixer_w[0], m);
+                m = fma(qd_ns[j], c.mixer_w[1], m);
+                m = fma(qd_jp[j], c.mixer_w[2], m);
+                if (!LEAN) nan = nan || (qd_vf[j] != qd_vf[j]) || (qd_ns[j] != qd_ns[j]) || (qd_jp[j] != qd_jp[j]);
+                mix[j] = m;
+            }
+    #pragma unroll
+            for (int e = 0; e < 3; ++e)
+                if (!LEAN && a.ext_cmd[e]) {
+    #pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const T x = j < nc ? __ldg(a.ext_cmd[e] + tN + j * 32) : T(0);
+                        nan = nan || (x != x);
+                        mix[j] = fma(x, c.mixer_w[3 + e], mix[j]);
+                    }
+                }
+        }
         T lead = T(0);
 #pragma unroll
         for (int j = 0; j < N; ++j) lead = Prec<T>::fmax_(lead, Prec<T>::fabs_(mix[j]));

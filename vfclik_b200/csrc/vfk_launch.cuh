@@ -115,8 +115,12 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #ifndef VFK_MINB_LEAN_K1
 #define VFK_MINB_LEAN_K1 4
 #endif
+#ifndef VFK_MINB_LEAN_BIG
+#define VFK_MINB_LEAN_BIG 2
+#endif
     constexpr int MINB = (HIOCC ? VFK_MINB_LEAN_K1
-                                : ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : 2) : (N <= 7 ? VFK_MINB_F64 : 1))) * (128 / kBlock);
+                                : ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : (LEAN ? VFK_MINB_LEAN_BIG : 2))
+                                                    : (N <= 7 ? VFK_MINB_F64 : 1))) * (128 / kBlock);
     auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB, G>;
     // per (instantiation, device, smem size): opt in to > 48 KB of dynamic shared memory and ask the occupancy once
     static PlanCache plans;
