@@ -153,7 +153,9 @@ typedef struct vfk_buffers {
                                     type 4 hemisphere repeller {x,y,z, nx,ny,nz, safe, order} (scripts/object_feeder:335-354),
                                     type 5 funnel attractor {x,y,z, ax,ay,az, cut angle, angle order, cut distance, distance order}
                                     (scripts/object_feeder:262-280); other type codes = empty slot */
-    const void* jp_ref;          /* [N]  joint reference (/jpctrl/ref) or NULL -> params.jp_ref   */
+    void*       jp_ref;          /* [N]  joint reference (/jpctrl/ref) or NULL -> params.jp_ref.  In/out when jp_lo / jp_hi are
+                                    given: the clamped reference is stored back, like the `ref` variable of the reference's loop
+                                    (scripts/joint_p_controller:121), so a clamp persists when the limits later widen */
     const void* ns_in;           /* PROJECTOR: qdot0 [N] or NULL -> limit-avoidance gradient;
                                     CONTROL:   control [4] or NULL -> params.ns_control             */
     void*       ns_lastvec;      /* CONTROL: [min(4, N-6) * N] in/out: the basis vectors of the previous cycle, vector i at
@@ -171,6 +173,9 @@ typedef struct vfk_buffers {
     int32_t*    flags;           /* out [1]  VFK_FLAG_*                                            */
     int32_t     n_aux;           /* slots in aux (0..64)                                           */
     int32_t     reserved;
+    const void* jp_lo;           /* [N]  per-instance joint limits the joint controller clamps its reference into --      */
+    const void* jp_hi;           /* [N]  config.updateJntLimits(q) (scripts/joint_p_controller:79-89; posture-dependent on the
+                                    iCub) evaluated by the caller per instance -- or NULL (both) -> the chain's static limits */
 } vfk_buffers;
 
 typedef struct vfk_ctx* vfk_handle;
@@ -252,6 +257,8 @@ int  vfk_session_set_obstacles(vfk_session s, const void* obst_host,         /* 
 int  vfk_session_set_aux(vfk_session s, const void* aux_host, int n_aux);   /* [n_aux * 12][n] records, or NULL / 0 to clear */
 int  vfk_session_set_q(vfk_session s, const void* q_host);                  /* [N][n] */
 int  vfk_session_set_jp_ref(vfk_session s, const void* ref_host);           /* [N][n] or NULL -> params.jp_ref */
+int  vfk_session_set_jp_limits(vfk_session s, const void* lo_host,          /* [N][n] each: per-instance limits of the joint */
+                               const void* hi_host);                        /* controller, or NULL (both) -> the chain's */
 int  vfk_session_set_ns_input(vfk_session s, const void* ns_host);          /* [N|4][n] or NULL */
 int  vfk_session_cycle(vfk_session s, const void* q_in_host, int k_cycles,
                        void* qdot_out_host, void* q_out_host, int32_t* flags_out_host);

@@ -414,8 +414,12 @@ def bridge_set_vel(prm: Params, mix: np.ndarray, q: np.ndarray, qc: np.ndarray, 
 # --------------------------------------------------------------------------- full cycle
 
 def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastvec=None,
-         q_cmded=None, ext_cmd=(None, None, None), k_cycles: int = 1, aux=None):
+         q_cmded=None, ext_cmd=(None, None, None), k_cycles: int = 1, aux=None, jp_limits=None):
     """K synchronous control cycles.
+
+    ``jp_limits = (lo[I, N], hi[I, N])``: what ``config.updateJntLimits(q)`` returned per instance (posture-dependent on the
+    iCub, ``scripts/joint_p_controller:79-89``); the clamped reference then replaces the reference, as the loop's ``ref =
+    check_limits(ref, q)`` does (``:121``), and is returned as ``jp_ref``.  Default: the chain's static limits.
 
     Returns a dict with the last cycle's ``qdot_vf, qdot_ns, qdot_jp, qdot_mix, qdot`` (clamped),
     ``cmd``, ``pose`` ([I,12]: R row-major, p of the tool frame), ``flags`` and the final ``q``
@@ -466,8 +470,11 @@ def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastve
             ref = np.broadcast_to(np.zeros(N) if prm.jp_ref is None else np.asarray(prm.jp_ref, dtype=np.float64)[:N], (I, N))
         else:
             ref = np.asarray(jp_ref, dtype=np.float64)
-        refc = np.where(ref < chain.q_lo[None, :], chain.q_lo[None, :],
-                        np.where(ref > chain.q_hi[None, :], chain.q_hi[None, :], ref))
+        lo, hi = (chain.q_lo[None, :], chain.q_hi[None, :]) if jp_limits is None else (np.asarray(jp_limits[0], dtype=np.float64),
+                                                                                        np.asarray(jp_limits[1], dtype=np.float64))
+        refc = np.where(ref < lo, lo, np.where(ref > hi, hi, ref))
+        if jp_limits is not None and jp_ref is not None:
+            jp_ref = refc                                # scripts/joint_p_controller:121: the clamp persists
         err = refc - q
         qd_jp = err * prm.jp_kp
         flags |= np.where(np.all(err < prm.jp_delta, axis=1), FLAG_AT_GOAL, 0).astype(np.int32)
@@ -489,6 +496,8 @@ def step(chain, prm: Params, q, goal, obst=None, jp_ref=None, ns_in=None, lastve
         if prm.integrate:
             q = q + prm.dt * qd
     out["q"] = q
+    if jp_limits is not None and jp_ref is not None:
+        out["jp_ref"] = np.asarray(jp_ref)
     if lastvec is not None:
         out["lastvec"] = lastvec
     return out

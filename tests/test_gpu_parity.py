@@ -782,6 +782,54 @@ def test_direct_host_io_keeps_the_sessions_device_state_current(lwr, built_lib, 
         e.close()
 
 
+def test_batched_posture_dependent_joint_limits(lwr, built_lib, golden):
+    """Row a12 at batch > 1: ``config.updateJntLimits(q)`` evaluated per instance and handed to the kernel as ``jp_lo`` /
+    ``jp_hi``; the clamped reference persists in ``jp_ref`` like the loop variable of scripts/joint_p_controller:121.
+    Instance 0 replays the trajectory recorded from the reference's own loop with posture-dependent limits
+    (tests/golden jp_out_dynamic / jp_at_goal_dynamic), the other instances run their own postures against the oracle."""
+    from vfclik_b200.engine import DeviceBatch, Engine, Params
+    from oracle import batch
+    chain, cfg = lwr
+    g = golden
+    q_gold, steps = g["jp_q"], g["jp_q"].shape[0]
+    kp, delta = g["jp_kp_delta"]
+    n = 96
+    rng = np.random.default_rng(61)
+    e = Engine(chain, precision=64, params=Params.from_config(cfg, jp_kp=float(kp), jp_delta=float(delta), integrate=0,
+                                                              mixer_w=(0, 0, 1.0, 0, 0, 0)))
+    prm = oracle_params(e.params)
+    try:
+        db = DeviceBatch(e, n, 0, outputs=("qdot_jp", "flags"), inputs=("jp_ref", "jp_lo", "jp_hi"))
+        goal = np.zeros((13, n)); goal[0] = goal[4] = goal[8] = 1.0
+        db.upload("goal", goal)
+        ref = np.tile(np.asarray(cfg.initial_joint_pos, dtype=np.float64)[:, None], (1, n))          # [7, n]
+        db.upload("jp_ref", ref)
+        ref_o = ref.T.copy()
+        msgs = {int(k): m for k, m in zip(g["jp_ref_steps"], g["jp_ref_msgs"])}
+        for k in range(steps):
+            q = rng.uniform(-1.0, 1.0, size=(n, 7))
+            q[0] = q_gold[k]
+            if k in msgs:                                            # a new reference arrives (instance 0: the recorded one)
+                ref_o = rng.uniform(-3.0, 3.0, size=(n, 7))
+                ref_o[0] = msgs[k]
+                db.upload("jp_ref", ref_o.T)
+            lo = np.tile((-0.5 - np.abs(q[:, 0]))[:, None], (1, 7))   # the golden record's hook, per instance
+            hi = np.tile((0.4 + np.abs(q[:, 1]))[:, None], (1, 7))
+            db.upload("q", q.T); db.upload("jp_lo", lo.T); db.upload("jp_hi", hi.T)
+            assert db.step(1) == 1
+            got = db.download("qdot_jp").T
+            flags = db.download("flags")[0]
+            o = batch.step(chain, prm, q, goal.T, None, jp_ref=ref_o, jp_limits=(lo, hi))
+            ref_o = o["jp_ref"]
+            assert np.allclose(got, o["qdot_jp"], rtol=1e-13, atol=1e-15)
+            assert np.array_equal(flags & 1, o["flags"] & 1)
+            assert np.allclose(db.download("jp_ref").T, ref_o, rtol=0, atol=0)          # the clamp persisted on the device
+            assert np.allclose(got[0], g["jp_out_dynamic"][k], rtol=1e-12, atol=1e-14), k
+            assert int(flags[0] & 1) == int(g["jp_at_goal_dynamic"][k]), k
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("which", ["config4", "config5"])
 def test_full_size_config4_and_config5_shards(lwr, built_lib, which):
     """BASELINE configs[3] / [4] at their per-GPU shard size on 8 GPUs (2,097,152 LWR instances x 256 obstacles;

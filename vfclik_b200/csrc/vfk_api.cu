@@ -266,7 +266,7 @@ static int step_impl(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, in
     int rc;
     if ((rc = check_layout(h, b->q, "q", true)) || (rc = check_layout(h, b->goal, "goal", true)) ||
         (rc = check_layout(h, b->obst, "obst", n_obst > 0)) || (rc = check_layout(h, b->obst_ext, "obst_ext", false)) || (rc = check_layout(h, b->aux, "aux", false)) ||
-        (rc = check_layout(h, b->jp_ref, "jp_ref", false)) || (rc = check_layout(h, b->ns_in, "ns_in", false)) ||
+        (rc = check_layout(h, b->jp_ref, "jp_ref", false)) || (rc = check_layout(h, b->jp_lo, "jp_lo", false)) || (rc = check_layout(h, b->jp_hi, "jp_hi", false)) || (rc = check_layout(h, b->ns_in, "ns_in", false)) ||
         (rc = check_layout(h, b->ns_lastvec, "ns_lastvec", h->params.ns_mode == VFK_NS_CONTROL && ns_ctrl_vectors(h->chain.n_joints) > 0)) ||
         (rc = check_layout(h, b->q_cmded, "q_cmded", false)) || (rc = check_layout(h, b->qdot_vf, "qdot_vf", false)) ||
         (rc = check_layout(h, b->qdot_ns, "qdot_ns", false)) || (rc = check_layout(h, b->qdot_jp, "qdot_jp", false)) ||
@@ -275,6 +275,7 @@ static int step_impl(vfk_ctx* h, const vfk_buffers* b, int64_t n, int n_obst, in
         return rc;
     for (int e = 0; e < 3; ++e)
         if ((rc = check_layout(h, b->ext_cmd[e], "ext_cmd", false))) return rc;
+    if ((b->jp_lo == nullptr) != (b->jp_hi == nullptr)) return fail(h, VFK_ERR_INVALID, "jp_lo and jp_hi go together");
     if (n == 0) return 0;
     VFK_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -452,9 +453,9 @@ struct vfk_session_s {
     vfk_buffers b;                   // blocked device buffers
     void* stage_in;                  // dense staging, big enough for the largest upload
     void* stage_out;                 // dense staging for outputs (max(N, 12) rows)
-    bool have_jp_ref, have_ns_in;
+    bool have_jp_ref, have_ns_in, have_jp_lim;
     bool en_vf, en_ns, en_jp, en_cmd, en_pose, en_twist;   // optional per-controller outputs (off by default)
-    void *d_jp_ref, *d_ns_in;
+    void *d_jp_ref, *d_ns_in, *d_jp_lo, *d_jp_hi;
     char* aux_dev;                   // auxiliary field records (blocked + dense staging), grown on demand
     char* pin;                       // pinned host staging: q in (N rows), qdot / q out (2N rows), flags
     size_t pin_bytes;
@@ -494,7 +495,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     const size_t obst_rows = (size_t)((n_obst + 1) & ~1) * 4 + (size_t)n_obst * (s->has_ext ? 2 : 0);
     // blocked: q N, goal 13, obst, jp_ref N, ns_in N, lastvec N, qdot_vf N, qdot_ns N, qdot_jp N, qdot N, cmd N, pose 12, twist 6, flags 1
     const int lv_rows = (ns_ctrl_vectors(N) > 0 ? ns_ctrl_vectors(N) : 1) * N;   // sign-continuity state: [min(4, N - 6)][N]
-    const size_t rows = (size_t)N * 8 + lv_rows + 13 + obst_rows + 12 + 6 + 1;
+    const size_t rows = (size_t)N * 10 + lv_rows + 13 + obst_rows + 12 + 6 + 1;
     const size_t stage_in_rows = obst_rows > (size_t)(N > 13 ? N : 13) ? obst_rows : (size_t)(N > 13 ? N : 13);
     const size_t first_out = (size_t)(lv_rows > 12 ? lv_rows : 12);
     const size_t stage_out_rows = first_out + (size_t)N;                          // qdot (or a read()) + q_out
@@ -509,6 +510,8 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->b.obst = n_obst ? take((size_t)((n_obst + 1) & ~1) * 4) : nullptr;     // whole pairs
     s->b.obst_ext = (n_obst && s->has_ext) ? take((size_t)n_obst * 2) : nullptr;
     s->d_jp_ref = take(N);
+    s->d_jp_lo = take(N);
+    s->d_jp_hi = take(N);
     s->d_ns_in = take(N);
     s->b.ns_lastvec = take(lv_rows);
     s->b.qdot_vf = take(N);
@@ -521,7 +524,7 @@ extern "C" int vfk_session_create(vfk_handle h, int64_t n, int n_obst, int with_
     s->b.flags = (int32_t*)take(1);
     s->stage_in = take(stage_in_rows);
     s->stage_out = take(stage_out_rows);
-    s->have_jp_ref = s->have_ns_in = false;
+    s->have_jp_ref = s->have_ns_in = s->have_jp_lim = false;
     s->en_vf = s->en_ns = s->en_jp = s->en_cmd = s->en_pose = s->en_twist = false;
     s->launches = 0;
     s->n_aux = 0;
@@ -619,6 +622,17 @@ extern "C" int vfk_session_set_jp_ref(vfk_session s, const void* r) {
     return upload_blocked(s, s->d_jp_ref, r, s->N, 1);
 }
 
+extern "C" int vfk_session_set_jp_limits(vfk_session s, const void* lo, const void* hi) {
+    if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_jp_limits: null session");
+    if ((lo == nullptr) != (hi == nullptr)) return fail(s->h, VFK_ERR_INVALID, "vfk_session_set_jp_limits: lo and hi go together");
+    s->have_jp_lim = lo != nullptr;
+    s->generation++;
+    if (!lo) return VFK_OK;
+    int rc = upload_blocked(s, s->d_jp_lo, lo, s->N, 1);
+    if (rc == VFK_OK) rc = upload_blocked(s, s->d_jp_hi, hi, s->N, 1);
+    return rc;
+}
+
 extern "C" int vfk_session_set_ns_input(vfk_session s, const void* x) {
     if (!s) return fail(nullptr, VFK_ERR_INVALID, "vfk_session_set_ns_input: null session");
     s->have_ns_in = x != nullptr;
@@ -635,7 +649,7 @@ static vfk_buffers offset_view(const vfk_buffers& b, int64_t tile0, int N, int M
     };
     o.q = off(b.q, N); o.goal = off(b.goal, 13); o.obst = off(b.obst, (size_t)((M + 1) & ~1) * 4); o.obst_ext = off(b.obst_ext, (size_t)M * 2);
     o.aux = off(b.aux, (size_t)b.n_aux * 12);
-    o.jp_ref = off(b.jp_ref, N); o.ns_lastvec = off(b.ns_lastvec, (size_t)(ns_ctrl_vectors(N) > 0 ? ns_ctrl_vectors(N) : 1) * N); o.q_cmded = off(b.q_cmded, N);
+    o.jp_ref = off(b.jp_ref, N); o.jp_lo = off(b.jp_lo, N); o.jp_hi = off(b.jp_hi, N); o.ns_lastvec = off(b.ns_lastvec, (size_t)(ns_ctrl_vectors(N) > 0 ? ns_ctrl_vectors(N) : 1) * N); o.q_cmded = off(b.q_cmded, N);
     for (int e = 0; e < 3; ++e) o.ext_cmd[e] = off(b.ext_cmd[e], N);
     o.qdot_vf = off(b.qdot_vf, N); o.qdot_ns = off(b.qdot_ns, N); o.qdot_jp = off(b.qdot_jp, N); o.qdot = off(b.qdot, N);
     o.cmd = off(b.cmd, N); o.pose = off(b.pose, 12); o.twist = off(b.twist, 6);
@@ -652,6 +666,8 @@ static int enqueue_cycle(vfk_session_s* s, const char* src_q, int k_cycles, char
     const size_t es = s->es;
     vfk_buffers b = s->b;
     b.jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
+    b.jp_lo = s->have_jp_lim ? s->d_jp_lo : nullptr;
+    b.jp_hi = s->have_jp_lim ? s->d_jp_hi : nullptr;
     b.ns_in = nullptr;                                          // offset separately below (4 or N components)
     if (!want_flags) b.flags = nullptr;
     if (!s->en_vf) b.qdot_vf = nullptr;
@@ -760,6 +776,8 @@ extern "C" int vfk_session_cycle(vfk_session s, const void* q_in, int k_cycles, 
     if (dq && (!qdot_out || dqd) && ((uintptr_t)dq % 16 == 0) && ((uintptr_t)dqd % 16 == 0)) {
         vfk_buffers b = s->b;
         b.jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
+    b.jp_lo = s->have_jp_lim ? s->d_jp_lo : nullptr;
+    b.jp_hi = s->have_jp_lim ? s->d_jp_hi : nullptr;
         b.ns_in = s->have_ns_in ? s->d_ns_in : nullptr;
         if (!flags_out) b.flags = nullptr;
         if (!s->en_vf) b.qdot_vf = nullptr;
@@ -883,6 +901,7 @@ extern "C" int vfk_session_read(vfk_session s, const char* what, void* out) {
     else if (!strcmp(what, "qdot")) src = s->b.qdot;
     else if (!strcmp(what, "cmd")) src = s->b.cmd;
     else if (!strcmp(what, "q")) src = s->b.q;
+    else if (!strcmp(what, "jp_ref")) src = s->d_jp_ref;
     else if (!strcmp(what, "lastvec")) { src = s->b.ns_lastvec; rows = (ns_ctrl_vectors(s->N) > 0 ? ns_ctrl_vectors(s->N) : 1) * s->N; }
     else if (!strcmp(what, "pose")) { src = s->b.pose; rows = 12; }
     else if (!strcmp(what, "twist")) { src = s->b.twist; rows = 6; }
@@ -900,6 +919,8 @@ extern "C" int vfk_session_buffers(vfk_session s, vfk_buffers* out) {
     if (!s || !out) return fail(s ? s->h : nullptr, VFK_ERR_INVALID, "vfk_session_buffers: null argument");
     *out = s->b;
     out->jp_ref = s->have_jp_ref ? s->d_jp_ref : nullptr;
+    out->jp_lo = s->have_jp_lim ? s->d_jp_lo : nullptr;
+    out->jp_hi = s->have_jp_lim ? s->d_jp_hi : nullptr;
     out->ns_in = s->have_ns_in ? s->d_ns_in : nullptr;
     return VFK_OK;
 }

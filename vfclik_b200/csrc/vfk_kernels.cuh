@@ -96,7 +96,9 @@ struct KArgs {
     const Vec4<T>* obst;       // pair-interleaved blocked [tile][Mp / 2][planes][32 x 16 B], Mp = M rounded up to even (ObstPairs)
     const Vec2<T>* obst_ext;   // blocked [tile][M][32] {safe, order} or null
     const T* aux;              // blocked [n_aux * 12] auxiliary field records or null
-    const T* jp_ref;
+    T* jp_ref;
+    const T* jp_lo;            // per-instance limits of the joint controller (both or neither), see vfk_buffers
+    const T* jp_hi;
     const T* ns_in;
     T* ns_lastvec;
     const T* q_cmded;
@@ -936,8 +938,11 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 bool all_reached = true;
     #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    T ref = (a.jp_ref && j < nc) ? __ldg(a.jp_ref + tN + j * 32) : c.jp_ref[j];
-                    ref = ref < c.q_lo[j] ? c.q_lo[j] : (ref > c.q_hi[j] ? c.q_hi[j] : ref);
+                    T ref = (a.jp_ref && j < nc) ? a.jp_ref[tN + j * 32] : c.jp_ref[j];
+                    const T lo = (a.jp_lo && j < nc) ? __ldg(a.jp_lo + tN + j * 32) : c.q_lo[j];
+                    const T hi = (a.jp_lo && j < nc) ? __ldg(a.jp_hi + tN + j * 32) : c.q_hi[j];
+                    ref = ref < lo ? lo : (ref > hi ? hi : ref);
+                    if (a.jp_lo && a.jp_ref && last && active && j < nc) a.jp_ref[tN + j * 32] = ref;      // the clamp persists
                     const T err = ref - q[j];
                     qd_jp[j] = err * c.jp_kp;
                     all_reached = all_reached && (err < c.jp_delta);

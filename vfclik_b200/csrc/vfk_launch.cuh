@@ -61,7 +61,7 @@ template <typename T>
 static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
     return c.tool_identity && c.unit_weights && c.share_factor && c.ns_mode == VFK_NS_PROJECTOR && !c.need_jp && !b->ns_in &&
            !c.shoulder_clamp &&
-           !b->jp_ref && !b->q_cmded && !b->ext_cmd[0] && !b->ext_cmd[1] && !b->ext_cmd[2] && !b->qdot_vf && !b->qdot_ns &&
+           !b->jp_ref && !b->jp_lo && !b->q_cmded && !b->ext_cmd[0] && !b->ext_cmd[1] && !b->ext_cmd[2] && !b->qdot_vf && !b->qdot_ns &&
            !b->qdot_jp && !b->cmd && !b->pose && !b->twist && !b->flags && !(b->aux && b->n_aux > 0) && b->qdot && !getenv("VFK_NO_LEAN");
 }
 
@@ -79,7 +79,9 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.obst_ext = static_cast<const Vec2<T>*>(b->obst_ext);
     a.aux = b->n_aux > 0 ? static_cast<const T*>(b->aux) : nullptr;
     a.n_aux = a.aux ? b->n_aux : 0;
-    a.jp_ref = static_cast<const T*>(b->jp_ref);
+    a.jp_ref = static_cast<T*>(b->jp_ref);
+    a.jp_lo = static_cast<const T*>(b->jp_lo);
+    a.jp_hi = static_cast<const T*>(b->jp_hi);
     a.ns_in = static_cast<const T*>(b->ns_in);
     a.ns_lastvec = static_cast<T*>(b->ns_lastvec);
     a.q_cmded = static_cast<const T*>(b->q_cmded);
@@ -118,9 +120,14 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #ifndef VFK_MINB_LEAN_BIG
 #define VFK_MINB_LEAN_BIG 2
 #endif
-    constexpr int MINB = (HIOCC ? VFK_MINB_LEAN_K1
-                                : ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : (LEAN ? VFK_MINB_LEAN_BIG : 2))
-                                                    : (N <= 7 ? VFK_MINB_F64 : 1))) * (128 / kBlock);
+    constexpr int MINB0 = (HIOCC ? VFK_MINB_LEAN_K1
+                                 : ((sizeof(T) == 4) ? (N <= 10 ? (LEAN ? VFK_MINB_LEAN : VFK_MINB_F32) : (LEAN ? VFK_MINB_LEAN_BIG : 2))
+                                                     : (N <= 7 ? VFK_MINB_F64 : 1))) * (128 / kBlock);
+#ifdef VFK_MINB_LEAN_BIG_ABS          // experiment: resident CTAs of kBlock threads for the long-chain lean FP32 kernel, as given
+    constexpr int MINB = (sizeof(T) == 4 && N > 10 && LEAN) ? VFK_MINB_LEAN_BIG_ABS : MINB0;
+#else
+    constexpr int MINB = MINB0;
+#endif
     auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB, G>;
     // per (instantiation, device, smem size): opt in to > 48 KB of dynamic shared memory and ask the occupancy once
     static PlanCache plans;

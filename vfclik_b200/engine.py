@@ -113,7 +113,7 @@ def round_up(n: int, m: int = 32) -> int:
     return (int(n) + m - 1) // m * m
 
 
-_BUF_FIELDS = ("q", "goal", "obst", "obst_ext", "aux", "jp_ref", "ns_in", "ns_lastvec", "q_cmded", "qdot_vf", "qdot_ns", "qdot_jp",
+_BUF_FIELDS = ("q", "goal", "obst", "obst_ext", "aux", "jp_ref", "jp_lo", "jp_hi", "ns_in", "ns_lastvec", "q_cmded", "qdot_vf", "qdot_ns", "qdot_jp",
                "qdot", "cmd", "pose", "twist", "flags")
 
 
@@ -338,6 +338,15 @@ class Session:
         else:
             a = self._arr(ref, self.e.n_joints)
             self.e._check(self.e._lib.vfk_session_set_jp_ref(self._s, _lib.np_ptr(a)))
+
+    def set_jp_limits(self, lo, hi):
+        """Per-instance limits the joint controller clamps its reference into (``config.updateJntLimits(q)`` evaluated per
+        instance, ``scripts/joint_p_controller:79-89``), ``[N, n]`` each; ``None, None`` -> the chain's static limits."""
+        if lo is None or hi is None:
+            self.e._check(self.e._lib.vfk_session_set_jp_limits(self._s, None, None))
+        else:
+            a, b = self._arr(lo, self.e.n_joints), self._arr(hi, self.e.n_joints)
+            self.e._check(self.e._lib.vfk_session_set_jp_limits(self._s, _lib.np_ptr(a), _lib.np_ptr(b)))
 
     def set_ns_input(self, x):
         if x is None:
