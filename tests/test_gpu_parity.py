@@ -10,7 +10,7 @@ import dataclasses
 import numpy as np
 import pytest
 
-from helpers import oracle_params, rel_err, to_oracle
+from helpers import oracle_parallel, oracle_params, rel_err, to_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -111,26 +111,39 @@ def test_fp32_cycle_matches_oracle(eng, lwr, n):
 
 @pytest.mark.parametrize("precision,traj_tol", [(64, 1e-9), (32, 2e-3)])
 def test_k_cycle_trajectory(eng, lwr, precision, traj_tol):
-    """K fused cycles == K oracle cycles: final q within the stated joint-space tolerance."""
+    """K fused cycles == K oracle cycles: final q within the stated joint-space tolerance (1e-9 rad FP64, 2e-3 rad FP32 after
+    50 cycles).  The cycle has two discontinuities -- the all-or-nothing nullspace limit check and the velocity clamp -- so in
+    FP32 an instance within rounding of a threshold may take the other branch in some cycle.  Those instances are identified
+    by comparing the per-cycle flags; the tolerance is asserted as a MAX over every instance whose flags agree in all 50
+    cycles, every outlier must be one of the flag-mismatch instances, and those must stay rare."""
     from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch
+    from oracle import batch
     chain, _ = lwr
     e = eng(precision)
-    w = workloads.random_batch(chain, 2048, 8, seed=2, dtype=np.float32 if precision == 32 else np.float64)
-    out = run_gpu(e, w, 8, k=50)
-    ref = run_oracle(chain, e.params, w, 8, k=50)
-    err = np.max(np.abs(out["q"] - ref["q"]), axis=1)
-    if precision == 64:
-        assert err.max() <= traj_tol
-    else:
-        # FP32: a handful of instances sit on a discontinuity (all-or-nothing limit check, clamp); bound the bulk
-        assert np.quantile(err, 0.995) <= traj_tol, float(np.quantile(err, 0.995))
-    # K launches of 1 cycle == 1 launch of K cycles (state round-trips HBM bit-exactly)
-    from vfclik_b200.engine import DeviceBatch
-    db = DeviceBatch(e, 2048, 8, outputs=("qdot",))
+    n, M, K = 2048, 8, 50
+    w = workloads.random_batch(chain, n, M, seed=2, dtype=np.float32 if precision == 32 else np.float64)
+    out = run_gpu(e, w, M, k=K)
+    # cycle by cycle on both sides, flags recorded
+    db = DeviceBatch(e, n, M, outputs=("qdot", "flags"))
     db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
-    for _ in range(50):
+    q_o, goal_o, obst_o = to_oracle(w, M)
+    prm = oracle_params(e.params)
+    mismatch = np.zeros(n, dtype=bool)
+    for _ in range(K):
         db.step(1)
-    assert np.array_equal(db.download("q").T, out["q"])
+        o = batch.step(chain, prm, q_o, goal_o, obst_o)
+        q_o = o["q"]
+        mismatch |= db.download("flags")[0] != o["flags"]
+    q_gpu = db.download("q").T
+    assert np.array_equal(q_gpu, out["q"])                  # K launches of 1 cycle == 1 launch of K cycles (bit-exact)
+    err = np.max(np.abs(q_gpu - q_o), axis=1)
+    if precision == 64:
+        assert not mismatch.any() and err.max() <= traj_tol
+    else:
+        assert err[~mismatch].max() <= traj_tol, float(err[~mismatch].max())
+        assert np.all(mismatch[err > traj_tol])             # every outlier took a different branch somewhere
+        assert mismatch.mean() < 0.02, float(mismatch.mean())
 
 
 @pytest.mark.parametrize("ns_mode", [0, 1, 2])
@@ -617,8 +630,8 @@ def test_auxiliary_fields_types_4_and_5(eng, lwr, precision):
 
 
 def test_full_size_config3_properties_and_sampled_oracle(lwr, built_lib):
-    """BASELINE configs[2] at full size (1,048,576 instances, 32 obstacles, FP32, nullspace on): the oracle on a
-    random sample of 16,384 instances plus size-independent properties on the whole batch -- permutation equivariance,
+    """BASELINE configs[2] at full size (1,048,576 instances, 32 obstacles, FP32, nullspace on): the oracle on ALL
+    instances (1e-4), flags on a sample, plus size-independent properties on the whole batch -- permutation equivariance,
     an empty obstacle slot changes nothing, K launches == one launch of K cycles, output finiteness and the clamp bound."""
     import torch
     from vfclik_b200 import workloads
@@ -636,13 +649,18 @@ def test_full_size_config3_properties_and_sampled_oracle(lwr, built_lib):
         q1 = db.download("q")
         assert np.all(np.isfinite(qd)) and np.max(np.abs(qd)) <= cfg.max_vel * (1 + 1e-6)
         assert np.allclose(q1, w["q"] + np.float32(cfg.rate) * qd, rtol=0, atol=5e-7)      # explicit Euler (fma vs mul+add: 1 ulp at |q| ~ 3)
-        # sampled oracle parity
+        # oracle parity on EVERY instance (the vectorised oracle fanned over the host cores), flags on a sample
+        ref = oracle_parallel(chain, e.params, w, M, keys=("qdot", "flags"))
+        err = rel_err(qd.T.astype(np.float64), ref["qdot"])
+        assert err.max() <= FP32_RTOL, (float(err.max()), int(np.argmax(err)))
         rng = np.random.default_rng(5)
         idx = np.sort(rng.choice(n, size=16384, replace=False))
         sub = dict(q=w["q"][:, idx], goal=w["goal"][:, idx], obst=np.ascontiguousarray(w["obst"][:, idx]))
-        ref = run_oracle(chain, e.params, sub, M)
-        err = rel_err(qd[:, idx].T.astype(np.float64), ref["qdot"])
-        assert err.max() <= FP32_RTOL, float(err.max())
+        gen = run_gpu(e, sub, M, outputs=("qdot", "flags"))          # the general instantiation writes the flags
+        fl_ref = ref["flags"][idx]
+        differ = gen["flags"] != fl_ref
+        assert differ.mean() < 1e-3, float(differ.mean())
+        assert rel_err(gen["qdot"].astype(np.float64), ref["qdot"][idx]).max() <= FP32_RTOL
         # permutation equivariance (bit-exact): instance order carries no information
         perm = rng.permutation(n)
         dbp = DeviceBatch(e, n, M, outputs=("qdot",))
@@ -861,6 +879,9 @@ def test_full_size_config4_and_config5_shards(lwr, built_lib, which):
         ref = run_oracle(chain, e.params, sub, M)
         err = rel_err(qd[:, idx].T.astype(np.float64), ref["qdot"])
         assert err.max() <= FP32_RTOL, float(err.max())
+        gen = run_gpu(e, sub, M, outputs=("qdot", "flags"))          # flags come from the general instantiation
+        assert (gen["flags"] != ref["flags"]).mean() < 2e-3
+        assert rel_err(gen["qdot"].astype(np.float64), ref["qdot"]).max() <= FP32_RTOL
         assert qd.shape == (N, n)
     finally:
         e.close()
