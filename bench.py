@@ -52,6 +52,20 @@ def algorithmic_bytes(n_joints: int, n_obst: int, elem: int) -> int:
     return elem * (3 * n_joints + 13 + 4 * n_obst)
 
 
+def kernel_source_stamp() -> str:
+    """sha256 over the CUDA sources and the ABI header the library is built from (with the compiler version): what a
+    profile-derived constant (``profiles/traffic.json``) is stamped with, so that a number measured on other kernels is
+    recognised as stale instead of being reported."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(ROOT, "vfclik_b200", "csrc", "*.cu*"))) + [os.path.join(ROOT, "include", "vfk.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 # ----------------------------------------------------------------------------------------- clocks
 
 class ClockSampler:
@@ -250,7 +264,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--kcycles", type=int, default=1, help="control cycles fused per launch (per step)")
     ap.add_argument("--instances", type=int, default=0, help="override instances per GPU")
-    ap.add_argument("--cpu-cycles", type=int, default=150, help="CPU arm: control cycles per core per step")
+    ap.add_argument("--cpu-cycles", type=int, default=1000, help="CPU arm: control cycles per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the K-fused and FP64 side measurements")
     args = ap.parse_args()
@@ -360,15 +374,32 @@ def main():
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, "no ncu capture on record for this workload"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.workload in tj:
+            if tj.get(args.workload + "_stamp") == kernel_source_stamp():
+                traffic, traffic_note = tj[args.workload], tj.get(args.workload + "_source")
+            else:
+                traffic_note = "stale: profiles/traffic.json was measured on other kernel sources (stamp %s, now %s)" % (
+                    tj.get(args.workload + "_stamp"), kernel_source_stamp())
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
+                "traffic": traffic, "traffic_source": traffic_note, "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_instance": algorithmic_bytes(N, n_obst, elem),
                 "kernel": "vfk_cycle_kernel<%s,%d>" % ("float" if precision == 32 else "double", N)}
+
+    # ---- sustained: >= 1000 back-to-back launches (where sw_power_cap, if the box has it, has had time to act), own clock record
+    if not args.no_extras:
+        sus_steps = max(1000, args.steps)
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        ms_sus = timed(lambda: step_rotating(args.kcycles), sus_steps) / sus_steps
+        clocks2 = sampler2.stop() if rank == 0 else None
+        ach2 = bytes_per_launch / (ms_sus * 1e-3) / 1e9
+        roofline["sustained"] = {"launches": sus_steps, "ms_per_step": ms_sus, "achieved": ach2, "frac": ach2 / peak_gbs, "clocks": clocks2}
 
     # ---- end-to-end arm: host buffers through the C-ABI session (H2D q + D2H qdot every step)
     e2e, e2e_launches = None, 0
@@ -464,7 +495,7 @@ def main():
                                              "peak_source": "profiles/r01_pipe_peaks.json (scripts/peaks.cu)"}
         except Exception as exc:      # the headline line must not depend on a side measurement
             extras["k_fused"]["roofline"] = {"error": str(exc)}
-        if args.workload == "config3" and world == 1:
+        if args.workload == "config3":
             n2, m2 = WORKLOADS["config2"][0], WORKLOADS["config2"][1]
             e64 = Engine(chain, precision=64, device=local_rank, params=params)
             w2 = workloads.random_batch(chain, n2, m2, seed=0)
@@ -484,13 +515,34 @@ def main():
             reps = 6
             ms2 = timed(lambda: [dc.step(1) for dc in copies], reps) / (reps * len(copies))
             b2 = algorithmic_bytes(N, m2, 8) * n2
-            extras["fp64_config2"] = {"instances": n2, "value": n2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_launch": ms2,
+            extras["fp64_config2"] = {"instances_per_gpu": n2, "value": world * n2 / (ms2 * 1e-3), "unit": UNIT, "ms_per_launch": ms2,
                                       "l2": "launches rotate over 7 copies of the batch (594 MB): inputs come from HBM",
                                       "roofline": {"bound": "hbm", "achieved": b2 / (ms2 * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                                                    "frac": b2 / (ms2 * 1e-3) / 1e9 / peak_gbs}}
-            for dc in copies[1:]:
-                del dc
+            del copies, d2
             e64.close()
+            torch.cuda.empty_cache()
+
+            # BASELINE configs[3] and configs[4] at their per-GPU shard size on 8 GPUs (2 M x 256 obstacles; 512 k x 17-DOF x 64
+            # obstacles), drawn on the device: every rank runs its shard, whatever N is, so the scaling run reports them too
+            for wname in ("config4", "config5"):
+                n4, m4, p4, d4 = WORKLOADS[wname]
+                ch4 = workloads.dual_arm_torso_chain() if wname == "config5" else chain
+                e4 = Engine(ch4, precision=p4, device=local_rank, params=params if wname == "config4" else Params())
+                db4 = workloads.random_batch_device(e4, n4, m4, seed=2 + rank if wname == "config4" else 3 + rank)
+                for _ in range(3):
+                    db4.step(1)
+                st4 = 30
+                ms4 = timed(lambda: db4.step(1), st4) / st4
+                b4 = algorithmic_bytes(ch4.n_joints, m4, 4) * n4
+                extras[wname] = {"workload": d4, "instances_per_gpu": n4, "value": world * n4 / (ms4 * 1e-3), "unit": UNIT, "ms_per_launch": ms4,
+                                 "chain_pattern": e4.chain_pattern,
+                                 "roofline": {"bound": "hbm", "achieved": b4 / (ms4 * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                                              "frac": b4 / (ms4 * 1e-3) / 1e9 / peak_gbs,
+                                              "algorithmic_bytes_per_instance": algorithmic_bytes(ch4.n_joints, m4, 4)}}
+                del db4
+                e4.close()
+                torch.cuda.empty_cache()
 
         if world == 1 and args.workload == "config3":
             # BASELINE configs[0] on the GPU: ONE LWR, the reference's first goal, 3 obstacles, 1000 control cycles fused
@@ -518,18 +570,21 @@ def main():
                 os.sched_setaffinity(0, all_cpus)        # the CPU arm uses every core of the box, not only the GPU's NUMA node
             arm = CpuArm(n_obst)
             arm.step(20)                       # warm the pool (imports)
-            c, t = arm.step(args.cpu_cycles * 4)
+            c, t = arm.step(max(1000, args.cpu_cycles))
             arm.close()
             cpu_baseline = {"value": c / t, "unit": UNIT, "cores": arm.cores, "kind": "port",
                             "sample": "%d cores x %d control cycles of one instance each (oracle/refshape.py, 7-DOF, %d obstacles, FP64)"
-                                      % (arm.cores, args.cpu_cycles * 4, n_obst),
+                                      % (arm.cores, max(1000, args.cpu_cycles), n_obst),
                             "vectorised_numpy_1core": cpu_vectorised(n_obst)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if precision == 32 else "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "instances_per_gpu": n_inst, "n_joints": N,
-                       "n_obstacles": n_obst, "kcycles_per_step": args.kcycles, "parallelism": "instances sharded x%d, no collective" % world,
+                       "n_obstacles": n_obst, "kcycles_per_step": args.kcycles,
+                       "precision_note": ("FP32 mode is mixed precision: everything that touches HBM and the whole field / IK / nullspace is FP32, "
+                                          "the kinematic chain (sin, cos, frame products) runs in FP64 (DESIGN.md section 2)") if precision == 32
+                                         else "FP64 throughout", "parallelism": "instances sharded x%d, no collective" % world,
                        "l2": "inputs per launch (%.0f MB) exceed the 126 MB L2" % (bytes_per_launch / 1e6)
                              if n_rot == 1 else "launches rotate over %d independent copies of the batch (%.0f MB in all, > 3x the 126 MB L2): "
                                                 "no launch finds its inputs in L2" % (n_rot, n_rot * bytes_per_launch / 1e6)},

@@ -37,6 +37,9 @@ tj = os.path.join(pr, "traffic.json")
 d = json.load(open(tj)) if os.path.exists(tj) else {}
 d[workload] = traffic
 d[workload + "_source"] = "%s_ncu_full_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches" % (tag, len(rd))
+sys.path.insert(0, root)
+import bench  # noqa: E402  (kernel_source_stamp: the sources this capture was taken on)
+d[workload + "_stamp"] = bench.kernel_source_stamp()
 json.dump(d, open(tj, "w"), indent=1)
 dur, du = col("gpu__time_duration.sum")
 dur = [x * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(du, 1.0) for x in dur]      # microseconds
