@@ -677,6 +677,31 @@ def gen_bridge_loop(rng):
             "bl_cfg": np.array([cfg.max_vel])}
 
 
+def gen_bridge_readpos(rng=None):
+    """``LWR_Bridge.read_pos`` (``scripts/bridge:163-180``) executed without any ``/cmded`` feedback, as in ``bridge -s`` where
+    that port is never connected (``:136-139``): ``last_qcmded`` is set ONCE, to the first measured q (the same list object),
+    and never follows q afterwards, so the non-direct command ``-q_cmded + q + qdot`` carries ``q - q_first``.  Pinned here
+    so that the deviation this repo's bridge makes in simulation (it refreshes q_cmded every cycle) is a
+    documented choice and its feedback-less real-robot path is checked against the reference (own seed)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from vfclik_b200 import ports as yarp
+    rng = np.random.default_rng(20261020)
+    N, steps = 7, 5
+    glb = {}
+    exec(load_reference_function("scripts/bridge", "ut_bottle2list"), glb)
+    ns = {}
+    exec(load_reference_function("scripts/bridge", "read_pos", cls="LWR_Bridge"), glb, ns)
+    qin, qcmded = ScriptIn(), ScriptIn()
+    bridge = types.SimpleNamespace(nJoints=N, last_q=N * [0.0], last_qcmded=[], torso_joints=[], qin_port=qin, qcmded_port=qcmded)
+    q = rng.uniform(-1, 1, size=(steps, N))
+    seen_q, seen_c = [], []
+    for k in range(steps):
+        qin.q.append(yarp.Bottle.from_list([float(v) for v in q[k]]))
+        seen_q.append(list(ns["read_pos"](bridge)))
+        seen_c.append(list(bridge.last_qcmded))
+    return {"rp_q": q, "rp_last_q": np.asarray(seen_q), "rp_last_qcmded": np.asarray(seen_c)}
+
+
 def gen_dmonitor(rng):
     """``scripts/monitor_distance``'s loop body (:107-221) with its own ``orientLength`` (:76-84); PyKDL ``Frame`` / ``diff``
     and ``vfl.length`` replaced by the oracle's stand-ins.  One iteration per scripted step: objects, the tool pose and the
@@ -897,6 +922,7 @@ def main():
     data.update(gen_nullspace_loop(rng))
     data.update(gen_handlers())
     data.update(gen_nullspace_wide())
+    data.update(gen_bridge_readpos())
     path = os.path.join(OUT_DIR, "reference_vectors.npz")
     np.savez_compressed(path, **data)
     print("wrote", path, {k: v.shape for k, v in data.items()})

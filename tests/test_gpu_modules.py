@@ -588,6 +588,35 @@ def test_bridge_module_matches_the_reference_main_loop(lwr, golden, built_lib, f
     capsys.readouterr()
 
 
+def test_bridge_read_pos_without_cmded_feedback(lwr, golden, built_lib, fresh_ports, capsys):
+    """``LWR_Bridge.read_pos`` with no ``/cmded`` feedback (tests/golden rp_*: the reference's own method executed): the
+    commanded position is taken from the FIRST measured q and then kept.  The real-robot path of this repo's bridge does the
+    same; in simulation (``sim=True``) it deliberately follows q instead (with the reference's rule the
+    non-direct command ``-q_cmded + q + qdot`` sent to the simulated plant as a velocity would carry the whole displacement
+    since start-up)."""
+    import copy
+    from vfclik_b200.bridge import BridgeModule
+    from vfclik_b200.runtime import ControlRuntime
+    _, cfg = lwr
+    g = golden
+    for sim in (False, True):
+        rt = ControlRuntime(copy.copy(cfg), n_instances=1, precision=64)
+        ns = "/8" if sim else "/9"
+        base = ns + cfg.robotarm_portbasename
+        br = BridgeModule(rt, ns, sim=sim)
+        try:
+            feed = _out_port(fresh_ports, ns + "/feed/pos", br.qin_port.getName())
+            for k in range(g["rp_q"].shape[0]):
+                fresh_ports.sendListPort(feed, [float(v) for v in g["rp_q"][k]])
+                q = br.read_pos()
+                assert np.array_equal(q, g["rp_last_q"][k])
+                want = g["rp_q"][k] if sim else g["rp_last_qcmded"][k]
+                assert np.array_equal(br.last_qcmded, want), (sim, k)
+        finally:
+            br.close(); rt.close()
+    capsys.readouterr()
+
+
 def test_nullspace_module_matches_the_reference_main_loop(lwr, golden, built_lib, fresh_ports, capsys):
     """/nullspace/qdotout against the reference's own main loop body (scripts/nullspace:159-187) running its own
     restrict / nullspace / move_in_nullspace / check_limits on the oracle's Lafik stand-in: the four-float control interface,

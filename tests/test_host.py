@@ -303,3 +303,133 @@ def test_handlers_send_what_the_reference_handlers_send(golden, capsys):
             assert got.pop("/bridge/weight") == got["/bridge/weights"]
         assert got == exp, (label, got, exp)
     capsys.readouterr()
+
+
+def test_injected_transport():
+    """Row f4: the host modules' ports come from ``ArcosYarp``, which creates and connects them through the transport chosen
+    with ``ports.use_transport`` -- the real ``yarp`` module where it exists (it does not in this image).  A duck-typed
+    stand-in with its OWN port class, bottle class and connection table proves nothing falls through to the in-process
+    registry: naming, direction of the links, strictness, and the list helpers all go through the injected objects."""
+    import types
+    from vfclik_b200 import ports
+
+    calls = {"open": [], "connect": [], "strict": []}
+
+    class Val:
+        def __init__(self, v):
+            self.v = v
+
+        def asDouble(self):
+            return float(self.v)
+
+        def asInt(self):
+            return int(self.v)
+
+        def asString(self):
+            return str(self.v)
+
+        def asList(self):
+            return self.v
+
+    class FBottle:
+        def __init__(self):
+            self.v = []
+
+        def clear(self):
+            self.v = []
+
+        def addDouble(self, x):
+            self.v.append(float(x))
+
+        def addInt(self, x):
+            self.v.append(int(x))
+
+        def addString(self, x):
+            self.v.append(str(x))
+
+        def addList(self):
+            b = FBottle()
+            self.v.append(b)
+            return b
+
+        def size(self):
+            return len(self.v)
+
+        def get(self, i):
+            return Val(self.v[i])
+
+    wires, inbox = {}, {}
+
+    class FPort:
+        __slots__ = ("name", "out")                      # like a SWIG proxy: no foreign attributes
+
+        def __init__(self):
+            self.name, self.out = None, FBottle()
+
+        def open(self, name):
+            self.name = name
+            calls["open"].append(name)
+            inbox[name] = []
+            return True
+
+        def close(self):
+            inbox.pop(self.name, None)
+
+        def getName(self):
+            return self.name
+
+        def setStrict(self, strict=True):
+            calls["strict"].append((self.name, bool(strict)))
+
+        def prepare(self):
+            return self.out
+
+        def write(self, force=False):
+            for dst in wires.get(self.name, []):
+                b = FBottle()
+                b.v = list(self.out.v)
+                inbox[dst].append(b)
+
+        writeStrict = write
+
+        def read(self, wait=True):
+            q = inbox[self.name]
+            return q.pop(0) if q else None
+
+    class FNetwork:
+        @staticmethod
+        def connect(src, dst, style=None):
+            calls["connect"].append((src, dst))
+            if dst not in wires.setdefault(src, []):        # connecting twice is a no-op, as in YARP
+                wires[src].append(dst)
+            return True
+
+        @staticmethod
+        def isConnected(src, dst):
+            return dst in wires.get(src, [])
+
+    fake = types.SimpleNamespace(BufferedPortBottle=FPort, Network=FNetwork, Bottle=FBottle)
+    ports.Network.reset()
+    ports.use_transport(fake)
+    try:
+        assert ports.transport() is fake
+        a = ports.ArcosYarp(ports_name_prefix="/0", module_name_prefix="/lwr/right/vectorField")
+        b = ports.ArcosYarp(ports_name_prefix="/0", module_name_prefix="/lwr/right/bridge")
+        out = a.create_yarp_port("/qdotOut", input_port=False)
+        inp = b.create_yarp_port("/vectorfieldcmd", strict=False)
+        assert isinstance(out, FPort) and isinstance(inp, FPort)
+        assert calls["open"] == ["/0/lwr/right/vectorField/qdotOut", "/0/lwr/right/bridge/vectorfieldcmd"]
+        assert calls["strict"] == [("/0/lwr/right/bridge/vectorfieldcmd", False)]
+        a.connect(out, "/lwr/right/bridge", "/vectorfieldcmd")           # an output port writes TO the remote
+        b.connect(inp, "/lwr/right/vectorField", "/qdotOut")             # an input port reads FROM it: same wire
+        assert calls["connect"] == [("/0/lwr/right/vectorField/qdotOut", "/0/lwr/right/bridge/vectorfieldcmd")] * 2
+        assert a.is_ready() and b.is_ready()
+        ports.sendListPort(out, [0.1, -0.2, 0.3])
+        assert ports.readListPort(inp) == [0.1, -0.2, 0.3]
+        ports.write_bottle_lists(out, ["add", 7, -10.0, 2, [0.5, 0.25, 1.0, 0.05, 0.001, 20]])
+        got = inp.read(False)
+        assert got.get(0).asString() == "add" and got.get(1).asInt() == 7 and got.get(4).asList().v == [0.5, 0.25, 1.0, 0.05, 0.001, 20.0]
+        assert not ports.Network.exists("/0/lwr/right/vectorField/qdotOut")     # the in-process registry never saw these ports
+    finally:
+        ports.use_transport(None)
+    assert ports.transport() is ports

@@ -296,6 +296,7 @@ def test_golden_is_reproducible_from_reference(golden):
     data.update(gen_golden.gen_nullspace_loop(rng))
     data.update(gen_golden.gen_handlers())
     data.update(gen_golden.gen_nullspace_wide())
+    data.update(gen_golden.gen_bridge_readpos())
     for k, v in data.items():
         if np.asarray(v).dtype.kind in "US":
             assert [str(x) for x in v] == [str(x) for x in golden[k]], k

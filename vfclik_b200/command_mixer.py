@@ -52,6 +52,8 @@ class CommandMixer:
 
     # -- device side -------------------------------------------------------------------------
     def _mix_on_device(self) -> List[float]:
+        """One ``vfk_mix`` launch: the single instance's tile-blocked arrays (element (c, 0) at ``c * 32``) are laid out on
+        the host, so the call is one H2D copy, one kernel, one D2H copy."""
         import torch
         e = self._engine or _utility_engine()
         P, n = len(self.ports), self.nChannels
@@ -59,16 +61,13 @@ class CommandMixer:
             raise ValueError("vfk_mix takes at most 8 command ports, got %d" % P)
         if self._dev is None or self._dev[0] is not e:
             dev = "cuda:%d" % e.device
-            self._dev = (e, torch.empty((P * n, 1), dtype=e.torch_dtype, device=dev),
-                         [e.alloc(n, 1) for _ in range(P)], e.alloc(n, 1), torch.empty((n, 1), dtype=e.torch_dtype, device=dev))
-        _, dense, blocked, out_b, out_d = self._dev
-        host = np.asarray(self.last_command, dtype=e.np_dtype).reshape(P * n, 1)
-        dense.copy_(torch.from_numpy(host))
-        for p in range(P):
-            e.pack(dense[p * n:(p + 1) * n], blocked[p], n, 1, 1)
-        e.mix(blocked, self.weights, out_b, n, 1)
-        e.unpack(out_b, out_d, n, 1, 1)
-        return [float(v) for v in out_d[:, 0].cpu().numpy()]
+            self._dev = (e, np.zeros((P, n, 32), dtype=e.np_dtype), torch.zeros((P, n, 32), dtype=e.torch_dtype, device=dev),
+                         torch.zeros((n, 32), dtype=e.torch_dtype, device=dev))
+        _, host, blocked, out_b = self._dev
+        host[:, :, 0] = np.asarray(self.last_command, dtype=e.np_dtype)
+        blocked.copy_(torch.from_numpy(host))
+        e.mix([blocked[p] for p in range(P)], self.weights, out_b, n, 1)
+        return [float(v) for v in out_b[:, 0].cpu().numpy()]
 
     # -- reference interface -----------------------------------------------------------------
     def read(self) -> List[float]:

@@ -5,8 +5,19 @@ The reference glues its modules with YARP ports (``yarp.BufferedPortBottle``,
 312-315,462-466``).  ``yarp`` is not installed here and the batched runtime lives in one
 process, so this module provides the same names with an in-process registry:
 ``Network.connect(src, dst)`` wires an output port to input ports, ``write()`` delivers a
-copy of the prepared bottle.  If a real ``yarp`` is importable a user can pass it to the
-host modules instead (they only use the calls implemented here).
+copy of the prepared bottle.
+
+Using a real YARP (row f4 of SURVEY.md section 8): every port the host modules own is created by
+``ArcosYarp.create_yarp_port`` and wired by ``ArcosYarp.connect``, and both go through the
+*transport* selected here.  ``use_transport(yarp)`` -- with the imported ``yarp`` python
+module, or anything with the same surface -- makes them create ``yarp.BufferedPortBottle``
+objects and call ``yarp.Network.connect``; the modules themselves only use the bottle / port
+calls this file implements (``read(False)``, ``prepare``, ``write``, ``writeStrict``, ``size``,
+``get(i).asDouble / asInt / asString / asList``, ``clear``, ``addDouble / addInt / addString /
+addList``), so nothing else changes.  ``use_transport(None)`` returns to the in-process
+registry.  ``yarp`` is not installed in this image, so the adapter is exercised by a
+duck-typed stand-in (``tests/test_host.py::test_injected_transport``); against a real
+``yarp`` it is untested.
 
 Semantics kept from YARP: non-strict input ports keep only the newest unread bottle
 (``read(False)`` returns it once, then ``None``); strict ports queue; ``read(True)`` on an
@@ -127,6 +138,22 @@ class _Registry:
 
 
 _REG = _Registry()
+
+
+_TRANSPORT = None          # None: the in-process classes of this module
+
+
+def use_transport(module=None):
+    """Select what ``ArcosYarp`` creates ports with and connects them through: ``module.BufferedPortBottle`` and
+    ``module.Network`` (e.g. the real ``yarp`` python module); ``None`` restores the in-process registry."""
+    global _TRANSPORT
+    _TRANSPORT = module
+
+
+def transport():
+    """The module ports are created from (this one unless ``use_transport`` chose another)."""
+    import sys
+    return _TRANSPORT if _TRANSPORT is not None else sys.modules[__name__]
 
 
 class ContactStyle:
@@ -261,7 +288,10 @@ def write_bottle_lists(port: BufferedPortBottle, items, strict: bool = False):
         if isinstance(x, (list, tuple)):
             sub = b.addList()
             for y in x:
-                sub.items.append(float(y) if isinstance(y, (int, float)) and not isinstance(y, bool) else y)
+                if isinstance(y, (int, float)) and not isinstance(y, bool):
+                    sub.addDouble(float(y))
+                else:
+                    sub.addString(y)
         elif isinstance(x, bool):
             b.addInt(int(x))
         elif isinstance(x, int):
@@ -286,11 +316,12 @@ class ArcosYarp:
         self.module = module_name_prefix
         self._ports = []
         self._wanted = []
+        self._is_input = {}
 
     def create_yarp_port(self, name: str, input_port: bool = True, strict: bool = True) -> BufferedPortBottle:
-        p = BufferedPortBottle()
+        p = transport().BufferedPortBottle()
         p.open(self.prefix + self.module + name)
-        p.is_input = input_port
+        self._is_input[id(p)] = input_port                 # kept here, not on the port: a SWIG proxy need not take attributes
         if input_port:
             p.setStrict(strict)
         self._ports.append(p)
@@ -298,12 +329,12 @@ class ArcosYarp:
 
     def connect(self, port: BufferedPortBottle, remote_module: str, remote_port: str, necessary: bool = True):
         remote = self.prefix + remote_module + remote_port
-        src, dst = (remote, port.getName()) if getattr(port, "is_input", True) else (port.getName(), remote)
-        Network.connect(src, dst)
+        src, dst = (remote, port.getName()) if self._is_input.get(id(port), True) else (port.getName(), remote)
+        transport().Network.connect(src, dst)
         self._wanted.append((src, dst, necessary))
 
     def is_ready(self) -> bool:
-        return all(Network.isConnected(s, d) for s, d, nec in self._wanted if nec)
+        return all(transport().Network.isConnected(s, d) for s, d, nec in self._wanted if nec)
 
     def update(self):
         pass
