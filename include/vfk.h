@@ -85,6 +85,14 @@ enum { VFK_NS_OFF = 0,           /* --no_nullspace (scripts/vfclik:73-79) */
                                     gain * check(sum_{i < min(4, k)} control_i u_i), u_i an orthonormal basis of null(J),
                                     k = N - 6 vectors, each kept sign-continuous from cycle to cycle.  Any N; ns_lambda unused. */
 
+/* Velocity IK behind Lafik.getIKV (scripts/vf:461).  The solver itself is un-vendored (KDL through arcospyu):
+ *   DLS        north_star's form, qdot = Wj Jw^T (Jw Jw^T + lambda^2 I)^-1 Wt t -- every singular value damped; both precisions
+ *   TRUNCATED  qdot = Wj V diag(f(sigma)) U^T Wt t with f = 1 / sigma for sigma >= ik_eps and sigma / (sigma^2 + lambda^2) below
+ *              -- how KDL's ChainIkSolverVel_wdls is recalled to treat lambda (a plain weighted pseudo-inverse away from
+ *              singularities); one-sided Jacobi SVD of Jw in the kernel, precision 64 only.  Provided so that a comparison
+ *              against a real Lafik, should one become available, is one flag away. */
+enum { VFK_IK_DLS = 0, VFK_IK_TRUNCATED = 1 };
+
 /* Robot back-end whose set_vel() the clamp / command step restates:
  *   LWR       leading-joint clamp; cmd = qdot_lim (direct) or -q_cmded + q + qdot_lim      (scripts/bridge:182-210)
  *   POWERCUBE leading-joint clamp, then the shoulder-speed clamp of joint 0.  Bug-compatible: the reference reuses one
@@ -134,10 +142,13 @@ typedef struct vfk_params {
     double ns_control[4];        /* used in VFK_NS_CONTROL when vfk_buffers.ns_in == NULL */
     double shoulder_vel[2];      /* VFK_BRIDGE_POWERCUBE: config.max_vel_shoulder_pos (> 0), max_vel_shoulder_neg (< 0)
                                     (scripts/bridge:296-303) */
+    double ik_eps;               /* VFK_IK_TRUNCATED: singular values below this are damped, the rest inverted plainly */
     int32_t ns_mode;             /* VFK_NS_* */
     int32_t direct_control;      /* -1: auto = all mixer weights zero (scripts/bridge:604); 0 / 1 force */
     int32_t integrate;           /* 1: q += dt * qdot_lim after every cycle (simulation plant) */
     int32_t bridge_kind;         /* VFK_BRIDGE_*: which set_vel the clamp / command step follows */
+    int32_t ik_mode;             /* VFK_IK_*: form of the velocity IK (scripts/vf:461, Lafik.getIKV) */
+    int32_t reserved;
 } vfk_params;
 
 /* Device buffers of one vfk_step() call, all in the tile-blocked layout above

@@ -169,6 +169,38 @@ def test_nullspace_modes_fp64(eng, lwr, ns_mode):
         e.set_params(old)
 
 
+def test_ik_mode_truncated_fp64(lwr, built_lib):
+    """VFK_IK_TRUNCATED: the KDL-wdls-style velocity IK (plain weighted pseudo-inverse above ik_eps, damped below; see
+    ORACLE_CHOICES 'velocity IK vs KDL') through the kernel's one-sided Jacobi SVD against the oracle's numpy SVD, unit and
+    non-unit weights, at the FP64 tolerance; FP32 refuses it."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import Engine, Params, VfkError
+    chain, cfg = lwr
+    e = Engine(chain, precision=64, params=Params.from_config(cfg, ik_mode=1, ik_eps=1e-5))
+    try:
+        for kw in ({}, {"w_task": (1, 1, 1, 0.5, 0.5, 0.5), "w_joint": (1, 0.8, 1, 1.2, 1, 1, 0.5)}):
+            e.set_params(**kw)
+            w = workloads.random_batch(chain, 2500, 6, seed=51)
+            out = run_gpu(e, w, 6, outputs=("qdot_vf", "qdot", "twist", "pose"))
+            ref = run_oracle(chain, e.params, w, 6)
+            check(out, ref, FP64_RTOL, keys=("qdot_vf", "qdot"))
+            # away from singularities the task twist is tracked exactly -- what distinguishes it from the damped form
+            from oracle import batch
+            J = batch.fk_jac(chain, w["q"].T)[2]
+            sig = np.linalg.svd(J, compute_uv=False)
+            if not kw:
+                ok = sig[:, -1] > 1e-3
+                assert np.allclose(np.einsum("ikn,in->ik", J, out["qdot_vf"])[ok], ref["twist"][ok], atol=1e-9)
+    finally:
+        e.close()
+    e32 = Engine(chain, precision=32, params=Params.from_config(cfg))
+    try:
+        with pytest.raises(VfkError):
+            e32.set_params(ik_mode=1)
+    finally:
+        e32.close()
+
+
 def test_undamped_projector_is_the_references_restrict(eng, lwr):
     """ns_lambda = 0 in projector mode: B x = (I - pinv(J) J) x of scripts/nullspace:75-79 (numpy SVD pinv in the oracle,
     Q diag(0, 1) Q^T x on the GPU) at the FP64 tolerance, and in the FP32 mode at its own."""

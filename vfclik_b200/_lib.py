@@ -69,8 +69,9 @@ class ParamsC(C.Structure):
         ("goal_force", C.c_double), ("obst_force", C.c_double), ("obst_safe", C.c_double), ("obst_order", C.c_double),
         ("mixer_w", C.c_double * VFK_N_PORTS), ("w_task", C.c_double * 6), ("w_joint", C.c_double * VFK_MAX_JOINTS),
         ("tool", C.c_double * 12), ("jp_ref", C.c_double * VFK_MAX_JOINTS), ("ns_control", C.c_double * 4),
-        ("shoulder_vel", C.c_double * 2),
+        ("shoulder_vel", C.c_double * 2), ("ik_eps", C.c_double),
         ("ns_mode", C.c_int32), ("direct_control", C.c_int32), ("integrate", C.c_int32), ("bridge_kind", C.c_int32),
+        ("ik_mode", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -68,6 +68,8 @@ static bool chain_matches(const vfk_chain_desc& ch, int n_expected) {
 template <typename T>
 static void build_const(const vfk_ctx& h, KConst<T>& c) {
     memset(&c, 0, sizeof c);
+    static const SinCosTab sincos_tab = VFK_SINCOS_TAB_INIT;
+    c.sincos = sincos_tab;
     const vfk_chain_desc& ch = h.canon;
     const vfk_params& p = h.params;
     const int n = ch.n_joints;
@@ -130,6 +132,9 @@ static void build_const(const vfk_ctx& h, KConst<T>& c) {
     // null(J) (vfk_nullspace.cuh): no normal equations, so no cond(J)^2 and no pivot to lose at ns_lambda = 0
     c.ns_qr = (p.ns_mode == VFK_NS_CONTROL || (p.ns_mode == VFK_NS_PROJECTOR && p.ns_lambda == 0.0)) ? 1 : 0;
     c.share_factor = (unit && p.ns_lambda == p.ik_lambda && !c.ns_qr) ? 1 : 0;
+    c.ik_mode = p.ik_mode;
+    c.ik_eps = p.ik_eps;
+    c.ik_lambda2_d = p.ik_lambda * p.ik_lambda;
     c.need_jp = p.mixer_w[2] != 0.0 ? 1 : 0;
     c.asin_series = (p.rot_slowdown > 0 && p.rot_slowdown <= 0.3) ? 1 : 0;
     c.order_int = (p.obst_order == std::floor(p.obst_order) && p.obst_order >= 1 && p.obst_order <= 64) ? (int)p.obst_order : 0;
@@ -162,6 +167,8 @@ extern "C" void vfk_default_params(vfk_params* p, int n_joints) {
     p->tool[0] = p->tool[4] = p->tool[8] = 1.0;
     p->ns_mode = VFK_NS_PROJECTOR;
     p->direct_control = -1;
+    p->ik_mode = VFK_IK_DLS;
+    p->ik_eps = 1e-5;
     p->integrate = 1;
     (void)n_joints;
 }
@@ -171,9 +178,13 @@ static int kernel_joints(int n) { return n <= 6 ? 6 : n <= 7 ? 7 : n <= 10 ? 10 
 
 static int check_params(vfk_ctx* h, const vfk_params* p) {
     if (!(p->ik_lambda >= 0) || !(p->ns_lambda >= 0)) return fail(h, VFK_ERR_INVALID, "lambda must be >= 0");
-    if (p->ik_lambda == 0 && h->precision == 32)
+    if (p->ik_lambda == 0 && h->precision == 32 && p->ik_mode == VFK_IK_DLS)
         return fail(h, VFK_ERR_INVALID, "ik_lambda = 0 is outside the FP32 mode's domain (use precision 64)");
     if (p->ns_mode < 0 || p->ns_mode > 2) return fail(h, VFK_ERR_INVALID, "ns_mode must be 0, 1 or 2");
+    if (p->ik_mode != VFK_IK_DLS && p->ik_mode != VFK_IK_TRUNCATED) return fail(h, VFK_ERR_INVALID, "ik_mode must be VFK_IK_DLS or VFK_IK_TRUNCATED");
+    if (p->ik_mode == VFK_IK_TRUNCATED && h->precision != 64)
+        return fail(h, VFK_ERR_UNSUPPORTED, "VFK_IK_TRUNCATED (one-sided Jacobi SVD) is built for precision 64 only");
+    if (p->ik_mode == VFK_IK_TRUNCATED && !(p->ik_eps >= 0)) return fail(h, VFK_ERR_INVALID, "ik_eps must be >= 0");
     if (!(p->max_vel >= 0)) return fail(h, VFK_ERR_INVALID, "max_vel must be >= 0");
     if (p->bridge_kind < VFK_BRIDGE_LWR || p->bridge_kind > VFK_BRIDGE_ICUB)
         return fail(h, VFK_ERR_INVALID, "bridge_kind must be VFK_BRIDGE_LWR, _POWERCUBE or _ICUB");

@@ -57,6 +57,7 @@ constexpr bool kF32PowChain = true;
 template <typename T>
 struct KConst {
     using W = typename WideOf<T>::type;
+    SinCosTab sincos;          // reduction constants and polynomial coefficients of sincos_wide
     W base[12];
     W tip[kMaxJ][12];
     T q_lo[kMaxJ], q_hi[kMaxJ];
@@ -86,6 +87,8 @@ struct KConst {
     int32_t asin_series;       // rot_slowdown <= 0.3 rad: small-angle series replaces atan2 in FP32
     int32_t order_int;         // obst_order when it is a small integer, else 0
     int32_t all_xtwist;        // every tip rotation is the identity or RotX(alpha): the lane-split kernel's uniform fast path
+    int32_t ik_mode;           // VFK_IK_*: 1 = truncated (KDL-wdls-style) form through a one-sided Jacobi SVD, FP64 general kernel only
+    double ik_eps, ik_lambda2_d;
     int32_t ns_qr;             // nullspace through the Householder basis of null(J): control mode, or the projector with ns_lambda = 0
 };
 
@@ -207,7 +210,7 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
             p[0] = fma(R[2], qj, p[0]); p[1] = fma(R[5], qj, p[1]); p[2] = fma(R[8], qj, p[2]);
         } else {
             W s, co;
-            sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(qj, &s, &co);
+            sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(c.sincos, qj, &s, &co);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const W a = R[3 * r + 0], b = R[3 * r + 1];
@@ -834,6 +837,22 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                     const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
                     const T acc = dot6(cj, yt, T(0), false);
                     qd_vf[j] = unitw ? acc : acc * c.w_joint[j] * c.w_joint[j];
+                }
+            }
+            if constexpr (!LEAN && sizeof(T) == 8) {
+                if (c.ik_mode == 1) {
+                    // VFK_IK_TRUNCATED: qdot = Wj V diag(f(sigma)) U^T Wt t through a one-sided Jacobi SVD of Jw = Wt J Wj
+                    double G[6 * N], yw[6], qdw[N];
+    #pragma unroll
+                    for (int j = 0; j < N; ++j)
+    #pragma unroll
+                        for (int r = 0; r < 6; ++r)
+                            G[r * N + j] = (double)(r < 3 ? Jl[j][r] : Ja[j][r - 3]) * (unitw ? 1.0 : (double)c.w_task[r] * (double)c.w_joint[j]);
+    #pragma unroll
+                    for (int r = 0; r < 6; ++r) yw[r] = unitw ? (double)tw[r] : (double)tw[r] * (double)c.w_task[r];
+                    ik_truncated(G, N, yw, c.ik_lambda2_d, c.ik_eps, qdw);
+    #pragma unroll
+                    for (int j = 0; j < N; ++j) qd_vf[j] = unitw ? (T)qdw[j] : (T)(qdw[j] * (double)c.w_joint[j]);
                 }
             }
 

@@ -18,7 +18,9 @@ static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, 
     using WS = WarpStage<T, N, EXT>;
     (void)k_cycles;
     *n_chunks = (n_obst + kChunk - 1) / kChunk;
-    int stages = 2;
+    // long FP32 chains run 2 CTAs per SM on registers, so a third stage is free: config 5 0.684 -> 0.708 of the HBM roofline
+    // (4: 0.697; 6 and 8 cost a resident CTA: 0.44); everywhere else a third stage costs occupancy (config 4: 1.009 -> 0.988)
+    int stages = (sizeof(T) == 4 && N >= 10) ? 3 : 2;
     if (const char* e = getenv("VFK_STAGES")) {
         const int v = atoi(e);
         if (v >= 1 && v <= kMaxStages) stages = v;
@@ -59,7 +61,7 @@ constexpr int64_t kCoopMaxInstances = 4096;      // <= 128 tiles: 1024 cooperati
 // The LEAN kernel's preconditions (see vfk_kernels.cuh).
 template <typename T>
 static bool is_lean(const KConst<T>& c, const vfk_buffers* b) {
-    return c.tool_identity && c.unit_weights && c.share_factor && c.ns_mode == VFK_NS_PROJECTOR && !c.need_jp && !b->ns_in &&
+    return c.tool_identity && c.unit_weights && c.share_factor && c.ik_mode == 0 && c.ns_mode == VFK_NS_PROJECTOR && !c.need_jp && !b->ns_in &&
            !c.shoulder_clamp &&
            !b->jp_ref && !b->jp_lo && !b->q_cmded && !b->ext_cmd[0] && !b->ext_cmd[1] && !b->ext_cmd[2] && !b->qdot_vf && !b->qdot_ns &&
            !b->qdot_jp && !b->cmd && !b->pose && !b->twist && !b->flags && !(b->aux && b->n_aux > 0) && b->qdot && !getenv("VFK_NO_LEAN");

@@ -169,17 +169,19 @@ struct SinCosTab {
     double s[7];     // -1/3!, 1/5!, -1/7!, 1/9!, -1/11!, 1/13!, -1/15!
     double c[7];     // 1/4!, -1/6!, 1/8!, -1/10!, 1/12!, -1/14!, 1/16!
 };
-static __device__ __constant__ SinCosTab kSinCos = {
-    0.63661977236758134308, 6755399441055744.0, 1.57079632679489655800e+00, 6.12323399573676603587e-17,
-    {-1.66666666666666666667e-01, 8.33333333333333333333e-03, -1.98412698412698412698e-04, 2.75573192239858906526e-06,
-     -2.50521083854417187751e-08, 1.60590438368216145994e-10, -7.64716373181981647590e-13},
-    {4.16666666666666666667e-02, -1.38888888888888888889e-03, 2.48015873015873015873e-05, -2.75573192239858906526e-07,
-     2.08767569878680989792e-09, -1.14707455977297247139e-11, 4.77947733238738529744e-14}};
+// The table travels inside the kernel's parameter block (KConst::sincos, constant bank 0) like every other constant: as a
+// __constant__ variable (bank 3) its first use in every tile was a constant-cache miss -- 14 % of the FP64 kernel's stall
+// samples sat on the one DFMA behind that LDC (ncu source page, r02m config 2).
+#define VFK_SINCOS_TAB_INIT                                                                                                      \
+    {0.63661977236758134308, 6755399441055744.0, 1.57079632679489655800e+00, 6.12323399573676603587e-17,                         \
+     {-1.66666666666666666667e-01, 8.33333333333333333333e-03, -1.98412698412698412698e-04, 2.75573192239858906526e-06,          \
+      -2.50521083854417187751e-08, 1.60590438368216145994e-10, -7.64716373181981647590e-13},                                     \
+     {4.16666666666666666667e-02, -1.38888888888888888889e-03, 2.48015873015873015873e-05, -2.75573192239858906526e-07,          \
+      2.08767569878680989792e-09, -1.14707455977297247139e-11, 4.77947733238738529744e-14}}
 
 // TERMS = 5: x^11 / x^12 (the FP32 mode's wide chain); TERMS = 7: x^15 / x^16, truncation < 5e-17 (FP64 mode).
 template <int TERMS>
-__device__ __forceinline__ void sincos_wide(double x, double* s, double* c) {
-    const SinCosTab& k = kSinCos;
+__device__ __forceinline__ void sincos_wide(const SinCosTab& k, double x, double* s, double* c) {
     const double t = fma(x, k.two_over_pi, k.magic);
     const int ki = __double2loint(t);
     const double kf = t - k.magic;
@@ -201,7 +203,7 @@ __device__ __forceinline__ void sincos_wide(double x, double* s, double* c) {
     *c = ((ki + 1) & 2) ? -cs : cs;
 }
 template <int TERMS>
-__device__ __forceinline__ void sincos_wide(float x, float* s, float* c) { Prec<float>::sincos_(x, s, c); }
+__device__ __forceinline__ void sincos_wide(const SinCosTab&, float x, float* s, float* c) { Prec<float>::sincos_(x, s, c); }
 
 // x^ORDER by a fixed multiplication chain (FP64 repeller fast path; ORDER = 0 means "use Prec<T>::pow_pos").
 template <int ORDER, typename T>

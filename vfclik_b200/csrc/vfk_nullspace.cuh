@@ -1,4 +1,5 @@
-// vfk_nullspace.cuh -- orthonormal basis of null(J) for the reference's nullspace interface.
+// vfk_nullspace.cuh -- rare-path dense linear algebra: orthonormal basis of null(J) for the reference's nullspace interface
+// (Householder QR), and the truncated velocity IK (one-sided Jacobi SVD) at the end of the file.
 //
 // scripts/nullspace:75-107 builds B = I - pinv(J) J (LAPACK SVD) and takes the left singular vectors of B^T whose
 // singular value is >= 1e-8: an orthonormal basis of null(J), k = N - rank(J) vectors.  Forming B through the normal
@@ -64,6 +65,51 @@ static __device__ __noinline__ void ns_qr_project(const double* a, const double*
     for (int j = 0; j < 6; ++j) ns_reflect(a, tau[j], j, n, w);          // Q^T w = H_5 ( ... (H_0 w))
     for (int r = 0; r < 6 && r < n; ++r) w[r] = 0.0;
     for (int j = 5; j >= 0; --j) ns_reflect(a, tau[j], j, n, w);
+}
+
+// ---- truncated weighted least squares (VFK_IK_TRUNCATED), same rare-path style.
+// g: Jw = Wt J Wj, 6 x n row-major (g[r * n + j]); y: Wt t (6).  One-sided Jacobi (Hestenes): plane rotations of row pairs
+// until the rows are mutually orthogonal -- G' = U^T Jw = Sigma V^T, the same rotations applied to y give U^T y -- which
+// resolves every singular value to relative accuracy (no squaring of the condition number).  Then
+//   qd = V diag(f(sigma)) U^T y = sum_i row_i * c_i * (U^T y)_i,  c_i = 1 / sigma_i^2 (sigma_i >= eps), 1 / (sigma_i^2 + lambda^2) below.
+// qd: n values (before the joint weights).  Restated by oracle/batch.py:ikv_dls (ik_mode 1) through numpy's SVD.
+static __device__ __noinline__ void ik_truncated(double* g, int n, double* y, double lambda2, double eps, double* qd) {
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 5; ++p)
+            for (int q = p + 1; q < 6; ++q) {
+                double a = 0.0, b = 0.0, c = 0.0;
+                for (int j = 0; j < n; ++j) {
+                    a = fma(g[p * n + j], g[p * n + j], a);
+                    b = fma(g[q * n + j], g[q * n + j], b);
+                    c = fma(g[p * n + j], g[q * n + j], c);
+                }
+                const double scale = sqrt(a * b);
+                if (!(fabs(c) > 1e-17 * scale) || scale == 0.0) continue;
+                off = fmax(off, fabs(c) / scale);
+                const double zeta = (b - a) / (2.0 * c);
+                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+                const double cs = 1.0 / sqrt(fma(t, t, 1.0)), sn = cs * t;
+                for (int j = 0; j < n; ++j) {
+                    const double u = g[p * n + j], v = g[q * n + j];
+                    g[p * n + j] = cs * u - sn * v;
+                    g[q * n + j] = sn * u + cs * v;
+                }
+                const double u = y[p], v = y[q];
+                y[p] = cs * u - sn * v;
+                y[q] = sn * u + cs * v;
+            }
+        if (off < 1e-15) break;
+    }
+    for (int j = 0; j < n; ++j) qd[j] = 0.0;
+    const double eps2 = eps * eps;
+    for (int r = 0; r < 6; ++r) {
+        double s2 = 0.0;
+        for (int j = 0; j < n; ++j) s2 = fma(g[r * n + j], g[r * n + j], s2);
+        if (s2 == 0.0) continue;
+        const double coef = y[r] / (s2 >= eps2 ? s2 : s2 + lambda2);
+        for (int j = 0; j < n; ++j) qd[j] = fma(coef, g[r * n + j], qd[j]);
+    }
 }
 
 // vectors of the basis the four-float control interface can address: min(4, N - 6) (scripts/nullspace:113)

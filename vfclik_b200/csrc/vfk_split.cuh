@@ -203,7 +203,7 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                     Jl[k][0] = (T)p[0]; Jl[k][1] = (T)p[1]; Jl[k][2] = (T)p[2];
                     const W* tp = tipb[k];
                     W s, co;
-                    sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>((W)q[k], &s, &co);
+                    sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(c.sincos, (W)q[k], &s, &co);
                     const W ca = tp[0], sa = tp[1], t0 = tp[2], t1 = tp[3], t2 = tp[4];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {

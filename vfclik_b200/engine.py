@@ -55,6 +55,8 @@ class Params:
     integrate: int = 1
     bridge_kind: int = 0                                   # BRIDGE_LWR / BRIDGE_POWERCUBE / BRIDGE_ICUB
     shoulder_vel: Sequence[float] = (0.0, 0.0)             # Powercube: config.max_vel_shoulder_pos, max_vel_shoulder_neg
+    ik_mode: int = 0                                       # 0: north_star's damped least squares; 1: KDL-wdls-style truncated form (FP64)
+    ik_eps: float = 1e-5                                   # ik_mode 1: singular values below this are damped, the rest inverted
 
     @staticmethod
     def from_config(config, **over) -> "Params":
@@ -100,6 +102,7 @@ class Params:
         p.ns_mode, p.direct_control, p.integrate = int(self.ns_mode), int(self.direct_control), int(self.integrate)
         p.bridge_kind = int(self.bridge_kind)
         p.shoulder_vel[0], p.shoulder_vel[1] = float(self.shoulder_vel[0]), float(self.shoulder_vel[1])
+        p.ik_mode, p.ik_eps = int(self.ik_mode), float(self.ik_eps)
         return p
 
 
