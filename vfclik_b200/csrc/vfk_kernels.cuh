@@ -509,36 +509,37 @@ struct WarpStage {
 // One bulk copy per obstacle chunk (and one for its ext rows): the chunk's kChunk x 32 vectors are contiguous.
 // Called by all lanes after a __syncwarp(); lane 0 issues.
 template <typename T, int N, bool EXT>
-__device__ __forceinline__ void issue_obst(const KArgs<T>& a, int64_t tile, int chunk, int stage, unsigned char* region,
-                                           uint64_t* bars, int lane) {
+__device__ __forceinline__ void issue_obst(const KArgs<T>& a, int64_t tile, int chunk, int stage, uint32_t region,
+                                           uint32_t bars, int lane) {
     using WS = WarpStage<T, N, EXT>;
     if (lane == 0) {
         const int m0 = chunk * kChunk;
         const uint32_t cnt = (uint32_t)min(kChunk, a.n_obst - m0);
         const uint32_t cntp = (cnt + 1u) & ~1u;                           // whole pairs (the odd one out carries a zero-radius slot)
-        unsigned char* dst = region + (size_t)stage * WS::kStage;
-        mbar_arrive_expect_tx(&bars[stage], cntp * WS::kRow + cnt * WS::kRowExt);
-        bulk_g2s(dst, a.obst + (tile * a.n_obst_p + m0) * 32, cntp * WS::kRow, &bars[stage]);
-        if (EXT) bulk_g2s(dst + kChunk * WS::kRow, a.obst_ext + (tile * a.n_obst + m0) * 32, cnt * WS::kRowExt, &bars[stage]);
+        const uint32_t dst = region + (uint32_t)stage * WS::kStage, bar = bars + 8u * (uint32_t)stage;
+        mbar_arrive_expect_tx_a(bar, cntp * WS::kRow + cnt * WS::kRowExt);
+        bulk_g2s_a(dst, a.obst + (tile * a.n_obst_p + m0) * 32, cntp * WS::kRow, bar);
+        if (EXT) bulk_g2s_a(dst + kChunk * WS::kRow, a.obst_ext + (tile * a.n_obst + m0) * 32, cnt * WS::kRowExt, bar);
     }
 }
 
 // q tile (N rows) + goal tile (13 rows): two bulk copies into q/goal buffer `buf`.
 template <typename T, int N, bool EXT>
-__device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile, int buf, unsigned char* region, uint64_t* bars,
+__device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile, int buf, uint32_t region, uint32_t bars,
                                          int lane, int nc) {
     using WS = WarpStage<T, N, EXT>;
     if (lane == 0) {
-        unsigned char* dst = region + (size_t)a.n_stages * WS::kStage + (size_t)buf * WS::kQg;
-        mbar_arrive_expect_tx(&bars[kMaxStages + buf], (uint32_t)(nc + 13) * WS::kQgRow);
+        const uint32_t dst = region + (uint32_t)a.n_stages * WS::kStage + (uint32_t)buf * WS::kQg;
+        const uint32_t bar = bars + 8u * (uint32_t)(kMaxStages + buf);
+        mbar_arrive_expect_tx_a(bar, (uint32_t)(nc + 13) * WS::kQgRow);
         if (a.q_src) {
 #pragma unroll
             for (int j = 0; j < N; ++j)
-                if (j < nc) bulk_g2s(dst + j * WS::kQgRow, a.q_src + j * a.q_src_ld + (tile << 5), WS::kQgRow, &bars[kMaxStages + buf]);
+                if (j < nc) bulk_g2s_a(dst + j * WS::kQgRow, a.q_src + j * a.q_src_ld + (tile << 5), WS::kQgRow, bar);
         } else {
-            bulk_g2s(dst, a.q + tile * (nc * 32), (uint32_t)nc * WS::kQgRow, &bars[kMaxStages + buf]);
+            bulk_g2s_a(dst, a.q + tile * (nc * 32), (uint32_t)nc * WS::kQgRow, bar);
         }
-        bulk_g2s(dst + N * WS::kQgRow, a.goal + tile * (13 * 32), 13 * WS::kQgRow, &bars[kMaxStages + buf]);
+        bulk_g2s_a(dst + N * WS::kQgRow, a.goal + tile * (13 * 32), 13 * WS::kQgRow, bar);
     }
 }
 
@@ -558,9 +559,12 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     using WS = WarpStage<T, N, EXT>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // read through a shuffle so that the compiler knows it is warp-uniform: tile numbers, ring positions and the addresses of
+    // the bulk copies then live in uniform registers, and the copies issue without an elect-one loop around them
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * WS::kBars;
     unsigned char* region = smem + kSmemHeader + (size_t)warp * WS::warp_bytes(a.n_stages);
+    const uint32_t bars_a = smem_u32(bars), region_a = smem_u32(region);       // shared-window addresses, once per warp
     static_assert(G == 1 || G == kChunk, "a cooperative group takes one obstacle of a chunk per lane");
     constexpr int kSub = G == 1 ? 1 : G;                        // work units per tile (G == 8: 8 units of 4 instances)
     const int64_t n_tiles = (a.n + 31) >> 5;
@@ -587,11 +591,11 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         mbar_fence_init();
     }
     __syncwarp();
-    issue_qg<T, N, EXT>(a, unit / kSub, 0, region, bars, lane, nc);
+    issue_qg<T, N, EXT>(a, unit / kSub, 0, region_a, bars_a, lane, nc);
     int64_t p_unit = unit;
     int p_u = 0, p_chunk = 0;
     for (int u = 0; u < S; ++u) {
-        issue_obst<T, N, EXT>(a, p_unit / kSub, p_chunk, u, region, bars, lane);
+        issue_obst<T, N, EXT>(a, p_unit / kSub, p_chunk, u, region_a, bars_a, lane);
         if (++p_chunk == a.n_chunks) p_chunk = 0;
         if (++p_u == U) { p_u = 0; p_unit += stride; }
     }
@@ -604,8 +608,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         const bool active = (tile << 5) + slot < a.n && ol == 0;     // padding / helper lanes compute, never store
         const int64_t tN = tile * (nc * 32) + slot;             // this instance's slot in a blocked array of nc joint components
         __syncwarp();
-        if (unit + stride < n_units) issue_qg<T, N, EXT>(a, (unit + stride) / kSub, (it + 1) & 1, region, bars, lane, nc);
-        mbar_wait(&bars[kMaxStages + (it & 1)], (uint32_t)(it >> 1) & 1u);
+        if (unit + stride < n_units) issue_qg<T, N, EXT>(a, (unit + stride) / kSub, (it + 1) & 1, region_a, bars_a, lane, nc);
+        mbar_wait_a(bars_a + 8u * (uint32_t)(kMaxStages + (it & 1)), (uint32_t)(it >> 1) & 1u);
         const T* qg = reinterpret_cast<const T*>(region + (size_t)a.n_stages * WS::kStage + (size_t)(it & 1) * WS::kQg) + slot;
 
     T q[N];
@@ -668,7 +672,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
             if constexpr (sizeof(T) == 4 && !EXT && G == 1) np2.set(pt);
             for (int ch = 0; ch < a.n_chunks; ++ch) {
                 const int stage = resident ? ch : c_stage;
-                mbar_wait(&bars[stage], resident ? (uint32_t)(it & 1) : c_phase);
+                mbar_wait_a(bars_a + 8u * (uint32_t)stage, resident ? (uint32_t)(it & 1) : c_phase);
                 const unsigned char* sb = region + (size_t)stage * WS::kStage;
                 const Vec4<T>* sp = reinterpret_cast<const Vec4<T>*>(sb);                      // pair p starts at sp + p * 64
                 const Vec2<T>* se = reinterpret_cast<const Vec2<T>*>(sb + kChunk * WS::kRow) + slot;
@@ -715,7 +719,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 // this slot is free again: request the chunk that will occupy it S uses from now
                 if (!resident || last) {
                     __syncwarp();
-                    if (p_unit < n_units) issue_obst<T, N, EXT>(a, p_unit / kSub, p_chunk, stage, region, bars, lane);
+                    if (p_unit < n_units) issue_obst<T, N, EXT>(a, p_unit / kSub, p_chunk, stage, region_a, bars_a, lane);
                     if (++p_chunk == a.n_chunks) p_chunk = 0;
                     if (++p_u == U) { p_u = 0; p_unit += stride; }
                 }
