@@ -588,6 +588,39 @@ def test_bridge_module_matches_the_reference_main_loop(lwr, golden, built_lib, f
     capsys.readouterr()
 
 
+def test_vf_module_drains_queued_param_messages(lwr, built_lib, fresh_ports, capsys):
+    """Deliberate deviation: one ``update()`` is one control cycle and applies EVERY ``/param`` message
+    queued since the last one (the reference's loop takes one per pass but spins ~10 passes per control period), except on
+    the pass after the first joint data, where the message read is swallowed by ``start_attractor`` as in the reference."""
+    from vfclik_b200.runtime import ControlRuntime
+    from vfclik_b200.vf import VectorFieldModule
+    _, cfg = lwr
+    rt = ControlRuntime(cfg, n_instances=1, precision=64)
+    vf = VectorFieldModule(rt, "/6")
+    try:
+        pfeed = _out_port(fresh_ports, "/6/feed/param", vf.paramPort.getName())
+        qfeed = _out_port(fresh_ports, "/6/feed/q", vf.qInPort.getName())
+        obstacle = lambda i: ["add", 5 + i, -10.0, 2, [0.4 + 0.05 * i, 0.1, 0.6, 0.05, 0.001, 20.0]]
+        q = [float(v) for v in cfg.initial_joint_pos]
+        fresh_ports.sendListPort(qfeed, q)
+        vf.update()                                                   # first joint data: arms start_attractor
+        n0 = len(rt.vectorFields)
+        for i in range(3):
+            fresh_ports.write_bottle_lists(pfeed, obstacle(i), strict=True)
+        fresh_ports.sendListPort(qfeed, q)
+        vf.update()                                                   # swallows ONE message (the reference's quirk), applies the rest
+        assert len(rt.vectorFields) == n0 + 2 and 5 not in rt.vectorFields
+        for i in range(3, 7):
+            fresh_ports.write_bottle_lists(pfeed, obstacle(i), strict=True)
+        fresh_ports.write_bottle_lists(pfeed, ["remove", 6], strict=True)
+        fresh_ports.sendListPort(qfeed, q)
+        vf.update()                                                   # all five applied within this one cycle, in order
+        assert sorted(k for k in rt.vectorFields if k >= 5) == [7, 8, 9, 10, 11]
+    finally:
+        vf.close(); rt.close()
+    capsys.readouterr()
+
+
 def test_bridge_read_pos_without_cmded_feedback(lwr, golden, built_lib, fresh_ports, capsys):
     """``LWR_Bridge.read_pos`` with no ``/cmded`` feedback (tests/golden rp_*: the reference's own method executed): the
     commanded position is taken from the FIRST measured q and then kept.  The real-robot path of this repo's bridge does the
