@@ -996,3 +996,66 @@ def test_outputs_stay_inside_their_buffers(eng, lwr, precision):
             assert rel_err(qd_view.T.astype(np.float64), ref["qdot"]).max() <= (FP32_RTOL if precision == 32 else FP64_RTOL)
         finally:
             s.close()
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_round2_shapes_stay_inside_their_buffers(lwr, built_lib, monkeypatch, precision):
+    """Guard bands (compute-sanitizer is closed on the pool) around everything the round-2 shapes write: the nullspace
+    state of a 10-joint chain (4 basis vectors), the joint-controller reference written back under per-instance limits, q and
+    qdot of a padded 8-joint chain, of the DH-pattern 17-joint kernel and of the lane-split kernel, and the obstacle array
+    packed from an odd obstacle count -- ragged batches, K = 2."""
+    import torch
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch, Engine, Params
+    dt = np.float32 if precision == 32 else np.float64
+    SENT = -777.25
+
+    def guard(db, names):
+        held = {}
+        for name in names:
+            t = db.t[name]
+            pad = 4096 // t.element_size()
+            big = torch.full((t.numel() + 2 * pad,), SENT, dtype=t.dtype, device=t.device)
+            big[pad:pad + t.numel()] = t.reshape(-1)
+            db.t[name] = big[pad:pad + t.numel()].view(t.shape)
+            held[name] = (big, pad, t.numel())
+        return held
+
+    def intact(held):
+        torch.cuda.synchronize()
+        for name, (big, pad, cnt) in held.items():
+            assert bool((big[:pad] == SENT).all()) and bool((big[pad + cnt:] == SENT).all()), name
+
+    cases = [
+        (workloads.torso_arm_chain(10), Params(ns_mode=2, ns_control=(0.3, -0.2, 0.1, 0.2)), ("qdot", "qdot_ns"), ("ns_lastvec",), {}),
+        (lwr[0], Params(mixer_w=(1.0, 1.0, 0.5, 0, 0, 0)), ("qdot", "qdot_jp"), ("jp_ref", "jp_lo", "jp_hi"), {}),
+        (workloads.torso_arm_chain(8), Params(), ("qdot", "qdot_vf", "flags"), (), {}),
+        (workloads.dual_arm_torso_chain(), Params(), ("qdot",), (), {}),
+        (workloads.dual_arm_torso_chain(), Params(), ("qdot",), (), {"VFK_SPLIT": "1"}),
+        (workloads.dual_arm_torso_chain(10), Params(), ("qdot",), (), {"VFK_SPLIT": "1"}),
+    ]
+    for chain, prm, outputs, inputs, env in cases:
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        n, M = 1000 - 7, 13
+        e = Engine(chain, precision=precision, params=prm)
+        try:
+            w = workloads.random_batch(chain, n, M, seed=93, dtype=dt)
+            db = DeviceBatch(e, n, M, outputs=outputs, inputs=inputs)
+            held = guard(db, ("obst",))
+            db.upload("q", w["q"]); db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+            intact(held)                                                        # packing 13 obstacles into 7 pairs
+            assert np.array_equal(db.download("obst"), w["obst"])
+            if "jp_lo" in inputs:
+                db.upload("jp_ref", np.full((chain.n_joints, n), 2.5, dtype=dt))
+                db.upload("jp_lo", np.full((chain.n_joints, n), -0.3, dtype=dt)); db.upload("jp_hi", np.full((chain.n_joints, n), 0.4, dtype=dt))
+            held.update(guard(db, tuple(x for x in outputs + inputs + ("q",) if db.t[x].dtype.is_floating_point)))
+            assert db.step(2) == 1
+            intact(held)
+            assert np.all(np.isfinite(db.download("qdot")))
+            if "jp_lo" in inputs:
+                assert np.all(db.download("jp_ref") == dt(0.4))                 # the clamp was stored back, inside its buffer
+        finally:
+            e.close()
+            for key in env:
+                monkeypatch.delenv(key)
