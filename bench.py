@@ -44,6 +44,7 @@ WORKLOADS = {
     "config2": (1 << 16, 32, 64, "BASELINE configs[1]: 65,536 LWR instances/GPU, 32 obstacles, FP64"),
     "config4": (1 << 21, 256, 32, "BASELINE configs[3] shard: 2M LWR instances/GPU, 256 obstacles, FP32"),
     "config5": (1 << 19, 64, 32, "BASELINE configs[4] shard: 512k 17-DOF instances/GPU, 64 obstacles, FP32"),
+    "config5_fp64": (1 << 18, 64, 64, "configs[4]'s chain in the FP64 mode: 256k 17-DOF instances/GPU, 64 obstacles (not a BASELINE config)"),
 }
 
 
@@ -301,8 +302,8 @@ def main():
     if args.instances:
         n_inst = args.instances
     cfg = load_config(config_filename(PACKAGE_CONFIG_DIR + "/lwr/", "lwr", "right"))
-    chain = workloads.dual_arm_torso_chain() if args.workload == "config5" else chain_from_config(cfg)
-    params = Params.from_config(cfg) if args.workload != "config5" else Params()
+    chain = workloads.dual_arm_torso_chain() if args.workload.startswith("config5") else chain_from_config(cfg)
+    params = Params.from_config(cfg) if not args.workload.startswith("config5") else Params()
     N = chain.n_joints
     np_dt = np.float32 if precision == 32 else np.float64
     elem = 4 if precision == 32 else 8

@@ -284,8 +284,9 @@ def test_control_nullspace_against_the_executed_reference_n10(built_lib, golden)
                                                         (64, 7, 32, 1, 4128), (64, 7, 3, 4, 37), (64, 17, 20, 2, 4100),
                                                         (64, 10, 8, 1, 999)])
 def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k, n):
-    """Two lanes per instance (vfk_split.cuh: long chains and FP64, the lean call shape; opt-in with VFK_SPLIT=1 because it
-    measured slower): against the oracle at the mode's tolerance, and against the one-thread-per-instance kernel."""
+    """Two lanes per instance (vfk_split.cuh; the lean call shape; default for long FP64 chains, where it measured 25 % faster,
+    opt-in with VFK_SPLIT=1 elsewhere, where it measured slower): against the oracle at the mode's tolerance, and against the
+    one-thread-per-instance kernel."""
     from vfclik_b200 import workloads
     from vfclik_b200.engine import Engine, Params
     chain = lwr[0] if n_joints == 7 else workloads.dual_arm_torso_chain(n_joints)       # DH form: what the split kernel takes
@@ -295,8 +296,12 @@ def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k
         w = workloads.random_batch(chain, n, m, seed=40 + n_joints + m, dtype=dt)
         monkeypatch.setenv("VFK_SPLIT", "1")
         out = run_gpu(e, w, m, k=k, outputs=("qdot",))
-        monkeypatch.delenv("VFK_SPLIT")
+        monkeypatch.setenv("VFK_SPLIT", "0")
         solo = run_gpu(e, w, m, k=k, outputs=("qdot",))
+        monkeypatch.delenv("VFK_SPLIT")
+        dflt = run_gpu(e, w, m, k=k, outputs=("qdot",))
+        # default policy: two lanes per instance for FP64 chains of 10 joints and more, one thread per instance elsewhere
+        assert np.array_equal(dflt["qdot"], out["qdot"] if (precision == 64 and n_joints >= 10) else solo["qdot"])
         ref = run_oracle(chain, e.params, w, m, k=k)
         # FP32 over several cycles: an instance within rounding of the all-or-nothing limit check or the clamp may take the
         # other branch in an earlier cycle; bound the bulk there, everything otherwise

@@ -179,13 +179,16 @@ static int encode_map3(vfk_ctx* h, CUtensorMap* m, const void* base, uint64_t in
 }
 
 // May this call run in the lane-split shape?  Lean call on blocked device buffers, DH-form chain of exactly the instantiated
-// length -- and VFK_SPLIT=1 in the environment: measured on B200 the shape LOSES to the one-thread-per-instance kernel on both
-// workloads it was built for (config 5: 184 vs 154 us per launch; FP64 config 2: 29.6 vs 23.4 us), so it
-// is kept as a tested opt-in, not a default.
+// length.  Default: ON for FP64 chains of 10 joints and more -- there the one-thread-per-instance kernel cannot hold its
+// Jacobian (102 doubles for 17 joints) and runs 1 CTA per SM with 568 B of spills, while two lanes per instance fit 255
+// registers without spills at 2 CTAs per SM: 173 us against 217 us per launch (256 k x 17 joints x 64 obstacles, 0.60 against
+// 0.48 of the HBM roofline).  OFF elsewhere, where it measured slower (FP32 config 5: 184 vs 154 us; FP64 config 2: 29.6 vs
+// 23.4 us).  VFK_SPLIT=1 / 0 forces it on (where instantiated) / off.
 template <typename T>
 static bool split_ok(vfk_ctx* h, int n_kernel, const KConst<T>& c, const vfk_buffers* b, const vfk_io* io) {
     const char* e = getenv("VFK_SPLIT");
-    return e && atoi(e) != 0 && h->dh_chain && h->chain.n_joints == n_kernel && is_lean<T>(c, b) && !(io && (io->q_src || io->qdot));
+    const bool on = e ? atoi(e) != 0 : (sizeof(T) == 8 && n_kernel >= 10);
+    return on && h->dh_chain && h->chain.n_joints == n_kernel && is_lean<T>(c, b) && !(io && (io->q_src || io->qdot));
 }
 
 template <typename T, int N, int L>
@@ -226,7 +229,7 @@ static int launch_split(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #define VFK_MINB_SPLIT_F32 4
 #endif
 #ifndef VFK_MINB_SPLIT_F64
-#define VFK_MINB_SPLIT_F64 3
+#define VFK_MINB_SPLIT_F64 2          // 255 registers: no spills for 17 joints (3 CTAs / 168 registers spill and measured equal to the solo kernel)
 #endif
     constexpr int MINB = (sizeof(T) == 4 ? VFK_MINB_SPLIT_F32 : VFK_MINB_SPLIT_F64) * (128 / kBlock);
     auto kern = vfk_split_kernel<T, N, L, MINB>;
@@ -257,7 +260,7 @@ static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, i
                              : launch_cycle<T, N, PAT, false, false, kChunk>(h, c, b, n, n_obst, k_cycles, st, io);
     }
     if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st, io);
-    // Long chains and FP64: two lanes per instance (vfk_split.cuh), opt-in.
+    // Two lanes per instance (vfk_split.cuh): default for long FP64 chains, opt-in elsewhere.
     if constexpr (kSplitLanes<T, N, PAT> > 0) {
         if (n_obst > 0 && split_ok<T>(h, N, c, b, io)) return launch_split<T, N, kSplitLanes<T, N, PAT>>(h, c, b, n, n_obst, k_cycles, st);
     }
