@@ -183,7 +183,9 @@ static int encode_map3(vfk_ctx* h, CUtensorMap* m, const void* base, uint64_t in
 // Jacobian (102 doubles for 17 joints) and runs 1 CTA per SM with 568 B of spills, while two lanes per instance fit 255
 // registers without spills at 2 CTAs per SM: 173 us against 217 us per launch (256 k x 17 joints x 64 obstacles, 0.60 against
 // 0.48 of the HBM roofline).  OFF elsewhere, where it measured slower (FP32 config 5: 184 vs 154 us; FP64 config 2: 29.6 vs
-// 23.4 us).  VFK_SPLIT=1 / 0 forces it on (where instantiated) / off.
+// 23.4 us).  Four lanes per instance (the kernel is written for L = 2 and 4) measured 231 us on the
+// FP64 17-joint shape: every lane repeats the attractor, the Cholesky and the solves.  VFK_SPLIT=1 / 0 forces the shape on
+// (where instantiated) / off.
 template <typename T>
 static bool split_ok(vfk_ctx* h, int n_kernel, const KConst<T>& c, const vfk_buffers* b, const vfk_io* io) {
     const char* e = getenv("VFK_SPLIT");
