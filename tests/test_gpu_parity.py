@@ -284,7 +284,7 @@ def test_control_nullspace_against_the_executed_reference_n10(built_lib, golden)
                                                         (64, 7, 32, 1, 4128), (64, 7, 3, 4, 37), (64, 17, 20, 2, 4100),
                                                         (64, 10, 8, 1, 999)])
 def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k, n):
-    """Two lanes per instance (vfk_split.cuh; the lean call shape; default for long FP64 chains, where it measured 25 % faster,
+    """Two lanes per instance (vfk_split.cuh; the lean call shape; default for the FP64 17-joint kernel, where it measured 25 % faster,
     opt-in with VFK_SPLIT=1 elsewhere, where it measured slower): against the oracle at the mode's tolerance, and against the
     one-thread-per-instance kernel."""
     from vfclik_b200 import workloads
@@ -300,8 +300,8 @@ def test_lane_split_shape(lwr, built_lib, monkeypatch, precision, n_joints, m, k
         solo = run_gpu(e, w, m, k=k, outputs=("qdot",))
         monkeypatch.delenv("VFK_SPLIT")
         dflt = run_gpu(e, w, m, k=k, outputs=("qdot",))
-        # default policy: two lanes per instance for FP64 chains of 10 joints and more, one thread per instance elsewhere
-        assert np.array_equal(dflt["qdot"], out["qdot"] if (precision == 64 and n_joints >= 10) else solo["qdot"])
+        # default policy: two lanes per instance for the FP64 17-joint kernel, one thread per instance elsewhere
+        assert np.array_equal(dflt["qdot"], out["qdot"] if (precision == 64 and n_joints == 17) else solo["qdot"])
         ref = run_oracle(chain, e.params, w, m, k=k)
         # FP32 over several cycles: an instance within rounding of the all-or-nothing limit check or the clamp may take the
         # other branch in an earlier cycle; bound the bulk there, everything otherwise

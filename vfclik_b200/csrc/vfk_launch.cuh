@@ -179,17 +179,18 @@ static int encode_map3(vfk_ctx* h, CUtensorMap* m, const void* base, uint64_t in
 }
 
 // May this call run in the lane-split shape?  Lean call on blocked device buffers, DH-form chain of exactly the instantiated
-// length.  Default: ON for FP64 chains of 10 joints and more -- there the one-thread-per-instance kernel cannot hold its
+// length.  Default: ON for the FP64 17-joint instantiation -- there the one-thread-per-instance kernel cannot hold its
 // Jacobian (102 doubles for 17 joints) and runs 1 CTA per SM with 568 B of spills, while two lanes per instance fit 255
 // registers without spills at 2 CTAs per SM: 173 us against 217 us per launch (256 k x 17 joints x 64 obstacles, 0.60 against
-// 0.48 of the HBM roofline).  OFF elsewhere, where it measured slower (FP32 config 5: 184 vs 154 us; FP64 config 2: 29.6 vs
+// 0.48 of the HBM roofline).  OFF elsewhere, where it measured slower (FP32 config 5: 184 vs 154 us; 10 joints: 98 vs 70 us in
+// FP64, 95 vs 70 us in FP32; FP64 config 2: 29.6 vs
 // 23.4 us).  Four lanes per instance (the kernel is written for L = 2 and 4) measured 231 us on the
 // FP64 17-joint shape: every lane repeats the attractor, the Cholesky and the solves.  VFK_SPLIT=1 / 0 forces the shape on
 // (where instantiated) / off.
 template <typename T>
 static bool split_ok(vfk_ctx* h, int n_kernel, const KConst<T>& c, const vfk_buffers* b, const vfk_io* io) {
     const char* e = getenv("VFK_SPLIT");
-    const bool on = e ? atoi(e) != 0 : (sizeof(T) == 8 && n_kernel >= 10);
+    const bool on = e ? atoi(e) != 0 : (sizeof(T) == 8 && n_kernel == 17);
     return on && h->dh_chain && h->chain.n_joints == n_kernel && is_lean<T>(c, b) && !(io && (io->q_src || io->qdot));
 }
 
@@ -262,7 +263,7 @@ static int dispatch_feat(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, i
                              : launch_cycle<T, N, PAT, false, false, kChunk>(h, c, b, n, n_obst, k_cycles, st, io);
     }
     if (ext) return launch_cycle<T, N, PAT, true, false>(h, c, b, n, n_obst, k_cycles, st, io);
-    // Two lanes per instance (vfk_split.cuh): default for long FP64 chains, opt-in elsewhere.
+    // Two lanes per instance (vfk_split.cuh): default for the FP64 17-joint kernel, opt-in elsewhere.
     if constexpr (kSplitLanes<T, N, PAT> > 0) {
         if (n_obst > 0 && split_ok<T>(h, N, c, b, io)) return launch_split<T, N, kSplitLanes<T, N, PAT>>(h, c, b, n, n_obst, k_cycles, st);
     }
