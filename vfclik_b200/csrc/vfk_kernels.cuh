@@ -4,15 +4,16 @@
 // consecutive instances.  All per-instance state (q, frame, the 6xN Jacobian, the 6x6
 // normal matrix) lives in registers across the K fused cycles.  Global arrays are
 // tile-blocked SoA (include/vfk.h): element (component c, instance i) of a C-component
-// array lives at ((i/32)*C + c)*32 + i%32, obstacles at (((i/32)*M + m)*32 + i%32) as
-// one {x,y,z,radius} vector, so everything a warp needs for a tile -- q (N rows),
-// goal (13 rows), every chunk of 8 obstacles -- is ONE contiguous burst.  Those bursts
-// are moved global -> shared with cp.async.bulk (TMA), one copy each, into per-warp
-// buffers guarded by mbarriers, one tile AHEAD of the arithmetic,
-// so HBM latency is hidden behind the previous tile's FK / Cholesky work; the repulsor
-// loop reads one conflict-free LDS.128 per obstacle.  Robot constants (chain, limits,
-// gains) arrive as a __grid_constant__ kernel parameter (constant bank), indexed at
-// compile time.
+// array lives at ((i/32)*C + c)*32 + i%32; obstacles {x,y,z,radius} are stored in pairs, each
+// lane's 16-byte vectors holding the same component(s) of both (ObstPairs below), so
+// everything a warp needs for a tile -- q (N rows), goal (13 rows), every chunk of 8
+// obstacles -- is ONE contiguous burst.  Those bursts are moved global -> shared with
+// cp.async.bulk (TMA), one copy each, into per-warp buffers guarded by mbarriers, one tile
+// AHEAD of the arithmetic, so HBM latency is hidden behind the previous tile's FK / Cholesky
+// work; the repulsor loop reads two conflict-free LDS.128 per obstacle PAIR and runs on the
+// packed FP32 instructions (FFMA2 / FMUL2 / FADD2).  Robot constants (chain, limits, gains,
+// the sin / cos table) arrive as a __grid_constant__ kernel parameter (constant bank 0),
+// indexed at compile time.
 //
 // Reference mapping (see include/vfk.h and SURVEY.md App. C.2):
 //   fk_jacobian()   scripts/vf:316-318, scripts/nullspace:175  (Lafik / KDL FK + Jacobian)
