@@ -59,11 +59,15 @@ def kernel_source_stamp() -> str:
     recognised as stale instead of being reported."""
     import glob
     import hashlib
+    import re
     h = hashlib.sha256()
     files = sorted(glob.glob(os.path.join(ROOT, "vfclik_b200", "csrc", "*.cu*"))) + [os.path.join(ROOT, "include", "vfk.h")]
     for f in files:
+        text = open(f, encoding="utf-8").read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)          # comments and layout do not change the code
+        text = re.sub(r"//[^\n]*", "", text)
         h.update(os.path.basename(f).encode())
-        h.update(open(f, "rb").read())
+        h.update("".join(text.split()).encode())
     return h.hexdigest()[:16]
 
 
