@@ -530,9 +530,13 @@ def main():
 
             # BASELINE configs[3] and configs[4] at their per-GPU shard size on 8 GPUs (2 M x 256 obstacles; 512 k x 17-DOF x 64
             # obstacles), drawn on the device: every rank runs its shard, whatever N is, so the scaling run reports them too
-            for wname in ("config4", "config5"):
-                n4, m4, p4, d4 = WORKLOADS[wname]
-                ch4 = workloads.dual_arm_torso_chain() if wname == "config5" else chain
+            for wname in ("config4", "config5", "config5_generic"):
+                n4, m4, p4, d4 = WORKLOADS["config5" if wname == "config5_generic" else wname]
+                # config5_generic: the same shape with the mixed-axis torso (a KDL RotX joint -> general tip rotation), which
+                # takes GenericPattern instead of DhPattern: reported so that the chain-pattern gain is visible in every record
+                ch4 = (workloads.dual_arm_torso_chain(dh=(wname == "config5")) if wname.startswith("config5") else chain)
+                if wname == "config5_generic":
+                    d4 = d4 + " -- mixed-axis torso variant (GenericPattern)"
                 e4 = Engine(ch4, precision=p4, device=local_rank, params=params if wname == "config4" else Params())
                 db4 = workloads.random_batch_device(e4, n4, m4, seed=2 + rank if wname == "config4" else 3 + rank)
                 for _ in range(3):
