@@ -443,6 +443,27 @@ def test_all_joint_types(built_lib):
         e.close()
 
 
+@pytest.mark.parametrize("precision, rtol, pose_atol", [(64, FP64_RTOL, 1e-12), (32, FP32_RTOL, 2e-6)])
+def test_joint_angles_beyond_one_turn(lwr, built_lib, precision, rtol, pose_atol):
+    """Continuous joints: angles of several turns (limits +-4 pi) go through the kernels' own sin / cos (whole-turn reduction of
+    the quarter angle in the FP32 mode's wide chain, quadrant reduction in the FP64 mode) and still match the oracle's libm."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import Engine, Params
+    chain, cfg = lwr
+    wide = dataclasses.replace(chain, q_lo=np.full(7, -4 * np.pi), q_hi=np.full(7, 4 * np.pi))
+    e = Engine(wide, precision=precision, params=Params.from_config(cfg))
+    try:
+        w = workloads.random_batch(wide, 4096, 8, seed=21, dtype=np.float64 if precision == 64 else np.float32)
+        assert np.abs(w["q"]).max() > 3 * np.pi
+        out = run_gpu(e, w, 8, outputs=("qdot_vf", "qdot_ns", "qdot", "pose"))
+        ref = run_oracle(wide, e.params, w, 8)
+        check(out, ref, rtol, keys=("qdot_vf", "qdot_ns", "qdot"), pose_atol=pose_atol)
+        lean = run_gpu(e, w, 8, outputs=("qdot",))          # the lean instantiation (q / qdot only) takes the same chain
+        check(lean, ref, rtol, keys=("qdot",))
+    finally:
+        e.close()
+
+
 def test_host_session_matches_device_path(eng, lwr):
     """The host-buffer C-ABI session (numpy in / numpy out) gives the same numbers as the device path."""
     from vfclik_b200 import workloads

@@ -68,8 +68,7 @@ static bool chain_matches(const vfk_chain_desc& ch, int n_expected) {
 template <typename T>
 static void build_const(const vfk_ctx& h, KConst<T>& c) {
     memset(&c, 0, sizeof c);
-    static const SinCosTab sincos_tab = VFK_SINCOS_TAB_INIT;
-    c.sincos = sincos_tab;
+    c.sincos = sincos_tab();
     const vfk_chain_desc& ch = h.canon;
     const vfk_params& p = h.params;
     const int n = ch.n_joints;

@@ -211,7 +211,10 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
             p[0] = fma(R[2], qj, p[0]); p[1] = fma(R[5], qj, p[1]); p[2] = fma(R[8], qj, p[2]);
         } else {
             W s, co;
-            sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(c.sincos, qj, &s, &co);
+            // FP32 mode's wide chain: the quarter-angle form (no quadrant logic, ~10 instructions fewer per joint; measured on B200
+            // against sincos_wide<5>: K = 1 headline 109.5 vs 109.9 us, K = 100 +3.2 %, 17 joints +2.6 % / +3.3 %)
+            if constexpr (sizeof(T) == 4 && sizeof(W) == 8) sincos_quarter<5>(c.sincos, qj, &s, &co);
+            else sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(c.sincos, qj, &s, &co);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const W a = R[3 * r + 0], b = R[3 * r + 1];
@@ -783,7 +786,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         static_for<0, N>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             WN col[6] = {(WN)Jl[j][0], (WN)Jl[j][1], (WN)Jl[j][2], (WN)Ja[j][0], (WN)Ja[j][1], (WN)Ja[j][2]};
-            if (ns_proj && share) axpy6(Jx, col, kSlim ? (WN)x_slim(j) : (WN)x[j]);
+            // (the short-chain lean tail wants the projector's right-hand side negated: -J x, see dot6x2 there)
+            if (ns_proj && share) axpy6(Jx, col, kSlim ? (WN)x_slim(j) : ((LEAN && !kSlim) ? -(WN)x[j] : (WN)x[j]));
             if (!unitw) {
 #pragma unroll
                 for (int r = 0; r < 6; ++r) col[r] *= (WN)c.w_task[r] * (WN)c.w_joint[j];
@@ -806,7 +810,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                 WN y[6];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) y[r] = (WN)tw[r];
-                chol6_fwd<WN>(A, invd, y);
+                chol6_fwd<WN>(A, invd, y);                 // (chol6_solve2's register pairs cost ~150 moves at this register count)
                 chol6_bwd<WN>(A, invd, y);
                 chol6_fwd<WN>(A, invd, Jx);
                 chol6_bwd<WN>(A, invd, Jx);
@@ -817,7 +821,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
-                const T d = fma(c.ns_lookahead, dot6(cj, yn, x_slim(j), true), q[j]);
+                const T d = fma(c.ns_lookahead, dot6_packed(cj, yn, x_slim(j), true), q[j]);
                 bad = bad || (d < c.q_lo[j]) || (d > c.q_hi[j]);
             }
             if (bad) flags |= 2;
@@ -825,8 +829,34 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 #pragma unroll
             for (int j = 0; j < N; ++j) {                   // pass 2: both controllers' velocities straight into the mixer sum
                 const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
-                mix[j] = fma(dot6(cj, yn, x_slim(j), true), w1, dot6(cj, yv, T(0), false) * c.mixer_w[0]);
+                mix[j] = fma(dot6_packed(cj, yn, x_slim(j), true), w1, dot6_packed(cj, yv, T(0), false) * c.mixer_w[0]);
             }
+        } else if constexpr (LEAN) {
+            // Short chains: both solves first, then per joint BOTH products J_j . y (IK) and x_j - J_j . y' (projector) from one
+            // packed chain (dot6x2).  Same operations in the same order as the general instantiation below, so asking for one
+            // more output never changes a bit of qdot; measured: FP64 config 2 21.2 against 21.8 us per launch, FP32 unchanged.
+            T yv[6], yn[6];
+            {
+                WN y[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) y[r] = (WN)tw[r];
+                chol6_solve2(A, invd, y, Jx);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) { yv[r] = (T)y[r]; yn[r] = (T)Jx[r]; }        // Jx holds -(J x) here
+            }
+            T raw[N];
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const T cj[6] = {Jl[j][0], Jl[j][1], Jl[j][2], Ja[j][0], Ja[j][1], Ja[j][2]};
+                dot6x2(cj, yv, yn, T(0), x[j], &mix[j], &raw[j]);
+                const T d = fma(c.ns_lookahead, raw[j], q[j]);
+                bad = bad || (d < c.q_lo[j]) || (d > c.q_hi[j]);
+            }
+            if (bad) flags |= 2;
+            const T gain = bad ? T(0) : c.ns_gain;
+#pragma unroll
+            for (int j = 0; j < N; ++j) mix[j] = fma(raw[j] * gain, c.mixer_w[1], mix[j] * c.mixer_w[0]);
         } else {
             {
                 WN y[6];

@@ -168,6 +168,10 @@ struct SinCosTab {
     double two_over_pi, magic, pio2_hi, pio2_lo;
     double s[7];     // -1/3!, 1/5!, -1/7!, 1/9!, -1/11!, 1/13!, -1/15!
     double c[7];     // 1/4!, -1/6!, 1/8!, -1/10!, 1/12!, -1/14!, 1/16!
+    // sincos_quarter: 1 / 2 pi, the 53-bit 2 pi, and the coefficients of sin(r / 4) / r - 1/4 and (cos(r / 4) - 1 + r^2 / 32) / r^4
+    // as polynomials in r^2: sq[i] = s[i] / (4 * 16^(i + 1)), cq[i] = c[i] / 16^(i + 2) (exact scalings, filled by sincos_tab())
+    double one_over_two_pi, two_pi_hi;
+    double sq[7], cq[7];
 };
 // The table travels inside the kernel's parameter block (KConst::sincos, constant bank 0) like every other constant: as a
 // __constant__ variable (bank 3) its first use in every tile was a constant-cache miss -- 14 % of the FP64 kernel's stall
@@ -177,7 +181,18 @@ struct SinCosTab {
      {-1.66666666666666666667e-01, 8.33333333333333333333e-03, -1.98412698412698412698e-04, 2.75573192239858906526e-06,          \
       -2.50521083854417187751e-08, 1.60590438368216145994e-10, -7.64716373181981647590e-13},                                     \
      {4.16666666666666666667e-02, -1.38888888888888888889e-03, 2.48015873015873015873e-05, -2.75573192239858906526e-07,          \
-      2.08767569878680989792e-09, -1.14707455977297247139e-11, 4.77947733238738529744e-14}}
+      2.08767569878680989792e-09, -1.14707455977297247139e-11, 4.77947733238738529744e-14},                                      \
+     0.15915494309189533577, 4.0 * 1.57079632679489655800e+00, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}}
+inline SinCosTab sincos_tab() {
+    SinCosTab t = VFK_SINCOS_TAB_INIT;
+    double p = 1.0 / 16.0;
+    for (int i = 0; i < 7; ++i) {
+        t.sq[i] = t.s[i] * p * 0.25;
+        p *= 1.0 / 16.0;
+        t.cq[i] = t.c[i] * p;
+    }
+    return t;
+}
 
 // TERMS = 5: x^11 / x^12 (the FP32 mode's wide chain); TERMS = 7: x^15 / x^16, truncation < 5e-17 (FP64 mode).
 template <int TERMS>
@@ -201,6 +216,37 @@ __device__ __forceinline__ void sincos_wide(const SinCosTab& k, double x, double
     const double cs = (ki & 1) ? sp : cp;
     *s = (ki & 2) ? -ss : ss;
     *c = ((ki + 1) & 2) ? -cs : cs;
+}
+// The same without quadrant logic: take whole turns off x (r = x - 2 pi k, k = rint(x / 2 pi), |r| <= pi), evaluate the
+// polynomials at the QUARTER angle u = r / 4 (|u| <= pi / 4) and double the angle twice (sin 2a = 2 sin a cos a,
+// cos 2a = 1 - 2 sin^2 a).  The division by four lives in the coefficients (sq, cq: the Taylor coefficients times exact
+// powers of 1/16, polynomials in r^2), so it costs nothing.  Five more FP64 operations than sincos_wide but none of its ~15
+// integer / select instructions per joint (the 64-bit swaps and sign flips of the quadrant selection); the two doublings
+// multiply the absolute error by < 10: 4e-11 for TERMS = 5 (checked against long double over [-12, 12]; 2 pi k is taken off
+// with the 53-bit 2 pi only, k * 2.4e-16 more), which is why only the FP32 mode's wide chain -- whose consumer keeps 6e-8 -- uses it.
+template <int TERMS>
+__device__ __forceinline__ void sincos_quarter(const SinCosTab& k, double x, double* s, double* c) {
+    const double t = fma(x, k.one_over_two_pi, k.magic);
+    const double kf = t - k.magic;
+    const double r = fma(kf, -k.two_pi_hi, x);
+    const double z = r * r;
+    double sp = k.sq[TERMS - 1], cp = k.cq[TERMS - 1];
+#pragma unroll
+    for (int i = TERMS - 2; i >= 0; --i) {
+        sp = fma(sp, z, k.sq[i]);
+        cp = fma(cp, z, k.cq[i]);
+    }
+    double sn = r * fma(sp, z, 0.25);                         // sin(r / 4)
+    double cn = fma(fma(cp, z, -0.03125), z, 1.0);            // cos(r / 4)
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const double u = sn + sn;
+        const double c2 = fma(-u, sn, 1.0);
+        sn = u * cn;
+        cn = c2;
+    }
+    *s = sn;
+    *c = cn;
 }
 template <int TERMS>
 __device__ __forceinline__ void sincos_wide(const SinCosTab&, float x, float* s, float* c) { Prec<float>::sincos_(x, s, c); }
@@ -278,7 +324,9 @@ __device__ __forceinline__ void axpy6(float (&y)[6], const float (&c)[6], float 
     }
 }
 
-// init + sign * (c . y)
+// init + sign * (c . y): one fma chain starting from init (both precisions).  dot6x2 below runs two such chains in the halves of
+// packed instructions, so the general instantiation (dot6) and the lean one (dot6x2) produce the same bits; dot6_packed is the
+// FP32 pairs-first form (5 instructions instead of 6, another association) kept for the long-chain lean shape.
 template <typename T>
 __device__ __forceinline__ T dot6(const T (&c)[6], const T (&y)[6], T init, bool negate) {
     T acc = init;
@@ -286,12 +334,32 @@ __device__ __forceinline__ T dot6(const T (&c)[6], const T (&y)[6], T init, bool
     for (int r = 0; r < 6; ++r) acc = fma(negate ? -c[r] : c[r], y[r], acc);
     return acc;
 }
-__device__ __forceinline__ float dot6(const float (&c)[6], const float (&y)[6], float init, bool negate) {
+template <typename T>
+__device__ __forceinline__ T dot6_packed(const T (&c)[6], const T (&y)[6], T init, bool negate) { return dot6(c, y, init, negate); }
+__device__ __forceinline__ float dot6_packed(const float (&c)[6], const float (&y)[6], float init, bool negate) {
     float2 v = __fmul2_rn(make_float2(c[0], c[1]), make_float2(y[0], y[1]));
     v = __ffma2_rn(make_float2(c[2], c[3]), make_float2(y[2], y[3]), v);
     v = __ffma2_rn(make_float2(c[4], c[5]), make_float2(y[4], y[5]), v);
     const float d = v.x + v.y;
     return negate ? init - d : init + d;
+}
+
+// Two dot products of one 6-vector at once: *ra = ia + c . ya, *rb = ib + c . yb.  FP32: the two right-hand sides travel as
+// register pairs and every step is one packed fma with c[r] as the broadcast scalar operand -- 6 instructions for both
+// products where two dot6 calls take 10.
+template <typename T>
+__device__ __forceinline__ void dot6x2(const T (&c)[6], const T (&ya)[6], const T (&yb)[6], T ia, T ib, T* ra, T* rb) {
+    T a = ia, b = ib;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { a = fma(c[r], ya[r], a); b = fma(c[r], yb[r], b); }
+    *ra = a; *rb = b;
+}
+__device__ __forceinline__ void dot6x2(const float (&c)[6], const float (&ya)[6], const float (&yb)[6], float ia, float ib,
+                                       float* ra, float* rb) {
+    float2 v = make_float2(ia, ib);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) v = __ffma2_rn(make_float2(c[r], c[r]), make_float2(ya[r], yb[r]), v);
+    *ra = v.x; *rb = v.y;
 }
 
 // In-place Cholesky A = L L^T of a packed SPD 6x6.  On return a[] holds L's strict
@@ -347,6 +415,42 @@ __device__ __forceinline__ void chol6_bwd(const T (&l)[21], const T (&inv_d)[6],
         });
         b[i] = t * inv_d[i];
     });
+}
+
+// Both triangular solves for TWO right-hand sides at once.  FP32: the pair {a[i], b[i]} travels in one register pair and every
+// step is one packed instruction with the matrix entry as the broadcast operand (21 instead of 42 per direction); each half
+// is the scalar solve's own operation sequence, so the results equal chol6_fwd / chol6_bwd applied to a and b separately.
+template <typename T>
+__device__ __forceinline__ void chol6_solve2(const T (&l)[21], const T (&inv_d)[6], T (&a)[6], T (&b)[6]) {
+    chol6_fwd<T>(l, inv_d, a);
+    chol6_bwd<T>(l, inv_d, a);
+    chol6_fwd<T>(l, inv_d, b);
+    chol6_bwd<T>(l, inv_d, b);
+}
+__device__ __forceinline__ void chol6_solve2(const float (&l)[21], const float (&inv_d)[6], float (&a)[6], float (&b)[6]) {
+    float2 v[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) v[r] = make_float2(a[r], b[r]);
+    static_for<0, 6>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        float2 t = v[i];
+        static_for<0, i>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            t = __ffma2_rn(make_float2(-l[tri(i, k)], -l[tri(i, k)]), v[k], t);
+        });
+        v[i] = __fmul2_rn(t, make_float2(inv_d[i], inv_d[i]));
+    });
+    static_for<0, 6>([&](auto ic) {
+        constexpr int i = 5 - decltype(ic)::value;
+        float2 t = v[i];
+        static_for<i + 1, 6>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            t = __ffma2_rn(make_float2(-l[tri(k, i)], -l[tri(k, i)]), v[k], t);
+        });
+        v[i] = __fmul2_rn(t, make_float2(inv_d[i], inv_d[i]));
+    });
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { a[r] = v[r].x; b[r] = v[r].y; }
 }
 
 // Unit quaternion (w >= 0) of a rotation matrix given row-major m[9]; Shepperd's

@@ -203,7 +203,8 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
                     Jl[k][0] = (T)p[0]; Jl[k][1] = (T)p[1]; Jl[k][2] = (T)p[2];
                     const W* tp = tipb[k];
                     W s, co;
-                    sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(c.sincos, (W)q[k], &s, &co);
+                    if constexpr (sizeof(T) == 4 && sizeof(W) == 8) sincos_quarter<5>(c.sincos, (W)q[k], &s, &co);
+                    else sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(c.sincos, (W)q[k], &s, &co);
                     const W ca = tp[0], sa = tp[1], t0 = tp[2], t1 = tp[3], t2 = tp[4];
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
@@ -419,11 +420,11 @@ vfk_split_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
 #pragma unroll
             for (int k = 0; k < NL; ++k) {
                 const T cj[6] = {Jl[k][0], Jl[k][1], Jl[k][2], Ja[k][0], Ja[k][1], Ja[k][2]};
-                const T raw = dot6(cj, yn, x[k], true);
+                const T raw = dot6_packed(cj, yn, x[k], true);
                 const T d = fma(c.ns_lookahead, raw, q[k]);
                 bad = bad || (d < limb[k][0]) || (d > limb[k][1]);
                 x[k] = raw;                                              // x is not needed any more
-                mix[k] = dot6(cj, yv, T(0), false) * c.mixer_w[0];
+                mix[k] = dot6_packed(cj, yv, T(0), false) * c.mixer_w[0];
             }
             {
                 int b = bad ? 1 : 0;
