@@ -42,6 +42,23 @@ constexpr int kSmallBlock = 128;     // threads per CTA of the small one-element
 constexpr int kChunk = VFK_CHUNK;            // obstacles per shared-memory stage (4 measured: FP64 config 2 -13 %, -30 % with 3 CTAs/SM; FP32 headline -14 %)
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 512;     // per-warp mbarriers live in the first 512 bytes of dynamic smem
+// TAB (kernel template parameter): the FP32 mode's wide kinematic chain takes sin / cos from a 128-entry table in shared
+// memory (sincos_table, vfk_math.cuh: 13 FP64 operations per joint instead of 23); the table sits between the header and
+// the per-warp regions and is built once per CTA behind the first tile's copies.  Measured on B200 (same-box A/B,
+// profiles/r02t_sincos_table_ab.txt): 17 joints K = 1 126.7 -> 123.6 us (0.820 -> 0.841 of the HBM roofline), K = 100 +3.2 %;
+// the headline shape K = 100 1.339e10 -> 1.410e10 inst-cycles/s (+5.3 %), but its single-cycle lean launch, which is
+// HBM-bound, LOSES 3.4 % (108.7 -> 112.4 us: the table's random 16-byte reads are ~10 shared-memory wavefronts each, +45 %
+// on the L1 data pipe that also takes the TMA deliveries), so the host turns it on for the long chains only
+// (launch_cycle).  -DVFK_NO_SINCOS_TABLE turns it off everywhere.
+#ifdef VFK_NO_SINCOS_TABLE
+constexpr bool kSinCosTable = false;
+#else
+constexpr bool kSinCosTable = true;
+#endif
+template <typename T>
+constexpr bool kCanTab = kSinCosTable && sizeof(T) == 4 && sizeof(typename WideOf<T>::type) == 8;
+template <typename T, bool TAB>
+constexpr uint32_t kTabBytes = (TAB && kCanTab<T>) ? kSinCosTabEntries * 16 : 0;
 // FP32 decay order 20 (the reference's typical value, old/README.old:75) by five multiplications instead of MUFU lg2 / ex2:
 // two more instructions per obstacle but two fewer on the quarter-rate XU pipe, which also carries rsqrt and the
 // FP64 <-> FP32 conversions.  Measured on B200 (1 M instances): 109.1 us vs 110.3 us per launch at K = 1, -0.6 % at
@@ -184,9 +201,10 @@ struct DhPattern {
 // tool position, which the order-20 repeller decay turns into 1e-4 relative field errors near obstacles).  Records the
 // joint axis z_j = R_j[:,2] and origin p_j before each joint, then forms J = [z x (p_e - p_j); z] (revolute) or [z; 0]
 // in T.  Outputs: R, and the tool-less flange position as hi + lo parts in T (lo = 0 when T is already wide).
-template <typename T, int N, class PAT>
+template <typename T, int N, class PAT, bool TAB = false>
 __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N], typename WideOf<T>::type (&R)[9],
-                                            typename WideOf<T>::type (&p)[3], T (&Jl)[N][3], T (&Ja)[N][3], int nc) {
+                                            typename WideOf<T>::type (&p)[3], T (&Jl)[N][3], T (&Ja)[N][3], int nc,
+                                            [[maybe_unused]] const double2* sctab) {
     using W = typename WideOf<T>::type;
     if constexpr (PAT::base_identity) {
 #pragma unroll
@@ -213,7 +231,8 @@ __device__ __forceinline__ void fk_jacobian(const KConst<T>& c, const T (&q)[N],
             W s, co;
             // FP32 mode's wide chain: the quarter-angle form (no quadrant logic, ~10 instructions fewer per joint; measured on B200
             // against sincos_wide<5>: K = 1 headline 109.5 vs 109.9 us, K = 100 +3.2 %, 17 joints +2.6 % / +3.3 %)
-            if constexpr (sizeof(T) == 4 && sizeof(W) == 8) sincos_quarter<5>(c.sincos, qj, &s, &co);
+            if constexpr (kTabBytes<T, TAB> != 0) sincos_table(c.sincos, sctab, qj, &s, &co);
+            else if constexpr (sizeof(T) == 4 && sizeof(W) == 8) sincos_quarter<5>(c.sincos, qj, &s, &co);
             else sincos_wide<(sizeof(T) == sizeof(W)) ? 7 : 5>(c.sincos, qj, &s, &co);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -557,7 +576,7 @@ __device__ __forceinline__ void issue_qg(const KArgs<T>& a, int64_t tile, int bu
 // small batches -- a warp takes 4 instances of a tile, the 8 lanes of a group split each chunk of 8 obstacles between
 // them and combine their partial repulsor sums with __shfl_xor_sync; the rest of the cycle is computed redundantly by
 // the group and lane 0 of the group stores.  A tile is then spread over 8 warps instead of one.
-template <typename T, int N, class PAT, bool EXT, bool LEAN, int MINB, int G = 1>
+template <typename T, int N, class PAT, bool EXT, bool LEAN, int MINB, int G = 1, bool TAB = false>
 __global__ void __launch_bounds__(kBlock, MINB)
 vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KArgs<T> a) {
     using WS = WarpStage<T, N, EXT>;
@@ -567,7 +586,8 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     // the bulk copies then live in uniform registers, and the copies issue without an elect-one loop around them
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem) + warp * WS::kBars;
-    unsigned char* region = smem + kSmemHeader + (size_t)warp * WS::warp_bytes(a.n_stages);
+    unsigned char* region = smem + kSmemHeader + kTabBytes<T, TAB> + (size_t)warp * WS::warp_bytes(a.n_stages);
+    [[maybe_unused]] const double2* sctab = reinterpret_cast<const double2*>(smem + kSmemHeader);
     const uint32_t bars_a = smem_u32(bars), region_a = smem_u32(region);       // shared-window addresses, once per warp
     static_assert(G == 1 || G == kChunk, "a cooperative group takes one obstacle of a chunk per lane");
     constexpr int kSub = G == 1 ? 1 : G;                        // work units per tile (G == 8: 8 units of 4 instances)
@@ -575,7 +595,9 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
     const int64_t n_units = n_tiles * kSub;
     const int64_t stride = (int64_t)gridDim.x * (kBlock / 32);
     int64_t unit = (int64_t)blockIdx.x * (kBlock / 32) + warp;
-    if (unit >= n_units) return;
+    if constexpr (kTabBytes<T, TAB> == 0) {
+        if (unit >= n_units) return;
+    }
     const int ol = lane & (G - 1);                              // obstacle lane within the group
     // Joint components in memory.  Chains with a joint count that has no instantiation of its own run in the next larger
     // generic one: joints >= nc are padding (zero Jacobian column, no motion, nothing loaded or stored for them).
@@ -595,13 +617,21 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         mbar_fence_init();
     }
     __syncwarp();
-    issue_qg<T, N, EXT>(a, unit / kSub, 0, region_a, bars_a, lane, nc);
     int64_t p_unit = unit;
     int p_u = 0, p_chunk = 0;
-    for (int u = 0; u < S; ++u) {
-        issue_obst<T, N, EXT>(a, p_unit / kSub, p_chunk, u, region_a, bars_a, lane);
-        if (++p_chunk == a.n_chunks) p_chunk = 0;
-        if (++p_u == U) { p_u = 0; p_unit += stride; }
+    if (kTabBytes<T, TAB> == 0 || unit < n_units) {
+        issue_qg<T, N, EXT>(a, unit / kSub, 0, region_a, bars_a, lane, nc);
+        for (int u = 0; u < S; ++u) {
+            issue_obst<T, N, EXT>(a, p_unit / kSub, p_chunk, u, region_a, bars_a, lane);
+            if (++p_chunk == a.n_chunks) p_chunk = 0;
+            if (++p_u == U) { p_u = 0; p_unit += stride; }
+        }
+    }
+    if constexpr (kTabBytes<T, TAB> != 0) {
+        // the sin / cos table is built behind the first tile's copies; the only CTA-wide barrier, passed once by every warp
+        // (those without work included) before any can leave
+        sincos_table_fill(c.sincos, reinterpret_cast<double2*>(smem + kSmemHeader), (int)threadIdx.x, kBlock);
+        __syncthreads();
     }
     int c_stage = 0;
     uint32_t c_phase = 0;
@@ -640,7 +670,7 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         Pos<T> pt;
         {
             W Rw[9], pw[3];
-            fk_jacobian<T, N, PAT>(c, q, Rw, pw, Jl, Ja, nc);
+            fk_jacobian<T, N, PAT, TAB>(c, q, Rw, pw, Jl, Ja, nc, sctab);
             if (LEAN || c.tool_identity) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Rt[k] = (T)Rw[k];

@@ -13,7 +13,7 @@ using namespace vfk;
 // obstacles x 32 instances) and two q/goal buffers.  Two stages measured best on B200 for both K = 1
 // (106 us vs 110 us with three at the headline shape) and K = 100 (streaming the ring from L2 every cycle at
 // full occupancy beats keeping four chunks resident at 2 CTAs/SM): gpurun_out t03, DESIGN.md section 4.1.
-template <typename T, int N, bool EXT>
+template <typename T, int N, bool EXT, bool TAB>
 static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, size_t* smem_bytes) {
     using WS = WarpStage<T, N, EXT>;
     (void)k_cycles;
@@ -28,7 +28,7 @@ static void plan_stages(int n_obst, int k_cycles, int* n_chunks, int* n_stages, 
     if (*n_chunks > 0 && *n_chunks < stages) stages = *n_chunks;
     if (*n_chunks == 0) stages = 0;
     *n_stages = stages;
-    *smem_bytes = kSmemHeader + (size_t)(kBlock / 32) * WS::warp_bytes(stages);
+    *smem_bytes = kSmemHeader + kTabBytes<T, TAB> + (size_t)(kBlock / 32) * WS::warp_bytes(stages);
 }
 
 // Lanes per instance of the split shape for (precision, joints, pattern); 0 = the one-thread-per-instance kernel only.
@@ -104,7 +104,12 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.n_obst_p = (n_obst + 1) & ~1;
     a.k_cycles = k_cycles;
     size_t smem = 0;
-    plan_stages<T, N, EXT>(n_obst, k_cycles, &a.n_chunks, &a.n_stages, &smem);
+    // sin / cos of the FP32 mode's wide chain from the shared-memory table for the long chains (vfk_kernels.cuh: TAB).  The
+    // short chains keep the polynomial in EVERY instantiation: their HBM-bound single-cycle lean launch loses 3.4 % with the
+    // table, and K fused cycles must stay bit-identical to K single-cycle launches, so the K-fused kernel cannot take it alone
+    // (it would gain 5.3 %: profiles/r02t_sincos_table_ab.txt).
+    constexpr bool TAB = kCanTab<T> && N >= 10 && G == 1;
+    plan_stages<T, N, EXT, TAB>(n_obst, k_cycles, &a.n_chunks, &a.n_stages, &smem);
     a.n_full = n_obst / kChunk;
     a.n_rem = n_obst % kChunk;
 #ifndef VFK_MINB_F32
@@ -130,7 +135,7 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
 #else
     constexpr int MINB = MINB0;
 #endif
-    auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB, G>;
+    auto kern = vfk_cycle_kernel<T, N, PAT, EXT, LEAN, MINB, G, TAB>;
     // per (instantiation, device, smem size): opt in to > 48 KB of dynamic shared memory and ask the occupancy once
     static PlanCache plans;
     int per_sm = 0;

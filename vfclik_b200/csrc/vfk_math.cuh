@@ -172,6 +172,7 @@ struct SinCosTab {
     // as polynomials in r^2: sq[i] = s[i] / (4 * 16^(i + 1)), cq[i] = c[i] / 16^(i + 2) (exact scalings, filled by sincos_tab())
     double one_over_two_pi, two_pi_hi;
     double sq[7], cq[7];
+    double tab_inv_h, tab_h;    // sincos_table: 128 / 2 pi and the 53-bit 2 pi / 128
 };
 // The table travels inside the kernel's parameter block (KConst::sincos, constant bank 0) like every other constant: as a
 // __constant__ variable (bank 3) its first use in every tile was a constant-cache miss -- 14 % of the FP64 kernel's stall
@@ -182,7 +183,8 @@ struct SinCosTab {
       -2.50521083854417187751e-08, 1.60590438368216145994e-10, -7.64716373181981647590e-13},                                     \
      {4.16666666666666666667e-02, -1.38888888888888888889e-03, 2.48015873015873015873e-05, -2.75573192239858906526e-07,          \
       2.08767569878680989792e-09, -1.14707455977297247139e-11, 4.77947733238738529744e-14},                                      \
-     0.15915494309189533577, 4.0 * 1.57079632679489655800e+00, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}}
+     0.15915494309189533577, 4.0 * 1.57079632679489655800e+00, {0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0},           \
+     128.0 * 0.15915494309189533577, 4.0 * 1.57079632679489655800e+00 / 128.0}
 inline SinCosTab sincos_tab() {
     SinCosTab t = VFK_SINCOS_TAB_INIT;
     double p = 1.0 / 16.0;
@@ -247,6 +249,32 @@ __device__ __forceinline__ void sincos_quarter(const SinCosTab& k, double x, dou
     }
     *s = sn;
     *c = cn;
+}
+// Table form (the FP32 mode's wide chain, -DVFK_SINCOS_TABLE): x = k h + r with h = 2 pi / 128, |r| <= h / 2 = 0.0245;
+// {sin(k h), cos(k h)} comes from a 128-entry table in shared memory (2 KB per CTA, filled once per CTA by
+// sincos_table_fill), sin r and cos r from r - r^3/6 + r^5/120 and 1 - r^2/2 + r^4/24 (truncation < 1e-15 and < 3e-13),
+// and the angle sum puts them together: 13 FP64 operations, one LOP3, one address and one LDS.128 per joint against the
+// quarter-angle form's 23 FP64 operations, no quadrant logic either, and a dependent chain half as long.
+constexpr int kSinCosTabEntries = 128;
+__device__ __forceinline__ void sincos_table(const SinCosTab& k, const double2* tab, double x, double* s, double* c) {
+    const double t = fma(x, k.tab_inv_h, k.magic);
+    const int ki = __double2loint(t);
+    const double kf = t - k.magic;
+    const double r = fma(kf, -k.tab_h, x);
+    const double2 sc = tab[ki & (kSinCosTabEntries - 1)];
+    const double z = r * r;
+    const double sr = fma(r * z, fma(z, 1.0 / 120.0, -1.0 / 6.0), r);
+    const double cr = fma(z, fma(z, 1.0 / 24.0, -0.5), 1.0);
+    *s = fma(sc.x, cr, sc.y * sr);
+    *c = fma(sc.y, cr, -(sc.x * sr));
+}
+// entry k = {sin, cos}(2 pi k / 128) to FP64 accuracy (the x^15 / x^16 polynomials); the caller synchronises the CTA afterwards
+__device__ __forceinline__ void sincos_table_fill(const SinCosTab& k, double2* tab, int tid, int nthreads) {
+    for (int e = tid; e < kSinCosTabEntries; e += nthreads) {
+        double s, c;
+        sincos_wide<7>(k, (double)e * k.tab_h, &s, &c);
+        tab[e] = make_double2(s, c);
+    }
 }
 template <int TERMS>
 __device__ __forceinline__ void sincos_wide(const SinCosTab&, float x, float* s, float* c) { Prec<float>::sincos_(x, s, c); }
