@@ -35,6 +35,7 @@ for precision in (32, 64):
     run(lwr, precision, 70, 33)                                             # lean, odd obstacle count (padding slot), ragged tile
     run(lwr, precision, 70, 9, outputs=full)                                # general
     run(workloads.dual_arm_torso_chain(), precision, 100, 20)               # DhPattern lean (slim path, 3 stages)
+    run(workloads.dual_arm_torso_chain(), precision, 40, 20)                # two tiles: two warps of the CTA have no work (they still pass the table barrier)
     run(workloads.dual_arm_torso_chain(), precision, 100, 20, env={"VFK_SPLIT": "1"})     # lane-split kernel (tensor-map TMA)
     run(workloads.dual_arm_torso_chain(10), precision, 100, 7, env={"VFK_SPLIT": "1"})
     run(workloads.torso_arm_chain(8), precision, 64, 5, outputs=full)       # padded chain in the 10-joint instantiation

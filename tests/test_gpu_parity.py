@@ -464,6 +464,39 @@ def test_joint_angles_beyond_one_turn(lwr, built_lib, precision, rtol, pose_atol
         e.close()
 
 
+@pytest.mark.parametrize("n", [40, 3000])
+def test_long_chain_fp32_table_sincos(built_lib, n):
+    """The FP32 mode's long chains (N >= 10) take the sin / cos of their FP64 kinematic chain from the 128-entry shared-memory
+    table (vfk_math.cuh: sincos_table): joint angles of several turns in both directions still match the oracle's libm, in
+    the lean and in the general instantiation; n = 40 leaves two warps of the only CTA without a tile (they must still pass
+    the table's barrier); K fused cycles stay bit-identical to K single-cycle launches (every long-chain instantiation uses
+    the table)."""
+    from vfclik_b200 import workloads
+    from vfclik_b200.engine import DeviceBatch, Engine
+    chain = workloads.dual_arm_torso_chain()
+    wide = dataclasses.replace(chain, q_lo=np.full(17, -4 * np.pi), q_hi=np.full(17, 4 * np.pi))
+    e = Engine(wide, precision=32)
+    try:
+        w = workloads.random_batch(wide, n, 20, seed=33, dtype=np.float32)
+        assert np.abs(w["q"]).max() > 3 * np.pi and w["q"].min() < -3 * np.pi
+        out = run_gpu(e, w, 20, outputs=("qdot_vf", "qdot_ns", "qdot", "pose"))
+        ref = run_oracle(wide, e.params, w, 20)
+        check(out, ref, FP32_RTOL, keys=("qdot_vf", "qdot_ns", "qdot"), pose_atol=1e-5)
+        lean = run_gpu(e, w, 20, outputs=("qdot",))
+        check(lean, ref, FP32_RTOL, keys=("qdot",))
+        db = DeviceBatch(e, n, 20, outputs=("qdot",))
+        db.upload("goal", w["goal"]); db.upload("obst", w["obst"])
+        db.upload("q", w["q"])
+        for _ in range(4):
+            db.step(1)
+        q_loop, qd_loop = db.download("q"), db.download("qdot")
+        db.upload("q", w["q"])
+        db.step(4)
+        assert np.array_equal(db.download("q"), q_loop) and np.array_equal(db.download("qdot"), qd_loop)
+    finally:
+        e.close()
+
+
 def test_host_session_matches_device_path(eng, lwr):
     """The host-buffer C-ABI session (numpy in / numpy out) gives the same numbers as the device path."""
     from vfclik_b200 import workloads
