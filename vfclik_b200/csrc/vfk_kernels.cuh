@@ -643,6 +643,25 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         const int64_t tN = tile * (nc * 32) + slot;             // this instance's slot in a blocked array of nc joint components
         __syncwarp();
         if (unit + stride < n_units) issue_qg<T, N, EXT>(a, (unit + stride) / kSub, (it + 1) & 1, region_a, bars_a, lane, nc);
+        // L2 prefetch of the rest of THIS tile.  The two-stage ring can request chunk c + S only when chunk c has been consumed,
+        // one chunk-time (~0.4 us) before it is needed -- less than the loaded DRAM latency, so every chunk from S onwards used to
+        // stall its warp (long-scoreboard 1.19 per issue on the headline launch).  One cp.async.bulk.prefetch.L2 (SASS UBLKPF.L2)
+        // per tile, issued before the tile's arithmetic starts, brings those chunks (contiguous: 8 KB at M = 32) into L2 2 - 3 us
+        // ahead, and the ring's copies hit there.  No shared memory, no extra DRAM traffic.  Measured on B200, same-box A/B
+        // (profiles/r02u_l2_prefetch_ab.txt): headline launch 110.1 -> 105.4 us (0.955 -> 0.998 of the HBM roofline), 17 joints
+        // 127.6 -> 119.1 us (0.815 -> 0.873).  Distance matters: the same instruction one TILE ahead (~7 us) cost 19 % -- the lines
+        // were evicted before use and read twice; after the previous tile's repulsor loop (~5 us) it gains nothing, after this
+        // tile's kinematic chain (~1.5 us) a third of what it gains here.  Blocks over 32 KB (M = 256) are left to the ring, which is at the copy peak
+        // there; a launch of fewer than four tiles per warp is dominated by its start, where every warp's demand copies are
+        // queued at once, and skips the prefetch on its first tile (FP64 config 2: -3 % otherwise).
+#ifndef VFK_NO_PREFETCH
+        if constexpr (G == 1) {
+            const int first = S * kChunk;
+            const uint32_t bytes = a.n_obst_p > first ? (uint32_t)(a.n_obst_p - first) * 32u * (uint32_t)sizeof(Vec4<T>) : 0u;
+            if (!resident && bytes != 0 && bytes <= 32768u && (it > 0 || n_units >= 4 * stride) && lane == 0)
+                bulk_prefetch_l2(a.obst + (tile * a.n_obst_p + first) * 32, bytes);
+        }
+#endif
         mbar_wait_a(bars_a + 8u * (uint32_t)(kMaxStages + (it & 1)), (uint32_t)(it >> 1) & 1u);
         const T* qg = reinterpret_cast<const T*>(region + (size_t)a.n_stages * WS::kStage + (size_t)(it & 1) * WS::kQg) + slot;
 

@@ -79,4 +79,9 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src_gmem, u
                  : "memory");
 }
 
+// Bulk prefetch of a contiguous block global -> L2 (no shared memory, no completion to wait for): the bulk copy that follows hits L2.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 }  // namespace vfk
