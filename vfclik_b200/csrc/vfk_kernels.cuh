@@ -43,13 +43,14 @@ constexpr int kChunk = VFK_CHUNK;            // obstacles per shared-memory stag
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 512;     // per-warp mbarriers live in the first 512 bytes of dynamic smem
 // TAB (kernel template parameter): the FP32 mode's wide kinematic chain takes sin / cos from a 128-entry table in shared
-// memory (sincos_table, vfk_math.cuh: 13 FP64 operations per joint instead of 23); the table sits between the header and
-// the per-warp regions and is built once per CTA behind the first tile's copies.  Measured on B200 (same-box A/B,
-// profiles/r02t_sincos_table_ab.txt): 17 joints K = 1 126.7 -> 123.6 us (0.820 -> 0.841 of the HBM roofline), K = 100 +3.2 %;
-// the headline shape K = 100 1.339e10 -> 1.410e10 inst-cycles/s (+5.3 %), but its single-cycle lean launch, which is
-// HBM-bound, LOSES 3.4 % (108.7 -> 112.4 us: the table's random 16-byte reads are ~10 shared-memory wavefronts each, +45 %
-// on the L1 data pipe that also takes the TMA deliveries), so the host turns it on for the long chains only
-// (launch_cycle).  -DVFK_NO_SINCOS_TABLE turns it off everywhere.
+// memory (sincos_table, vfk_math.cuh: 13 FP64 operations per joint instead of 23, a dependent chain half as long); the
+// table sits between the header and the per-warp regions and is built once per CTA behind the first tile's copies.
+// Measured on B200 (same-box A/Bs, profiles/r02t_sincos_table_ab.txt): 17 joints K = 1 126.7 -> 123.6 us, K = 100 +3.2 %;
+// the headline shape K = 100 +4.7 - 5.3 % (1.34 -> 1.40e10 inst-cycles/s) and 0.983 instead of 0.960 of the HBM roofline
+// over 1000 launches (less FP64 work, later power cap).  Its HBM-bound single-cycle launch lost 3.4 % with the table while
+// every chunk still waited for DRAM (the table's random 16-byte reads are ~10 shared-memory wavefronts each, +45 % on the
+// L1 data pipe that also takes the TMA deliveries); with the L2 prefetch in place it is unchanged, so the host turns the
+// table on for every FP32 instantiation (launch_cycle).  -DVFK_NO_SINCOS_TABLE turns it off everywhere.
 #ifdef VFK_NO_SINCOS_TABLE
 constexpr bool kSinCosTable = false;
 #else

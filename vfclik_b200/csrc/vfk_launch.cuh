@@ -104,11 +104,15 @@ static int launch_cycle(vfk_ctx* h, const KConst<T>& c, const vfk_buffers* b, in
     a.n_obst_p = (n_obst + 1) & ~1;
     a.k_cycles = k_cycles;
     size_t smem = 0;
-    // sin / cos of the FP32 mode's wide chain from the shared-memory table for the long chains (vfk_kernels.cuh: TAB).  The
-    // short chains keep the polynomial in EVERY instantiation: their HBM-bound single-cycle lean launch loses 3.4 % with the
-    // table, and K fused cycles must stay bit-identical to K single-cycle launches, so the K-fused kernel cannot take it alone
-    // (it would gain 5.3 %: profiles/r02t_sincos_table_ab.txt).
-    constexpr bool TAB = kCanTab<T> && N >= 10 && G == 1;
+    // sin / cos of the FP32 mode's wide chain from the shared-memory table (vfk_kernels.cuh: TAB) in EVERY instantiation of the
+    // throughput shape, so that K fused cycles stay bit-identical to K single-cycle launches.  Before the L2 prefetch of the
+    // obstacle block the HBM-bound single-cycle lean launch of the short chains lost 3.4 % with the table; with the prefetch
+    // it is unchanged (104.9 vs 104.7 us) and the K-fused launch gains 4.7 % (profiles/r02t_sincos_table_ab.txt).
+    // -DVFK_TAB_MIN_JOINTS=10 restricts the table to the long chains again.
+#ifndef VFK_TAB_MIN_JOINTS
+#define VFK_TAB_MIN_JOINTS 1
+#endif
+    constexpr bool TAB = kCanTab<T> && N >= VFK_TAB_MIN_JOINTS && G == 1;
     plan_stages<T, N, EXT, TAB>(n_obst, k_cycles, &a.n_chunks, &a.n_stages, &smem);
     a.n_full = n_obst / kChunk;
     a.n_rem = n_obst % kChunk;
