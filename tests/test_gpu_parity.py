@@ -445,8 +445,9 @@ def test_all_joint_types(built_lib):
 
 @pytest.mark.parametrize("precision, rtol, pose_atol", [(64, FP64_RTOL, 1e-12), (32, FP32_RTOL, 2e-6)])
 def test_joint_angles_beyond_one_turn(lwr, built_lib, precision, rtol, pose_atol):
-    """Continuous joints: angles of several turns (limits +-4 pi) go through the kernels' own sin / cos (whole-turn reduction of
-    the quarter angle in the FP32 mode's wide chain, quadrant reduction in the FP64 mode) and still match the oracle's libm."""
+    """Continuous joints: angles of several turns (limits +-4 pi) go through the kernels' own sin / cos (reduction to the
+    nearest of 128 table angles in the FP32 mode's wide chain, quadrant reduction in the FP64 mode) and still match the
+    oracle's libm."""
     from vfclik_b200 import workloads
     from vfclik_b200.engine import Engine, Params
     chain, cfg = lwr
@@ -466,11 +467,11 @@ def test_joint_angles_beyond_one_turn(lwr, built_lib, precision, rtol, pose_atol
 
 @pytest.mark.parametrize("n", [40, 3000])
 def test_long_chain_fp32_table_sincos(built_lib, n):
-    """The FP32 mode's long chains (N >= 10) take the sin / cos of their FP64 kinematic chain from the 128-entry shared-memory
-    table (vfk_math.cuh: sincos_table): joint angles of several turns in both directions still match the oracle's libm, in
-    the lean and in the general instantiation; n = 40 leaves two warps of the only CTA without a tile (they must still pass
-    the table's barrier); K fused cycles stay bit-identical to K single-cycle launches (every long-chain instantiation uses
-    the table)."""
+    """The FP32 mode takes the sin / cos of its FP64 kinematic chain from the 128-entry shared-memory table (vfk_math.cuh:
+    sincos_table); here on the 17-joint chain: joint angles of several turns in both directions still match the oracle's
+    libm, in the lean and in the general instantiation; n = 40 leaves two warps of the only CTA without a tile (they must
+    still pass the table's barrier); K fused cycles stay bit-identical to K single-cycle launches (every instantiation
+    uses the table)."""
     from vfclik_b200 import workloads
     from vfclik_b200.engine import DeviceBatch, Engine
     chain = workloads.dual_arm_torso_chain()

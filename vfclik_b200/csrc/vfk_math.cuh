@@ -250,7 +250,7 @@ __device__ __forceinline__ void sincos_quarter(const SinCosTab& k, double x, dou
     *s = sn;
     *c = cn;
 }
-// Table form (the FP32 mode's wide chain, -DVFK_SINCOS_TABLE): x = k h + r with h = 2 pi / 128, |r| <= h / 2 = 0.0245;
+// Table form (the FP32 mode's wide chain; vfk_kernels.cuh: TAB): x = k h + r with h = 2 pi / 128, |r| <= h / 2 = 0.0245;
 // {sin(k h), cos(k h)} comes from a 128-entry table in shared memory (2 KB per CTA, filled once per CTA by
 // sincos_table_fill), sin r and cos r from r - r^3/6 + r^5/120 and 1 - r^2/2 + r^4/24 (truncation < 1e-15 and < 3e-13),
 // and the angle sum puts them together: 13 FP64 operations, one LOP3, one address and one LDS.128 per joint against the
