@@ -433,3 +433,23 @@ def test_injected_transport():
     finally:
         ports.use_transport(None)
     assert ports.transport() is ports
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU: one JSON line with the GPU
+    arm's metric / unit / config, `impl`, a `cpu_baseline` describing this very run and an `e2e` that copies no bytes."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--cpu-cycles", "10"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "instance-control-cycles/sec" and d["unit"] == "inst-cycles/s"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert d["config"]["workload"].startswith("config3")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "control cycles" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
