@@ -652,9 +652,9 @@ vfk_cycle_kernel(const __grid_constant__ KConst<T> c, const __grid_constant__ KA
         // (profiles/r02u_l2_prefetch_ab.txt): headline launch 110.1 -> 105.4 us (0.955 -> 0.998 of the HBM roofline), 17 joints
         // 127.6 -> 119.1 us (0.815 -> 0.873).  Distance matters: the same instruction one TILE ahead (~7 us) cost 19 % -- the lines
         // were evicted before use and read twice; after the previous tile's repulsor loop (~5 us) it gains nothing, after this
-        // tile's kinematic chain (~1.5 us) a third of what it gains here.  Blocks over 32 KB (M = 256) are left to the ring, which is at the copy peak
-        // there; a launch of fewer than four tiles per warp is dominated by its start, where every warp's demand copies are
-        // queued at once, and skips the prefetch on its first tile (FP64 config 2: -3 % otherwise).
+        // tile's kinematic chain (~1.5 us) a third of what it gains here.  Blocks over 32 KB (M = 256) are left to the ring,
+        // which is at the copy peak there; a launch of fewer than four tiles per warp is dominated by its start, where every
+        // warp's demand copies are queued at once, and skips the prefetch on its first tile (FP64 config 2: -3 % otherwise).
 #ifndef VFK_NO_PREFETCH
         if constexpr (G == 1) {
             const int first = S * kChunk;
